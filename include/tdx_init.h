@@ -1,0 +1,164 @@
+/*
+ * tdx_init.h -- C ABI of the B200 (sm_100a) fused-initialisation kernel library
+ * (libtdx_init.so).
+ *
+ * This is the drop-in boundary BELOW the Python/pybind surface of
+ * torchdistx.deferred_init.  The reference replays every recorded aten op
+ * through the PyTorch dispatcher, one ATen kernel per op
+ * (reference: src/cc/torchdistx/deferred_init.cc:218-220 `handle.callBoxed`,
+ * :256-272 `Op::materialize`, :506-528 `OpNode::materialize`).  Here the whole
+ * recorded expression of one tensor (empty -> uniform_/normal_/fill_/zero_ ->
+ * mul/add/erfinv/clamp ...) is folded by the host-side planner into ONE
+ * `TdxInitDesc`, and a table of descriptors is executed by one persistent
+ * kernel launch per kernel family.
+ *
+ * Rules of the ABI: plain C, no torch types, no exceptions, no allocation.
+ * Every buffer (destination tensors, device workspace) is owned by the caller.
+ * All functions return 0 on success or a (positive) cudaError_t value /
+ * negative TDX_E* code on failure; tdx_last_error() gives a message.
+ *
+ * Random stream specification (normative; restated on the CPU in
+ * oracle/tdx_oracle.c and pinned by tests/golden):
+ *
+ *   Philox4x32-R (R = 10 unless TDX_ALGO_*_R7), key = (seed_lo, seed_hi),
+ *   counter = (blk_lo, blk_hi, off_lo, off_hi | 0x80000000)
+ *   where off = TdxInitDesc.philox_offset (the torch generator offset at the
+ *   time the op was issued == unique id of this RNG op under that seed) and
+ *   blk = floor(g / EPB) for GLOBAL linear element index g of the unsharded
+ *   tensor.  EPB = 8 for 16-bit outputs (16 random bits per element), 4 for
+ *   32-bit outputs.  Bit 31 of counter.w keeps the stream disjoint from
+ *   ATen's own (offset, thread-id) use of the same generator
+ *   (ATen/native/cuda/DistributionTemplates.h:72-88); bits 30/29 of counter.w
+ *   select the two tail-refinement blocks of the 16-bit normal.
+ *   Because the value of element g depends only on (seed, off, g), any
+ *   partition of [0, numel) over ranks reproduces the unsharded tensor
+ *   bit-for-bit.
+ */
+#ifndef TDX_INIT_H_
+#define TDX_INIT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define TDX_C_API __attribute__((visibility("default")))
+#else
+#define TDX_C_API
+#endif
+
+#define TDX_ABI_VERSION 1
+
+/* element type of the destination */
+enum {
+  TDX_F32 = 0,
+  TDX_BF16 = 1,
+  TDX_F16 = 2,
+  /* raw widths: only valid with TDX_SRC_CONST (bit-pattern fill) */
+  TDX_RAW8 = 8,
+  TDX_RAW16 = 9,
+  TDX_RAW32 = 10,
+  TDX_RAW64 = 11,
+};
+
+/* source of the expression (what the LAST full-tensor writer produces) */
+enum {
+  TDX_SRC_CONST = 0,   /* fill_/zero_/zeros/ones/full, constant-folded chains */
+  TDX_SRC_UNIFORM = 1, /* uniform_(from,to), rand, kaiming_uniform_, xavier_uniform_ */
+  TDX_SRC_NORMAL = 2,  /* normal_(mean,std), randn, kaiming_normal_, xavier_normal_ */
+};
+
+/* sampling algorithm.  0 = the shipped default for (src, dtype). */
+enum {
+  TDX_ALGO_DEFAULT = 0,
+  TDX_ALGO_ICDF16 = 1, /* 16-bit dtypes: inverse-CDF on 16 random bits/element + tail refinement */
+  TDX_ALGO_BM32 = 2,   /* Box-Muller on 32 random bits/element (f32 default) */
+  TDX_ALGO_BM16 = 3,   /* experimental: Box-Muller on 16-bit pairs, no tail refinement */
+  TDX_ALGO_R7 = 0x10,  /* OR-able flag, experimental: Philox4x32-7 instead of -10 */
+};
+
+/* epilogue steps, applied in order after the source transform; every step
+ * rounds its result to the destination dtype, exactly like a chain of in-place
+ * ATen ops on a tensor of that dtype does. */
+enum {
+  TDX_EPI_MUL = 1,    /* x = x * a            (mul_, mul.Tensor/Scalar)  */
+  TDX_EPI_ADD = 2,    /* x = x + a            (add_, add.Tensor/Scalar with alpha folded) */
+  TDX_EPI_ERFINV = 3, /* x = erfinv(x)        (trunc_normal_)            */
+  TDX_EPI_CLAMP = 4,  /* x = min(max(x,a),b)  (clamp_)                   */
+};
+#define TDX_MAX_EPI 4
+
+typedef struct TdxEpiStep {
+  uint32_t op;
+  float a;
+  float b;
+} TdxEpiStep;
+
+/* One fused per-tensor (or per-shard) initialisation program.  128 bytes. */
+typedef struct TdxInitDesc {
+  void* dst;              /* device address where element `elem_begin` is written */
+  uint64_t elem_begin;    /* global linear index (unsharded tensor) of the first element written */
+  uint64_t elem_count;    /* number of consecutive elements written */
+  uint64_t philox_seed;   /* generator seed           (RNG sources) */
+  uint64_t philox_offset; /* generator offset at issue (RNG sources) */
+  double p0;              /* UNIFORM: from   NORMAL: mean */
+  double p1;              /* UNIFORM: to     NORMAL: std  */
+  uint64_t fill_bits[2];  /* CONST: 16-byte store pattern (element bits replicated) */
+  uint8_t dtype;          /* TDX_F32 ... */
+  uint8_t src;            /* TDX_SRC_* */
+  uint8_t algo;           /* TDX_ALGO_* */
+  uint8_t n_epi;          /* number of valid epilogue steps */
+  uint32_t reserved;
+  TdxEpiStep epi[TDX_MAX_EPI];
+} TdxInitDesc;
+
+/* Bytes of device workspace tdx_init_launch() needs for `n` descriptors. */
+TDX_C_API size_t tdx_init_workspace_bytes(int n);
+
+/*
+ * Validates and executes `n` descriptors on `stream` (a cudaStream_t passed as
+ * void*; NULL = legacy default stream) of the CURRENT device.
+ * `descs` is host memory; `workspace` is device memory of at least
+ * tdx_init_workspace_bytes(n) bytes that must stay untouched until the
+ * launches complete.  Asynchronous w.r.t. the host.
+ * Replaces: the per-op replay loop of OpNode::materialize
+ * (reference deferred_init.cc:506-528).
+ */
+TDX_C_API int tdx_init_launch(const TdxInitDesc* descs, int n, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
+/*
+ * Two-phase variant for callers that re-launch one plan (benchmarks, CUDA
+ * graphs): upload once, launch many times.  `tdx_plan_upload` copies the
+ * grouped descriptor table into `workspace`; `tdx_plan_launch` only issues the
+ * kernels (plus one 4-byte memset per family for the work counter).
+ */
+typedef struct TdxPlan {
+  uint64_t opaque[128]; /* host-side copy of the plan header; owned by the caller */
+} TdxPlan;
+TDX_C_API int tdx_plan_upload(const TdxInitDesc* descs, int n, void* workspace,
+                              size_t workspace_bytes, void* stream, TdxPlan* plan);
+TDX_C_API int tdx_plan_launch(const TdxPlan* plan, void* workspace, void* stream);
+
+/* Number of kernel launches the last tdx_plan_launch/tdx_init_launch on this
+ * thread issued (one per non-empty kernel family). */
+TDX_C_API int tdx_last_launch_count(void);
+
+/* Elements of the global tensor covered by one Philox block for this dtype/algo
+ * (the planner rounds RNG consumption with it). */
+TDX_C_API int tdx_elems_per_block(int dtype, int src, int algo);
+
+TDX_C_API int tdx_abi_version(void);
+TDX_C_API const char* tdx_last_error(void);
+
+#define TDX_E_BADARG (-1)
+#define TDX_E_WORKSPACE (-2)
+#define TDX_E_NODEVICE (-3)
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDX_INIT_H_ */

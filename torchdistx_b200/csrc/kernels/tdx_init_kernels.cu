@@ -1,0 +1,869 @@
+// libtdx_init.so -- fused parameter-initialisation kernels for B200 (sm_100a).
+//
+// What this replaces: the reference materialises a deferred tensor by replaying
+// every recorded aten op through the dispatcher, one stock ATen kernel per op,
+// dead (overwritten) ops included
+// (reference src/cc/torchdistx/deferred_init.cc:506-528 OpNode::materialize,
+//  :256-272 Op::materialize, :218-220 handle.callBoxed).
+// Here one TdxInitDesc carries the folded expression of a whole tensor and a
+// persistent kernel streams it to HBM exactly once: Philox counter-based RNG in
+// registers, 128-bit coalesced stores, zero reads, no intermediates.
+//
+// Roofline: pure HBM write.  Algorithmic bytes = elem_count * itemsize per
+// descriptor.  The secondary ceiling is instruction issue: Philox4x32-10 costs
+// 40 slots per 128 random bits, so 16-bit outputs draw 16 random bits per
+// element (8 elements per Philox block) and the normal transform is a
+// branch-free inverse CDF (1 MUFU + 8 FMA-pipe ops per element) instead of
+// Box-Muller (2 MUFU per element, which caps below the HBM roof on B200's
+// 16 MUFU lanes/SM/clk).  See DESIGN.md "Kernels".
+//
+// Scheduling: one kernel launch per kernel family (<= a handful per module, not
+// one per tensor).  Grid = #SM x resident CTAs; CTAs grab 256 KiB chunks of the
+// family's global tile space from an atomic counter, so small and large
+// tensors, shards and ragged tails balance across all 148 SMs.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "philox.cuh"
+#include "tdx_init.h"
+
+namespace tdx {
+
+constexpr int kThreads = 256;
+constexpr int kVecsPerThread = 4;
+constexpr int kTileVecs = kThreads * kVecsPerThread;  // 1024 x 16 B = 16 KiB per tile
+constexpr int kTilesPerChunk = 16;                    // 256 KiB per work grab
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float mufu_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_sqrt(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_sin(float x) {
+  float y;
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_cos(float x) {
+  float y;
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 128-bit streaming store: the data is written once and never re-read by this kernel.
+__device__ __forceinline__ void store_vec(void* p, uint4 v) {
+  asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+
+template <class Out>
+struct OutTraits;
+template <>
+struct OutTraits<float> {
+  static constexpr int kEpv = 4;
+  static constexpr int kDtype = TDX_F32;
+  __device__ static __forceinline__ float round_through(float v) { return v; }
+  __device__ static __forceinline__ void store_one(void* dst, uint64_t i, float v) {
+    static_cast<float*>(dst)[i] = v;
+  }
+  __device__ static __forceinline__ uint4 pack(const float (&v)[4]) {
+    return make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]),
+                      __float_as_uint(v[3]));
+  }
+  // largest representable value strictly below `to`
+  __device__ static __forceinline__ float prev(float to) {
+    uint32_t b = __float_as_uint(to);
+    if (to > 0.f) return __uint_as_float(b - 1);
+    if (to < 0.f) return __uint_as_float(b + 1);
+    return __uint_as_float(0x80000001u);
+  }
+};
+template <>
+struct OutTraits<__nv_bfloat16> {
+  static constexpr int kEpv = 8;
+  static constexpr int kDtype = TDX_BF16;
+  __device__ static __forceinline__ float round_through(float v) {
+    return __bfloat162float(__float2bfloat16_rn(v));
+  }
+  __device__ static __forceinline__ void store_one(void* dst, uint64_t i, float v) {
+    static_cast<__nv_bfloat16*>(dst)[i] = __float2bfloat16_rn(v);
+  }
+  __device__ static __forceinline__ uint4 pack(const float (&v)[8]) {
+    uint4 r;
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]);
+    __nv_bfloat162 d = __floats2bfloat162_rn(v[6], v[7]);
+    r.x = *reinterpret_cast<uint32_t*>(&a);
+    r.y = *reinterpret_cast<uint32_t*>(&b);
+    r.z = *reinterpret_cast<uint32_t*>(&c);
+    r.w = *reinterpret_cast<uint32_t*>(&d);
+    return r;
+  }
+  __device__ static __forceinline__ float prev(float to) {  // `to` is exactly a bf16 value
+    uint32_t b = __float_as_uint(to);
+    if (to > 0.f) return __uint_as_float(b - 0x10000u);
+    if (to < 0.f) return __uint_as_float(b + 0x10000u);
+    return __uint_as_float(0x80010000u);
+  }
+};
+template <>
+struct OutTraits<__half> {
+  static constexpr int kEpv = 8;
+  static constexpr int kDtype = TDX_F16;
+  __device__ static __forceinline__ float round_through(float v) {
+    return __half2float(__float2half_rn(v));
+  }
+  __device__ static __forceinline__ void store_one(void* dst, uint64_t i, float v) {
+    static_cast<__half*>(dst)[i] = __float2half_rn(v);
+  }
+  __device__ static __forceinline__ uint4 pack(const float (&v)[8]) {
+    uint4 r;
+    __half2 a = __floats2half2_rn(v[0], v[1]);
+    __half2 b = __floats2half2_rn(v[2], v[3]);
+    __half2 c = __floats2half2_rn(v[4], v[5]);
+    __half2 d = __floats2half2_rn(v[6], v[7]);
+    r.x = *reinterpret_cast<uint32_t*>(&a);
+    r.y = *reinterpret_cast<uint32_t*>(&b);
+    r.z = *reinterpret_cast<uint32_t*>(&c);
+    r.w = *reinterpret_cast<uint32_t*>(&d);
+    return r;
+  }
+  __device__ static __forceinline__ float prev(float to) {  // `to` is exactly an fp16 value
+    unsigned short h = __half_as_ushort(__float2half_rn(to));
+    if (to > 0.f) return __half2float(__ushort_as_half(static_cast<unsigned short>(h - 1)));
+    if (to < 0.f) return __half2float(__ushort_as_half(static_cast<unsigned short>(h + 1)));
+    return __half2float(__ushort_as_half(static_cast<unsigned short>(0x8001)));
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// epilogue: the in-place elementwise ops recorded after the source op
+// ---------------------------------------------------------------------------------------------
+struct EpiParams {
+  uint32_t n;
+  uint32_t op[TDX_MAX_EPI];
+  float a[TDX_MAX_EPI];
+  float b[TDX_MAX_EPI];
+};
+
+__device__ __forceinline__ EpiParams load_epi(const TdxInitDesc& d) {
+  EpiParams e;
+  e.n = d.n_epi;
+#pragma unroll
+  for (int i = 0; i < TDX_MAX_EPI; ++i) {
+    e.op[i] = d.epi[i].op;
+    e.a[i] = d.epi[i].a;
+    e.b[i] = d.epi[i].b;
+  }
+  return e;
+}
+
+template <class Out>
+__device__ __forceinline__ float apply_epi(const EpiParams& e, float v) {
+  using T = OutTraits<Out>;
+  v = T::round_through(v);
+#pragma unroll
+  for (int i = 0; i < TDX_MAX_EPI; ++i) {
+    if (i < static_cast<int>(e.n)) {
+      switch (e.op[i]) {
+        case TDX_EPI_MUL: v = v * e.a[i]; break;
+        case TDX_EPI_ADD: v = v + e.a[i]; break;
+        case TDX_EPI_ERFINV: v = erfinvf(v); break;
+        case TDX_EPI_CLAMP: v = fminf(fmaxf(v, e.a[i]), e.b[i]); break;
+        default: break;
+      }
+      v = T::round_through(v);
+    }
+  }
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generators.  Each produces the EPV final values (as fp32, before the rounding of the store) of
+// global vector `gv`, i.e. of global elements [gv*EPV, gv*EPV+EPV).
+// ---------------------------------------------------------------------------------------------
+struct PhiloxCtx {
+  uint32_t k0, k1;  // key = seed
+  uint32_t cz, cw;  // counter.z/.w = stream id (generator offset), bit 31 of w set
+};
+__device__ __forceinline__ PhiloxCtx load_philox(const TdxInitDesc& d) {
+  PhiloxCtx c;
+  c.k0 = static_cast<uint32_t>(d.philox_seed);
+  c.k1 = static_cast<uint32_t>(d.philox_seed >> 32);
+  c.cz = static_cast<uint32_t>(d.philox_offset);
+  c.cw = static_cast<uint32_t>(d.philox_offset >> 32) | 0x80000000u;
+  return c;
+}
+template <int R>
+__device__ __forceinline__ uint4 philox_block(const PhiloxCtx& c, uint64_t blk, uint32_t wflag = 0) {
+  return philox4x32<R>(
+      make_uint4(static_cast<uint32_t>(blk), static_cast<uint32_t>(blk >> 32), c.cz, c.cw | wflag),
+      c.k0, c.k1);
+}
+
+// half-word `e` (0..7) of a Philox block as a float holding 2^23 + k, k in [0, 65535]
+__device__ __forceinline__ float halfword_as_magic(const uint4& w, int e) {
+  const uint32_t word = (e >> 1) == 0 ? w.x : (e >> 1) == 1 ? w.y : (e >> 1) == 2 ? w.z : w.w;
+  // one PRMT each: {0x4b, 0x00, k_hi, k_lo}
+  const uint32_t bits = __byte_perm(word, 0x4b000000u, (e & 1) ? 0x7432 : 0x7410);
+  return __uint_as_float(bits);
+}
+
+// ---- uniform, 16 random bits per element (bf16 / fp16 outputs) -----------------------------
+template <class Out, int R, bool EPI>
+struct GenUniform16 {
+  using OutT = Out;
+  static constexpr int kEpv = 8;
+  struct Params {
+    PhiloxCtx ph;
+    float from, scale, to_prev;
+    EpiParams epi;
+  };
+  __device__ static __forceinline__ Params setup(const TdxInitDesc& d) {
+    Params p;
+    p.ph = load_philox(d);
+    const float from = static_cast<float>(d.p0), to = static_cast<float>(d.p1);
+    p.from = from;
+    p.scale = (to - from) * 1.52587890625e-05f;  // * 2^-16, exact
+    p.to_prev = (to > from) ? OutTraits<Out>::prev(to) : to;
+    if (EPI) p.epi = load_epi(d);
+    return p;
+  }
+  __device__ static __forceinline__ void gen(const Params& p, uint64_t gv, float (&v)[8]) {
+    const uint4 w = philox_block<R>(p.ph, gv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float k = halfword_as_magic(w, e) - 8388608.0f;  // exact
+      float x = fminf(fmaf(k, p.scale, p.from), p.to_prev);
+      v[e] = EPI ? apply_epi<Out>(p.epi, x) : x;
+    }
+  }
+};
+
+// ---- uniform, 24-bit mantissa from 32 random bits per element (fp32 outputs) ----------------
+template <int R, bool EPI>
+struct GenUniform32 {
+  using OutT = float;
+  static constexpr int kEpv = 4;
+  struct Params {
+    PhiloxCtx ph;
+    float from, scale, to_prev;
+    EpiParams epi;
+  };
+  __device__ static __forceinline__ Params setup(const TdxInitDesc& d) {
+    Params p;
+    p.ph = load_philox(d);
+    const float from = static_cast<float>(d.p0), to = static_cast<float>(d.p1);
+    p.from = from;
+    p.scale = (to - from) * 5.9604644775390625e-08f;  // * 2^-24, exact
+    p.to_prev = (to > from) ? OutTraits<float>::prev(to) : to;
+    if (EPI) p.epi = load_epi(d);
+    return p;
+  }
+  __device__ static __forceinline__ void gen(const Params& p, uint64_t gv, float (&v)[4]) {
+    const uint4 w = philox_block<R>(p.ph, gv);
+    const uint32_t x[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float k = __uint2float_rn(x[e] >> 8);  // 24 bits, exact
+      float r = fminf(fmaf(k, p.scale, p.from), p.to_prev);
+      v[e] = EPI ? apply_epi<float>(p.epi, r) : r;
+    }
+  }
+};
+
+// ---- normal: Box-Muller on 2 x 32 random bits per pair -------------------------------------
+// (x, y) -> radius from x (32-bit resolution, (0,1]), angle from the top 23 bits of y.
+__device__ __forceinline__ void box_muller32(uint32_t x, uint32_t y, float& n0, float& n1) {
+  const float u1 = fmaf(__uint2float_rn(x), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  // r = sqrt(-2 ln u1) = sqrt(-2 ln2 * lg2 u1)
+  const float r = mufu_sqrt(-1.3862943611198906f * mufu_lg2(u1));
+  const float t = __uint_as_float((y >> 9) | 0x3f800000u);            // [1, 2)
+  const float ang = fmaf(t, 6.2831853071795865f, -9.4247779607693797f);  // [-pi, pi)
+  n0 = r * mufu_cos(ang);
+  n1 = r * mufu_sin(ang);
+}
+
+template <class Out, int R, bool EPI>
+struct GenNormalBM32 {
+  using OutT = Out;
+  static constexpr int kEpv = OutTraits<Out>::kEpv;  // 4 (f32) or 8 (16-bit outputs: 2 blocks)
+  struct Params {
+    PhiloxCtx ph;
+    float mean, std;
+    EpiParams epi;
+  };
+  __device__ static __forceinline__ Params setup(const TdxInitDesc& d) {
+    Params p;
+    p.ph = load_philox(d);
+    p.mean = static_cast<float>(d.p0);
+    p.std = static_cast<float>(d.p1);
+    if (EPI) p.epi = load_epi(d);
+    return p;
+  }
+  __device__ static __forceinline__ void gen(const Params& p, uint64_t gv, float (&v)[kEpv]) {
+#pragma unroll
+    for (int b = 0; b < kEpv / 4; ++b) {
+      const uint4 w = philox_block<R>(p.ph, gv * (kEpv / 4) + b);
+      float n[4];
+      box_muller32(w.x, w.y, n[0], n[1]);
+      box_muller32(w.z, w.w, n[2], n[3]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float r = fmaf(n[e], p.std, p.mean);
+        v[b * 4 + e] = EPI ? apply_epi<Out>(p.epi, r) : r;
+      }
+    }
+  }
+};
+
+// ---- normal: inverse CDF on 16 random bits per element (bf16 / fp16 outputs) ----------------
+// k in [1, 65535]: x = k/32768 - 1 (a grid symmetric about 0), z = sqrt(2) erfinv(x)
+//                  = x * P(lg2(1 - x^2)),  P = degree-5 minimax fit, |rel err| < 6.5e-5 on the grid.
+// k == 0 (probability 2^-16): the two half-bins beyond the last grid points, i.e. the tails
+//                  u < 2^-17 and u > 1 - 2^-17; resolved with 32 more Philox bits (sign + 31-bit
+//                  position inside the tail), reaching |z| ~ 7.9 sigma.
+__device__ __noinline__ float icdf16_tail(uint32_t word) {
+  const float sgn = (word & 0x80000000u) ? 1.0f : -1.0f;
+  // p in (0, 2^-17): lower-tail probability
+  const float p = (static_cast<float>(word & 0x7fffffffu) + 0.5f) * 4.656612873077393e-10f *
+                  7.62939453125e-06f;
+  return sgn * -normcdfinvf(p);
+}
+
+template <class Out, int R, bool EPI>
+struct GenNormalICDF16 {
+  using OutT = Out;
+  static constexpr int kEpv = 8;
+  struct Params {
+    PhiloxCtx ph;
+    float mean, std;
+    float c0, c1, c2, c3, c4, c5;  // std * P coefficients
+    EpiParams epi;
+  };
+  __device__ static __forceinline__ Params setup(const TdxInitDesc& d) {
+    Params p;
+    p.ph = load_philox(d);
+    p.mean = static_cast<float>(d.p0);
+    p.std = static_cast<float>(d.p1);
+    p.c0 = p.std * 0x1.40de66p+0f;
+    p.c1 = p.std * -0x1.d03266p-3f;
+    p.c2 = p.std * 0x1.26ef76p-7f;
+    p.c3 = p.std * 0x1.bfaecap-10f;
+    p.c4 = p.std * 0x1.9c35c0p-14f;
+    p.c5 = p.std * 0x1.152c90p-19f;
+    if (EPI) p.epi = load_epi(d);
+    return p;
+  }
+  // cold path (k == 0), kept out of line so the hot loop stays inside the instruction cache;
+  // scalar in / scalar out so that nothing of the hot path is forced into local memory
+  __device__ static __noinline__ float refine_one(uint32_t k0, uint32_t k1, uint32_t cz, uint32_t cw,
+                                                  uint64_t gv, int e) {
+    PhiloxCtx c{k0, k1, cz, cw};
+    const uint4 t = philox_block<R>(c, gv, e < 4 ? 0x40000000u : 0x20000000u);
+    const int s = e & 3;
+    return icdf16_tail(s == 0 ? t.x : s == 1 ? t.y : s == 2 ? t.z : t.w);
+  }
+  __device__ static __forceinline__ void gen(const Params& p, uint64_t gv, float (&v)[8]) {
+    const uint4 w = philox_block<R>(p.ph, gv);
+    float tmin = 1.0f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float x = fmaf(halfword_as_magic(w, e), 3.0517578125e-05f, -257.0f);  // k/32768 - 1
+      const float t = fmaf(-x, x, 1.0f);
+      tmin = fminf(tmin, t);
+      const float l = mufu_lg2(t);
+      float q = fmaf(p.c5, l, p.c4);
+      q = fmaf(q, l, p.c3);
+      q = fmaf(q, l, p.c2);
+      q = fmaf(q, l, p.c1);
+      q = fmaf(q, l, p.c0);
+      v[e] = fmaf(q, x, p.mean);
+    }
+    if (tmin <= 0.0f) {  // some k == 0 in this vector: ~1.2e-4 of the vectors
+      const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (((ws[e >> 1] >> (16 * (e & 1))) & 0xffffu) == 0)
+          v[e] = fmaf(refine_one(p.ph.k0, p.ph.k1, p.ph.cz, p.ph.cw, gv, e), p.std, p.mean);
+      }
+    }
+    if (EPI) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = apply_epi<Out>(p.epi, v[e]);
+    }
+  }
+};
+
+// ---- normal: Box-Muller on 16-bit pairs (experimental; no tail refinement) ------------------
+template <class Out, int R, bool EPI>
+struct GenNormalBM16 {
+  using OutT = Out;
+  static constexpr int kEpv = 8;
+  struct Params {
+    PhiloxCtx ph;
+    float mean, std;
+    EpiParams epi;
+  };
+  __device__ static __forceinline__ Params setup(const TdxInitDesc& d) {
+    Params p;
+    p.ph = load_philox(d);
+    p.mean = static_cast<float>(d.p0);
+    p.std = static_cast<float>(d.p1);
+    if (EPI) p.epi = load_epi(d);
+    return p;
+  }
+  __device__ static __forceinline__ void gen(const Params& p, uint64_t gv, float (&v)[8]) {
+    const uint4 w = philox_block<R>(p.ph, gv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = halfword_as_magic(w, 2 * j);      // 2^23 + k1
+      const float b = halfword_as_magic(w, 2 * j + 1);  // 2^23 + k2
+      const float u1 = fmaf(a - 8388608.0f, 1.52587890625e-05f, 7.62939453125e-06f);  // (k1+.5)/65536
+      const float r = mufu_sqrt(-1.3862943611198906f * mufu_lg2(u1)) * p.std;
+      const float ang = fmaf(b, 9.5873799242852573e-05f, -804.24771931898707f - 3.1415926535f);
+      v[2 * j] = fmaf(r, mufu_cos(ang), p.mean);
+      v[2 * j + 1] = fmaf(r, mufu_sin(ang), p.mean);
+    }
+    if (EPI) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = apply_epi<Out>(p.epi, v[e]);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// persistent scheduler shared by all kernels
+// ---------------------------------------------------------------------------------------------
+struct GroupArgs {
+  const unsigned long long* tile_prefix;  // [n_desc + 1], exclusive prefix sum of tiles per desc
+  const TdxInitDesc* descs;               // [n_desc]
+  unsigned long long total_tiles;
+  unsigned int* counter;  // chunk counter, zeroed before every launch
+  uint32_t n_desc;
+};
+
+// Calls f(desc_index, first_tile_in_desc, n_tiles) for runs of consecutive tiles of one descriptor.
+template <class F>
+__device__ __forceinline__ void for_each_tile_run(const GroupArgs& g, F&& f) {
+  __shared__ unsigned int s_chunk;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_chunk = atomicAdd(g.counter, 1u);
+    __syncthreads();
+    unsigned long long t = static_cast<unsigned long long>(s_chunk) * kTilesPerChunk;
+    if (t >= g.total_tiles) return;
+    const unsigned long long last = min(t + kTilesPerChunk, g.total_tiles);
+    uint32_t lo = 0, hi = g.n_desc;  // find d with prefix[d] <= t < prefix[d+1]
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (__ldg(g.tile_prefix + mid) <= t) lo = mid; else hi = mid;
+    }
+    uint32_t d = lo;
+    while (t < last) {
+      unsigned long long dend = __ldg(g.tile_prefix + d + 1);
+      while (dend <= t) dend = __ldg(g.tile_prefix + (++d) + 1);  // skip empty descriptors
+      const unsigned long long stop = min(dend, last);
+      f(d, t - __ldg(g.tile_prefix + d), stop - t);
+      t = stop;
+    }
+  }
+}
+
+template <class Gen>
+__global__ void __launch_bounds__(kThreads) tdx_rng_kernel(const GroupArgs g) {
+  using Out = typename Gen::OutT;
+  using T = OutTraits<Out>;
+  constexpr int EPV = Gen::kEpv;
+  for_each_tile_run(g, [&](uint32_t di, unsigned long long tile0, unsigned long long ntiles) {
+    const TdxInitDesc& d = g.descs[di];
+    const typename Gen::Params P = Gen::setup(d);
+    const uint64_t begin = d.elem_begin, count = d.elem_count;
+    const uint64_t gv0 = begin / EPV;
+    const uint64_t nvec = (begin + count - 1) / EPV - gv0 + 1;
+    char* const dst = static_cast<char*>(d.dst);
+    // vector stores need: shard starts on a vector boundary and lands on a 16-byte address
+    const bool aligned = (begin % EPV == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
+    const uint64_t nfull = aligned ? count / EPV : 0;  // vectors [0, nfull) are full + aligned
+    for (unsigned long long tile = tile0; tile < tile0 + ntiles; ++tile) {
+      const uint64_t base = tile * kTileVecs + threadIdx.x;
+      if (base - threadIdx.x + kTileVecs <= nfull) {  // hot path: whole tile is full vectors
+#pragma unroll
+        for (int i = 0; i < kVecsPerThread; ++i) {
+          const uint64_t j = base + static_cast<uint64_t>(i) * kThreads;
+          float v[EPV];
+          Gen::gen(P, gv0 + j, v);
+          store_vec(dst + j * 16, T::pack(v));
+        }
+      } else {  // ragged edge: partial vectors, unaligned shards, last tile
+        for (int i = 0; i < kVecsPerThread; ++i) {
+          const uint64_t j = base + static_cast<uint64_t>(i) * kThreads;
+          if (j >= nvec) break;
+          float v[EPV];
+          Gen::gen(P, gv0 + j, v);
+          if (j < nfull) {
+            store_vec(dst + j * 16, T::pack(v));
+          } else {
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) {
+              const uint64_t gidx = (gv0 + j) * EPV + e;
+              if (gidx >= begin && gidx < begin + count) T::store_one(dst, gidx - begin, v[e]);
+            }
+          }
+        }
+      }
+    }
+  });
+}
+
+// constant fill: 16-byte pattern, frame = absolute 16-byte lines of the destination
+__global__ void __launch_bounds__(kThreads) tdx_fill_kernel(const GroupArgs g) {
+  for_each_tile_run(g, [&](uint32_t di, unsigned long long tile0, unsigned long long ntiles) {
+    const TdxInitDesc& d = g.descs[di];
+    const uint4 pat = make_uint4(static_cast<uint32_t>(d.fill_bits[0]),
+                                 static_cast<uint32_t>(d.fill_bits[0] >> 32),
+                                 static_cast<uint32_t>(d.fill_bits[1]),
+                                 static_cast<uint32_t>(d.fill_bits[1] >> 32));
+    const int isz = d.dtype == TDX_F32 || d.dtype == TDX_RAW32 ? 4
+                    : d.dtype == TDX_RAW64                    ? 8
+                    : d.dtype == TDX_RAW8                     ? 1
+                                                              : 2;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(d.dst);
+    const uintptr_t end = a + d.elem_count * isz;
+    const uintptr_t a0 = a & ~static_cast<uintptr_t>(15);
+    const uint64_t nvec = (end - a0 + 15) / 16;
+    for (unsigned long long tile = tile0; tile < tile0 + ntiles; ++tile) {
+#pragma unroll
+      for (int i = 0; i < kVecsPerThread; ++i) {
+        const uint64_t j = tile * kTileVecs + static_cast<uint64_t>(i) * kThreads + threadIdx.x;
+        if (j >= nvec) break;
+        const uintptr_t p = a0 + j * 16;
+        if (p >= a && p + 16 <= end) {
+          store_vec(reinterpret_cast<void*>(p), pat);
+        } else {  // head / tail line: byte-granular, the pattern phase follows the address
+          const unsigned char* pb = reinterpret_cast<const unsigned char*>(&pat);
+          for (int b = 0; b < 16; ++b) {
+            const uintptr_t q = p + b;
+            if (q >= a && q < end) *reinterpret_cast<unsigned char*>(q) = pb[(q - a) % isz];
+          }
+        }
+      }
+    }
+  });
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: validation, grouping into kernel families, plan upload, launch
+// ---------------------------------------------------------------------------------------------
+using KernelFn = void (*)(const GroupArgs);
+
+struct Family {
+  int src, dtype, algo /*resolved, without R7*/, rounds, epi;
+  KernelFn fn;
+  const char* name;
+};
+
+#define TDX_FAM(src, dt, algo, rounds, epi, ...) \
+  { src, dt, algo, rounds, epi, static_cast<KernelFn>(tdx_rng_kernel<__VA_ARGS__>), #__VA_ARGS__ }
+
+using bf16 = __nv_bfloat16;
+using f16 = __half;
+
+static const Family kFamilies[] = {
+    {TDX_SRC_CONST, -1, 0, 0, 0, tdx_fill_kernel, "fill"},
+    // shipped defaults
+    TDX_FAM(TDX_SRC_UNIFORM, TDX_F32, 0, 10, 0, GenUniform32<10, false>),
+    TDX_FAM(TDX_SRC_UNIFORM, TDX_F32, 0, 10, 1, GenUniform32<10, true>),
+    TDX_FAM(TDX_SRC_UNIFORM, TDX_BF16, 0, 10, 0, GenUniform16<bf16, 10, false>),
+    TDX_FAM(TDX_SRC_UNIFORM, TDX_BF16, 0, 10, 1, GenUniform16<bf16, 10, true>),
+    TDX_FAM(TDX_SRC_UNIFORM, TDX_F16, 0, 10, 0, GenUniform16<f16, 10, false>),
+    TDX_FAM(TDX_SRC_UNIFORM, TDX_F16, 0, 10, 1, GenUniform16<f16, 10, true>),
+    TDX_FAM(TDX_SRC_NORMAL, TDX_F32, TDX_ALGO_BM32, 10, 0, GenNormalBM32<float, 10, false>),
+    TDX_FAM(TDX_SRC_NORMAL, TDX_F32, TDX_ALGO_BM32, 10, 1, GenNormalBM32<float, 10, true>),
+    TDX_FAM(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_ICDF16, 10, 0, GenNormalICDF16<bf16, 10, false>),
+    TDX_FAM(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_ICDF16, 10, 1, GenNormalICDF16<bf16, 10, true>),
+    TDX_FAM(TDX_SRC_NORMAL, TDX_F16, TDX_ALGO_ICDF16, 10, 0, GenNormalICDF16<f16, 10, false>),
+    TDX_FAM(TDX_SRC_NORMAL, TDX_F16, TDX_ALGO_ICDF16, 10, 1, GenNormalICDF16<f16, 10, true>),
+    // experimental variants, reachable only through an explicit TdxInitDesc.algo (bench sweeps)
+    TDX_FAM(TDX_SRC_UNIFORM, TDX_BF16, 0, 7, 0, GenUniform16<bf16, 7, false>),
+    TDX_FAM(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_ICDF16, 7, 0, GenNormalICDF16<bf16, 7, false>),
+    TDX_FAM(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_BM16, 10, 0, GenNormalBM16<bf16, 10, false>),
+    TDX_FAM(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_BM16, 7, 0, GenNormalBM16<bf16, 7, false>),
+    TDX_FAM(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_BM32, 10, 0, GenNormalBM32<bf16, 10, false>),
+    TDX_FAM(TDX_SRC_NORMAL, TDX_F32, TDX_ALGO_BM32, 7, 0, GenNormalBM32<float, 7, false>),
+};
+constexpr int kNumFamilies = sizeof(kFamilies) / sizeof(kFamilies[0]);
+
+thread_local char g_err[256] = "";
+thread_local int g_last_launches = 0;
+
+int fail(int code, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+  return static_cast<int>(e);
+}
+
+int itemsize_of(int dtype) {
+  switch (dtype) {
+    case TDX_F32: case TDX_RAW32: return 4;
+    case TDX_BF16: case TDX_F16: case TDX_RAW16: return 2;
+    case TDX_RAW8: return 1;
+    case TDX_RAW64: return 8;
+    default: return 0;
+  }
+}
+
+int resolve_algo(const TdxInitDesc& d) {
+  const int a = d.algo & 0x0f;
+  if (d.src == TDX_SRC_NORMAL) {
+    if (a != TDX_ALGO_DEFAULT) return a;
+    return d.dtype == TDX_F32 ? TDX_ALGO_BM32 : TDX_ALGO_ICDF16;
+  }
+  return 0;
+}
+
+int family_of(const TdxInitDesc& d) {
+  if (d.src == TDX_SRC_CONST) return 0;
+  const int algo = resolve_algo(d);
+  const int rounds = (d.algo & TDX_ALGO_R7) ? 7 : 10;
+  const int epi = d.n_epi ? 1 : 0;
+  for (int f = 1; f < kNumFamilies; ++f) {
+    const Family& F = kFamilies[f];
+    if (F.src == d.src && F.dtype == d.dtype && F.algo == algo && F.rounds == rounds && F.epi == epi)
+      return f;
+  }
+  return -1;
+}
+
+uint64_t tiles_of(const TdxInitDesc& d) {
+  if (d.elem_count == 0) return 0;
+  uint64_t nvec;
+  if (d.src == TDX_SRC_CONST) {
+    const uint64_t a = reinterpret_cast<uintptr_t>(d.dst);
+    const uint64_t end = a + d.elem_count * itemsize_of(d.dtype);
+    nvec = (end - (a & ~15ull) + 15) / 16;
+  } else {
+    const uint64_t epv = 16 / itemsize_of(d.dtype);
+    nvec = (d.elem_begin + d.elem_count - 1) / epv - d.elem_begin / epv + 1;
+  }
+  return (nvec + kTileVecs - 1) / kTileVecs;
+}
+
+// Device-resident plan header.  Lives at the start of the caller's workspace.
+struct PlanGroup {
+  unsigned long long total_tiles;
+  unsigned long long prefix_off;  // byte offsets from the workspace base
+  unsigned long long desc_off;
+  uint32_t n_desc;
+  uint32_t family;
+};
+struct PlanHeader {
+  uint32_t magic;
+  uint32_t n_groups;
+  unsigned int counters[32];
+  PlanGroup groups[kNumFamilies];
+};
+constexpr uint32_t kPlanMagic = 0x58445431u;  // "TDX1"
+static_assert(kNumFamilies <= 32, "counter slots");
+
+size_t plan_bytes(int n) {
+  // header + per-family prefix arrays (n + #families entries worst case) + descriptors
+  return sizeof(PlanHeader) + (static_cast<size_t>(n) + kNumFamilies) * sizeof(unsigned long long) +
+         static_cast<size_t>(n) * sizeof(TdxInitDesc) + 64;
+}
+
+struct DeviceInfo {
+  int sm_count = 0;
+  int blocks_per_sm[kNumFamilies] = {};
+};
+DeviceInfo* device_info() {
+  static DeviceInfo infos[64];
+  static bool ready[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!ready[dev]) {
+    DeviceInfo& I = infos[dev];
+    if (cudaDeviceGetAttribute(&I.sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      return nullptr;
+    for (int f = 0; f < kNumFamilies; ++f) {
+      int nb = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+              &nb, reinterpret_cast<const void*>(kFamilies[f].fn), kThreads, 0) != cudaSuccess)
+        return nullptr;
+      I.blocks_per_sm[f] = std::max(nb, 1);
+    }
+    ready[dev] = true;
+  }
+  return &infos[dev];
+}
+
+// Builds the host image of the plan.  Returns 0 or an error code.
+int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img, PlanHeader& hdr) {
+  if (n < 0 || (n > 0 && descs == nullptr)) return fail(TDX_E_BADARG, "descs == NULL or n < 0");
+  std::vector<int> fam(static_cast<size_t>(n));
+  int per_family[kNumFamilies] = {};
+  for (int i = 0; i < n; ++i) {
+    const TdxInitDesc& d = descs[i];
+    const int isz = itemsize_of(d.dtype);
+    if (isz == 0) return fail(TDX_E_BADARG, "unknown dtype");
+    if (d.src != TDX_SRC_CONST && d.dtype >= TDX_RAW8)
+      return fail(TDX_E_BADARG, "raw dtypes are only valid with TDX_SRC_CONST");
+    if (d.n_epi > TDX_MAX_EPI) return fail(TDX_E_BADARG, "n_epi > TDX_MAX_EPI");
+    if (d.elem_count && d.dst == nullptr) return fail(TDX_E_BADARG, "dst == NULL");
+    if (reinterpret_cast<uintptr_t>(d.dst) % isz) return fail(TDX_E_BADARG, "dst not element-aligned");
+    fam[i] = family_of(d);
+    if (fam[i] < 0) return fail(TDX_E_BADARG, "no kernel for (src, dtype, algo, epilogue)");
+    per_family[fam[i]]++;
+  }
+  memset(&hdr, 0, sizeof(hdr));
+  hdr.magic = kPlanMagic;
+  img.assign(plan_bytes(n), 0);
+  size_t off = (sizeof(PlanHeader) + 15) & ~static_cast<size_t>(15);
+  for (int f = 0; f < kNumFamilies; ++f) {
+    if (!per_family[f]) continue;
+    PlanGroup& G = hdr.groups[hdr.n_groups++];
+    G.family = f;
+    G.n_desc = per_family[f];
+    G.prefix_off = off;
+    auto* prefix = reinterpret_cast<unsigned long long*>(img.data() + off);
+    off += (static_cast<size_t>(G.n_desc) + 1) * sizeof(unsigned long long);
+    off = (off + 15) & ~static_cast<size_t>(15);
+    G.desc_off = off;
+    auto* out = reinterpret_cast<TdxInitDesc*>(img.data() + off);
+    off += static_cast<size_t>(G.n_desc) * sizeof(TdxInitDesc);
+    unsigned long long acc = 0;
+    uint32_t k = 0;
+    for (int i = 0; i < n; ++i) {
+      if (fam[i] != f) continue;
+      prefix[k] = acc;
+      out[k] = descs[i];
+      acc += tiles_of(descs[i]);
+      ++k;
+    }
+    prefix[k] = acc;
+    G.total_tiles = acc;
+  }
+  memcpy(img.data(), &hdr, sizeof(hdr));
+  img.resize(off);
+  return 0;
+}
+
+int launch_groups(const PlanHeader& hdr, void* workspace, cudaStream_t stream) {
+  DeviceInfo* info = device_info();
+  if (!info) return fail(TDX_E_NODEVICE, "no CUDA device / occupancy query failed");
+  auto* base = static_cast<unsigned char*>(workspace);
+  auto* dev_hdr = reinterpret_cast<PlanHeader*>(base);
+  int launches = 0;
+  bool zeroed = false;
+  for (uint32_t gi = 0; gi < hdr.n_groups; ++gi) {
+    const PlanGroup& G = hdr.groups[gi];
+    if (G.total_tiles == 0) continue;
+    if (!zeroed) {
+      cudaError_t e = cudaMemsetAsync(dev_hdr->counters, 0, sizeof(dev_hdr->counters), stream);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(counters)");
+      zeroed = true;
+    }
+    GroupArgs a;
+    a.tile_prefix = reinterpret_cast<const unsigned long long*>(base + G.prefix_off);
+    a.descs = reinterpret_cast<const TdxInitDesc*>(base + G.desc_off);
+    a.total_tiles = G.total_tiles;
+    a.counter = &dev_hdr->counters[gi];
+    a.n_desc = G.n_desc;
+    const unsigned long long chunks = (G.total_tiles + kTilesPerChunk - 1) / kTilesPerChunk;
+    const unsigned long long resident =
+        static_cast<unsigned long long>(info->sm_count) * info->blocks_per_sm[G.family];
+    const unsigned int grid = static_cast<unsigned int>(std::min(chunks, resident));
+    kFamilies[G.family].fn<<<grid, kThreads, 0, stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, kFamilies[G.family].name);
+    ++launches;
+  }
+  g_last_launches = launches;
+  return 0;
+}
+
+}  // namespace tdx
+
+extern "C" {
+
+TDX_C_API size_t tdx_init_workspace_bytes(int n) { return tdx::plan_bytes(n < 0 ? 0 : n); }
+
+TDX_C_API int tdx_plan_upload(const TdxInitDesc* descs, int n, void* workspace,
+                              size_t workspace_bytes, void* stream, TdxPlan* plan) {
+  static_assert(sizeof(tdx::PlanHeader) <= sizeof(TdxPlan), "TdxPlan too small");
+  thread_local std::vector<unsigned char> img;
+  tdx::PlanHeader hdr;
+  if (plan == nullptr) return tdx::fail(TDX_E_BADARG, "plan == NULL");
+  if (int rc = tdx::build_plan(descs, n, img, hdr)) return rc;
+  memcpy(plan, &hdr, sizeof(hdr));
+  if (workspace == nullptr || workspace_bytes < img.size())
+    return tdx::fail(TDX_E_WORKSPACE, "workspace too small (see tdx_init_workspace_bytes)");
+  cudaError_t e = cudaMemcpyAsync(workspace, img.data(), img.size(), cudaMemcpyHostToDevice,
+                                  static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return tdx::cuda_fail(e, "cudaMemcpyAsync(plan)");
+  // the staging image is reused by the next call on this thread: make sure the copy has left it
+  e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return tdx::cuda_fail(e, "cudaStreamSynchronize(plan upload)");
+  return 0;
+}
+
+TDX_C_API int tdx_plan_launch(const TdxPlan* plan, void* workspace, void* stream) {
+  if (workspace == nullptr) return tdx::fail(TDX_E_WORKSPACE, "workspace == NULL");
+  if (plan == nullptr) return tdx::fail(TDX_E_BADARG, "plan == NULL");
+  tdx::PlanHeader hdr;
+  memcpy(&hdr, plan, sizeof(hdr));
+  if (hdr.magic != tdx::kPlanMagic) return tdx::fail(TDX_E_BADARG, "plan was not produced by tdx_plan_upload");
+  return tdx::launch_groups(hdr, workspace, static_cast<cudaStream_t>(stream));
+}
+
+TDX_C_API int tdx_init_launch(const TdxInitDesc* descs, int n, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  thread_local std::vector<unsigned char> img;
+  tdx::PlanHeader hdr;
+  if (int rc = tdx::build_plan(descs, n, img, hdr)) return rc;
+  if (hdr.n_groups == 0) {
+    tdx::g_last_launches = 0;
+    return 0;
+  }
+  if (workspace == nullptr || workspace_bytes < img.size())
+    return tdx::fail(TDX_E_WORKSPACE, "workspace too small (see tdx_init_workspace_bytes)");
+  // pageable source: the runtime stages the bytes before returning, so `img` may be reused
+  cudaError_t e = cudaMemcpyAsync(workspace, img.data(), img.size(), cudaMemcpyHostToDevice,
+                                  static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return tdx::cuda_fail(e, "cudaMemcpyAsync(plan)");
+  return tdx::launch_groups(hdr, workspace, static_cast<cudaStream_t>(stream));
+}
+
+TDX_C_API int tdx_last_launch_count(void) { return tdx::g_last_launches; }
+
+TDX_C_API int tdx_elems_per_block(int dtype, int src, int algo) {
+  if (src == TDX_SRC_CONST) return 0;
+  if (dtype == TDX_F32) return 4;
+  if (dtype != TDX_BF16 && dtype != TDX_F16) return 0;
+  if (src == TDX_SRC_NORMAL && (algo & 0x0f) == TDX_ALGO_BM32) return 4;
+  return 8;
+}
+
+TDX_C_API int tdx_abi_version(void) { return TDX_ABI_VERSION; }
+TDX_C_API const char* tdx_last_error(void) { return tdx::g_err; }
+
+}  // extern "C"
