@@ -89,6 +89,12 @@ enum {
   TDX_EPI_ERFINV = 3, /* x = erfinv(x)        (trunc_normal_)            */
   TDX_EPI_CLAMP = 4,  /* x = min(max(x,a),b)  (clamp_)                   */
 };
+/* OR-able into TdxEpiStep.op: do not round to the destination dtype after this step (the step
+ * was recorded on an fp32 intermediate that is cast to the destination dtype later). */
+#define TDX_EPI_NOROUND 0x100u
+/* TdxInitDesc.reserved bit 0: the source op itself produced an fp32 intermediate (do not round
+ * the generated value to the destination dtype before the first epilogue step). */
+#define TDX_FLAG_SRC_NOROUND 0x1u
 #define TDX_MAX_EPI 4
 
 typedef struct TdxEpiStep {

@@ -1,0 +1,199 @@
+"""API behaviour of torchdistx_b200.deferred_init on the CPU (generic replay): the cases the
+reference pins in tests/python/test_deferred_init.py:21-75 plus BASELINE config #1
+(`deferred_init(nn.Linear(128,128))` == eager same-seed init, bit-exact) and the recording
+semantics SURVEY.md section 3.4 lists."""
+import pytest
+import torch
+from torch import nn
+from torch.nn import Module, Parameter
+
+from torchdistx.deferred_init import deferred_init, is_deferred, materialize_module, materialize_tensor
+from torchdistx.fake import is_fake
+from torchdistx_b200.deferred_init import last_materialize_stats
+
+
+class TwoParams(Module):
+    def __init__(self):
+        super().__init__()
+        self.param1 = Parameter(torch.ones([5]))
+        self.param2 = Parameter(torch.ones([5]))
+
+
+class Tied(Module):
+    def __init__(self):
+        super().__init__()
+        self.param1 = Parameter(torch.ones([5]))
+        self.param2 = self.param1
+
+
+def test_real_tensor_is_returned_unchanged():
+    a = torch.ones([10])
+    assert materialize_tensor(a) is a
+
+
+def test_repeated_and_aliased_materialize_return_one_object():
+    module = deferred_init(Tied)
+    a = materialize_tensor(module.param1)
+    b = materialize_tensor(module.param1)
+    c = materialize_tensor(module.param2)
+    assert a is b and a is c
+    assert isinstance(a, Parameter) and not is_fake(a)
+    assert torch.equal(a, torch.ones(5))
+
+
+def test_is_deferred_transitions():
+    assert not is_deferred(TwoParams())
+    module = deferred_init(TwoParams)
+    assert is_deferred(module)
+    materialize_module(module)
+    assert not is_deferred(module)
+
+    module = deferred_init(TwoParams)
+    module.param1 = materialize_tensor(module.param1)
+    assert is_deferred(module)
+    module.param2 = materialize_tensor(module.param2)
+    assert not is_deferred(module)
+
+
+def test_is_deferred_rejects_other_types():
+    with pytest.raises(ValueError):
+        is_deferred(3)
+
+
+def test_materialize_tensor_rejects_non_tensors():
+    with pytest.raises(TypeError):
+        materialize_tensor("weight")
+
+
+def test_linear_128_equals_eager_same_seed_bit_exact():
+    # BASELINE.json configs[0]
+    torch.manual_seed(0)
+    m = deferred_init(nn.Linear, 128, 128)
+    assert is_fake(m.weight) and m.weight.shape == (128, 128)
+    torch.manual_seed(0)
+    materialize_module(m)
+    torch.manual_seed(0)
+    e = nn.Linear(128, 128)
+    assert torch.equal(m.weight, e.weight) and torch.equal(m.bias, e.bias)
+    assert isinstance(m.weight, Parameter) and m.weight.requires_grad
+    assert last_materialize_stats()["generic_ops"] > 0  # CPU tensors replay through ATen
+    m(torch.ones(2, 128)).sum().backward()
+    assert m.weight.grad is not None
+
+
+def test_rng_follows_materialize_order_and_dead_ops_consume():
+    # bias-then-weight differs from eager; a dead uniform_ still advances mt19937
+    def build():
+        lin = nn.Linear(16, 16, bias=False)
+        nn.init.normal_(lin.weight, 0.0, 0.02)
+        return lin
+
+    m = deferred_init(build)
+    torch.manual_seed(7)
+    materialize_module(m)
+    torch.manual_seed(7)
+    e = build()
+    assert torch.equal(m.weight, e.weight)
+
+
+def test_buffers_only_and_check_fn():
+    class Net(Module):
+        def __init__(self):
+            super().__init__()
+            self.bn = nn.BatchNorm1d(4)
+            self.fc = nn.Linear(4, 4)
+
+    m = deferred_init(Net)
+    materialize_module(m, buffers_only=True)
+    assert not is_fake(m.bn.running_mean) and is_fake(m.bn.weight) and is_fake(m.fc.weight)
+    materialize_module(m, check_fn=lambda mod: not isinstance(mod, nn.Linear))
+    assert not is_fake(m.bn.weight) and is_fake(m.fc.weight)
+    materialize_module(m)
+    assert not is_deferred(m)
+    assert torch.equal(m.bn.running_var, torch.ones(4))
+
+
+def test_views_and_in_place_ops_through_views():
+    class V(Module):
+        def __init__(self):
+            super().__init__()
+            w = torch.zeros(4, 4)
+            w.view(-1)[::5] = 1.0  # identity through a strided view
+            w[0].mul_(3.0)
+            self.w = Parameter(w)
+
+    m = deferred_init(V)
+    materialize_module(m)
+    expect = torch.eye(4)
+    expect[0] *= 3
+    assert torch.equal(m.w, expect)
+
+
+def test_external_tensor_version_check():
+    ext = torch.ones(3)
+
+    def build():
+        return Parameter(torch.zeros(3) + ext)
+
+    p = deferred_init(build)
+    ext.add_(1)
+    with pytest.raises(RuntimeError, match="updated in-place"):
+        materialize_tensor(p)
+
+
+def test_item_is_terminal_and_keeps_recording():
+    def build():
+        a = torch.full((3,), 2.0)
+        s = a.sum().item()  # needs a real value now
+        return Parameter(a * s)
+
+    p = deferred_init(build)
+    assert is_fake(p)
+    assert torch.equal(materialize_tensor(p), torch.full((3,), 12.0))
+
+
+def test_data_setter_and_getter_are_recorded():
+    def build():
+        lin = nn.Linear(3, 3)
+        lin.weight.data.fill_(0.5)
+        lin.bias.data = torch.arange(3.0)
+        return lin
+
+    m = deferred_init(build)
+    materialize_module(m)
+    assert torch.equal(m.weight, torch.full((3, 3), 0.5))
+    assert torch.equal(m.bias, torch.arange(3.0))
+
+
+def test_default_dtype_and_explicit_generator_are_honoured():
+    g = torch.Generator().manual_seed(123)
+
+    def build():
+        return Parameter(torch.empty(64).normal_(generator=g))
+
+    p = deferred_init(build)
+    out = materialize_tensor(p)
+    g2 = torch.Generator().manual_seed(123)
+    assert torch.equal(out, torch.empty(64).normal_(generator=g2))
+
+
+def test_fake_tensor_from_plain_fake_mode_is_rejected():
+    from torchdistx.fake import fake_mode
+
+    with fake_mode():
+        a = torch.ones(3)
+    with pytest.raises(ValueError):
+        deferred_init(lambda: a + 1)
+
+
+def test_nested_deferred_init_and_cross_scope_inputs():
+    emb = deferred_init(nn.Embedding, 10, 4)
+
+    def build():
+        return Parameter(emb.weight.detach() * 2.0)
+
+    p = deferred_init(build)
+    torch.manual_seed(3)
+    out = materialize_tensor(p)
+    w = materialize_tensor(emb.weight)
+    assert torch.equal(out, w.detach() * 2.0)

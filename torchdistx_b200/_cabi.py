@@ -15,7 +15,8 @@ import os
 from typing import Iterable, Optional, Sequence
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtdx_init.so")
+# TDX_INIT_LIB: kernel-experiment builds only (benchmarks/); the product always uses the in-tree library
+LIB_PATH = os.environ.get("TDX_INIT_LIB") or os.path.join(_HERE, "libtdx_init.so")
 
 # enums of tdx_init.h
 TDX_F32, TDX_BF16, TDX_F16 = 0, 1, 2

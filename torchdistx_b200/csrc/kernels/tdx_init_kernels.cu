@@ -65,10 +65,25 @@ __device__ __forceinline__ float mufu_cos(float x) {
   return y;
 }
 // 128-bit streaming store: the data is written once and never re-read by this kernel.
+#ifndef TDX_STORE_MODE
+#define TDX_STORE_MODE 0
+#endif
 __device__ __forceinline__ void store_vec(void* p, uint4 v) {
+#if TDX_STORE_MODE == 0
   asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
                "r"(v.w)
                : "memory");
+#elif TDX_STORE_MODE == 1
+  *reinterpret_cast<uint4*>(p) = v;
+#elif TDX_STORE_MODE == 2
+  asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+#else
+  asm volatile("st.global.wt.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+#endif
 }
 
 template <class Out>
@@ -157,6 +172,7 @@ struct OutTraits<__half> {
 // ---------------------------------------------------------------------------------------------
 struct EpiParams {
   uint32_t n;
+  uint32_t flags;
   uint32_t op[TDX_MAX_EPI];
   float a[TDX_MAX_EPI];
   float b[TDX_MAX_EPI];
@@ -165,6 +181,7 @@ struct EpiParams {
 __device__ __forceinline__ EpiParams load_epi(const TdxInitDesc& d) {
   EpiParams e;
   e.n = d.n_epi;
+  e.flags = d.reserved;
 #pragma unroll
   for (int i = 0; i < TDX_MAX_EPI; ++i) {
     e.op[i] = d.epi[i].op;
@@ -177,18 +194,18 @@ __device__ __forceinline__ EpiParams load_epi(const TdxInitDesc& d) {
 template <class Out>
 __device__ __forceinline__ float apply_epi(const EpiParams& e, float v) {
   using T = OutTraits<Out>;
-  v = T::round_through(v);
+  if (!(e.flags & TDX_FLAG_SRC_NOROUND)) v = T::round_through(v);
 #pragma unroll
   for (int i = 0; i < TDX_MAX_EPI; ++i) {
     if (i < static_cast<int>(e.n)) {
-      switch (e.op[i]) {
+      switch (e.op[i] & 0xffu) {
         case TDX_EPI_MUL: v = v * e.a[i]; break;
         case TDX_EPI_ADD: v = v + e.a[i]; break;
         case TDX_EPI_ERFINV: v = erfinvf(v); break;
         case TDX_EPI_CLAMP: v = fminf(fmaxf(v, e.a[i]), e.b[i]); break;
         default: break;
       }
-      v = T::round_through(v);
+      if (!(e.op[i] & TDX_EPI_NOROUND)) v = T::round_through(v);
     }
   }
   return v;

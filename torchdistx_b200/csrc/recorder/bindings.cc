@@ -1,0 +1,164 @@
+// torchdistx_b200._C -- the native surface behind torchdistx_b200.fake / .deferred_init.
+//
+// Exports the same 8 functions as the reference's `_C` module
+// (reference src/python/torchdistx/_C.pyi:9-16; _C/deferred_init.cc:99-105; _C/fake.cc:40-51):
+//   enter_deferred_init, leave_deferred_init, enter_fake_mode, leave_fake_mode, is_fake,
+//   can_materialize, materialize_tensor, meta_like
+// plus the batched / sharded entry points the B200 engine adds (materialize_tensors, stats,
+// philox state access for cross-rank seed agreement).
+//
+// Python-object fidelity (reference _C/deferred_init.cc:61-95 materializeVariable):
+//   * a real tensor is returned unchanged (same object);
+//   * a fake tensor materialised twice returns the same Python object;
+//   * the result has the Python class of the fake tensor (e.g. torch.nn.Parameter).
+// torch 2.11 no longer exposes pyobj_slot()->init_pyobj/check_pyobj, so the class is applied with
+// torch.Tensor._make_subclass and identity is kept by caching the wrapped tensor on the tape.
+#include <torch/csrc/utils/device_lazy_init.h>
+#include <torch/extension.h>
+
+#include "fake_tensor.h"
+#include "planner.h"
+#include "tape.h"
+#include "tdx_init.h"
+
+namespace py = pybind11;
+
+namespace {
+
+void py_enter_fake_mode(bool fake_cuda) {
+  tdx::enter_fake_mode(fake_cuda);
+  // Without a usable CUDA device the Python arg parser would try (and fail) to initialise CUDA for
+  // every `device="cuda"` factory call.
+  if (fake_cuda && !at::hasCUDA()) torch::utils::set_requires_device_init(at::kCUDA, false);
+}
+
+void py_leave_fake_mode() {
+  tdx::leave_fake_mode();
+  if (!tdx::fake_mode_active() && !at::hasCUDA())
+    torch::utils::set_requires_device_init(at::kCUDA, true);
+}
+
+tdx::MaterializeOptions make_options(const py::object& device, const py::object& shard, bool fused) {
+  tdx::MaterializeOptions o;
+  if (!device.is_none()) o.device = py::cast<c10::Device>(device);
+  if (!shard.is_none()) {
+    auto t = py::cast<std::pair<int64_t, int64_t>>(shard);
+    TORCH_CHECK_VALUE(t.second >= 1 && t.first >= 0 && t.first < t.second,
+                      "shard must be (rank, world_size) with 0 <= rank < world_size");
+    o.shard = tdx::ShardSpec{t.first, t.second};
+  }
+  o.fused = fused;
+  return o;
+}
+
+// Gives `out` the Python class of `like` and remembers the result for identity.
+py::object wrap_like(const py::handle& like, const at::Tensor& fake, const at::Tensor& out) {
+  at::Tensor cached = tdx::cached_python_tensor(fake);
+  if (cached.defined()) return py::cast(cached);
+  py::object result;
+  PyTypeObject* type = Py_TYPE(like.ptr());
+  if (reinterpret_cast<PyObject*>(type) == reinterpret_cast<PyObject*>(THPVariableClass)) {
+    result = py::cast(out);
+  } else {
+    static py::object make_subclass = py::module_::import("torch").attr("Tensor").attr("_make_subclass");
+    result = make_subclass(py::reinterpret_borrow<py::object>(reinterpret_cast<PyObject*>(type)),
+                           py::cast(out), out.requires_grad());
+  }
+  tdx::cache_python_tensor(fake, py::cast<at::Tensor>(result));
+  return result;
+}
+
+py::object py_materialize_tensor(const py::object& var, const py::object& device,
+                                 const py::object& shard, bool fused) {
+  if (!THPVariable_Check(var.ptr())) {
+    throw py::type_error(std::string("`var` has to be a `Variable`, but got `") +
+                         Py_TYPE(var.ptr())->tp_name + "`.");
+  }
+  const at::Tensor& t = THPVariable_Unpack(var.ptr());
+  if (!tdx::can_materialize(t)) return var;  // real tensors: a no-op returning the same object
+  {
+    at::Tensor cached = tdx::cached_python_tensor(t);
+    if (cached.defined()) return py::cast(cached);
+  }
+  const tdx::MaterializeOptions opts = make_options(device, shard, fused);
+  at::Tensor out;
+  {
+    py::gil_scoped_release nogil;
+    out = tdx::materialize_one(t, opts);
+  }
+  return wrap_like(var, t, out);
+}
+
+py::list py_materialize_tensors(const py::list& vars, const py::object& device,
+                                const py::object& shard, bool fused) {
+  std::vector<at::Tensor> fakes;
+  fakes.reserve(vars.size());
+  for (const py::handle& h : vars) {
+    if (!THPVariable_Check(h.ptr()))
+      throw py::type_error(std::string("expected a list of tensors, but got `") +
+                           Py_TYPE(h.ptr())->tp_name + "`.");
+    fakes.push_back(THPVariable_Unpack(h.ptr()));
+  }
+  const tdx::MaterializeOptions opts = make_options(device, shard, fused);
+  // tensors that were already handed out keep their identity and are not touched again
+  std::vector<at::Tensor> todo;
+  std::vector<size_t> todo_idx;
+  for (size_t i = 0; i < fakes.size(); ++i) {
+    if (tdx::can_materialize(fakes[i]) && !tdx::cached_python_tensor(fakes[i]).defined()) {
+      todo.push_back(fakes[i]);
+      todo_idx.push_back(i);
+    }
+  }
+  std::vector<at::Tensor> done;
+  {
+    py::gil_scoped_release nogil;
+    done = tdx::materialize_many(todo, opts);
+  }
+  py::list result(fakes.size());
+  size_t k = 0;
+  for (size_t i = 0; i < fakes.size(); ++i) {
+    if (!tdx::can_materialize(fakes[i])) {
+      result[i] = vars[i];
+    } else if (k < todo_idx.size() && todo_idx[k] == i) {
+      result[i] = wrap_like(vars[i], fakes[i], done[k]);
+      ++k;
+    } else {
+      result[i] = py::cast(tdx::cached_python_tensor(fakes[i]));
+    }
+  }
+  return result;
+}
+
+py::dict py_last_stats() {
+  const tdx::MaterializeStats s = tdx::last_stats();
+  py::dict d;
+  d["tensors"] = s.tensors;
+  d["fused_tensors"] = s.fused_tensors;
+  d["generic_ops"] = s.generic_ops;
+  d["elided_rng_ops"] = s.elided_rng_ops;
+  d["kernel_launches"] = s.kernel_launches;
+  d["bytes_written"] = s.bytes_written;
+  d["descriptors"] = s.descriptors;
+  return d;
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "torchdistx_b200 native runtime (fake tensors, deferred-init tape, fused materialiser)";
+  // ---- the reference's 8-function surface --------------------------------------------------
+  m.def("enter_deferred_init", &tdx::enter_deferred_init);
+  m.def("leave_deferred_init", &tdx::leave_deferred_init);
+  m.def("enter_fake_mode", &py_enter_fake_mode, py::arg("fake_cuda") = false);
+  m.def("leave_fake_mode", &py_leave_fake_mode);
+  m.def("is_fake", [](const at::Tensor& t) { return tdx::is_fake(t); });
+  m.def("can_materialize", [](const at::Tensor& t) { return tdx::can_materialize(t); });
+  m.def("materialize_tensor", &py_materialize_tensor, py::arg("tensor"),
+        py::arg("device") = py::none(), py::arg("shard") = py::none(), py::arg("fused") = true);
+  m.def("meta_like", &tdx::meta_like);
+  // ---- B200 engine additions --------------------------------------------------------------
+  m.def("materialize_tensors", &py_materialize_tensors, py::arg("tensors"),
+        py::arg("device") = py::none(), py::arg("shard") = py::none(), py::arg("fused") = true);
+  m.def("last_stats", &py_last_stats);
+  m.def("kernel_abi_version", [] { return tdx_abi_version(); });
+}

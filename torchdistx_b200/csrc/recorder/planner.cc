@@ -1,0 +1,731 @@
+#include "planner.h"
+
+#include <ATen/Context.h>
+#include <ATen/Functions.h>
+#include <ATen/core/Generator.h>
+#include <c10/core/DeviceGuard.h>
+#include <c10/core/impl/LocalDispatchKeySet.h>
+#include <c10/cuda/CUDAStream.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <mutex>
+
+#include "fake_tensor.h"
+#include "stack_walk.h"
+#include "tape.h"
+#include "tdx_init.h"
+
+namespace tdx {
+
+using c10::IValue;
+using c10::ScalarType;
+using torch::jit::Stack;
+
+namespace {
+
+thread_local MaterializeStats g_stats;
+
+// Never record / fake anything we do while materialising.
+struct NoInterception {
+  c10::impl::ExcludeDispatchKeyGuard a{c10::DispatchKey::DeferredInit};
+  c10::impl::ExcludeDispatchKeyGuard b{c10::DispatchKey::Fake};
+};
+
+// ---------------------------------------------------------------------------------------------
+// symbolic state of a storage: what its elements are, as a function of the element index
+// ---------------------------------------------------------------------------------------------
+struct Sym {
+  enum Src { Opaque, Uninit, Const, Uniform, Normal } src = Opaque;
+  ScalarType dtype = ScalarType::Undefined;  // dtype of the tensor currently holding the state
+  ScalarType gen_dtype = ScalarType::Undefined;  // dtype the RNG source op ran in
+  at::Tensor cval;                           // Const: a 1-element CPU tensor of `dtype`
+  double p0 = 0, p1 = 1;                     // Uniform: from,to   Normal: mean,std
+  uint32_t rng_op = kNoValue;                // the live RNG op
+  std::vector<uint32_t> rng_chain;           // every RNG op met, live or dead, chronological
+  std::vector<TdxEpiStep> epi;
+  bool opaque() const { return src == Opaque; }
+};
+
+Sym make_opaque() { return Sym{}; }
+
+bool is_fused_float(ScalarType t) {
+  return t == ScalarType::Float || t == ScalarType::BFloat16 || t == ScalarType::Half;
+}
+
+// Value of argument `pos` of a recorded op as a double, if it is a number or a real 1-element
+// tensor (the form Python scalars take in mul_.Tensor / add_.Tensor).
+std::optional<double> scalar_arg(const TapeOp& op, size_t pos) {
+  if (pos >= op.args.size()) return std::nullopt;
+  const IValue& v = op.args[pos];
+  if (v.isDouble()) return v.toDouble();
+  if (v.isInt()) return static_cast<double>(v.toInt());
+  if (v.isBool()) return v.toBool() ? 1.0 : 0.0;
+  if (v.isTensor()) {
+    size_t slot = 0;  // which tensor slot of the frame is this argument?
+    for (size_t i = 0; i < pos; ++i) {
+      if (op.args[i].isTensor()) ++slot;
+      else if (op.args[i].isList())
+        for (const IValue& e : op.args[i].toListRef()) slot += e.isTensor();
+    }
+    if (slot >= op.inputs.size()) return std::nullopt;
+    const at::Tensor& t = op.inputs[slot].real;
+    if (!t.defined() || t.numel() != 1 || !t.is_cpu() || t.is_complex()) return std::nullopt;
+    if (!t.is_inference() && static_cast<int64_t>(t._version()) != op.inputs[slot].real_version)
+      return std::nullopt;  // mutated since recording: let generic replay raise the error
+    return t.item<double>();
+  }
+  return std::nullopt;
+}
+
+// ATen casts uniform_'s bounds to the tensor dtype before use
+// ($TORCH/include/ATen/native/cuda/DistributionTemplates.h uniform_kernel, and the CPU twin).
+double round_to_dtype(double x, ScalarType t) {
+  switch (t) {
+    case ScalarType::Float: return static_cast<double>(static_cast<float>(x));
+    case ScalarType::BFloat16: return static_cast<double>(static_cast<float>(c10::BFloat16(static_cast<float>(x))));
+    case ScalarType::Half: return static_cast<double>(static_cast<float>(c10::Half(static_cast<float>(x))));
+    default: return x;
+  }
+}
+
+size_t find_arg(const TapeOp& op, const char* name) {
+  const auto& args = op.handle->schema().arguments();
+  for (size_t i = 0; i < args.size(); ++i)
+    if (args[i].name() == name) return i;
+  return static_cast<size_t>(-1);
+}
+
+// Runs the recorded operator on `self` (a 1-element CPU tensor standing for a constant tensor),
+// with the recorded scalar arguments: exact ATen semantics for constant folding.
+bool fold_const(const TapeOp& op, Sym& st, bool inplace) {
+  if (!op.handle || !st.cval.defined()) return false;
+  Stack stack;
+  size_t slot = 0;
+  bool ok = true, first_tensor = true;
+  for (const IValue& a : op.args) {
+    if (a.isTensor()) {
+      if (slot >= op.inputs.size()) return false;
+      const InputRef& in = op.inputs[slot++];
+      if (first_tensor) {
+        stack.emplace_back(st.cval);
+        first_tensor = false;
+      } else if (in.real.defined() && in.real.numel() == 1 && in.real.is_cpu()) {
+        stack.emplace_back(in.real);
+      } else if (!in.real.defined() && in.value == kNoValue && !in.foreign) {
+        stack.emplace_back(at::Tensor());
+      } else {
+        ok = false;
+      }
+    } else if (a.isList()) {
+      for (const IValue& e : a.toListRef()) ok &= !e.isTensor();
+      stack.push_back(a);
+    } else if (a.isDevice()) {
+      stack.emplace_back(c10::Device(c10::kCPU));
+    } else {
+      stack.push_back(a);
+    }
+  }
+  if (!ok) return false;
+  NoInterception guard;
+  op.handle->callBoxed(stack);
+  if (stack.empty() || !stack.back().isTensor()) return false;
+  at::Tensor out = stack.back().toTensor();
+  if (out.numel() != 1) return false;
+  st.cval = inplace ? st.cval : out;
+  st.dtype = st.cval.scalar_type();
+  return true;
+}
+
+Sym eval_storage(Tape& tape, uint32_t S, uint32_t upto);
+
+// Applies one recorded op whose output lives on the storage being evaluated.
+void transition(Tape& tape, uint32_t op_idx, uint32_t S, Sym& st) {
+  TapeOp& op = tape.ops[op_idx];
+  // the output of this op on S
+  uint32_t out_v = kNoValue;
+  for (uint32_t v : op.outputs)
+    if (v != kNoValue && tape.values[v].storage == S) out_v = v;
+  const ValueInfo& out = tape.values[out_v];
+  auto need_cover = [&] { return out.covers_storage; };
+  auto push_epi = [&](uint32_t code, double a, double b = 0) {
+    if (st.epi.size() >= TDX_MAX_EPI) { st = make_opaque(); return; }
+    TdxEpiStep s;
+    s.op = code;  // every step rounds to the tensor dtype, like the in-place ATen op it stands for
+    s.a = static_cast<float>(a);
+    s.b = static_cast<float>(b);
+    st.epi.push_back(s);
+  };
+
+  switch (op.kind) {
+    case OpKind::Empty:
+      if (!need_cover()) { st = make_opaque(); return; }
+      st = Sym{};
+      st.src = Sym::Uninit;
+      st.dtype = out.dtype;
+      return;
+    case OpKind::Zeros:
+    case OpKind::Ones:
+    case OpKind::Full: {
+      if (!need_cover()) { st = make_opaque(); return; }
+      st = Sym{};
+      st.src = Sym::Const;
+      st.dtype = out.dtype;
+      NoInterception guard;
+      const auto opt = at::TensorOptions().dtype(out.dtype).device(c10::kCPU);
+      if (op.kind == OpKind::Zeros) st.cval = at::zeros({1}, opt);
+      else if (op.kind == OpKind::Ones) st.cval = at::ones({1}, opt);
+      else {
+        const size_t pos = find_arg(op, "fill_value");
+        if (pos == static_cast<size_t>(-1) || !op.args[pos].isScalar()) { st = make_opaque(); return; }
+        st.cval = at::full({1}, op.args[pos].toScalar(), opt);
+      }
+      return;
+    }
+    case OpKind::Randn:
+    case OpKind::Rand:
+      if (!need_cover() || !is_fused_float(out.dtype)) { st = make_opaque(); return; }
+      {
+        std::vector<uint32_t> chain = std::move(st.rng_chain);
+        st = Sym{};
+        st.rng_chain = std::move(chain);
+      }
+      st.src = op.kind == OpKind::Randn ? Sym::Normal : Sym::Uniform;
+      st.dtype = st.gen_dtype = out.dtype;
+      st.p0 = 0.0;
+      st.p1 = 1.0;
+      st.rng_op = op_idx;
+      st.rng_chain.push_back(op_idx);
+      return;
+    case OpKind::Alias:
+    case OpKind::HookVariableData:
+      return;  // same elements under another tensor object
+    case OpKind::UniformInplace:
+    case OpKind::NormalInplace: {
+      if (!need_cover() || !is_fused_float(out.dtype) || st.opaque()) { st = make_opaque(); return; }
+      const bool uni = op.kind == OpKind::UniformInplace;
+      const auto a = scalar_arg(op, 1), b = scalar_arg(op, 2);
+      if (!a || !b) { st = make_opaque(); return; }
+      std::vector<uint32_t> chain = std::move(st.rng_chain);
+      st = Sym{};
+      st.rng_chain = std::move(chain);
+      st.src = uni ? Sym::Uniform : Sym::Normal;
+      st.dtype = st.gen_dtype = out.dtype;
+      if (uni) {
+        TORCH_CHECK(*a <= *b, "uniform_ expects to return a [from, to) range, but found from=", *a,
+                    " > to=", *b);
+        st.p0 = round_to_dtype(*a, out.dtype);
+        st.p1 = round_to_dtype(*b, out.dtype);
+      } else {
+        TORCH_CHECK(*b >= 0.0, "normal expects std >= 0.0, but found std ", *b);
+        st.p0 = *a;
+        st.p1 = *b;
+      }
+      st.rng_op = op_idx;
+      st.rng_chain.push_back(op_idx);
+      return;
+    }
+    case OpKind::FillInplace:
+    case OpKind::ZeroInplace: {
+      if (!need_cover() || st.opaque()) { st = make_opaque(); return; }
+      std::vector<uint32_t> chain = std::move(st.rng_chain);
+      const ScalarType dt = out.dtype;
+      st = Sym{};
+      st.rng_chain = std::move(chain);
+      st.src = Sym::Const;
+      st.dtype = dt;
+      NoInterception guard;
+      const auto opt = at::TensorOptions().dtype(dt).device(c10::kCPU);
+      if (op.kind == OpKind::ZeroInplace) {
+        st.cval = at::zeros({1}, opt);
+      } else if (op.args.size() > 1 && op.args[1].isScalar()) {
+        st.cval = at::full({1}, op.args[1].toScalar(), opt);
+      } else if (op.inputs.size() > 1 && op.inputs[1].real.defined() &&
+                 op.inputs[1].real.numel() == 1 && op.inputs[1].real.is_cpu()) {
+        st.cval = op.inputs[1].real.detach().to(dt).reshape({1}).clone();
+      } else {
+        st = make_opaque();
+      }
+      return;
+    }
+    case OpKind::MulInplace:
+    case OpKind::AddInplace:
+    case OpKind::ErfinvInplace:
+    case OpKind::ClampInplace:
+    case OpKind::MulOut:
+    case OpKind::AddOut:
+    case OpKind::CastOut: {
+      const bool inplace = op.kind == OpKind::MulInplace || op.kind == OpKind::AddInplace ||
+                           op.kind == OpKind::ErfinvInplace || op.kind == OpKind::ClampInplace;
+      if (!inplace) {
+        // state comes from the (other) storage of the first tensor argument, as of this op
+        if (op.inputs.empty() || op.inputs[0].value == kNoValue) { st = make_opaque(); return; }
+        const ValueInfo& in = tape.values[op.inputs[0].value];
+        if (!in.covers_storage || in.numel != out.numel || in.storage == S) { st = make_opaque(); return; }
+        st = eval_storage(tape, in.storage, op_idx);
+      }
+      if (st.opaque() || st.src == Sym::Uninit || !need_cover()) { st = make_opaque(); return; }
+      if (st.src == Sym::Const) {
+        if (!fold_const(op, st, inplace)) st = make_opaque();
+        return;
+      }
+      // RNG source followed by an elementwise op
+      if (op.kind == OpKind::CastOut) {
+        if (!is_fused_float(out.dtype) || !st.epi.empty()) { st = make_opaque(); return; }
+        st.dtype = out.dtype;  // generate straight into the destination dtype
+        st.gen_dtype = out.dtype;
+        if (st.src == Sym::Uniform) {
+          st.p0 = round_to_dtype(st.p0, out.dtype);
+          st.p1 = round_to_dtype(st.p1, out.dtype);
+        }
+        return;
+      }
+      if (out.dtype != st.dtype) { st = make_opaque(); return; }  // type promotion: not modelled
+      if (op.kind == OpKind::MulInplace || op.kind == OpKind::MulOut) {
+        const auto c = scalar_arg(op, 1);
+        if (!c) { st = make_opaque(); return; }
+        push_epi(TDX_EPI_MUL, *c);
+      } else if (op.kind == OpKind::AddInplace || op.kind == OpKind::AddOut) {
+        const auto c = scalar_arg(op, 1), alpha = scalar_arg(op, 2);
+        if (!c || !alpha) { st = make_opaque(); return; }
+        push_epi(TDX_EPI_ADD, *c * *alpha);
+      } else if (op.kind == OpKind::ErfinvInplace) {
+        push_epi(TDX_EPI_ERFINV, 0);
+      } else {  // clamp_(min, max), either may be None
+        const bool has_min = !op.args[1].isNone(), has_max = !op.args[2].isNone();
+        const auto lo = scalar_arg(op, 1), hi = scalar_arg(op, 2);
+        if ((has_min && !lo) || (has_max && !hi)) { st = make_opaque(); return; }
+        push_epi(TDX_EPI_CLAMP, has_min ? *lo : -std::numeric_limits<double>::infinity(),
+                 has_max ? *hi : std::numeric_limits<double>::infinity());
+      }
+      return;
+    }
+    default:
+      st = make_opaque();
+      return;
+  }
+}
+
+// State of storage S after every recorded op with index < upto.
+Sym eval_storage(Tape& tape, uint32_t S, uint32_t upto) {
+  const StorageInfo& si = tape.storages[S];
+  Sym st;
+  bool any = false;
+  // index of the last op (< upto) that writes S
+  uint32_t last_writer = kNoValue;
+  for (uint32_t oi : si.touching_ops) {
+    if (oi >= upto) break;
+    for (uint32_t v : tape.ops[oi].outputs)
+      if (v != kNoValue && tape.values[v].storage == S) last_writer = oi;
+  }
+  for (uint32_t oi : si.touching_ops) {
+    if (oi >= upto) break;
+    const TapeOp& op = tape.ops[oi];
+    bool writes = false;
+    for (uint32_t v : op.outputs) writes |= (v != kNoValue && tape.values[v].storage == S);
+    if (!writes) {
+      // A reader that saw an intermediate state which a later op overwrote must run at its own
+      // point in history: only generic replay can do that.
+      if (!op.done && last_writer != kNoValue && oi < last_writer) return make_opaque();
+      continue;
+    }
+    if (op.done && op.kind == OpKind::Generic) return make_opaque();
+    if (!any) {
+      // the first writer must be a factory (or an out-of-place op producing this storage)
+      any = true;
+    }
+    transition(tape, oi, S, st);
+    if (st.opaque()) return st;
+  }
+  if (!any) return make_opaque();
+  return st;
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched fused execution
+// ---------------------------------------------------------------------------------------------
+struct Batch {
+  c10::Device device = c10::Device(c10::kCPU);
+  std::vector<TdxInitDesc> descs;
+  std::vector<at::Tensor> keep_alive;
+  void flush();
+};
+
+void Batch::flush() {
+  if (descs.empty()) return;
+  NoInterception guard;
+  c10::DeviceGuard dg(device);
+  const int n = static_cast<int>(descs.size());
+  const size_t ws_bytes = tdx_init_workspace_bytes(n);
+  at::Tensor ws = at::empty({static_cast<int64_t>(ws_bytes)},
+                            at::TensorOptions().dtype(at::kByte).device(device));
+  auto stream = c10::cuda::getCurrentCUDAStream(device.index());
+  const int rc = tdx_init_launch(descs.data(), n, ws.data_ptr(), ws_bytes, stream.stream());
+  TORCH_CHECK(rc == 0, "libtdx_init: launch failed (", rc, "): ", tdx_last_error());
+  g_stats.kernel_launches += tdx_last_launch_count();
+  g_stats.descriptors += n;
+  descs.clear();
+  keep_alive.clear();
+}
+
+int tdx_dtype_of(ScalarType t) {
+  switch (t) {
+    case ScalarType::Float: return TDX_F32;
+    case ScalarType::BFloat16: return TDX_BF16;
+    case ScalarType::Half: return TDX_F16;
+    default: return -1;
+  }
+}
+
+// Gives an RNG op its Philox stream id (once) and advances the generator, so that replaying in
+// the same order with the same seed reproduces the same tensors, dead passes included.
+void assign_rng(TapeOp& op, int64_t numel, c10::Device device) {
+  if (op.rng_assigned) return;
+  at::Generator gen;
+  if (op.handle) {
+    const size_t pos = find_arg(op, "generator");
+    if (pos != static_cast<size_t>(-1) && op.args[pos].isGenerator()) gen = op.args[pos].toGenerator();
+  }
+  if (!gen.defined()) gen = at::globalContext().defaultGenerator(device);
+  TORCH_CHECK(gen.device().type() == device.type(), "Expected a '", device.type(),
+              "' device type for generator but found '", gen.device().type(), "'");
+  std::lock_guard<std::mutex> lock(gen.mutex());
+  op.rng_seed = gen.current_seed();
+  op.rng_offset = gen.get_offset();
+  // consumption is a function of the GLOBAL element count only: shard-invariant by construction
+  const uint64_t blocks = (static_cast<uint64_t>(numel) + 3) / 4;
+  gen.set_offset(op.rng_offset + ((blocks + 3) / 4) * 4 + 4);
+  op.rng_assigned = true;
+}
+
+struct ShardGeom {
+  int64_t begin = 0, count = 0;
+  std::vector<int64_t> sizes;
+};
+
+ShardGeom shard_of(const ValueInfo& v, const std::optional<ShardSpec>& shard) {
+  ShardGeom g;
+  g.sizes = v.sizes;
+  g.begin = 0;
+  g.count = v.numel;
+  if (!shard || shard->world <= 1 || v.sizes.empty()) return g;  // 0-dim tensors are replicated
+  const int64_t d0 = v.sizes[0];
+  const int64_t inner = d0 ? v.numel / d0 : 0;
+  const int64_t per = (d0 + shard->world - 1) / shard->world;  // torch.chunk row count
+  const int64_t start = std::min(d0, shard->rank * per);
+  const int64_t len = std::min(per, d0 - start);
+  g.begin = start * inner;
+  g.count = len * inner;
+  g.sizes[0] = len;
+  return g;
+}
+
+at::Tensor alias_of(const at::Tensor& base, const ValueInfo& v) {
+  NoInterception guard;
+  at::Tensor t = base.detach();
+  if (t.sizes() != c10::IntArrayRef(v.sizes) || t.strides() != c10::IntArrayRef(v.strides) ||
+      t.storage_offset() != v.storage_offset) {
+    t.as_strided_(v.sizes, v.strides, v.storage_offset);
+  }
+  return t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic replay
+// ---------------------------------------------------------------------------------------------
+struct Engine {
+  const MaterializeOptions& opts;
+  Batch& batch;
+
+  at::Tensor real_of(Tape& tape, uint32_t v) {
+    ValueInfo& vi = tape.values[v];
+    if (vi.real.defined()) return vi.real;
+    StorageInfo& si = tape.storages[vi.storage];
+    TORCH_INTERNAL_ASSERT(si.fused_done, "value of `", tape.ops[vi.op].name(),
+                          "` requested before it was materialised");
+    if (opts.shard && opts.shard->world > 1 && !vi.sizes.empty()) {
+      // the backing tensor is this rank's dim-0 chunk; only whole-storage tensors can name it
+      TORCH_CHECK(vi.covers_storage,
+                  "sharded materialisation only supports tensors that cover their whole storage");
+      NoInterception guard;
+      vi.real = si.base.detach();
+      return vi.real;
+    }
+    vi.real = alias_of(si.base, vi);
+    return vi.real;
+  }
+
+  c10::Device target_device(c10::Device recorded) const { return opts.device ? *opts.device : recorded; }
+
+  void collect_storage(Tape& tape, uint32_t S, uint32_t upto, std::vector<uint8_t>& mark,
+                       std::vector<uint32_t>& visited_upto) {
+    if (visited_upto[S] >= upto) return;
+    visited_upto[S] = upto;
+    const auto& touching = tape.storages[S].touching_ops;
+    uint32_t last_writer = kNoValue;
+    for (uint32_t oi : touching) {
+      if (oi >= upto) break;
+      for (uint32_t v : tape.ops[oi].outputs)
+        if (v != kNoValue && tape.values[v].storage == S) last_writer = oi;
+    }
+    if (last_writer == kNoValue) return;
+    for (size_t k = 0; k < touching.size(); ++k) {
+      const uint32_t oi = tape.storages[S].touching_ops[k];
+      if (oi > last_writer) break;
+      collect_op(tape, oi, mark, visited_upto);
+    }
+  }
+
+  void collect_op(Tape& tape, uint32_t oi, std::vector<uint8_t>& mark,
+                  std::vector<uint32_t>& visited_upto) {
+    if (mark[oi] || tape.ops[oi].done) return;
+    mark[oi] = 1;
+    for (size_t k = 0; k < tape.ops[oi].inputs.size(); ++k) {
+      const uint32_t v = tape.ops[oi].inputs[k].value;
+      if (v == kNoValue) continue;
+      if (tape.values[v].real.defined()) continue;
+      collect_storage(tape, tape.values[v].storage, oi, mark, visited_upto);
+    }
+  }
+
+  void replay(Tape& tape, uint32_t oi) {
+    TapeOp& op = tape.ops[oi];
+    if (op.done) return;
+    const size_t nargs = op.args.size();
+    Stack stack;
+    stack.reserve(nargs);
+    for (const IValue& a : op.args) {
+      if (a.isList()) {  // fresh list: we are about to put tensors into it
+        const auto& src = a.toList();
+        c10::impl::GenericList l(src.elementType());
+        for (const IValue& e : a.toListRef()) l.push_back(e);
+        stack.emplace_back(std::move(l));
+      } else {
+        stack.push_back(a);
+      }
+    }
+    size_t slot = 0;
+    for_each_tensor_mut(stack, nargs, [&](at::Tensor& t) {
+      InputRef& in = op.inputs[slot++];
+      if (in.value != kNoValue) {
+        t = real_of(tape, in.value);
+      } else if (in.foreign) {
+        t = materialize_value(in.foreign, in.foreign_value);
+      } else if (in.real.defined()) {
+        TORCH_CHECK(!in.real.is_inference(), "A `Tensor` argument required for the materialization of `",
+                    op.name(), "` was created in inference mode. Materialization cannot be performed "
+                    "because in-place updates to inference tensors cannot be tracked.");
+        TORCH_CHECK(static_cast<int64_t>(in.real._version()) == in.real_version,
+                    "A `Tensor` argument required for the materialization of `", op.name(),
+                    "` was updated in-place. Materialization cannot be performed.");
+        t = in.real;
+        if (opts.device && t.dim() != 0 && t.device() != *opts.device) t = t.to(*opts.device);
+      }
+    });
+    if (opts.device && op.handle) {
+      const int di = device_argument_index(*op.handle);
+      if (di >= 0 && (stack[di].isDevice() || stack[di].isNone())) stack[di] = *opts.device;
+    }
+    {
+      at::ThreadLocalStateGuard tls(*op.tls);
+      NoInterception guard;
+      if (op.handle) {
+        op.handle->callBoxed(stack);
+      } else if (op.kind == OpKind::HookVariableData) {
+        at::Tensor self = stack[0].toTensor();
+        stack.clear();
+        stack.emplace_back(at::Tensor(self.variable_data()));
+      } else {  // HookSetData
+        at::Tensor self = stack[0].toTensor(), data = stack[1].toTensor();
+        self.set_data(data);
+        stack.clear();
+        stack.emplace_back(self);
+      }
+    }
+    size_t k = 0;
+    for_each_tensor(stack, op.num_returns, [&](const at::Tensor& t) {
+      if (k < op.outputs.size() && op.outputs[k] != kNoValue) tape.values[op.outputs[k]].real = t;
+      ++k;
+    });
+    op.results = std::move(stack);
+    op.done = true;
+    op.tls.reset();
+    op.args.clear();
+    g_stats.generic_ops++;
+  }
+
+  // Fused path for the storage of value `v`.  Returns false if the program is not fusible.
+  bool try_fused(Tape& tape, uint32_t v) {
+    ValueInfo& vi = tape.values[v];
+    const uint32_t S = vi.storage;
+    StorageInfo& si = tape.storages[S];
+    if (!opts.fused) return false;
+    const c10::Device dev = target_device(vi.device);
+    if (!dev.is_cuda()) return false;
+    const bool sharded = opts.shard && opts.shard->world > 1 && !vi.sizes.empty();
+    if (sharded && !vi.covers_storage) return false;
+
+    Sym st = eval_storage(tape, S, static_cast<uint32_t>(tape.ops.size()));
+    if (st.opaque()) return false;
+    const size_t isz = c10::elementSize(st.dtype);
+    if (isz == 0 || si.nbytes % isz) return false;
+    const int64_t numel = static_cast<int64_t>(si.nbytes / isz);
+    if (numel == 0) return false;
+    if (st.src == Sym::Uniform || st.src == Sym::Normal) {
+      if (tdx_dtype_of(st.dtype) < 0) return false;
+    } else if (st.src == Sym::Const) {
+      if (!(isz == 1 || isz == 2 || isz == 4 || isz == 8)) return false;
+    }
+
+    // geometry of what this rank writes
+    ShardGeom g;
+    if (vi.covers_storage) {
+      g = shard_of(vi, opts.shard);
+    } else {
+      g.begin = 0;
+      g.count = numel;
+      g.sizes = {numel};
+    }
+
+    if (batch.device != dev) {
+      batch.flush();
+      batch.device = dev;
+    }
+    at::Tensor base;
+    {
+      NoInterception guard;
+      base = at::empty(g.sizes, at::TensorOptions().dtype(st.dtype).device(dev));
+    }
+
+    // every RNG pass on the chain consumes its slice of the stream, live or dead
+    for (uint32_t r : st.rng_chain) {
+      if (!tape.ops[r].rng_assigned) {
+        assign_rng(tape.ops[r], numel, dev);
+        if (r != st.rng_op) g_stats.elided_rng_ops++;
+      }
+    }
+
+    if (st.src != Sym::Uninit && g.count > 0) {
+      TdxInitDesc d;
+      std::memset(&d, 0, sizeof(d));
+      d.dst = base.data_ptr();
+      d.elem_begin = static_cast<uint64_t>(g.begin);
+      d.elem_count = static_cast<uint64_t>(g.count);
+      if (st.src == Sym::Const) {
+        d.src = TDX_SRC_CONST;
+        d.dtype = isz == 1 ? TDX_RAW8 : isz == 2 ? TDX_RAW16 : isz == 4 ? TDX_RAW32 : TDX_RAW64;
+        unsigned char pat[16];
+        const at::Tensor c = st.cval.contiguous();
+        for (size_t i = 0; i < 16; i += isz) std::memcpy(pat + i, c.data_ptr(), isz);
+        std::memcpy(d.fill_bits, pat, 16);
+      } else {
+        d.src = st.src == Sym::Uniform ? TDX_SRC_UNIFORM : TDX_SRC_NORMAL;
+        d.dtype = static_cast<uint8_t>(tdx_dtype_of(st.dtype));
+        d.p0 = st.p0;
+        d.p1 = st.p1;
+        const TapeOp& r = tape.ops[st.rng_op];
+        d.philox_seed = r.rng_seed;
+        d.philox_offset = r.rng_offset;
+        d.n_epi = static_cast<uint8_t>(st.epi.size());
+        for (size_t i = 0; i < st.epi.size(); ++i) d.epi[i] = st.epi[i];
+      }
+      batch.descs.push_back(d);
+      batch.keep_alive.push_back(base);
+      g_stats.bytes_written += g.count * static_cast<int64_t>(isz);
+    }
+
+    si.base = base;
+    si.fused_done = true;
+    for (uint32_t oi : si.touching_ops) {
+      TapeOp& op = tape.ops[oi];
+      bool writes = false;
+      for (uint32_t ov : op.outputs) writes |= (ov != kNoValue && tape.values[ov].storage == S);
+      if (writes && !op.done) {
+        op.done = true;
+        op.tls.reset();
+      }
+    }
+    g_stats.fused_tensors++;
+    return true;
+  }
+
+  at::Tensor materialize_value(const std::shared_ptr<Tape>& tape_ptr, uint32_t v) {
+    Tape& tape = *tape_ptr;
+    ValueInfo& vi = tape.values[v];
+    if (vi.real.defined()) return vi.real;
+    if (tape.storages[vi.storage].fused_done) return real_of(tape, v);
+    if (try_fused(tape, v)) return real_of(tape, v);
+
+    // generic replay, in recorded order, of everything that determines this storage
+    batch.flush();
+    std::vector<uint8_t> mark(tape.ops.size(), 0);
+    std::vector<uint32_t> visited(tape.storages.size(), 0);
+    collect_storage(tape, vi.storage, static_cast<uint32_t>(tape.ops.size()), mark, visited);
+    for (uint32_t oi = 0; oi < mark.size(); ++oi)
+      if (mark[oi]) replay(tape, oi);
+    TORCH_INTERNAL_ASSERT(vi.real.defined(), "replay did not produce `", tape.ops[vi.op].name(), "`");
+    if (opts.shard && opts.shard->world > 1 && !vi.sizes.empty()) {
+      NoInterception guard;
+      const ShardGeom g = shard_of(vi, opts.shard);
+      const int64_t inner = vi.sizes[0] ? vi.numel / vi.sizes[0] : 0;
+      const int64_t start = inner ? g.begin / inner : 0;
+      return vi.real.narrow(0, start, g.sizes[0]).clone();
+    }
+    return vi.real;
+  }
+};
+
+at::Tensor finish(const at::Tensor& fake, at::Tensor out) {
+  // requires_grad_() is not an operator and cannot be recorded: re-apply it on leaves
+  // (same rule as reference deferred_init.cc:722-726)
+  if (fake.is_leaf() && fake.requires_grad() && !out.requires_grad() &&
+      (out.is_floating_point() || out.is_complex())) {
+    out.set_requires_grad(true);
+  }
+  return out;
+}
+
+}  // namespace
+
+std::vector<at::Tensor> materialize_many(const std::vector<at::Tensor>& fakes,
+                                         const MaterializeOptions& opts) {
+  g_stats = MaterializeStats{};
+  std::vector<at::Tensor> out;
+  out.reserve(fakes.size());
+  Batch batch;
+  Engine eng{opts, batch};
+  for (const at::Tensor& t : fakes) {
+    g_stats.tensors++;
+    if (!can_materialize(t)) {
+      out.push_back(t);
+      continue;
+    }
+    const auto rec = fake_impl(t)->record();  // copy: keeps the tape alive while we work
+    out.push_back(finish(t, eng.materialize_value(rec->tape, rec->value)));
+  }
+  batch.flush();
+  return out;
+}
+
+at::Tensor materialize_one(const at::Tensor& fake, const MaterializeOptions& opts) {
+  if (!can_materialize(fake)) return fake;
+  return materialize_many({fake}, opts)[0];
+}
+
+MaterializeStats last_stats() { return g_stats; }
+
+at::Tensor cached_python_tensor(const at::Tensor& fake) {
+  if (!can_materialize(fake)) return {};
+  const auto& rec = fake_impl(fake)->record();
+  return rec->tape->values[rec->value].py_wrapped;
+}
+
+void cache_python_tensor(const at::Tensor& fake, const at::Tensor& wrapped) {
+  if (!can_materialize(fake)) return;
+  const auto& rec = fake_impl(fake)->record();
+  rec->tape->values[rec->value].py_wrapped = wrapped;
+}
+
+}  // namespace tdx

@@ -1,0 +1,64 @@
+// Materialisation: turning recorded tapes into real tensors.
+//
+// Replaces the reference's materialise path
+//   materializeTensor / detail::materialize      reference deferred_init.cc:1163-1173, :713-729
+//   OpNode::materialize / buildCallStack / ...   reference deferred_init.cc:506-667
+//   Op::materialize -> handle.callBoxed          reference deferred_init.cc:256-272, :218-220
+// with a two-tier executor:
+//   1. FUSED (CUDA tensors): the ops that determine a storage are evaluated symbolically
+//      (last-writer analysis; overwritten RNG passes only advance the Philox offset) into ONE
+//      TdxInitDesc; all descriptors of a materialize call are executed by O(#kernel families)
+//      launches of libtdx_init (include/tdx_init.h).  Under sharding each rank's descriptor covers
+//      only its slice [elem_begin, elem_begin+elem_count) and writes into a shard-sized buffer:
+//      the unsharded tensor never exists.
+//   2. GENERIC replay through the dispatcher, in recorded order, for CPU-device tensors (bit-exact
+//      with eager initialisation, same mt19937 stream) and for programs the planner does not
+//      understand (executed by ATen on the recorded device).  Same semantics as the reference.
+#pragma once
+
+#include <ATen/Tensor.h>
+
+#include <cstdint>
+#include <optional>
+#include <vector>
+
+namespace tdx {
+
+struct ShardSpec {
+  int64_t rank = 0;
+  int64_t world = 1;
+  // dim-0 chunking as torch.chunk / FSDP2 Shard(0): rank r owns rows [r*ceil(d0/W), ...)
+  // (reference callers: $TORCH/distributed/fsdp/_fully_shard/_fsdp_param.py:381-402)
+};
+
+struct MaterializeOptions {
+  std::optional<c10::Device> device;  // override of the recorded device (e.g. record on cpu, build on cuda)
+  std::optional<ShardSpec> shard;     // materialise only this rank's dim-0 chunk
+  bool fused = true;                  // false: force generic replay (tests: elision must not change results)
+};
+
+struct MaterializeStats {
+  int64_t tensors = 0;          // tensors requested
+  int64_t fused_tensors = 0;    // served by the fused CUDA path
+  int64_t generic_ops = 0;      // ops replayed through the dispatcher
+  int64_t elided_rng_ops = 0;   // dead RNG passes that only advanced the Philox offset
+  int64_t kernel_launches = 0;  // libtdx_init launches
+  int64_t bytes_written = 0;    // algorithmic bytes of the fused descriptors
+  int64_t descriptors = 0;
+};
+
+// Materialises `fake` (a no-op returning `fake` itself for real tensors).
+at::Tensor materialize_one(const at::Tensor& fake, const MaterializeOptions& opts);
+
+// Materialises many tensors with one batched kernel submission; order defines RNG consumption.
+std::vector<at::Tensor> materialize_many(const std::vector<at::Tensor>& fakes,
+                                         const MaterializeOptions& opts);
+
+MaterializeStats last_stats();
+
+// The tensor that a previous materialisation handed to Python for this fake tensor (keeps the
+// Python object identity stable), and the hook to store it.
+at::Tensor cached_python_tensor(const at::Tensor& fake);
+void cache_python_tensor(const at::Tensor& fake, const at::Tensor& wrapped);
+
+}  // namespace tdx

@@ -1,0 +1,131 @@
+// Deferred-init recording: a flat, append-only tape of operator records.
+//
+// The reference records a pointer graph of OpNode objects holding std::function closures over
+// the dispatcher (reference src/cc/torchdistx/deferred_init.cc:157-301 Op, :313-402 OpNode) and
+// materialises a tensor by walking dependency / dependent edges (:530-622).  Here recording is
+// an arena ("Tape"): every intercepted operator appends one TapeOp that names its tensor inputs
+// and outputs by integer value ids and its storages by integer storage ids.  A tape is a plain
+// data structure the planner (planner.h) can analyse -- last-writer analysis, dead-op
+// elimination, pattern matching to fused sm_100a kernels -- without touching the dispatcher.
+// Ops that the planner does not understand are still replayable through the dispatcher
+// (generic replay), which keeps the reference's semantics for the long tail.
+//
+// Observable behaviour kept from the reference:
+//   * ops are recorded only if they consume or produce a fake tensor   (deferred_init.cc:790-796)
+//   * `aten::item` is terminal: fake arguments are materialised first  (:773-781, :813-825)
+//   * external (real) tensor arguments are version-checked at replay   (:482-489, :652-654)
+//   * Tensor.data get/set are recorded through the autograd hooks      (:889-948, :1050-1073)
+//   * thread-local state at record time is restored at replay          (:205-215, :256-272)
+//   * modes are per-thread and nestable; op order is per-thread        (:672, :1135-1161)
+#pragma once
+
+#include <ATen/Tensor.h>
+#include <ATen/ThreadLocalState.h>
+#include <ATen/core/dispatch/Dispatcher.h>
+#include <ATen/core/ivalue.h>
+#include <c10/core/Storage.h>
+
+#include <cstdint>
+#include <memory>
+#include <optional>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace tdx {
+
+constexpr uint32_t kNoValue = 0xffffffffu;
+
+// What the planner knows about an operator (classified once per schema).
+enum class OpKind : uint8_t {
+  Generic = 0,
+  // factories (new storage)
+  Empty, Zeros, Ones, Full, Randn, Rand,
+  // full aliases of the input (same storage, same elements)
+  Alias,  // detach, alias, view-like ops are classified Alias only when they cover the storage
+  // in-place writers
+  UniformInplace, NormalInplace, FillInplace, ZeroInplace,
+  MulInplace, AddInplace, ErfinvInplace, ClampInplace,
+  // out-of-place unary elementwise (new storage, same geometry)
+  MulOut, AddOut, CastOut,
+  // autograd hook pseudo-ops
+  HookVariableData, HookSetData,
+};
+
+struct Tape;
+
+// Geometry of one recorded tensor value, captured from the meta twin at record time.
+struct ValueInfo {
+  uint32_t op = 0;        // producing op (index into Tape::ops)
+  uint32_t storage = 0;   // index into Tape::storages
+  c10::ScalarType dtype = c10::ScalarType::Undefined;
+  c10::Device device = c10::Device(c10::kCPU);
+  std::vector<int64_t> sizes, strides;
+  int64_t storage_offset = 0;
+  int64_t numel = 0;
+  bool covers_storage = false;  // contiguous, offset 0, numel*itemsize == storage bytes
+  bool requires_grad = false;
+  at::Tensor real;        // set once materialised
+  at::Tensor py_wrapped;  // what the Python binding returned for it (keeps object identity stable)
+};
+
+struct StorageInfo {
+  c10::Storage meta;      // keeps the meta StorageImpl (our identity key) alive
+  size_t nbytes = 0;
+  std::vector<uint32_t> touching_ops;  // every op with an input or output on this storage, in order
+  at::Tensor base;        // real backing tensor once the fused path materialised the storage
+  bool fused_done = false;
+};
+
+// A tensor argument of a recorded op.
+struct InputRef {
+  uint32_t value = kNoValue;          // value id in this tape, or kNoValue
+  std::shared_ptr<Tape> foreign;      // set if the fake argument was recorded on another tape
+  uint32_t foreign_value = kNoValue;
+  at::Tensor real;                    // a real (external) tensor argument
+  int64_t real_version = 0;           // its version counter at record time
+};
+
+struct TapeOp {
+  std::optional<c10::OperatorHandle> handle;  // empty for hook pseudo-ops
+  OpKind kind = OpKind::Generic;
+  uint64_t seq = 0;                     // thread-wide chronological number
+  std::vector<c10::IValue> args;        // deep-copied call frame; fake tensors replaced by undefined
+  std::vector<InputRef> inputs;         // one per tensor slot of `args`, in stack_walk order
+  std::vector<uint32_t> outputs;        // value id per tensor output (kNoValue for non-fake outputs)
+  uint32_t num_returns = 0;
+  std::optional<at::ThreadLocalState> tls;
+  std::vector<c10::IValue> results;     // real outputs after generic replay
+  bool done = false;
+  // RNG ops on the fused path: the Philox stream id they were given (once, in materialise order)
+  bool rng_assigned = false;
+  uint64_t rng_seed = 0, rng_offset = 0;
+  const char* name() const;
+};
+
+struct Tape : std::enable_shared_from_this<Tape> {
+  std::vector<TapeOp> ops;
+  std::vector<ValueInfo> values;
+  std::vector<StorageInfo> storages;
+  std::unordered_map<const c10::StorageImpl*, uint32_t> storage_ids;
+  uint32_t storage_id(const c10::Storage& s);
+};
+
+// Recording state attached to a fake tensor (FakeTensorImpl::record()).
+struct TensorRecord {
+  std::shared_ptr<Tape> tape;
+  uint32_t value = kNoValue;  // the tensor's CURRENT value (updated by in-place ops)
+};
+
+// ---- runtime API (mirrors reference src/cc/torchdistx/deferred_init.h:25-37) -----------------
+void enter_deferred_init();
+void leave_deferred_init() noexcept;
+bool can_materialize(const at::Tensor& t) noexcept;
+
+struct NoDeferredInit {
+  c10::impl::ExcludeDispatchKeyGuard guard{c10::DispatchKey::DeferredInit};
+};
+
+OpKind classify(const c10::OperatorHandle& op);
+
+}  // namespace tdx
