@@ -1,0 +1,86 @@
+"""Module builders shared by the product tests and the reference oracle (TEST INFRASTRUCTURE).
+
+Each case is `name -> callable() -> nn.Module`, pure PyTorch / transformers, importing neither
+torchdistx_b200 nor the reference.  Sizes are small enough for the CPU reference to run in seconds.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+
+
+def linear128():
+    return nn.Linear(128, 128)
+
+
+class InitZoo(nn.Module):
+    """One tensor per init idiom the planner folds."""
+
+    def __init__(self):
+        super().__init__()
+        self.kaiming = nn.Linear(48, 32)
+        self.embed = nn.Embedding(64, 16)
+        self.norm = nn.LayerNorm(16)
+        self.bn = nn.BatchNorm1d(8)
+        self.xavier = nn.Parameter(torch.empty(24, 40))
+        nn.init.xavier_uniform_(self.xavier)
+        self.xavier_n = nn.Parameter(torch.empty(24, 40))
+        nn.init.xavier_normal_(self.xavier_n, gain=0.5)
+        self.trunc = nn.Parameter(torch.empty(32, 32))
+        nn.init.trunc_normal_(self.trunc, mean=0.1, std=0.02, a=-0.04, b=0.06)
+        self.twice = nn.Linear(32, 32, bias=False)
+        nn.init.normal_(self.twice.weight, mean=0.0, std=0.02)  # dead uniform_ + live normal_
+        self.const = nn.Parameter(torch.ones(17) * 3.0 + 1.0)
+        self.scaled = nn.Parameter(torch.randn(33, 7) * 0.02 + 1.0)
+        self.zeros = nn.Parameter(torch.zeros(5, 3))
+        self.full = nn.Parameter(torch.full((9,), 0.25))
+        self.register_buffer("mask", torch.tril(torch.ones(6, 6)).bool())
+        self.register_buffer("steps", torch.arange(10))
+        self.register_buffer("int_fill", torch.full((4,), 7, dtype=torch.int64))
+
+
+def init_zoo():
+    return InitZoo()
+
+
+def tiny_llama():
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    cfg = LlamaConfig(vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                      num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=64)
+    return LlamaForCausalLM(cfg)
+
+
+def tiny_gpt2():
+    from transformers import GPT2Config, GPT2LMHeadModel
+
+    cfg = GPT2Config(n_layer=2, n_embd=64, n_head=4, vocab_size=512, n_positions=64)
+    return GPT2LMHeadModel(cfg)
+
+
+def mlp_stack():
+    return nn.Sequential(nn.Linear(64, 256), nn.GELU(), nn.Linear(256, 64), nn.LayerNorm(64))
+
+
+CASES = {
+    "linear128": linear128,
+    "init_zoo": init_zoo,
+    "tiny_llama": tiny_llama,
+    "tiny_gpt2": tiny_gpt2,
+    "mlp_stack": mlp_stack,
+}
+
+DTYPES = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}
+
+
+def build(name: str, dtype: str = "fp32", device: str = "cpu"):
+    """Builds the case with `dtype` as default dtype and `device` as default device."""
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(DTYPES[dtype])
+    try:
+        with torch.device(device):
+            return CASES[name]()
+    finally:
+        torch.set_default_dtype(prev)

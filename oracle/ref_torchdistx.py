@@ -18,9 +18,18 @@ from __future__ import annotations
 import importlib.machinery
 import importlib.util
 import os
+import sys
 from contextlib import contextmanager
 
-import torch
+# torch.distributed.fsdp probes `import torchdistx` ($TORCH/distributed/fsdp/_init_utils.py:53-57);
+# in this repo that name resolves to the shim over torchdistx_b200, whose native module would
+# register the same dispatch-key fallbacks as the reference.  Block it in oracle processes.
+if "torchdistx_b200._C" in sys.modules:
+    raise ImportError("the reference oracle cannot share a process with torchdistx_b200")
+sys.modules.setdefault("torchdistx", None)  # type: ignore[arg-type]
+sys.modules.setdefault("torchdistx_b200", None)  # type: ignore[arg-type]
+
+import torch  # noqa: E402
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_ref", "_tdx_ref.so")

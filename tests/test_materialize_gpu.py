@@ -1,0 +1,246 @@
+"""GPU parity, engine level: deferred_init -> materialize_module on cuda through the public API,
+against the REAL reference (oracle/_ref, CPU, subprocess) and against the engine's own invariants.
+
+Tiers:
+  T0  tensors whose recorded program is deterministic: bit-exact with the reference;
+  T1  RNG tensors: same distribution as the reference's CPU sample under the same seed --
+      |mean - mean_ref| <= 5 sigma sqrt(2/N), |std/std_ref - 1| <= 5/sqrt(N) (+2^-8 for bf16 vs the
+      reference's bf16 path, which draws its normals from 8-bit uniforms:
+      $TORCH/include/ATen/native/cpu/DistributionTemplates.h:207-256 with
+      $TORCH/include/ATen/core/TransformationHelper.h:84-99 digits = 8), hard range checks,
+      two-sample KS at alpha = 1e-4 on tensors >= 4096 elements, no NaN/Inf;
+  T2  exact self-consistency: same seed -> same bits, other seed -> other bits, shards
+      concatenate to the unsharded tensor, dead-pass elision == explicit offset skip, the torch
+      generator is advanced.
+"""
+import math
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+from oracle import cases
+from oracle import tdx_oracle as O
+from torchdistx_b200.deferred_init import (deferred_init, is_deferred, last_materialize_stats,
+                                           materialize_module, materialize_tensor)
+from torchdistx_b200.fake import is_fake
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CASES = [("init_zoo", "fp32"), ("init_zoo", "bf16"), ("tiny_llama", "fp32"), ("tiny_llama", "bf16"),
+         ("tiny_gpt2", "fp32"), ("mlp_stack", "fp32")]
+
+
+@pytest.fixture(scope="module")
+def reference(tmp_path_factory):
+    """The real reference, CPU device, two seeds: tensors equal across seeds are deterministic."""
+    out = {}
+    for seed in (5, 6):
+        d = tmp_path_factory.mktemp(f"ref{seed}")
+        subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_driver.py"), "--cases",
+                        ",".join(f"{c}:{t}" for c, t in CASES), "--seed", str(seed), "--outdir", str(d)],
+                       check=True, cwd=ROOT)
+        out[seed] = {(c, t): torch.load(d / f"{c}_{t}.pt") for c, t in CASES}
+    return out
+
+
+def build_on_cuda(case, dtype, seed=5, **kw):
+    torch.set_default_dtype(cases.DTYPES[dtype])
+    try:
+        m = deferred_init(lambda: cases.build(case, dtype, "cuda"))
+    finally:
+        torch.set_default_dtype(torch.float32)
+    assert is_deferred(m)
+    torch.manual_seed(seed)
+    materialize_module(m, **kw)
+    return m
+
+
+def named_tensors(m):
+    return dict(list(m.named_parameters()) + list(m.named_buffers()))
+
+
+@pytest.mark.parametrize("case,dtype", CASES)
+def test_t0_t1_against_reference(case, dtype, reference):
+    from scipy import stats
+
+    ref, ref2 = reference[5][(case, dtype)], reference[6][(case, dtype)]
+    m = build_on_cuda(case, dtype)
+    st = last_materialize_stats()
+    mine = named_tensors(m)
+    assert set(mine) <= set(ref)
+    n_rng = 0
+    for k, t in mine.items():
+        r = ref[k]
+        assert t.is_cuda and not is_fake(t) and t.dtype == r.dtype and t.shape == r.shape, k
+        assert isinstance(t, nn.Parameter) == (k in dict(m.named_parameters())), k
+        x = t.detach().cpu()
+        if torch.equal(r, ref2[k]):  # T0: deterministic program
+            assert torch.equal(x, r), k
+            continue
+        n_rng += 1  # T1
+        xf, rf = x.double().flatten(), r.double().flatten()
+        n = xf.numel()
+        assert torch.isfinite(xf).all(), k
+        sd = rf.std().item()
+        slack = 2 ** -8 if dtype == "bf16" else 0.0
+        assert abs(xf.mean().item() - rf.mean().item()) <= 5 * sd * math.sqrt(2 / n) + slack * sd, k
+        assert abs(xf.std().item() / sd - 1) <= 5 / math.sqrt(n) + 4 * slack, k
+        lo, hi = rf.min().item(), rf.max().item()
+        span = hi - lo
+        assert xf.min().item() >= lo - 0.5 * span and xf.max().item() <= hi + 0.5 * span, k
+        if n >= 4096 and dtype == "fp32":
+            assert stats.ks_2samp(xf.numpy(), rf.numpy()).pvalue > 1e-4, k
+    assert n_rng > 0
+    # everything large went through the fused path
+    fused_bytes = st["bytes_written"]
+    total = sum(t.numel() * t.element_size() for t in mine.values())
+    assert fused_bytes >= 0.95 * total, (st, total)
+
+
+def test_t1_bf16_against_fp32_reference_distribution(reference):
+    """The reference's own bf16 CPU normal is coarse (8-bit uniforms); the engine's bf16 output is
+    checked against the reference's fp32 sample of the same program instead."""
+    from scipy import stats
+
+    ref = reference[5][("tiny_llama", "fp32")]
+    m = build_on_cuda("tiny_llama", "bf16")
+    for k, t in named_tensors(m).items():
+        r = ref[k].double().flatten()
+        if r.numel() < 4096 or r.std() == 0:
+            continue
+        x = t.detach().double().flatten().cpu()
+        rb = ref[k].to(torch.bfloat16).double().flatten()  # same rounding grid
+        assert stats.ks_2samp(x.numpy(), rb.numpy()).pvalue > 1e-4, k
+        assert abs(x.std().item() / r.std().item() - 1) <= 5 / math.sqrt(r.numel()) + 2 ** -9, k
+
+
+def test_t2_determinism_seed_and_generator_advance():
+    a = named_tensors(build_on_cuda("tiny_llama", "bf16", seed=11))
+    off_after = torch.cuda.default_generators[0].get_offset()
+    b = named_tensors(build_on_cuda("tiny_llama", "bf16", seed=11))
+    c = named_tensors(build_on_cuda("tiny_llama", "bf16", seed=12))
+    assert off_after > 0 and off_after % 4 == 0
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    w = "model.layers.0.mlp.up_proj.weight"
+    assert (a[w] != c[w]).float().mean() > 0.9
+    # later torch RNG does not replay our stream
+    torch.manual_seed(11)
+    m = build_on_cuda("mlp_stack", "fp32", seed=11)
+    x = torch.randn(4096, device="cuda")
+    assert not torch.equal(x, named_tensors(m)["0.weight"].flatten()[:4096])
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_t2_dim0_shards_concatenate_bit_exact(world):
+    full = named_tensors(build_on_cuda("tiny_llama", "bf16", seed=3))
+    params = dict(build_on_cuda("tiny_llama", "bf16", seed=3).named_parameters()).keys()
+    shards = [named_tensors(build_on_cuda("tiny_llama", "bf16", seed=3, shard=(r, world))) for r in range(world)]
+    for k, t in full.items():
+        if k in params and t.dim() > 0:
+            assert shards[0][k].shape[0] == -(-t.shape[0] // world)
+            assert torch.equal(torch.cat([s[k] for s in shards], 0), t), k
+        else:  # buffers are replicated
+            for s in shards:
+                assert torch.equal(s[k], t), k
+    assert sum(s["lm_head.weight"].numel() for s in shards) == full["lm_head.weight"].numel()
+
+
+def test_t2_ragged_shards_match_torch_chunk():
+    class Odd(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = nn.Parameter(torch.empty(10, 7, device="cuda").normal_())
+            self.v = nn.Parameter(torch.empty(3, device="cuda").uniform_())
+            self.s = nn.Parameter(torch.zeros((), device="cuda"))
+
+    def build(**kw):
+        m = deferred_init(Odd)
+        torch.manual_seed(1)
+        materialize_module(m, **kw)
+        return m
+
+    full = build()
+    for world in (3, 4, 8):
+        for r in range(world):
+            s = build(shard=(r, world))
+            for name in ("w", "v"):
+                chunks = torch.chunk(getattr(full, name).detach(), world, 0)
+                exp = chunks[r] if r < len(chunks) else getattr(full, name).detach()[:0]
+                assert torch.equal(getattr(s, name).detach(), exp), (name, world, r)
+            assert torch.equal(s.s, full.s)
+
+
+def test_t2_dead_pass_elision_equals_explicit_offset_skip():
+    n = 64 * 48
+
+    def double_init():
+        lin = nn.Linear(48, 64, bias=False, device="cuda")  # records uniform_ (dead) ...
+        nn.init.normal_(lin.weight, 0.0, 0.02)  # ... then normal_ (live)
+        return lin
+
+    def single_init():
+        return nn.Parameter(torch.empty(64, 48, device="cuda").normal_(0.0, 0.02))
+
+    m = deferred_init(double_init)
+    torch.manual_seed(21)
+    materialize_module(m)
+    st = last_materialize_stats()
+    assert st["elided_rng_ops"] == 1 and st["fused_tensors"] == 1 and st["kernel_launches"] == 1
+    p = deferred_init(single_init)
+    torch.manual_seed(21)
+    g = torch.cuda.default_generators[0]
+    g.set_offset(g.get_offset() + O.offset_increment(n))  # what the dead uniform_ consumed
+    assert torch.equal(materialize_tensor(p), m.weight)
+
+
+def test_device_override_builds_cpu_recordings_on_cuda(reference):
+    torch.set_default_dtype(torch.float32)
+    m = deferred_init(lambda: cases.build("init_zoo", "fp32", "cpu"))
+    assert m.kaiming.weight.device.type == "cpu"
+    torch.manual_seed(5)
+    materialize_module(m, device="cuda")
+    ref, ref2 = reference[5][("init_zoo", "fp32")], reference[6][("init_zoo", "fp32")]
+    for k, t in named_tensors(m).items():
+        assert t.is_cuda, k
+        if torch.equal(ref[k], ref2[k]):
+            assert torch.equal(t.detach().cpu(), ref[k]), k
+    # and the same recording built on cuda directly gives the same bits
+    m2 = build_on_cuda("init_zoo", "fp32", seed=5)
+    for k, t in named_tensors(m).items():
+        assert torch.equal(t, named_tensors(m2)[k]), k
+
+
+def test_identity_class_and_requires_grad_on_cuda():
+    m = deferred_init(lambda: nn.Linear(8, 8, device="cuda"))
+    w = materialize_tensor(m.weight)
+    assert materialize_tensor(m.weight) is w and isinstance(w, nn.Parameter) and w.requires_grad
+    materialize_module(m)
+    assert m.weight is w and not is_deferred(m)
+
+
+def test_generic_replay_on_cuda_for_unfusable_programs():
+    def build():
+        a = torch.randn(16, 16, device="cuda")
+        return nn.Parameter(a @ a.t())  # not an init pattern: replayed by ATen on the GPU
+
+    p = deferred_init(build)
+    out = materialize_tensor(p)
+    st = last_materialize_stats()
+    assert out.is_cuda and st["generic_ops"] >= 2 and st["fused_tensors"] == 0
+    assert torch.allclose(out, out.t())
+
+
+def test_cfg1_linear128_on_cpu_still_bit_exact_with_cuda_present():
+    torch.manual_seed(0)
+    m = deferred_init(nn.Linear, 128, 128)
+    torch.manual_seed(0)
+    materialize_module(m)
+    torch.manual_seed(0)
+    e = nn.Linear(128, 128)
+    assert torch.equal(m.weight, e.weight) and torch.equal(m.bias, e.bias)

@@ -1,0 +1,110 @@
+"""CPU-side checks: the oracle is pinned to golden vectors, the C-ABI library loads and exports
+every symbol include/tdx_init.h declares (no compute calls without a GPU), and the oracle's
+transforms have the distributions they claim."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import tdx_oracle as O
+from torchdistx_b200 import _cabi as C
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_oracle_philox_matches_golden_vectors():
+    kat = json.load(open(os.path.join(ROOT, "tests", "golden", "philox_kat.json")))
+    assert len(kat["vectors"]) >= 32
+    assert sum(v["source"].startswith("random123") for v in kat["vectors"]) == 3
+    for v in kat["vectors"]:
+        assert O.philox4x32(v["ctr"], v["key"]) == v["out"], v
+
+
+def test_abi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "tdx_init.h")).read()
+    declared = set(re.findall(r"TDX_C_API\s+[\w\s\*]+?\b(tdx_\w+)\s*\(", header))
+    assert declared == set(C.EXPORTED_SYMBOLS), declared ^ set(C.EXPORTED_SYMBOLS)
+    lib = C.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.tdx_abi_version() == 1
+    assert ctypes.sizeof(C.TdxInitDesc) == 128 and ctypes.sizeof(C.TdxPlan) == 1024
+    assert lib.tdx_init_workspace_bytes(100) >= 100 * 128
+    assert lib.tdx_elems_per_block(C.TDX_BF16, C.TDX_SRC_NORMAL, 0) == 8
+    assert lib.tdx_elems_per_block(C.TDX_F32, C.TDX_SRC_UNIFORM, 0) == 4
+
+
+def test_abi_rejects_bad_descriptors_without_touching_the_gpu():
+    lib = C.load()
+    d = C.make_desc(0x1000, dtype=C.TDX_RAW32, src=C.TDX_SRC_UNIFORM, elem_count=4)
+    arr = (C.TdxInitDesc * 1)(d)
+    assert lib.tdx_init_launch(arr, 1, None, 0, None) == -1  # TDX_E_BADARG
+    assert b"raw dtypes" in lib.tdx_last_error()
+    d = C.make_desc(0x1001, dtype=C.TDX_F32, src=C.TDX_SRC_UNIFORM, elem_count=4)
+    arr = (C.TdxInitDesc * 1)(d)
+    assert lib.tdx_init_launch(arr, 1, None, 0, None) == -1
+    assert b"aligned" in lib.tdx_last_error()
+    assert lib.tdx_init_launch(None, 0, None, 0, None) == 0  # nothing to do is not an error
+
+
+def bits_to_float(a, dtype):
+    if dtype == C.TDX_F32:
+        return a.view(np.float32).astype(np.float64)
+    if dtype == C.TDX_BF16:
+        return (a.astype(np.uint32) << 16).view(np.float32).astype(np.float64)
+    return a.view(np.float16).astype(np.float64)
+
+
+@pytest.mark.parametrize("dtype", [C.TDX_F32, C.TDX_BF16, C.TDX_F16])
+def test_oracle_uniform_distribution_and_bounds(dtype):
+    n = 1 << 18
+    d = C.make_desc(0, dtype=dtype, src=C.TDX_SRC_UNIFORM, elem_count=n, seed=3, offset=4, p0=-0.5, p1=0.25)
+    x = bits_to_float(O.generate(d), dtype)
+    assert x.min() >= -0.5 and x.max() < 0.25
+    assert abs(x.mean() - (-0.125)) < 5 * (0.75 / 12 ** 0.5) / n ** 0.5 + 1e-3
+    assert abs(x.std() / (0.75 / 12 ** 0.5) - 1) < 0.01
+
+
+@pytest.mark.parametrize("dtype", [C.TDX_F32, C.TDX_BF16, C.TDX_F16])
+def test_oracle_normal_distribution(dtype):
+    from scipy import stats
+
+    n = 1 << 18
+    d = C.make_desc(0, dtype=dtype, src=C.TDX_SRC_NORMAL, elem_count=n, seed=11, offset=0, p0=1.0, p1=0.5)
+    x = bits_to_float(O.generate(d), dtype)
+    assert abs(x.mean() - 1.0) < 5 * 0.5 / n ** 0.5 + 2e-3
+    assert abs(x.std() / 0.5 - 1) < 5 / (2 * n) ** 0.5 + 4e-3
+    # two-sample Kolmogorov-Smirnov (alpha = 1e-3) against exact N(1, 0.5^2) draws rounded to the
+    # same dtype (the rounding grid is coarse enough to matter for 16-bit types)
+    import torch
+
+    tdt = {C.TDX_F32: torch.float32, C.TDX_BF16: torch.bfloat16, C.TDX_F16: torch.float16}[dtype]
+    ref = torch.from_numpy(np.random.default_rng(0).normal(1.0, 0.5, n)).to(tdt).double().numpy()
+    assert stats.ks_2samp(x, ref).pvalue > 1e-3
+
+
+def test_oracle_icdf16_tail_bins_reach_beyond_the_grid():
+    # k == 0 has probability 2^-16 per element: 2^22 elements hold ~64 of them
+    n = 1 << 22
+    d = C.make_desc(0, dtype=C.TDX_BF16, src=C.TDX_SRC_NORMAL, elem_count=n, seed=5, offset=0, p0=0.0, p1=1.0)
+    x = bits_to_float(O.generate(d), C.TDX_BF16)
+    assert np.isfinite(x).all()
+    grid_max = 4.17  # Phi^-1(1 - 2^-17)
+    assert 20 <= (np.abs(x) > grid_max).sum() <= 140
+    assert np.abs(x).max() < 8.5
+
+
+def test_oracle_is_shard_invariant_and_offsets_disjoint():
+    full = C.make_desc(0, dtype=C.TDX_BF16, src=C.TDX_SRC_NORMAL, elem_count=1000, seed=9, offset=16, p1=0.02)
+    a = O.generate(full)
+    parts = []
+    for b, c in ((0, 123), (123, 500), (623, 377)):
+        parts.append(O.generate(C.make_desc(0, dtype=C.TDX_BF16, src=C.TDX_SRC_NORMAL, elem_begin=b,
+                                            elem_count=c, seed=9, offset=16, p1=0.02)))
+    assert np.array_equal(a, np.concatenate(parts))
+    other = O.generate(C.make_desc(0, dtype=C.TDX_BF16, src=C.TDX_SRC_NORMAL, elem_count=1000, seed=9,
+                                   offset=20, p1=0.02))
+    assert (a != other).mean() > 0.9
