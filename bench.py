@@ -1,0 +1,378 @@
+"""bench.py -- params/s and HBM GB/s of `materialize_module` (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model llama3-8b] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" is one `materialize_module` of one freshly recorded (deferred_init, zero-storage) model:
+every parameter and buffer written to HBM once.  Recording (Python module construction under
+`deferred_init`) is outside the timed region -- the metric is named for materialize_module.
+
+  value  : params/s with the descriptor plan already resident in HBM (tdx_plan_launch only:
+           the kernels, nothing else), whole job (all ranks), max time over ranks.
+  e2e    : the same metric through the public API `materialize_module(m, device=cuda[, shard=...])`
+           -- planning, allocation, descriptor H2D copy, kernels, and a D2H read of 64 result bytes
+           inside the timed region.
+  N > 1  : one model, dim-0 sharded across the ranks (each rank writes only its rows; the
+           unsharded tensors never exist) => "scaling": "strong".  The only collective is the
+           16-byte seed/offset broadcast (torchdistx_b200.parallel.sync_rng), outside the kernels.
+  --impl reference : the reference's own CPU materialize (oracle/_ref = pytorch/torchdistx
+           compiled from /root/reference) on a bounded sample of the same model, on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODELS = {
+    # name: (family, kwargs, dtype)
+    "llama3-8b": ("llama", dict(vocab_size=128256, hidden_size=4096, intermediate_size=14336,
+                                num_hidden_layers=32, num_attention_heads=32, num_key_value_heads=8,
+                                max_position_embeddings=8192, rope_theta=500000.0), "bf16"),
+    "llama3-70b": ("llama", dict(vocab_size=128256, hidden_size=8192, intermediate_size=28672,
+                                 num_hidden_layers=80, num_attention_heads=64, num_key_value_heads=8,
+                                 max_position_embeddings=8192, rope_theta=500000.0), "bf16"),
+    "gpt2-xl": ("gpt2", dict(n_layer=48, n_embd=1600, n_head=25, vocab_size=50257, n_positions=1024), "fp32"),
+    "llama-tiny": ("llama", dict(vocab_size=4096, hidden_size=512, intermediate_size=1024,
+                                 num_hidden_layers=4, num_attention_heads=8, num_key_value_heads=2), "bf16"),
+}
+
+
+def build_model(name: str, layers: int | None = None, vocab: int | None = None):
+    """Constructs the HF model (random init, no checkpoint); call under deferred_init."""
+    import torch
+    family, kw, dtype = MODELS[name]
+    kw = dict(kw)
+    if layers is not None:
+        kw["num_hidden_layers" if family == "llama" else "n_layer"] = layers
+    if vocab is not None:
+        kw["vocab_size"] = vocab
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype({"bf16": torch.bfloat16, "fp32": torch.float32}[dtype])
+    try:
+        if family == "llama":
+            from transformers import LlamaConfig, LlamaForCausalLM
+            return LlamaForCausalLM(LlamaConfig(**kw))
+        from transformers import GPT2Config, GPT2LMHeadModel
+        return GPT2LMHeadModel(GPT2Config(**kw))
+    finally:
+        torch.set_default_dtype(prev)
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v == "Active"})
+        busy = [c for c in sm if c > 500] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the real reference on the host cores, bounded sample
+# ---------------------------------------------------------------------------------------------
+REF_SNIPPET = r"""
+import json, sys, time, torch
+sys.path.insert(0, {root!r})
+from oracle import ref_torchdistx as R
+import bench
+torch.set_default_dtype({{'bf16': torch.bfloat16, 'fp32': torch.float32}}[{dtype!r}])
+times, n = [], 0
+for i in range({reps}):
+    m = R.deferred_init(lambda: bench.build_model({model!r}, layers={layers}, vocab={vocab}))
+    n = sum(p.numel() for p in m.parameters())
+    torch.manual_seed(i)
+    t0 = time.perf_counter(); R.materialize_module(m); times.append(time.perf_counter() - t0)
+    del m
+print(json.dumps({{"times": times, "params": n, "threads": torch.get_num_threads()}}))
+"""
+
+
+def reference_sample(model: str, layers: int, reps: int):
+    """Runs the reference (subprocess: it registers the same dispatch keys as torchdistx_b200)."""
+    dtype = MODELS[model][2]
+    code = REF_SNIPPET.format(root=ROOT, model=model, layers=layers, reps=reps, dtype=dtype,
+                              vocab=SAMPLE_VOCAB.get(model))
+    out = subprocess.run([sys.executable, "-c", code], check=True, capture_output=True, text=True, cwd=ROOT)
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+# Bounded CPU sample of the same workload (a few seconds of CPU work per repetition): one decoder
+# layer of the named model at full width (all seven Llama linears: dead uniform_ + live normal_,
+# exactly the chains of the full model) with the vocabulary cut to 2048 rows so that the two
+# vocab-sized matrices do not dominate; GPT-2 XL: 4 of its 48 blocks, full vocabulary.
+SAMPLE_VOCAB = {"llama3-8b": 2048, "llama3-70b": 2048}
+
+
+def sample_layers(model: str) -> int:
+    return {"llama3-8b": 1, "llama3-70b": 1, "gpt2-xl": 4, "llama-tiny": 4}[model]
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    layers = sample_layers(a.model)
+    res = reference_sample(a.model, layers, a.warmup + a.steps)
+    ts = res["times"][a.warmup:]
+    ms = 1e3 * sum(ts) / len(ts)
+    value = res["params"] / (sum(ts) / len(ts))
+    sample = (f"{a.model} cut to {layers} decoder layer(s)"
+              f"{', vocab ' + str(SAMPLE_VOCAB[a.model]) if a.model in SAMPLE_VOCAB else ''} "
+              f"({res['params']:,} params), {MODELS[a.model][2]}, device=cpu, reference materialize_module")
+    line = {"impl": "reference", "metric": "materialize_module params/s", "value": value, "unit": "params/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": MODELS[a.model][2], "data": "synthetic (random init of the named architecture)",
+            "config": {"workload": f"{a.model} materialize_module", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "params/s", "cores": res["threads"], "kind": "reference",
+                             "sample": sample,
+                             "note": "ATen CPU RNG kernels are serial under the generator mutex; threads only help fills"},
+            "e2e": {"value": value, "unit": "params/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    from torchdistx_b200 import _cabi as C
+    from torchdistx_b200 import parallel
+    from torchdistx_b200.deferred_init import (deferred_init, last_descriptors, last_materialize_stats,
+                                               materialize_module)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+    shard = (rank, world) if world > 1 else None
+    lib = C.load()
+    stream = torch.cuda.current_stream().cuda_stream
+    dtype = MODELS[a.model][2]
+
+    # ---- record K+W+1 zero-storage models (untimed) -----------------------------------------
+    t0 = time.perf_counter()
+    fakes = [deferred_init(build_model, a.model) for _ in range(a.warmup + a.steps + 1)]
+    record_s = (time.perf_counter() - t0) / len(fakes)
+    n_params = sum(p.numel() for p in fakes[0].parameters())
+    n_tensors = len(list(fakes[0].parameters())) + len(list(fakes[0].buffers()))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- e2e: public API, H2D of descriptors + D2H of a result inside the timed region ---------
+    torch.manual_seed(1234)
+    parallel.sync_rng(dev)  # the one collective: 16 bytes, rank 0 -> all
+    probe = torch.empty(32, dtype=torch.bfloat16 if dtype == "bf16" else torch.float32).pin_memory()
+
+    def step(m):
+        materialize_module(m, device=dev, shard=shard)
+        last = next(reversed(list(m.parameters())))
+        probe.copy_(last.detach().flatten()[:32], non_blocking=True)  # D2H read of the step's result
+        torch.cuda.current_stream().synchronize()
+
+    for i in range(a.warmup):
+        step(fakes[i])
+        fakes[i] = None
+    st = last_materialize_stats()
+    h2d = lib.tdx_init_workspace_bytes(st["descriptors"])  # plan image copied H2D per step (upper bound)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk_e2e:
+        e0.record()
+        for i in range(a.warmup, a.warmup + a.steps):
+            step(fakes[i])
+            fakes[i] = None  # release the 16 GB before the next step allocates
+        e1.record()
+        barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1) / a.steps)
+
+    # ---- value: plan resident in HBM, kernels only ----------------------------------------------
+    model = fakes[-1]
+    materialize_module(model, device=dev, shard=shard)  # allocates the outputs we re-launch into
+    descs = last_descriptors()
+    st = last_materialize_stats()
+    my_bytes = sum(d.elem_count * (4 if d.dtype in (C.TDX_F32, C.TDX_RAW32) else 8 if d.dtype == C.TDX_RAW64
+                                   else 1 if d.dtype == C.TDX_RAW8 else 2) for d in descs)
+    ws_bytes = lib.tdx_init_workspace_bytes(len(descs))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    plan = C.TdxPlan()
+    C.check(lib.tdx_plan_upload(descs, len(descs), ws.data_ptr(), ws_bytes, stream, ctypes.byref(plan)))
+    for _ in range(max(a.warmup, 3)):
+        C.check(lib.tdx_plan_launch(ctypes.byref(plan), ws.data_ptr(), stream))
+    launches_per_step = lib.tdx_last_launch_count()
+    barrier()
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(a.steps):
+            C.check(lib.tdx_plan_launch(ctypes.byref(plan), ws.data_ptr(), stream))
+        e1.record()
+        barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1) / a.steps)
+
+    # ---- roofline of the dominant kernel (most bytes), timed alone with the same events ----------
+    fam = {}
+    for d in descs:
+        key = (d.src, d.dtype if d.src != C.TDX_SRC_CONST else -1)
+        fam.setdefault(key, []).append(d)
+    isz = lambda d: 4 if d.dtype in (C.TDX_F32, C.TDX_RAW32) else 8 if d.dtype == C.TDX_RAW64 else 1 if d.dtype == C.TDX_RAW8 else 2
+    dom_key = max(fam, key=lambda k: sum(d.elem_count * isz(d) for d in fam[k]))
+    dom = (C.TdxInitDesc * len(fam[dom_key]))(*fam[dom_key])
+    dom_bytes = sum(d.elem_count * isz(d) for d in dom)
+    ws2 = torch.empty(lib.tdx_init_workspace_bytes(len(dom)), dtype=torch.uint8, device=dev)
+    plan2 = C.TdxPlan()
+    C.check(lib.tdx_plan_upload(dom, len(dom), ws2.data_ptr(), ws2.numel(), stream, ctypes.byref(plan2)))
+    for _ in range(3):
+        C.check(lib.tdx_plan_launch(ctypes.byref(plan2), ws2.data_ptr(), stream))
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(a.steps):
+        C.check(lib.tdx_plan_launch(ctypes.byref(plan2), ws2.data_ptr(), stream))
+    e1.record()
+    torch.cuda.synchronize()
+    dom_ms = e0.elapsed_time(e1) / a.steps
+    peak, peak_src = peaks()
+    achieved = dom_bytes / dom_ms / 1e6
+    kname = {C.TDX_SRC_CONST: "tdx_fill_kernel", C.TDX_SRC_UNIFORM: "tdx_rng_kernel<GenUniform*>",
+             C.TDX_SRC_NORMAL: "tdx_rng_kernel<GenNormalICDF16<bf16>>" if dtype == "bf16" else "tdx_rng_kernel<GenNormalBM32<float>>"}[dom_key[0]]
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_bench_summary.json"))).get(a.model, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline: the reference itself on a bounded sample (rank 0, N = 1 only) ---------------
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        try:
+            layers = sample_layers(a.model)
+            res = reference_sample(a.model, layers, 1)
+            cpu = {"value": res["params"] / res["times"][0], "unit": "params/s", "cores": res["threads"],
+                   "kind": "reference",
+                   "sample": f"{a.model} cut to {layers} decoder layer(s)"
+                             f"{', vocab ' + str(SAMPLE_VOCAB[a.model]) if a.model in SAMPLE_VOCAB else ''} "
+                             f"({res['params']:,} params), {dtype}, device=cpu, 1 repetition, {res['times'][0]:.1f} s"}
+        except Exception as e:  # the oracle is test infrastructure: report, do not hide
+            cpu = {"value": None, "unit": "params/s", "cores": os.cpu_count(), "kind": "reference",
+                   "sample": f"unavailable: {type(e).__name__}: {str(e)[-200:]}"}
+
+    c1, c2 = clk.summary(), clk_e2e.summary()
+    total_bytes = my_bytes * world if world > 1 else my_bytes
+    line = {
+        "metric": "materialize_module params/s", "value": n_params / (ms / 1e3), "unit": "params/s",
+        "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": dtype, "data": "synthetic (random init of the named architecture, HF config; no checkpoint)",
+        "config": {"workload": f"{a.model} deferred_init -> materialize_module on cuda, dim-0 sharded over {world} GPU(s)",
+                   "params": n_params, "tensors": n_tensors, "descriptors_per_rank": len(descs),
+                   "fused_tensors": st["fused_tensors"], "generic_ops": st["generic_ops"],
+                   "elided_rng_ops": st["elided_rng_ops"], "record_s_per_model": record_s,
+                   "l2": "outputs per step (GBs) exceed the 126 MB L2; no flush needed",
+                   "timed_region_value": "tdx_plan_launch only (plan resident in HBM)",
+                   "timed_region_e2e": "materialize_module (plan, alloc, H2D descriptors, kernels) + 64 B D2H"},
+        "hbm_gbs": total_bytes / (ms / 1e3) / 1e9, "hbm_gbs_per_gpu": my_bytes / (ms / 1e3) / 1e9,
+        "e2e": {"value": n_params / (e2e_ms / 1e3), "unit": "params/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": probe.numel() * probe.element_size()},
+        "gpu_launches": launches_per_step * a.steps,
+        "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
+                     "secondary_ceiling": "instruction issue (Philox4x32-10 + inverse-CDF): see DESIGN.md"},
+        "cpu_baseline": cpu,
+        "clocks": {"sm_mhz": c1["sm_mhz"], "sm_max_mhz": c1["sm_max_mhz"], "reasons": c1["reasons"],
+                   "e2e_sm_mhz": c2["sm_mhz"], "e2e_reasons": c2["reasons"]},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--model", default="llama3-8b", choices=sorted(MODELS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -3,7 +3,10 @@ the CPU oracle (oracle/tdx_oracle.c) on the same descriptors.
 
 Bars (stated here, enforced below):
   * constant fills, uniform (all dtypes), every rounding/epilogue/sharding/ragged-edge case: BIT-EXACT;
-  * normal fp32 (Box-Muller through MUFU lg2/sqrt/sin/cos vs libm): |gpu - oracle| <= 4e-6 * (|x - mean| + std);
+  * normal fp32 (Box-Muller through MUFU lg2/sqrt/sin/cos vs libm), with z = (x - mean)/std:
+      |gpu - oracle| <= std * min(1e-3, 4e-7/|z| + 2e-6 (1 + |z|)) + 2 ulp(x)
+    (lg2.approx has 2^-22 ABSOLUTE error, so the radius sqrt(-2 ln u) of a draw with u ~ 1 carries
+    an error ~2e-7/r: large relative to a tiny radius, irrelevant to the distribution);
   * normal bf16/fp16 (inverse CDF through MUFU lg2 vs libm log2f): identical bits except where the
     fp32 value sits within MUFU error of a rounding boundary: <= 0.2 % of elements may differ, and
     then by exactly 1 ulp of the output dtype.
@@ -71,7 +74,10 @@ def test_normal_within_stated_tolerance(dtype, n):
     got, exp = gpu_bits(buf, dtype), O.generate(d)
     if dtype == C.TDX_F32:
         g, e = as_float(got, dtype), as_float(exp, dtype)
-        assert np.all(np.abs(g - e) <= 4e-6 * (np.abs(e - mean) + std))
+        z = np.abs(e - mean) / std
+        tol = std * np.minimum(1e-3, 4e-7 / np.maximum(z, 1e-30) + 2e-6 * (1 + z)) + 2 * np.spacing(np.abs(e).astype(np.float32))
+        assert np.all(np.abs(g - e) <= tol), float((np.abs(g - e) / tol).max())
+        assert np.mean(np.abs(g - e) <= 2e-6 * std * (1 + z) + 2 * np.spacing(np.abs(e).astype(np.float32))) > 0.99
     else:
         diff = got.astype(np.int64) - exp.astype(np.int64)
         assert np.abs(diff).max() <= 1
@@ -147,7 +153,8 @@ def test_epilogue_trunc_normal_chain_bit_exact_in_uniform_part():
                         p0=lo, p1=hi, epi=epi)
         run_descs([d], [buf])
         g, e = as_float(gpu_bits(buf, dtype), dtype), as_float(O.generate(d), dtype)
-        assert g.min() >= a - 1e-7 and g.max() <= b + 1e-7
+        ra, rb = (float(torch.tensor(v, dtype=TORCH_DT[dtype])) for v in (a, b))  # clamp_ sees bounds in dtype
+        assert g.min() >= ra - 1e-7 and g.max() <= rb + 1e-7
         # erfinvf (CUDA libm, ~2 ulp) vs the oracle's double-precision inverse: 1 ulp of slack
         tol = 3e-7 if dtype == C.TDX_F32 else 2 ** -8 * 0.1
         assert np.abs(g - e).max() <= tol + 1e-6 * np.abs(e).max()

@@ -90,7 +90,7 @@ py::object py_materialize_tensor(const py::object& var, const py::object& device
 }
 
 py::list py_materialize_tensors(const py::list& vars, const py::object& device,
-                                const py::object& shard, bool fused) {
+                                const py::object& shard, bool fused, const py::object& shard_mask) {
   std::vector<at::Tensor> fakes;
   fakes.reserve(vars.size());
   for (const py::handle& h : vars) {
@@ -101,18 +101,25 @@ py::list py_materialize_tensors(const py::list& vars, const py::object& device,
   }
   const tdx::MaterializeOptions opts = make_options(device, shard, fused);
   // tensors that were already handed out keep their identity and are not touched again
+  std::vector<uint8_t> mask_all;
+  if (!shard_mask.is_none()) {
+    for (const py::handle& h : py::cast<py::list>(shard_mask)) mask_all.push_back(py::cast<bool>(h) ? 1 : 0);
+    TORCH_CHECK_VALUE(mask_all.size() == fakes.size(), "shard_mask must have one flag per tensor");
+  }
   std::vector<at::Tensor> todo;
   std::vector<size_t> todo_idx;
+  std::vector<uint8_t> mask;
   for (size_t i = 0; i < fakes.size(); ++i) {
     if (tdx::can_materialize(fakes[i]) && !tdx::cached_python_tensor(fakes[i]).defined()) {
       todo.push_back(fakes[i]);
       todo_idx.push_back(i);
+      if (!mask_all.empty()) mask.push_back(mask_all[i]);
     }
   }
   std::vector<at::Tensor> done;
   {
     py::gil_scoped_release nogil;
-    done = tdx::materialize_many(todo, opts);
+    done = tdx::materialize_many(todo, opts, mask_all.empty() ? nullptr : &mask);
   }
   py::list result(fakes.size());
   size_t k = 0;
@@ -158,7 +165,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("meta_like", &tdx::meta_like);
   // ---- B200 engine additions --------------------------------------------------------------
   m.def("materialize_tensors", &py_materialize_tensors, py::arg("tensors"),
-        py::arg("device") = py::none(), py::arg("shard") = py::none(), py::arg("fused") = true);
+        py::arg("device") = py::none(), py::arg("shard") = py::none(), py::arg("fused") = true,
+        py::arg("shard_mask") = py::none());
   m.def("last_stats", &py_last_stats);
+  m.def("last_descriptors", [] { return py::bytes(tdx::last_descriptors()); });
   m.def("kernel_abi_version", [] { return tdx_abi_version(); });
 }

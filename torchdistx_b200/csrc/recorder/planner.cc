@@ -27,6 +27,7 @@ using torch::jit::Stack;
 namespace {
 
 thread_local MaterializeStats g_stats;
+thread_local std::vector<TdxInitDesc> g_last_descs;  // what the last materialize call launched
 
 // Never record / fake anything we do while materialising.
 struct NoInterception {
@@ -366,6 +367,7 @@ void Batch::flush() {
   TORCH_CHECK(rc == 0, "libtdx_init: launch failed (", rc, "): ", tdx_last_error());
   g_stats.kernel_launches += tdx_last_launch_count();
   g_stats.descriptors += n;
+  g_last_descs.insert(g_last_descs.end(), descs.begin(), descs.end());
   descs.clear();
   keep_alive.clear();
 }
@@ -436,7 +438,7 @@ at::Tensor alias_of(const at::Tensor& base, const ValueInfo& v) {
 // generic replay
 // ---------------------------------------------------------------------------------------------
 struct Engine {
-  const MaterializeOptions& opts;
+  MaterializeOptions opts;
   Batch& batch;
 
   at::Tensor real_of(Tape& tape, uint32_t v) {
@@ -690,18 +692,22 @@ at::Tensor finish(const at::Tensor& fake, at::Tensor out) {
 }  // namespace
 
 std::vector<at::Tensor> materialize_many(const std::vector<at::Tensor>& fakes,
-                                         const MaterializeOptions& opts) {
+                                         const MaterializeOptions& opts,
+                                         const std::vector<uint8_t>* shard_mask) {
   g_stats = MaterializeStats{};
+  g_last_descs.clear();
   std::vector<at::Tensor> out;
   out.reserve(fakes.size());
   Batch batch;
   Engine eng{opts, batch};
-  for (const at::Tensor& t : fakes) {
+  for (size_t i = 0; i < fakes.size(); ++i) {
+    const at::Tensor& t = fakes[i];
     g_stats.tensors++;
     if (!can_materialize(t)) {
       out.push_back(t);
       continue;
     }
+    eng.opts.shard = (shard_mask && !(*shard_mask)[i]) ? std::nullopt : opts.shard;
     const auto rec = fake_impl(t)->record();  // copy: keeps the tape alive while we work
     out.push_back(finish(t, eng.materialize_value(rec->tape, rec->value)));
   }
@@ -715,6 +721,11 @@ at::Tensor materialize_one(const at::Tensor& fake, const MaterializeOptions& opt
 }
 
 MaterializeStats last_stats() { return g_stats; }
+
+std::string last_descriptors() {
+  return std::string(reinterpret_cast<const char*>(g_last_descs.data()),
+                     g_last_descs.size() * sizeof(TdxInitDesc));
+}
 
 at::Tensor cached_python_tensor(const at::Tensor& fake) {
   if (!can_materialize(fake)) return {};

@@ -20,6 +20,7 @@
 
 #include <cstdint>
 #include <optional>
+#include <string>
 #include <vector>
 
 namespace tdx {
@@ -51,10 +52,16 @@ struct MaterializeStats {
 at::Tensor materialize_one(const at::Tensor& fake, const MaterializeOptions& opts);
 
 // Materialises many tensors with one batched kernel submission; order defines RNG consumption.
+// `shard_mask` (optional, one flag per tensor): apply opts.shard only where the flag is set
+// (parameters are chunked, buffers replicated -- one ordered batch either way).
 std::vector<at::Tensor> materialize_many(const std::vector<at::Tensor>& fakes,
-                                         const MaterializeOptions& opts);
+                                         const MaterializeOptions& opts,
+                                         const std::vector<uint8_t>* shard_mask = nullptr);
 
 MaterializeStats last_stats();
+// The TdxInitDesc table (raw bytes) the last materialize call on this thread submitted; lets
+// benchmarks and tests re-launch / inspect exactly what the engine ran.
+std::string last_descriptors();
 
 // The tensor that a previous materialisation handed to Python for this fake tensor (keeps the
 // Python object identity stable), and the hook to store it.

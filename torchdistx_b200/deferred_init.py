@@ -33,6 +33,7 @@ __all__ = [
     "materialize_tensor",
     "materialize_module",
     "last_materialize_stats",
+    "last_descriptors",
 ]
 
 M = TypeVar("M", bound=Module)
@@ -117,30 +118,15 @@ def materialize_module(
     if not slots:
         return
     dev = _device(device)
-    if shard is None:
-        tensors = [group[key] for group, key in slots]
-        try:
-            results = _C.materialize_tensors(tensors, dev, None)
-        except ValueError:
-            _raise_already_materialized(slots)
-            raise
-        for (group, key), out in zip(slots, results):
-            group[key] = out
-        return
-    # sharded: parameters are chunked, buffers replicated -- two batches, same traversal order
-    is_param = [isinstance(group[key], torch.nn.Parameter) for group, key in slots]
-    order = [i for i, p in enumerate(is_param)]
-    results: List[Optional[Tensor]] = [None] * len(slots)
-    # keep RNG consumption in traversal order: run maximal runs of same-kind tensors
-    start = 0
-    while start < len(order):
-        end = start
-        while end < len(order) and is_param[end] == is_param[start]:
-            end += 1
-        chunk = [slots[i][0][slots[i][1]] for i in range(start, end)]
-        outs = _C.materialize_tensors(chunk, dev, shard if is_param[start] else None)
-        results[start:end] = outs
-        start = end
+    tensors = [group[key] for group, key in slots]
+    # parameters are chunked, buffers replicated; one ordered batch keeps RNG consumption in
+    # traversal order
+    mask = None if shard is None else [isinstance(t, torch.nn.Parameter) for t in tensors]
+    try:
+        results = _C.materialize_tensors(tensors, dev, shard, True, mask)
+    except ValueError:
+        _raise_already_materialized(slots)
+        raise
     for (group, key), out in zip(slots, results):
         group[key] = out
 
@@ -151,6 +137,16 @@ def _raise_already_materialized(slots) -> None:
             _C.can_materialize(group[key])
         except ValueError:
             raise ValueError(f"'{key}' has already been materialized.") from None
+
+
+def last_descriptors():
+    """The `TdxInitDesc` table the last ``materialize_*`` call on this thread submitted to the
+    kernels, as a ctypes array (see ``include/tdx_init.h``)."""
+    from . import _cabi
+
+    raw = _C.last_descriptors()
+    n = len(raw) // 128
+    return (_cabi.TdxInitDesc * n).from_buffer_copy(raw)
 
 
 def last_materialize_stats() -> Dict[str, int]:
