@@ -208,7 +208,8 @@ def run_ours(a):
 
     # ---- record K+W+1 zero-storage models (untimed) -----------------------------------------
     t0 = time.perf_counter()
-    fakes = [deferred_init(build_model, a.model) for _ in range(a.warmup + a.steps + 1)]
+    n_models = 1 if a.roofline_only else a.warmup + a.steps + 1
+    fakes = [deferred_init(build_model, a.model) for _ in range(n_models)]
     record_s = (time.perf_counter() - t0) / len(fakes)
     n_params = sum(p.numel() for p in fakes[0].parameters())
     n_tensors = len(list(fakes[0].parameters())) + len(list(fakes[0].buffers()))
@@ -237,21 +238,24 @@ def run_ours(a):
         probe.copy_(last.detach().flatten()[:32], non_blocking=True)  # D2H read of the step's result
         torch.cuda.current_stream().synchronize()
 
-    for i in range(a.warmup):
+    e2e_ms, h2d = 0.0, 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clk_e2e = ClockSampler(local)
+    for i in range(0 if a.roofline_only else a.warmup):
         step(fakes[i])
         fakes[i] = None
-    st = last_materialize_stats()
+    st = last_materialize_stats() if not a.roofline_only else {"descriptors": 0}
     h2d = lib.tdx_init_workspace_bytes(st["descriptors"])  # plan image copied H2D per step (upper bound)
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk_e2e:
-        e0.record()
-        for i in range(a.warmup, a.warmup + a.steps):
-            step(fakes[i])
-            fakes[i] = None  # release the 16 GB before the next step allocates
-        e1.record()
-        barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1) / a.steps)
+    if not a.roofline_only:
+        with clk_e2e:
+            e0.record()
+            for i in range(a.warmup, a.warmup + a.steps):
+                step(fakes[i])
+                fakes[i] = None  # release the 16 GB before the next step allocates
+            e1.record()
+            barrier()
+        e2e_ms = max_over_ranks(e0.elapsed_time(e1) / a.steps)
 
     # ---- value: plan resident in HBM, kernels only ----------------------------------------------
     model = fakes[-1]
@@ -264,17 +268,20 @@ def run_ours(a):
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     plan = C.TdxPlan()
     C.check(lib.tdx_plan_upload(descs, len(descs), ws.data_ptr(), ws_bytes, stream, ctypes.byref(plan)))
-    for _ in range(max(a.warmup, 3)):
-        C.check(lib.tdx_plan_launch(ctypes.byref(plan), ws.data_ptr(), stream))
-    launches_per_step = lib.tdx_last_launch_count()
-    barrier()
-    with ClockSampler(local) as clk:
-        e0.record()
-        for _ in range(a.steps):
+    clk = ClockSampler(local)
+    ms, launches_per_step = 1.0, 0
+    if not a.roofline_only:
+        for _ in range(max(a.warmup, 3)):
             C.check(lib.tdx_plan_launch(ctypes.byref(plan), ws.data_ptr(), stream))
-        e1.record()
+        launches_per_step = lib.tdx_last_launch_count()
         barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1) / a.steps)
+        with clk:
+            e0.record()
+            for _ in range(a.steps):
+                C.check(lib.tdx_plan_launch(ctypes.byref(plan), ws.data_ptr(), stream))
+            e1.record()
+            barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1) / a.steps)
 
     # ---- roofline of the dominant kernel (most bytes), timed alone with the same events ----------
     fam = {}
@@ -300,7 +307,10 @@ def run_ours(a):
     peak, peak_src = peaks()
     achieved = dom_bytes / dom_ms / 1e6
     kname = {C.TDX_SRC_CONST: "tdx_fill_kernel", C.TDX_SRC_UNIFORM: "tdx_rng_kernel<GenUniform*>",
-             C.TDX_SRC_NORMAL: "tdx_rng_kernel<GenNormalICDF16<bf16>>" if dtype == "bf16" else "tdx_rng_kernel<GenNormalBM32<float>>"}[dom_key[0]]
+             C.TDX_SRC_NORMAL: "tdx_normal16_lut_kernel<bf16> (+ tdx_rng_kernel<GenNormalICDF16<bf16>> for descriptors < 2^20 elements)"
+             if dtype == "bf16" else "tdx_rng_kernel<GenNormalBM32<float>>"}[dom_key[0]]
+    if a.roofline_only:
+        return
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_bench_summary.json"))).get(a.model, {}).get("dram_bytes_per_launch")
@@ -338,6 +348,7 @@ def run_ours(a):
                    "params": n_params, "tensors": n_tensors, "descriptors_per_rank": len(descs),
                    "fused_tensors": st["fused_tensors"], "generic_ops": st["generic_ops"],
                    "elided_rng_ops": st["elided_rng_ops"], "record_s_per_model": record_s,
+                   "host_us": {k: round(st[k]) for k in ("plan_us", "launch_us", "wrap_us")},
                    "l2": "outputs per step (GBs) exceed the 126 MB L2; no flush needed",
                    "timed_region_value": "tdx_plan_launch only (plan resident in HBM)",
                    "timed_region_e2e": "materialize_module (plan, alloc, H2D descriptors, kernels) + 64 B D2H"},
@@ -366,6 +377,9 @@ def main():
     ap.add_argument("--model", default="llama3-8b", choices=sorted(MODELS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--roofline-only", action="store_true",
+                    help="for ncu: one materialize (1 launch per family), then 3+steps launches of the "
+                         "dominant kernel's plan only; prints nothing")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":

@@ -33,6 +33,7 @@ VARIANTS = {
     "uniform_bf16_r7": (C.TDX_BF16, torch.bfloat16, C.TDX_SRC_UNIFORM, C.TDX_ALGO_R7, -0.05, 0.05),
     "uniform_f32": (C.TDX_F32, torch.float32, C.TDX_SRC_UNIFORM, 0, -0.05, 0.05),
     "normal_bf16_icdf16": (C.TDX_BF16, torch.bfloat16, C.TDX_SRC_NORMAL, C.TDX_ALGO_ICDF16, 0.0, 0.02),
+    "normal_bf16_icdf16_nolut": (C.TDX_BF16, torch.bfloat16, C.TDX_SRC_NORMAL, C.TDX_ALGO_ICDF16 | C.TDX_ALGO_NOLUT, 0.0, 0.02),
     "normal_bf16_icdf16_r7": (C.TDX_BF16, torch.bfloat16, C.TDX_SRC_NORMAL, C.TDX_ALGO_ICDF16 | C.TDX_ALGO_R7, 0.0, 0.02),
     "normal_bf16_bm16": (C.TDX_BF16, torch.bfloat16, C.TDX_SRC_NORMAL, C.TDX_ALGO_BM16, 0.0, 0.02),
     "normal_bf16_bm16_r7": (C.TDX_BF16, torch.bfloat16, C.TDX_SRC_NORMAL, C.TDX_ALGO_BM16 | C.TDX_ALGO_R7, 0.0, 0.02),

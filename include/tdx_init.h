@@ -78,6 +78,8 @@ enum {
   TDX_ALGO_BM32 = 2,   /* Box-Muller on 32 random bits/element (f32 default) */
   TDX_ALGO_BM16 = 3,   /* experimental: Box-Muller on 16-bit pairs, no tail refinement */
   TDX_ALGO_R7 = 0x10,  /* OR-able flag, experimental: Philox4x32-7 instead of -10 */
+  TDX_ALGO_NOLUT = 0x20, /* OR-able flag: never use the shared-memory-table twin of ICDF16
+                          * (same bits either way; for A/B measurements) */
 };
 
 /* epilogue steps, applied in order after the source transform; every step

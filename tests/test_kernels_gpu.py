@@ -181,3 +181,35 @@ def test_determinism_and_seed_sensitivity():
     mk = lambda t, seed: C.make_desc(t.data_ptr(), dtype=C.TDX_BF16, src=C.TDX_SRC_NORMAL, elem_count=n, seed=seed, offset=0)
     run_descs([mk(a, 1)], [a]); run_descs([mk(b, 1)], [b]); run_descs([mk(c, 2)], [c])
     assert torch.equal(a, b) and (a != c).float().mean() > 0.9
+
+
+@pytest.mark.parametrize("dtype", [C.TDX_BF16, C.TDX_F16])
+def test_table_driven_normal_is_bit_identical_to_the_direct_kernel(dtype):
+    """Large descriptors take the shared-memory-table kernel; TDX_ALGO_NOLUT forces the direct one.
+    Mixed sizes in one launch, two different (mean, std) so that CTAs rebuild their table."""
+    sizes = [(1 << 22) + 9, 1 << 20, (1 << 21) + 12345, 5000]
+    outs = {}
+    for flag in (0, C.TDX_ALGO_NOLUT):
+        bufs, descs = [], []
+        for i, n in enumerate(sizes):
+            t = torch.zeros(n, dtype=TORCH_DT[dtype], device="cuda")
+            bufs.append(t)
+            descs.append(C.make_desc(t.data_ptr(), dtype=dtype, src=C.TDX_SRC_NORMAL, elem_count=n, seed=77,
+                                     offset=1000 * i, p0=0.0 if i % 2 else 0.5, p1=0.02 if i % 2 else 1.5,
+                                     algo=C.TDX_ALGO_ICDF16 | flag))
+        launches = run_descs(descs, bufs)
+        assert launches == (2 if flag == 0 else 1)  # table kernel + direct kernel (small descriptor)
+        outs[flag] = bufs
+    for a, b in zip(outs[0], outs[C.TDX_ALGO_NOLUT]):
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+    # and a table-kernel shard boundary in the middle of a vector
+    n = (1 << 21) + 3
+    full = torch.zeros(n, dtype=TORCH_DT[dtype], device="cuda")
+    run_descs([C.make_desc(full.data_ptr(), dtype=dtype, src=C.TDX_SRC_NORMAL, elem_count=n, seed=5, offset=8, p1=0.02)], [full])
+    cut = (1 << 20) + 5
+    a = torch.zeros(cut, dtype=TORCH_DT[dtype], device="cuda")
+    b = torch.zeros(n - cut, dtype=TORCH_DT[dtype], device="cuda")
+    run_descs([C.make_desc(a.data_ptr(), dtype=dtype, src=C.TDX_SRC_NORMAL, elem_count=cut, seed=5, offset=8, p1=0.02),
+               C.make_desc(b.data_ptr(), dtype=dtype, src=C.TDX_SRC_NORMAL, elem_begin=cut, elem_count=n - cut, seed=5,
+                           offset=8, p1=0.02)], [a, b])
+    assert torch.equal(torch.cat([a, b]).view(torch.int16), full.view(torch.int16))

@@ -24,6 +24,7 @@ TDX_RAW8, TDX_RAW16, TDX_RAW32, TDX_RAW64 = 8, 9, 10, 11
 TDX_SRC_CONST, TDX_SRC_UNIFORM, TDX_SRC_NORMAL = 0, 1, 2
 TDX_ALGO_DEFAULT, TDX_ALGO_ICDF16, TDX_ALGO_BM32, TDX_ALGO_BM16 = 0, 1, 2, 3
 TDX_ALGO_R7 = 0x10
+TDX_ALGO_NOLUT = 0x20
 TDX_EPI_MUL, TDX_EPI_ADD, TDX_EPI_ERFINV, TDX_EPI_CLAMP = 1, 2, 3, 4
 TDX_MAX_EPI = 4
 

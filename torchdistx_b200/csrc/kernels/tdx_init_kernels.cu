@@ -28,6 +28,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -130,6 +131,17 @@ struct OutTraits<__nv_bfloat16> {
     r.w = *reinterpret_cast<uint32_t*>(&d);
     return r;
   }
+  __device__ static __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&p);
+  }
+  __device__ static __forceinline__ bool any_nan4(const uint32_t (&r)[4]) {
+    const __nv_bfloat162 s = __hadd2(__hadd2(*reinterpret_cast<const __nv_bfloat162*>(&r[0]),
+                                             *reinterpret_cast<const __nv_bfloat162*>(&r[1])),
+                                     __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&r[2]),
+                                             *reinterpret_cast<const __nv_bfloat162*>(&r[3])));
+    return !__hbeq2(s, s);  // all-equal test fails iff a half is NaN
+  }
   __device__ static __forceinline__ float prev(float to) {  // `to` is exactly a bf16 value
     uint32_t b = __float_as_uint(to);
     if (to > 0.f) return __uint_as_float(b - 0x10000u);
@@ -158,6 +170,17 @@ struct OutTraits<__half> {
     r.z = *reinterpret_cast<uint32_t*>(&c);
     r.w = *reinterpret_cast<uint32_t*>(&d);
     return r;
+  }
+  __device__ static __forceinline__ uint32_t pack2(float a, float b) {
+    __half2 p = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&p);
+  }
+  __device__ static __forceinline__ bool any_nan4(const uint32_t (&r)[4]) {
+    const __half2 s = __hadd2(__hadd2(*reinterpret_cast<const __half2*>(&r[0]),
+                                      *reinterpret_cast<const __half2*>(&r[1])),
+                              __hadd2(*reinterpret_cast<const __half2*>(&r[2]),
+                                      *reinterpret_cast<const __half2*>(&r[3])));
+    return !__hbeq2(s, s);
   }
   __device__ static __forceinline__ float prev(float to) {  // `to` is exactly an fp16 value
     unsigned short h = __half_as_ushort(__float2half_rn(to));
@@ -397,21 +420,26 @@ struct GenNormalICDF16 {
     const int s = e & 3;
     return icdf16_tail(s == 0 ? t.x : s == 1 ? t.y : s == 2 ? t.z : t.w);
   }
+  // one element: `magic` = 2^23 + k as a float; returns the value, `t` = 1 - x^2 (0 iff k == 0)
+  __device__ static __forceinline__ float element(const Params& p, float magic, float& t) {
+    const float x = fmaf(magic, 3.0517578125e-05f, -257.0f);  // k/32768 - 1
+    t = fmaf(-x, x, 1.0f);
+    const float l = mufu_lg2(t);
+    float q = fmaf(p.c5, l, p.c4);
+    q = fmaf(q, l, p.c3);
+    q = fmaf(q, l, p.c2);
+    q = fmaf(q, l, p.c1);
+    q = fmaf(q, l, p.c0);
+    return fmaf(q, x, p.mean);
+  }
   __device__ static __forceinline__ void gen(const Params& p, uint64_t gv, float (&v)[8]) {
     const uint4 w = philox_block<R>(p.ph, gv);
     float tmin = 1.0f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float x = fmaf(halfword_as_magic(w, e), 3.0517578125e-05f, -257.0f);  // k/32768 - 1
-      const float t = fmaf(-x, x, 1.0f);
+      float t;
+      v[e] = element(p, halfword_as_magic(w, e), t);
       tmin = fminf(tmin, t);
-      const float l = mufu_lg2(t);
-      float q = fmaf(p.c5, l, p.c4);
-      q = fmaf(q, l, p.c3);
-      q = fmaf(q, l, p.c2);
-      q = fmaf(q, l, p.c1);
-      q = fmaf(q, l, p.c0);
-      v[e] = fmaf(q, x, p.mean);
     }
     if (tmin <= 0.0f) {  // some k == 0 in this vector: ~1.2e-4 of the vectors
       const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
@@ -477,7 +505,7 @@ struct GroupArgs {
 };
 
 // Calls f(desc_index, first_tile_in_desc, n_tiles) for runs of consecutive tiles of one descriptor.
-template <class F>
+template <int TILE_VECS = kTileVecs, class F>
 __device__ __forceinline__ void for_each_tile_run(const GroupArgs& g, F&& f) {
   __shared__ unsigned int s_chunk;
   for (;;) {
@@ -585,19 +613,146 @@ __global__ void __launch_bounds__(kThreads) tdx_fill_kernel(const GroupArgs g) {
   });
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// 16-bit normal through a shared-memory table
+// ---------------------------------------------------------------------------------------------
+// The 16-bit normal is a pure function of k in [0, 65535] once (mean, std) are fixed, so a CTA
+// can evaluate GenNormalICDF16::element once per k into a 128 KiB shared-memory table and then
+// turn every Philox half-word into an output with one LDS.U16 instead of 1 MUFU + 8 FMA-pipe
+// instructions.  The table is built by the SAME device function as the direct kernel, so the
+// two kernels are bit-identical (tests/test_kernels_gpu.py checks it); the host picks this
+// kernel for large descriptors only, because the table costs 65536 evaluations per CTA.
+// Per 8-element vector: Philox 40 slots + 12 address + 8 LDS + 4 pack + ~6 tail check.
+#ifndef TDX_LUT_WORDS
+#define TDX_LUT_WORDS 4
+#endif
+constexpr int kLutThreads = 1024;
+constexpr int kLutVecsPerThread = 4;
+constexpr int kLutTileVecs = kLutThreads * kLutVecsPerThread;  // 64 KiB per tile
+constexpr uint32_t kLutBytes = 65536u * 2u;
+constexpr unsigned short kLutSentinel = 0xffffu;  // a NaN pattern in bf16 and fp16: never a value
+
+// LUT_WORDS of the 4 Philox words of a vector (2 elements each) go through the table, the rest
+// through the polynomial: the table loads keep the LSU/shared-memory pipe busy, the polynomial the
+// otherwise idle FMA and MUFU pipes.
+// cold path of the table kernel (a vector that contains k == 0): out of line, to keep the hot loop
+// small enough for the instruction cache
+template <class Out, int R>
+__device__ __noinline__ uint4 lut_slow_vector(const TdxInitDesc* d, uint64_t gv) {
+  using Gen = GenNormalICDF16<Out, R, false>;
+  const typename Gen::Params P = Gen::setup(*d);
+  float v[8];
+  Gen::gen(P, gv, v);
+  return OutTraits<Out>::pack(v);
+}
+
+template <class Out, int R, int LUT_WORDS = 4>
+__global__ void __launch_bounds__(kLutThreads, 1) tdx_normal16_lut_kernel(const GroupArgs g) {
+  using Gen = GenNormalICDF16<Out, R, false>;
+  using T = OutTraits<Out>;
+  extern __shared__ __align__(16) unsigned short lut[];
+  float have_mean = 0.f, have_std = -1.f;  // table contents (uniform across the CTA)
+  for_each_tile_run<kLutTileVecs>(g, [&](uint32_t di, unsigned long long tile0, unsigned long long ntiles) {
+    const TdxInitDesc& d = g.descs[di];
+    const typename Gen::Params P = Gen::setup(d);
+    if (P.mean != have_mean || P.std != have_std) {
+      __syncthreads();  // everyone is done reading the old table
+      for (uint32_t k = threadIdx.x; k < 65536u; k += kLutThreads) {
+        float t;
+        const float v = Gen::element(P, __uint_as_float(0x4b000000u | k), t);
+        const Out o = static_cast<Out>(v);
+        lut[k] = k == 0 ? kLutSentinel : *reinterpret_cast<const unsigned short*>(&o);
+      }
+      __syncthreads();
+      have_mean = P.mean;
+      have_std = P.std;
+    }
+    const uint64_t begin = d.elem_begin, count = d.elem_count;
+    const uint64_t gv0 = begin / 8;
+    const uint64_t nvec = (begin + count - 1) / 8 - gv0 + 1;
+    char* const dst = static_cast<char*>(d.dst);
+    const bool aligned = (begin % 8 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
+    const uint64_t nfull = aligned ? count / 8 : 0;
+    const char* const lut_bytes = reinterpret_cast<const char*>(lut);
+    for (unsigned long long tile = tile0; tile < tile0 + ntiles; ++tile) {
+      const uint64_t base = tile * kLutTileVecs + threadIdx.x;
+      if (base - threadIdx.x + kLutTileVecs <= nfull) {
+#pragma unroll
+        for (int i = 0; i < kLutVecsPerThread; ++i) {
+          const uint64_t j = base + static_cast<uint64_t>(i) * kLutThreads;
+          const uint4 w = philox_block<R>(P.ph, gv0 + j);
+          const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+          uint32_t r[4];
+          float tmin = 1.0f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (q < LUT_WORDS) {
+              // byte offsets 2*k of the two half-words: one PRMT (zero-extend) on the ALU pipe and
+              // one multiply-by-2 on the FMA pipe each.  The ALU pipe (half rate) also carries
+              // Philox's 20 LOP3, so everything that can be phrased otherwise stays off it.
+              const uint32_t lo = __byte_perm(ws[q], 0u, 0x4410) * 2u;
+              const uint32_t hi = __byte_perm(ws[q], 0u, 0x4432) * 2u;
+              const uint32_t a = *reinterpret_cast<const unsigned short*>(lut_bytes + lo);
+              const uint32_t b = *reinterpret_cast<const unsigned short*>(lut_bytes + hi);
+              r[q] = a | (b << 16);
+            } else {
+              float ta, tb;
+              const float va = Gen::element(P, halfword_as_magic(w, 2 * q), ta);
+              const float vb = Gen::element(P, halfword_as_magic(w, 2 * q + 1), tb);
+              tmin = fminf(tmin, fminf(ta, tb));
+              r[q] = T::pack2(va, vb);
+            }
+          }
+          uint4 out = make_uint4(r[0], r[1], r[2], r[3]);
+          // k == 0 reads the NaN sentinel; a packed add of the four result words propagates it
+          // (3 HADD2 on the FMA pipe + 1 test instead of 8 integer mins on the ALU pipe)
+          if (T::any_nan4(r) || tmin <= 0.0f)  // rare: direct path for this vector
+            out = lut_slow_vector<Out, R>(&d, gv0 + j);
+          store_vec(dst + j * 16, out);
+        }
+      } else {
+        for (int i = 0; i < kLutVecsPerThread; ++i) {
+          const uint64_t j = base + static_cast<uint64_t>(i) * kLutThreads;
+          if (j >= nvec) break;
+          float v[8];
+          Gen::gen(P, gv0 + j, v);
+          if (j < nfull) {
+            store_vec(dst + j * 16, T::pack(v));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const uint64_t gidx = (gv0 + j) * 8 + e;
+              if (gidx >= begin && gidx < begin + count) T::store_one(dst, gidx - begin, v[e]);
+            }
+          }
+        }
+      }
+    }
+  });
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side: validation, grouping into kernel families, plan upload, launch
 // ---------------------------------------------------------------------------------------------
 using KernelFn = void (*)(const GroupArgs);
 
 struct Family {
-  int src, dtype, algo /*resolved, without R7*/, rounds, epi;
+  int src, dtype, algo /*resolved, without flags*/, rounds, epi;
   KernelFn fn;
   const char* name;
+  int threads = kThreads;
+  int tile_vecs = kTileVecs;
+  int dyn_smem = 0;
+  bool lut = false;
 };
 
 #define TDX_FAM(src, dt, algo, rounds, epi, ...) \
   { src, dt, algo, rounds, epi, static_cast<KernelFn>(tdx_rng_kernel<__VA_ARGS__>), #__VA_ARGS__ }
+#define TDX_FAM_LUT(dt, rounds, ...)                                                             \
+  { TDX_SRC_NORMAL, dt, TDX_ALGO_ICDF16, rounds, 0,                                              \
+    static_cast<KernelFn>(tdx_normal16_lut_kernel<__VA_ARGS__>), "lut<" #__VA_ARGS__ ">",        \
+    kLutThreads, kLutTileVecs, static_cast<int>(kLutBytes), true }
 
 using bf16 = __nv_bfloat16;
 using f16 = __half;
@@ -617,6 +772,9 @@ static const Family kFamilies[] = {
     TDX_FAM(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_ICDF16, 10, 1, GenNormalICDF16<bf16, 10, true>),
     TDX_FAM(TDX_SRC_NORMAL, TDX_F16, TDX_ALGO_ICDF16, 10, 0, GenNormalICDF16<f16, 10, false>),
     TDX_FAM(TDX_SRC_NORMAL, TDX_F16, TDX_ALGO_ICDF16, 10, 1, GenNormalICDF16<f16, 10, true>),
+    // table-driven twins of the 16-bit normal for large descriptors (bit-identical output)
+    TDX_FAM_LUT(TDX_BF16, 10, bf16, 10, TDX_LUT_WORDS),
+    TDX_FAM_LUT(TDX_F16, 10, f16, 10, TDX_LUT_WORDS),
     // experimental variants, reachable only through an explicit TdxInitDesc.algo (bench sweeps)
     TDX_FAM(TDX_SRC_UNIFORM, TDX_BF16, 0, 7, 0, GenUniform16<bf16, 7, false>),
     TDX_FAM(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_ICDF16, 7, 0, GenNormalICDF16<bf16, 7, false>),
@@ -658,20 +816,34 @@ int resolve_algo(const TdxInitDesc& d) {
   return 0;
 }
 
+// Descriptors at least this large use the table-driven 16-bit normal (TDX_LUT_MIN_ELEMS overrides;
+// 0 disables).  Below it the 65536-entry table would cost more than it saves.
+uint64_t lut_min_elems() {
+  static const uint64_t v = [] {
+    const char* e = getenv("TDX_LUT_MIN_ELEMS");
+    return e ? strtoull(e, nullptr, 10) : (1ull << 20);
+  }();
+  return v;
+}
+
 int family_of(const TdxInitDesc& d) {
   if (d.src == TDX_SRC_CONST) return 0;
   const int algo = resolve_algo(d);
   const int rounds = (d.algo & TDX_ALGO_R7) ? 7 : 10;
   const int epi = d.n_epi ? 1 : 0;
+  const bool want_lut = d.src == TDX_SRC_NORMAL && algo == TDX_ALGO_ICDF16 && !epi && rounds == 10 &&
+                        !(d.algo & TDX_ALGO_NOLUT) && lut_min_elems() != 0 &&
+                        d.elem_count >= lut_min_elems();
   for (int f = 1; f < kNumFamilies; ++f) {
     const Family& F = kFamilies[f];
-    if (F.src == d.src && F.dtype == d.dtype && F.algo == algo && F.rounds == rounds && F.epi == epi)
+    if (F.src == d.src && F.dtype == d.dtype && F.algo == algo && F.rounds == rounds &&
+        F.epi == epi && F.lut == want_lut)
       return f;
   }
   return -1;
 }
 
-uint64_t tiles_of(const TdxInitDesc& d) {
+uint64_t tiles_of(const TdxInitDesc& d, int tile_vecs) {
   if (d.elem_count == 0) return 0;
   uint64_t nvec;
   if (d.src == TDX_SRC_CONST) {
@@ -682,7 +854,7 @@ uint64_t tiles_of(const TdxInitDesc& d) {
     const uint64_t epv = 16 / itemsize_of(d.dtype);
     nvec = (d.elem_begin + d.elem_count - 1) / epv - d.elem_begin / epv + 1;
   }
-  return (nvec + kTileVecs - 1) / kTileVecs;
+  return (nvec + tile_vecs - 1) / tile_vecs;
 }
 
 // Device-resident plan header.  Lives at the start of the caller's workspace.
@@ -723,8 +895,14 @@ DeviceInfo* device_info() {
       return nullptr;
     for (int f = 0; f < kNumFamilies; ++f) {
       int nb = 0;
+      if (kFamilies[f].dyn_smem &&
+          cudaFuncSetAttribute(reinterpret_cast<const void*>(kFamilies[f].fn),
+                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               kFamilies[f].dyn_smem) != cudaSuccess)
+        return nullptr;
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-              &nb, reinterpret_cast<const void*>(kFamilies[f].fn), kThreads, 0) != cudaSuccess)
+              &nb, reinterpret_cast<const void*>(kFamilies[f].fn), kFamilies[f].threads,
+              kFamilies[f].dyn_smem) != cudaSuccess)
         return nullptr;
       I.blocks_per_sm[f] = std::max(nb, 1);
     }
@@ -773,7 +951,7 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
       if (fam[i] != f) continue;
       prefix[k] = acc;
       out[k] = descs[i];
-      acc += tiles_of(descs[i]);
+      acc += tiles_of(descs[i], kFamilies[f].tile_vecs);
       ++k;
     }
     prefix[k] = acc;
@@ -781,6 +959,51 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
   }
   memcpy(img.data(), &hdr, sizeof(hdr));
   img.resize(off);
+  return 0;
+}
+
+// ---- pinned staging ring for plan uploads ------------------------------------------------------
+struct StageSlot {
+  void* host = nullptr;
+  size_t cap = 0;
+  cudaEvent_t done = nullptr;
+  int device = -1;
+  bool pending = false;
+};
+constexpr int kStageSlots = 8;
+thread_local StageSlot g_stage[kStageSlots];
+thread_local int g_stage_pos = 0;
+
+int stage(const void* src, size_t bytes, cudaStream_t stream, void* dst_device, void** pinned_out) {
+  StageSlot& s = g_stage[g_stage_pos];
+  g_stage_pos = (g_stage_pos + 1) % kStageSlots;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  if (s.pending) {  // the copy that last used this slot must have left it
+    e = cudaEventSynchronize(s.done);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize(staging)");
+    s.pending = false;
+  }
+  if (s.done == nullptr || s.device != dev) {
+    if (s.done) cudaEventDestroy(s.done);
+    e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate(staging)");
+    s.device = dev;
+  }
+  if (s.cap < bytes) {
+    if (s.host) cudaFreeHost(s.host);
+    s.cap = std::max<size_t>(bytes * 2, 64 << 10);
+    e = cudaHostAlloc(&s.host, s.cap, cudaHostAllocPortable);
+    if (e != cudaSuccess) { s.host = nullptr; s.cap = 0; return cuda_fail(e, "cudaHostAlloc(staging)"); }
+  }
+  memcpy(s.host, src, bytes);
+  e = cudaMemcpyAsync(dst_device, s.host, bytes, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(plan)");
+  e = cudaEventRecord(s.done, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaEventRecord(staging)");
+  s.pending = true;
+  *pinned_out = s.host;
   return 0;
 }
 
@@ -809,7 +1032,8 @@ int launch_groups(const PlanHeader& hdr, void* workspace, cudaStream_t stream) {
     const unsigned long long resident =
         static_cast<unsigned long long>(info->sm_count) * info->blocks_per_sm[G.family];
     const unsigned int grid = static_cast<unsigned int>(std::min(chunks, resident));
-    kFamilies[G.family].fn<<<grid, kThreads, 0, stream>>>(a);
+    const Family& F = kFamilies[G.family];
+    F.fn<<<grid, F.threads, F.dyn_smem, stream>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, kFamilies[G.family].name);
     ++launches;
@@ -863,10 +1087,11 @@ TDX_C_API int tdx_init_launch(const TdxInitDesc* descs, int n, void* workspace,
   }
   if (workspace == nullptr || workspace_bytes < img.size())
     return tdx::fail(TDX_E_WORKSPACE, "workspace too small (see tdx_init_workspace_bytes)");
-  // pageable source: the runtime stages the bytes before returning, so `img` may be reused
-  cudaError_t e = cudaMemcpyAsync(workspace, img.data(), img.size(), cudaMemcpyHostToDevice,
-                                  static_cast<cudaStream_t>(stream));
-  if (e != cudaSuccess) return tdx::cuda_fail(e, "cudaMemcpyAsync(plan)");
+  // The plan image goes through a small ring of pinned staging buffers so that the copy is truly
+  // asynchronous: the host can go on planning the next batch while the GPU works on this one.
+  void* pinned = nullptr;
+  if (int rc = tdx::stage(img.data(), img.size(), static_cast<cudaStream_t>(stream), workspace, &pinned))
+    return rc;
   return tdx::launch_groups(hdr, workspace, static_cast<cudaStream_t>(stream));
 }
 

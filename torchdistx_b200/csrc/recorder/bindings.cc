@@ -16,6 +16,8 @@
 #include <torch/csrc/utils/device_lazy_init.h>
 #include <torch/extension.h>
 
+#include <chrono>
+
 #include "fake_tensor.h"
 #include "planner.h"
 #include "tape.h"
@@ -121,6 +123,7 @@ py::list py_materialize_tensors(const py::list& vars, const py::object& device,
     py::gil_scoped_release nogil;
     done = tdx::materialize_many(todo, opts, mask_all.empty() ? nullptr : &mask);
   }
+  const auto t0 = std::chrono::steady_clock::now();
   py::list result(fakes.size());
   size_t k = 0;
   for (size_t i = 0; i < fakes.size(); ++i) {
@@ -133,6 +136,7 @@ py::list py_materialize_tensors(const py::list& vars, const py::object& device,
       result[i] = py::cast(tdx::cached_python_tensor(fakes[i]));
     }
   }
+  tdx::add_wrap_time(std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
   return result;
 }
 
@@ -146,6 +150,9 @@ py::dict py_last_stats() {
   d["kernel_launches"] = s.kernel_launches;
   d["bytes_written"] = s.bytes_written;
   d["descriptors"] = s.descriptors;
+  d["plan_us"] = s.plan_us;
+  d["launch_us"] = s.launch_us;
+  d["wrap_us"] = s.wrap_us;
   return d;
 }
 

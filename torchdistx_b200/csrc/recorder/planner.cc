@@ -8,7 +8,9 @@
 #include <c10/cuda/CUDAStream.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -347,15 +349,41 @@ Sym eval_storage(Tape& tape, uint32_t S, uint32_t upto) {
 // ---------------------------------------------------------------------------------------------
 // batched fused execution
 // ---------------------------------------------------------------------------------------------
+double now_us();
+
 struct Batch {
   c10::Device device = c10::Device(c10::kCPU);
   std::vector<TdxInitDesc> descs;
   std::vector<at::Tensor> keep_alive;
+  // Early submission: the first descriptors are launched as soon as a modest amount of work has
+  // accumulated and the threshold doubles after every submission, so the GPU starts writing while
+  // the host is still planning the rest of the module and the launch count stays logarithmic.
+  int64_t pending_bytes = 0;
+  int64_t flush_threshold = flush_start();
+  static int64_t flush_start() {
+    static const int64_t v = [] {
+      const char* e = getenv("TDX_FLUSH_BYTES");  // 0 = submit once, at the end
+      return e ? static_cast<int64_t>(strtoll(e, nullptr, 10)) : (int64_t{128} << 20);
+    }();
+    return v;
+  }
+  void note(int64_t bytes) {
+    pending_bytes += bytes;
+    if (flush_threshold > 0 && pending_bytes >= flush_threshold) {
+      flush();
+      flush_threshold = std::min<int64_t>(flush_threshold * 2, int64_t{4} << 30);
+    }
+  }
   void flush();
 };
 
+double now_us() {
+  return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 void Batch::flush() {
   if (descs.empty()) return;
+  const double t0 = now_us();
   NoInterception guard;
   c10::DeviceGuard dg(device);
   const int n = static_cast<int>(descs.size());
@@ -370,6 +398,8 @@ void Batch::flush() {
   g_last_descs.insert(g_last_descs.end(), descs.begin(), descs.end());
   descs.clear();
   keep_alive.clear();
+  pending_bytes = 0;
+  g_stats.launch_us += now_us() - t0;
 }
 
 int tdx_dtype_of(ScalarType t) {
@@ -637,6 +667,7 @@ struct Engine {
       batch.keep_alive.push_back(base);
       g_stats.bytes_written += g.count * static_cast<int64_t>(isz);
     }
+    const int64_t submitted = (st.src != Sym::Uninit) ? g.count * static_cast<int64_t>(isz) : 0;
 
     si.base = base;
     si.fused_done = true;
@@ -650,6 +681,7 @@ struct Engine {
       }
     }
     g_stats.fused_tensors++;
+    batch.note(submitted);  // may submit what has accumulated so far
     return true;
   }
 
@@ -696,6 +728,7 @@ std::vector<at::Tensor> materialize_many(const std::vector<at::Tensor>& fakes,
                                          const std::vector<uint8_t>* shard_mask) {
   g_stats = MaterializeStats{};
   g_last_descs.clear();
+  const double t_begin = now_us();
   std::vector<at::Tensor> out;
   out.reserve(fakes.size());
   Batch batch;
@@ -712,8 +745,11 @@ std::vector<at::Tensor> materialize_many(const std::vector<at::Tensor>& fakes,
     out.push_back(finish(t, eng.materialize_value(rec->tape, rec->value)));
   }
   batch.flush();
+  g_stats.plan_us = now_us() - t_begin - g_stats.launch_us;
   return out;
 }
+
+void add_wrap_time(double us) { g_stats.wrap_us += us; }
 
 at::Tensor materialize_one(const at::Tensor& fake, const MaterializeOptions& opts) {
   if (!can_materialize(fake)) return fake;

@@ -46,6 +46,9 @@ struct MaterializeStats {
   int64_t kernel_launches = 0;  // libtdx_init launches
   int64_t bytes_written = 0;    // algorithmic bytes of the fused descriptors
   int64_t descriptors = 0;
+  double plan_us = 0;    // host time: slicing, symbolic evaluation, allocation, descriptor build
+  double launch_us = 0;  // host time inside tdx_init_launch (plan image + H2D copy + launches)
+  double wrap_us = 0;    // host time giving results their Python class / identity
 };
 
 // Materialises `fake` (a no-op returning `fake` itself for real tensors).
@@ -59,6 +62,7 @@ std::vector<at::Tensor> materialize_many(const std::vector<at::Tensor>& fakes,
                                          const std::vector<uint8_t>* shard_mask = nullptr);
 
 MaterializeStats last_stats();
+void add_wrap_time(double us);
 // The TdxInitDesc table (raw bytes) the last materialize call on this thread submitted; lets
 // benchmarks and tests re-launch / inspect exactly what the engine ran.
 std::string last_descriptors();
