@@ -23,7 +23,7 @@ def build(verbose: bool = False) -> str:
         sources=[os.path.join(SRC, f) for f in ("fake_tensor.cc", "tape.cc", "planner.cc", "bindings.cc")],
         extra_include_paths=[os.path.join(ROOT, "include"), SRC, "/usr/local/cuda/include"],
         extra_cflags=["-O2", "-std=c++17", "-fvisibility=hidden"],
-        extra_ldflags=[f"-L{PKG}", "-ltdx_init", '-Wl,-rpath,\'$$ORIGIN\'', f"-Wl,-rpath,{PKG}", "-lc10_cuda", "-ltorch_cuda"],
+        extra_ldflags=[f"-L{PKG}", "-ltdx_init", '-Wl,-rpath,\'$$ORIGIN\'', f"-Wl,-rpath,{PKG}", "-lc10_cuda", "-Wl,--no-as-needed", "-ltorch_cuda", "-Wl,--as-needed"],
         build_directory=build_dir,
         with_cuda=False,
         verbose=verbose,

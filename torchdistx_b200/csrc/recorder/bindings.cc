@@ -16,6 +16,7 @@
 #include <torch/csrc/utils/device_lazy_init.h>
 #include <torch/extension.h>
 
+#include <algorithm>
 #include <chrono>
 
 #include "fake_tensor.h"
@@ -140,6 +141,48 @@ py::list py_materialize_tensors(const py::list& vars, const py::object& device,
   return result;
 }
 
+// Whole-module entry point: the traversal of materialize_module (children first, then the module's
+// own parameters, then its buffers; reference deferred_init.py:104-124) done natively -- for a
+// 300-tensor model the Python-level walk costs as much as the kernels' launch.
+void collect_slots(const py::handle& module, bool buffers_only, const py::object& check_fn,
+                   std::vector<std::pair<py::dict, py::object>>& slots) {
+  py::dict children = py::reinterpret_borrow<py::dict>(module.attr("_modules"));
+  std::vector<PyObject*> seen;  // Module.children() yields each distinct child once
+  for (auto item : children) {
+    if (item.second.is_none()) continue;
+    if (std::find(seen.begin(), seen.end(), item.second.ptr()) != seen.end()) continue;
+    seen.push_back(item.second.ptr());
+    collect_slots(item.second, buffers_only, check_fn, slots);
+  }
+  if (!check_fn.is_none() && !py::cast<bool>(check_fn(module))) return;
+  for (const char* group : {"_parameters", "_buffers"}) {
+    if (buffers_only && group[1] == 'p') continue;
+    py::dict d = py::reinterpret_borrow<py::dict>(module.attr(group));
+    for (auto item : d)
+      if (!item.second.is_none()) slots.emplace_back(d, py::reinterpret_borrow<py::object>(item.first));
+  }
+}
+
+void py_materialize_module(const py::object& module, bool buffers_only, const py::object& check_fn,
+                           const py::object& device, const py::object& shard, bool fused) {
+  std::vector<std::pair<py::dict, py::object>> slots;
+  collect_slots(module, buffers_only, check_fn, slots);
+  if (slots.empty()) return;
+  py::list vars(slots.size());
+  py::object mask = py::none();
+  static py::object parameter_cls = py::module_::import("torch.nn").attr("Parameter");
+  py::list mask_list(shard.is_none() ? 0 : slots.size());
+  for (size_t i = 0; i < slots.size(); ++i) {
+    vars[i] = slots[i].first[slots[i].second];
+    // parameters are chunked, buffers replicated; one ordered batch keeps RNG consumption in
+    // traversal order
+    if (!shard.is_none()) mask_list[i] = py::bool_(py::isinstance(vars[i], parameter_cls));
+  }
+  if (!shard.is_none()) mask = mask_list;
+  py::list out = py_materialize_tensors(vars, device, shard, fused, mask);
+  for (size_t i = 0; i < slots.size(); ++i) slots[i].first[slots[i].second] = out[i];
+}
+
 py::dict py_last_stats() {
   const tdx::MaterializeStats s = tdx::last_stats();
   py::dict d;
@@ -153,6 +196,7 @@ py::dict py_last_stats() {
   d["plan_us"] = s.plan_us;
   d["launch_us"] = s.launch_us;
   d["wrap_us"] = s.wrap_us;
+  d["plan_phases_us"] = tdx::last_subtimers();
   return d;
 }
 
@@ -174,6 +218,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("materialize_tensors", &py_materialize_tensors, py::arg("tensors"),
         py::arg("device") = py::none(), py::arg("shard") = py::none(), py::arg("fused") = true,
         py::arg("shard_mask") = py::none());
+  m.def("materialize_module", &py_materialize_module, py::arg("module"), py::arg("buffers_only") = false,
+        py::arg("check_fn") = py::none(), py::arg("device") = py::none(), py::arg("shard") = py::none(),
+        py::arg("fused") = true);
   m.def("last_stats", &py_last_stats);
   m.def("last_descriptors", [] { return py::bytes(tdx::last_descriptors()); });
   m.def("kernel_abi_version", [] { return tdx_abi_version(); });

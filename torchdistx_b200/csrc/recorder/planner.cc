@@ -3,6 +3,7 @@
 #include <ATen/Context.h>
 #include <ATen/Functions.h>
 #include <ATen/core/Generator.h>
+#include <ATen/cuda/EmptyTensor.h>
 #include <c10/core/DeviceGuard.h>
 #include <c10/core/impl/LocalDispatchKeySet.h>
 #include <c10/cuda/CUDAStream.h>
@@ -29,6 +30,7 @@ using torch::jit::Stack;
 namespace {
 
 thread_local MaterializeStats g_stats;
+thread_local double g_sub[6] = {0, 0, 0, 0, 0, 0};  // eval, alloc, rng, desc, mark, alias (us)
 thread_local std::vector<TdxInitDesc> g_last_descs;  // what the last materialize call launched
 
 // Never record / fake anything we do while materialising.
@@ -44,7 +46,9 @@ struct Sym {
   enum Src { Opaque, Uninit, Const, Uniform, Normal } src = Opaque;
   ScalarType dtype = ScalarType::Undefined;  // dtype of the tensor currently holding the state
   ScalarType gen_dtype = ScalarType::Undefined;  // dtype the RNG source op ran in
-  at::Tensor cval;                           // Const: a 1-element CPU tensor of `dtype`
+  at::Tensor cval;                           // Const: a 1-element CPU tensor of `dtype` (built lazily)
+  c10::Scalar cscalar;                       // Const: the value, while no folding has needed a tensor
+  bool has_scalar = false;
   double p0 = 0, p1 = 1;                     // Uniform: from,to   Normal: mean,std
   uint32_t rng_op = kNoValue;                // the live RNG op
   std::vector<uint32_t> rng_chain;           // every RNG op met, live or dead, chronological
@@ -53,6 +57,33 @@ struct Sym {
 };
 
 Sym make_opaque() { return Sym{}; }
+
+// Element bits of `v` converted to `dtype` (the conversion at::full performs), without building a
+// tensor.  Returns false for dtypes that are not handled here.
+bool scalar_bits(const c10::Scalar& v, ScalarType dtype, unsigned char* out, size_t* isz) {
+  auto put = [&](auto x) { std::memcpy(out, &x, sizeof(x)); *isz = sizeof(x); return true; };
+  switch (dtype) {
+    case ScalarType::Float: return put(v.to<float>());
+    case ScalarType::Double: return put(v.to<double>());
+    case ScalarType::BFloat16: return put(v.to<c10::BFloat16>());
+    case ScalarType::Half: return put(v.to<c10::Half>());
+    case ScalarType::Long: return put(v.to<int64_t>());
+    case ScalarType::Int: return put(v.to<int32_t>());
+    case ScalarType::Short: return put(v.to<int16_t>());
+    case ScalarType::Char: return put(v.to<int8_t>());
+    case ScalarType::Byte: return put(v.to<uint8_t>());
+    case ScalarType::Bool: return put(v.to<bool>());
+    default: return false;
+  }
+}
+
+// The 1-element tensor form of a constant state (needed to fold further ops through ATen).
+void ensure_cval(Sym& st) {
+  if (st.cval.defined() || !st.has_scalar) return;
+  c10::impl::ExcludeDispatchKeyGuard a{c10::DispatchKey::DeferredInit};
+  c10::impl::ExcludeDispatchKeyGuard b{c10::DispatchKey::Fake};
+  st.cval = at::full({1}, st.cscalar, at::TensorOptions().dtype(st.dtype).device(c10::kCPU));
+}
 
 bool is_fused_float(ScalarType t) {
   return t == ScalarType::Float || t == ScalarType::BFloat16 || t == ScalarType::Half;
@@ -104,6 +135,8 @@ size_t find_arg(const TapeOp& op, const char* name) {
 // Runs the recorded operator on `self` (a 1-element CPU tensor standing for a constant tensor),
 // with the recorded scalar arguments: exact ATen semantics for constant folding.
 bool fold_const(const TapeOp& op, Sym& st, bool inplace) {
+  ensure_cval(st);
+  st.has_scalar = false;
   if (!op.handle || !st.cval.defined()) return false;
   Stack stack;
   size_t slot = 0;
@@ -176,14 +209,13 @@ void transition(Tape& tape, uint32_t op_idx, uint32_t S, Sym& st) {
       st = Sym{};
       st.src = Sym::Const;
       st.dtype = out.dtype;
-      NoInterception guard;
-      const auto opt = at::TensorOptions().dtype(out.dtype).device(c10::kCPU);
-      if (op.kind == OpKind::Zeros) st.cval = at::zeros({1}, opt);
-      else if (op.kind == OpKind::Ones) st.cval = at::ones({1}, opt);
+      st.has_scalar = true;
+      if (op.kind == OpKind::Zeros) st.cscalar = 0;
+      else if (op.kind == OpKind::Ones) st.cscalar = 1;
       else {
         const size_t pos = find_arg(op, "fill_value");
         if (pos == static_cast<size_t>(-1) || !op.args[pos].isScalar()) { st = make_opaque(); return; }
-        st.cval = at::full({1}, op.args[pos].toScalar(), opt);
+        st.cscalar = op.args[pos].toScalar();
       }
       return;
     }
@@ -239,14 +271,15 @@ void transition(Tape& tape, uint32_t op_idx, uint32_t S, Sym& st) {
       st.rng_chain = std::move(chain);
       st.src = Sym::Const;
       st.dtype = dt;
-      NoInterception guard;
-      const auto opt = at::TensorOptions().dtype(dt).device(c10::kCPU);
       if (op.kind == OpKind::ZeroInplace) {
-        st.cval = at::zeros({1}, opt);
+        st.cscalar = 0;
+        st.has_scalar = true;
       } else if (op.args.size() > 1 && op.args[1].isScalar()) {
-        st.cval = at::full({1}, op.args[1].toScalar(), opt);
+        st.cscalar = op.args[1].toScalar();
+        st.has_scalar = true;
       } else if (op.inputs.size() > 1 && op.inputs[1].real.defined() &&
                  op.inputs[1].real.numel() == 1 && op.inputs[1].real.is_cpu()) {
+        NoInterception guard;
         st.cval = op.inputs[1].real.detach().to(dt).reshape({1}).clone();
       } else {
         st = make_opaque();
@@ -356,8 +389,9 @@ struct Batch {
   std::vector<TdxInitDesc> descs;
   std::vector<at::Tensor> keep_alive;
   // Early submission: the first descriptors are launched as soon as a modest amount of work has
-  // accumulated and the threshold doubles after every submission, so the GPU starts writing while
-  // the host is still planning the rest of the module and the launch count stays logarithmic.
+  // accumulated and the threshold doubles after every submission, so the GPU starts
+  // writing while the host is still planning the rest of the module; the threshold quadruples after
+  // every submission so that the launch count (each launch has a ~10-20 us tail) stays logarithmic.
   int64_t pending_bytes = 0;
   int64_t flush_threshold = flush_start();
   static int64_t flush_start() {
@@ -371,7 +405,7 @@ struct Batch {
     pending_bytes += bytes;
     if (flush_threshold > 0 && pending_bytes >= flush_threshold) {
       flush();
-      flush_threshold = std::min<int64_t>(flush_threshold * 2, int64_t{4} << 30);
+      flush_threshold = std::min<int64_t>(flush_threshold * 4, int64_t{16} << 30);
     }
   }
   void flush();
@@ -411,9 +445,41 @@ int tdx_dtype_of(ScalarType t) {
   }
 }
 
+// Generator state is read once per materialize call and written back once (a CUDA generator's
+// set_offset() asks the driver whether the stream is capturing: ~1 us, twice per tensor).
+struct GenCache {
+  struct Entry {
+    at::Generator gen;
+    uint64_t seed = 0, offset = 0;
+    bool dirty = false;
+  };
+  std::vector<Entry> entries;
+  Entry& get(const at::Generator& g) {
+    for (auto& e : entries)
+      if (e.gen.unsafeGetGeneratorImpl() == g.unsafeGetGeneratorImpl()) return e;
+    Entry e;
+    e.gen = g;
+    std::lock_guard<std::mutex> lock(e.gen.mutex());
+    e.seed = g.current_seed();
+    e.offset = g.get_offset();
+    entries.push_back(std::move(e));
+    return entries.back();
+  }
+  // must run before anything else (ATen replay, the user) looks at the generators
+  void write_back() {
+    for (auto& e : entries) {
+      if (!e.dirty) continue;
+      std::lock_guard<std::mutex> lock(e.gen.mutex());
+      e.gen.set_offset(e.offset);
+      e.dirty = false;
+    }
+    entries.clear();
+  }
+};
+
 // Gives an RNG op its Philox stream id (once) and advances the generator, so that replaying in
 // the same order with the same seed reproduces the same tensors, dead passes included.
-void assign_rng(TapeOp& op, int64_t numel, c10::Device device) {
+void assign_rng(TapeOp& op, int64_t numel, c10::Device device, GenCache& cache) {
   if (op.rng_assigned) return;
   at::Generator gen;
   if (op.handle) {
@@ -423,12 +489,13 @@ void assign_rng(TapeOp& op, int64_t numel, c10::Device device) {
   if (!gen.defined()) gen = at::globalContext().defaultGenerator(device);
   TORCH_CHECK(gen.device().type() == device.type(), "Expected a '", device.type(),
               "' device type for generator but found '", gen.device().type(), "'");
-  std::lock_guard<std::mutex> lock(gen.mutex());
-  op.rng_seed = gen.current_seed();
-  op.rng_offset = gen.get_offset();
+  GenCache::Entry& e = cache.get(gen);
+  op.rng_seed = e.seed;
+  op.rng_offset = e.offset;
   // consumption is a function of the GLOBAL element count only: shard-invariant by construction
   const uint64_t blocks = (static_cast<uint64_t>(numel) + 3) / 4;
-  gen.set_offset(op.rng_offset + ((blocks + 3) / 4) * 4 + 4);
+  e.offset += ((blocks + 3) / 4) * 4 + 4;
+  e.dirty = true;
   op.rng_assigned = true;
 }
 
@@ -454,13 +521,14 @@ ShardGeom shard_of(const ValueInfo& v, const std::optional<ShardSpec>& shard) {
   return g;
 }
 
-at::Tensor alias_of(const at::Tensor& base, const ValueInfo& v) {
+at::Tensor alias_of(const at::Tensor& base, const ValueInfo& v, bool first) {
+  const bool same = base.sizes() == c10::IntArrayRef(v.sizes) &&
+                    base.strides() == c10::IntArrayRef(v.strides) &&
+                    base.storage_offset() == v.storage_offset;
+  if (same && first) return base;  // the common case: the parameter IS the backing tensor
   NoInterception guard;
   at::Tensor t = base.detach();
-  if (t.sizes() != c10::IntArrayRef(v.sizes) || t.strides() != c10::IntArrayRef(v.strides) ||
-      t.storage_offset() != v.storage_offset) {
-    t.as_strided_(v.sizes, v.strides, v.storage_offset);
-  }
+  if (!same) t.as_strided_(v.sizes, v.strides, v.storage_offset);
   return t;
 }
 
@@ -470,6 +538,7 @@ at::Tensor alias_of(const at::Tensor& base, const ValueInfo& v) {
 struct Engine {
   MaterializeOptions opts;
   Batch& batch;
+  GenCache gens;
 
   at::Tensor real_of(Tape& tape, uint32_t v) {
     ValueInfo& vi = tape.values[v];
@@ -481,11 +550,12 @@ struct Engine {
       // the backing tensor is this rank's dim-0 chunk; only whole-storage tensors can name it
       TORCH_CHECK(vi.covers_storage,
                   "sharded materialisation only supports tensors that cover their whole storage");
-      NoInterception guard;
-      vi.real = si.base.detach();
+      vi.real = si.base_taken ? [&] { NoInterception guard; return si.base.detach(); }() : si.base;
+      si.base_taken = true;
       return vi.real;
     }
-    vi.real = alias_of(si.base, vi);
+    vi.real = alias_of(si.base, vi, !si.base_taken);
+    si.base_taken = true;
     return vi.real;
   }
 
@@ -561,7 +631,7 @@ struct Engine {
       if (di >= 0 && (stack[di].isDevice() || stack[di].isNone())) stack[di] = *opts.device;
     }
     {
-      at::ThreadLocalStateGuard tls(*op.tls);
+      at::ThreadLocalStateGuard tls(*op.tls);  // (a shared snapshot: see tape.cc)
       NoInterception guard;
       if (op.handle) {
         op.handle->callBoxed(stack);
@@ -599,7 +669,9 @@ struct Engine {
     const bool sharded = opts.shard && opts.shard->world > 1 && !vi.sizes.empty();
     if (sharded && !vi.covers_storage) return false;
 
+    double tq = now_us();
     Sym st = eval_storage(tape, S, static_cast<uint32_t>(tape.ops.size()));
+    g_sub[0] += now_us() - tq;
     if (st.opaque()) return false;
     const size_t isz = c10::elementSize(st.dtype);
     if (isz == 0 || si.nbytes % isz) return false;
@@ -625,20 +697,22 @@ struct Engine {
       batch.flush();
       batch.device = dev;
     }
-    at::Tensor base;
-    {
-      NoInterception guard;
-      base = at::empty(g.sizes, at::TensorOptions().dtype(st.dtype).device(dev));
-    }
+    // straight to the caching allocator: no dispatcher round trip per tensor
+    tq = now_us();
+    at::Tensor base = at::detail::empty_cuda(g.sizes, st.dtype, dev, std::nullopt);
+    g_sub[1] += now_us() - tq;
+    tq = now_us();
 
     // every RNG pass on the chain consumes its slice of the stream, live or dead
     for (uint32_t r : st.rng_chain) {
       if (!tape.ops[r].rng_assigned) {
-        assign_rng(tape.ops[r], numel, dev);
+        assign_rng(tape.ops[r], numel, dev, gens);
         if (r != st.rng_op) g_stats.elided_rng_ops++;
       }
     }
 
+    g_sub[2] += now_us() - tq;
+    tq = now_us();
     if (st.src != Sym::Uninit && g.count > 0) {
       TdxInitDesc d;
       std::memset(&d, 0, sizeof(d));
@@ -648,9 +722,13 @@ struct Engine {
       if (st.src == Sym::Const) {
         d.src = TDX_SRC_CONST;
         d.dtype = isz == 1 ? TDX_RAW8 : isz == 2 ? TDX_RAW16 : isz == 4 ? TDX_RAW32 : TDX_RAW64;
-        unsigned char pat[16];
-        const at::Tensor c = st.cval.contiguous();
-        for (size_t i = 0; i < 16; i += isz) std::memcpy(pat + i, c.data_ptr(), isz);
+        unsigned char pat[16], one[16];
+        size_t got = 0;
+        if (!(st.has_scalar && scalar_bits(st.cscalar, st.dtype, one, &got) && got == isz)) {
+          ensure_cval(st);
+          std::memcpy(one, st.cval.contiguous().data_ptr(), isz);
+        }
+        for (size_t i = 0; i < 16; i += isz) std::memcpy(pat + i, one, isz);
         std::memcpy(d.fill_bits, pat, 16);
       } else {
         d.src = st.src == Sym::Uniform ? TDX_SRC_UNIFORM : TDX_SRC_NORMAL;
@@ -669,6 +747,8 @@ struct Engine {
     }
     const int64_t submitted = (st.src != Sym::Uninit) ? g.count * static_cast<int64_t>(isz) : 0;
 
+    g_sub[3] += now_us() - tq;
+    tq = now_us();
     si.base = base;
     si.fused_done = true;
     for (uint32_t oi : si.touching_ops) {
@@ -681,6 +761,7 @@ struct Engine {
       }
     }
     g_stats.fused_tensors++;
+    g_sub[4] += now_us() - tq;
     batch.note(submitted);  // may submit what has accumulated so far
     return true;
   }
@@ -690,10 +771,16 @@ struct Engine {
     ValueInfo& vi = tape.values[v];
     if (vi.real.defined()) return vi.real;
     if (tape.storages[vi.storage].fused_done) return real_of(tape, v);
-    if (try_fused(tape, v)) return real_of(tape, v);
+    if (try_fused(tape, v)) {
+      const double tq = now_us();
+      at::Tensor r = real_of(tape, v);
+      g_sub[5] += now_us() - tq;
+      return r;
+    }
 
     // generic replay, in recorded order, of everything that determines this storage
     batch.flush();
+    gens.write_back();  // ATen's own RNG kernels read the generators
     std::vector<uint8_t> mark(tape.ops.size(), 0);
     std::vector<uint32_t> visited(tape.storages.size(), 0);
     collect_storage(tape, vi.storage, static_cast<uint32_t>(tape.ops.size()), mark, visited);
@@ -728,11 +815,16 @@ std::vector<at::Tensor> materialize_many(const std::vector<at::Tensor>& fakes,
                                          const std::vector<uint8_t>* shard_mask) {
   g_stats = MaterializeStats{};
   g_last_descs.clear();
+  for (double& x : g_sub) x = 0;
   const double t_begin = now_us();
   std::vector<at::Tensor> out;
   out.reserve(fakes.size());
   Batch batch;
   Engine eng{opts, batch};
+  struct WriteBack {  // also on error paths: offsets already handed out must stay consumed
+    GenCache& g;
+    ~WriteBack() { try { g.write_back(); } catch (...) {} }
+  } write_back{eng.gens};
   for (size_t i = 0; i < fakes.size(); ++i) {
     const at::Tensor& t = fakes[i];
     g_stats.tensors++;
@@ -745,6 +837,7 @@ std::vector<at::Tensor> materialize_many(const std::vector<at::Tensor>& fakes,
     out.push_back(finish(t, eng.materialize_value(rec->tape, rec->value)));
   }
   batch.flush();
+  eng.gens.write_back();
   g_stats.plan_us = now_us() - t_begin - g_stats.launch_us;
   return out;
 }
@@ -757,6 +850,8 @@ at::Tensor materialize_one(const at::Tensor& fake, const MaterializeOptions& opt
 }
 
 MaterializeStats last_stats() { return g_stats; }
+
+std::vector<double> last_subtimers() { return std::vector<double>(g_sub, g_sub + 6); }
 
 std::string last_descriptors() {
   return std::string(reinterpret_cast<const char*>(g_last_descs.data()),

@@ -1,6 +1,8 @@
 #include "tape.h"
 
+#include <ATen/autocast_mode.h>
 #include <ATen/core/VariableHooksInterface.h>
+#include <c10/core/AutogradState.h>
 #include <c10/core/impl/LocalDispatchKeySet.h>
 #include <torch/library.h>
 
@@ -97,6 +99,51 @@ namespace {
 thread_local uint64_t tls_seq = 0;             // chronological op number of this thread
 thread_local size_t tls_level = 0;             // deferred_init nesting
 thread_local std::shared_ptr<Tape> tls_tape;   // tape of the outermost active deferred_init
+thread_local uint64_t tls_session = 0;         // bumped by every outermost enter_deferred_init
+
+// Thread-local state (grad mode, autocast, dispatch keys, ...) is restored when an op is replayed
+// (reference deferred_init.cc:205-215, 256-272).  Snapshots are expensive to take and to destroy
+// and almost never change between consecutive ops: reuse the previous one while a cheap
+// fingerprint of the state is unchanged.
+std::shared_ptr<const at::ThreadLocalState> current_tls_snapshot() {
+  struct Fingerprint {
+    uint64_t included = 0, excluded = 0;
+    bool grad = false, inference = false, fw_grad = false, multithreading = false, view_replay = false;
+    uint64_t autocast = 0;
+    bool operator==(const Fingerprint& o) const {
+      return included == o.included && excluded == o.excluded && grad == o.grad &&
+             inference == o.inference && fw_grad == o.fw_grad && multithreading == o.multithreading &&
+             view_replay == o.view_replay && autocast == o.autocast;
+    }
+  };
+  thread_local Fingerprint last_fp;
+  thread_local uint64_t last_session = ~0ull;
+  thread_local std::shared_ptr<const at::ThreadLocalState> last;
+  if (last_session != tls_session) {  // never carry a snapshot over from an earlier deferred_init
+    last.reset();
+    last_session = tls_session;
+  }
+  Fingerprint fp;
+  const auto ks = c10::impl::tls_local_dispatch_key_set();
+  fp.included = ks.included_.raw_repr();
+  fp.excluded = ks.excluded_.raw_repr();
+  const auto ag = c10::AutogradState::get_tls_state();
+  fp.grad = ag.get_grad_mode();
+  fp.inference = ag.get_inference_mode();
+  fp.fw_grad = ag.get_fw_grad_mode();
+  fp.multithreading = ag.get_multithreading_enabled();
+  fp.view_replay = ag.get_view_replay_enabled();
+  for (int dt = 0; dt < static_cast<int>(c10::DeviceType::COMPILE_TIME_MAX_DEVICE_TYPES); ++dt) {
+    const auto d = static_cast<c10::DeviceType>(dt);
+    if (d == c10::kCPU || d == c10::kCUDA)
+      fp.autocast = fp.autocast * 131 + (at::autocast::is_autocast_enabled(d) ? 1 + static_cast<int>(at::autocast::get_autocast_dtype(d)) : 0);
+  }
+  if (!last || !(fp == last_fp)) {
+    last = std::make_shared<const at::ThreadLocalState>();
+    last_fp = fp;
+  }
+  return last;
+}
 
 // Call frames are replayed much later: deep-copy containers so that a caller mutating its list
 // cannot change the recording, and refuse values whose state we cannot freeze.
@@ -159,7 +206,7 @@ void append(std::optional<OperatorHandle> handle, OpKind kind, Stack frame, size
   op->kind = kind;
   op->seq = tls_seq++;
   op->num_returns = static_cast<uint32_t>(nret);
-  op->tls.emplace();  // thread-local state (grad mode, autocast, dispatch keys, ...) at record time
+  op->tls = current_tls_snapshot();
 
   c10::SmallVector<const c10::TensorImpl*, 4> fake_inputs;
   for_each_tensor_mut(frame, nargs, [&](at::Tensor& t) {
@@ -387,6 +434,7 @@ void uninstall_hooks() noexcept {
 void enter_deferred_init() {
   if (++tls_level == 1) {
     tls_tape.reset();  // a fresh tape per outermost scope; old tapes live on in their tensors
+    ++tls_session;
     c10::impl::tls_set_dispatch_key_included(DispatchKey::DeferredInit, true);
     install_hooks();
   }

@@ -75,6 +75,7 @@ struct StorageInfo {
   std::vector<uint32_t> touching_ops;  // every op with an input or output on this storage, in order
   at::Tensor base;        // real backing tensor once the fused path materialised the storage
   bool fused_done = false;
+  bool base_taken = false;  // `base` itself has been handed out as some value's tensor
 };
 
 // A tensor argument of a recorded op.
@@ -94,7 +95,9 @@ struct TapeOp {
   std::vector<InputRef> inputs;         // one per tensor slot of `args`, in stack_walk order
   std::vector<uint32_t> outputs;        // value id per tensor output (kNoValue for non-fake outputs)
   uint32_t num_returns = 0;
-  std::optional<at::ThreadLocalState> tls;
+  // thread-local state at record time; consecutive ops recorded under the same grad-mode /
+  // autocast / dispatch-key state share one snapshot
+  std::shared_ptr<const at::ThreadLocalState> tls;
   std::vector<c10::IValue> results;     // real outputs after generic replay
   bool done = false;
   // RNG ops on the fused path: the Philox stream id they were given (once, in materialise order)

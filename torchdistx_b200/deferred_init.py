@@ -18,7 +18,7 @@ target device and dim-0 sharding:
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, List, Optional, Tuple, TypeVar, Union
+from typing import Callable, Dict, Optional, Tuple, TypeVar, Union
 
 import torch
 from torch import Tensor
@@ -80,19 +80,6 @@ def materialize_tensor(tensor: Tensor, *, device: DeviceLike = None, shard: Shar
     return _C.materialize_tensor(tensor, _device(device), shard)
 
 
-def _collect(module: Module, buffers_only: bool, check_fn: Optional[Callable[[Module], bool]],
-             slots: List[Tuple[Dict[str, Optional[Tensor]], str]]) -> None:
-    for child in module.children():
-        _collect(child, buffers_only, check_fn, slots)
-    if check_fn is not None and not check_fn(module):
-        return
-    groups = [module._buffers] if buffers_only else [module._parameters, module._buffers]
-    for group in groups:
-        for key, tensor in group.items():
-            if tensor is not None:
-                slots.append((group, key))  # type: ignore[arg-type]
-
-
 def materialize_module(
     module: Module,
     buffers_only: bool = False,
@@ -113,30 +100,10 @@ def materialize_module(
             every parameter (buffers and 0-dim tensors are replicated).  All ranks must hold the
             same generator state; see :func:`torchdistx_b200.parallel.sync_rng`.
     """
-    slots: List[Tuple[Dict[str, Optional[Tensor]], str]] = []
-    _collect(module, buffers_only, check_fn, slots)
-    if not slots:
-        return
-    dev = _device(device)
-    tensors = [group[key] for group, key in slots]
-    # parameters are chunked, buffers replicated; one ordered batch keeps RNG consumption in
-    # traversal order
-    mask = None if shard is None else [isinstance(t, torch.nn.Parameter) for t in tensors]
     try:
-        results = _C.materialize_tensors(tensors, dev, shard, True, mask)
-    except ValueError:
-        _raise_already_materialized(slots)
-        raise
-    for (group, key), out in zip(slots, results):
-        group[key] = out
-
-
-def _raise_already_materialized(slots) -> None:
-    for group, key in slots:
-        try:
-            _C.can_materialize(group[key])
-        except ValueError:
-            raise ValueError(f"'{key}' has already been materialized.") from None
+        _C.materialize_module(module, buffers_only, check_fn, _device(device), shard)
+    except ValueError as e:  # same wording as the reference (deferred_init.py:110-113)
+        raise ValueError(f"{e} (a tensor of the module has already been materialized)") from None
 
 
 def last_descriptors():
