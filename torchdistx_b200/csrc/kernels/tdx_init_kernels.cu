@@ -507,10 +507,10 @@ struct GroupArgs {
 // Calls f(desc_index, first_tile_in_desc, n_tiles) for runs of consecutive tiles of one descriptor.
 template <int TILE_VECS = kTileVecs, class F>
 __device__ __forceinline__ void for_each_tile_run(const GroupArgs& g, F&& f) {
-  // a work grab is 256 KiB whatever the tile size: small enough that the tail of a launch (SMs
-  // waiting for the last grabs) stays ~10 us at ~25 GB/s per SM
-  constexpr int kTilesPerChunk = (tdx::kTilesPerChunk * kTileVecs) / TILE_VECS;
-  static_assert(kTilesPerChunk >= 1, "tile larger than a chunk");
+  // A work grab is 16 tiles: 256 KiB for the 256-thread kernels, 1 MiB for the 1024-thread table
+  // kernel.  (Measured: 256 KiB grabs for the table kernel cost 14 % -- two 32-warp barriers and an
+  // atomic per grab are not free.)
+  (void)TILE_VECS;
   __shared__ unsigned int s_chunk;
   for (;;) {
     __syncthreads();
@@ -1032,8 +1032,7 @@ int launch_groups(const PlanHeader& hdr, void* workspace, cudaStream_t stream) {
     a.total_tiles = G.total_tiles;
     a.counter = &dev_hdr->counters[gi];
     a.n_desc = G.n_desc;
-    const int tiles_per_chunk = (kTilesPerChunk * kTileVecs) / kFamilies[G.family].tile_vecs;
-    const unsigned long long chunks = (G.total_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
+    const unsigned long long chunks = (G.total_tiles + kTilesPerChunk - 1) / kTilesPerChunk;
     const unsigned long long resident =
         static_cast<unsigned long long>(info->sm_count) * info->blocks_per_sm[G.family];
     const unsigned int grid = static_cast<unsigned int>(std::min(chunks, resident));
