@@ -60,6 +60,27 @@ def tiny_gpt2():
     return GPT2LMHeadModel(cfg)
 
 
+def torch_transformer():
+    # deepcopy'd layers (aten::clone of initialised tensors) + a second init pass over every matrix
+    return nn.Transformer(d_model=32, nhead=4, num_encoder_layers=2, num_decoder_layers=1, dim_feedforward=64)
+
+
+class Clones(nn.Module):
+    """deepcopy / .data.clone() of an RNG-initialised parameter must reproduce its values."""
+
+    def __init__(self):
+        super().__init__()
+        import copy
+        self.a = nn.Parameter(torch.empty(40, 24).normal_(0.0, 0.5))
+        self.b = copy.deepcopy(self.a)
+        self.c = nn.Parameter(self.a.data.clone())
+        self.d = nn.Parameter(self.a.detach().clone() * 2.0)
+
+
+def clones():
+    return Clones()
+
+
 def mlp_stack():
     return nn.Sequential(nn.Linear(64, 256), nn.GELU(), nn.Linear(256, 64), nn.LayerNorm(64))
 
@@ -70,6 +91,8 @@ CASES = {
     "tiny_llama": tiny_llama,
     "tiny_gpt2": tiny_gpt2,
     "mlp_stack": mlp_stack,
+    "torch_transformer": torch_transformer,
+    "clones": clones,
 }
 
 DTYPES = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}

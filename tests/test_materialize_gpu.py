@@ -32,7 +32,7 @@ from torchdistx_b200.fake import is_fake
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CASES = [("init_zoo", "fp32"), ("init_zoo", "bf16"), ("tiny_llama", "fp32"), ("tiny_llama", "bf16"),
-         ("tiny_gpt2", "fp32"), ("mlp_stack", "fp32")]
+         ("tiny_gpt2", "fp32"), ("mlp_stack", "fp32"), ("torch_transformer", "fp32"), ("clones", "fp32")]
 
 
 @pytest.fixture(scope="module")
@@ -247,3 +247,12 @@ def test_cfg1_linear128_on_cpu_still_bit_exact_with_cuda_present():
     torch.manual_seed(0)
     e = nn.Linear(128, 128)
     assert torch.equal(m.weight, e.weight) and torch.equal(m.bias, e.bias)
+
+
+def test_clones_of_rng_tensors_are_bit_identical_to_their_source():
+    m = build_on_cuda("clones", "fp32", seed=9)
+    st = last_materialize_stats()
+    assert st["fused_tensors"] == 4 and st["generic_ops"] == 0
+    assert torch.equal(m.a, m.b) and torch.equal(m.a, m.c)
+    assert torch.equal(m.d, m.a * 2.0)
+    assert m.a.data_ptr() != m.b.data_ptr()

@@ -1,0 +1,90 @@
+"""Planner verdicts without a GPU (`plan_report` evaluates the recorded programs symbolically and
+allocates nothing): the init idioms of SURVEY.md section 3.4 fold into single descriptors, dead RNG
+passes are seen, and whole model families stay on the fused path."""
+import math
+
+import pytest
+import torch
+from torch import nn
+
+from oracle import cases
+from torchdistx_b200.deferred_init import deferred_init, plan_report
+
+
+def report(fn):
+    return plan_report(deferred_init(fn))
+
+
+def test_init_idioms_fold_as_documented():
+    r = report(lambda: cases.build("init_zoo", "fp32"))
+    k = r["kaiming.weight"]
+    assert k["source"] == "uniform" and k["rng_ops"] == 1 and k["n_epilogue"] == 0
+    bound = 1 / math.sqrt(48)
+    assert k["p0"] == pytest.approx(-bound, rel=1e-6) and k["p1"] == pytest.approx(bound, rel=1e-6)
+    assert r["embed.weight"]["source"] == "normal" and (r["embed.weight"]["p0"], r["embed.weight"]["p1"]) == (0.0, 1.0)
+    assert r["norm.weight"]["source"] == "const" and r["norm.bias"]["source"] == "const"
+    t = r["trunc"]  # uniform_ -> erfinv_ -> mul_ -> add_ -> clamp_
+    assert t["source"] == "uniform" and t["n_epilogue"] == 4 and t["fusible"]
+    tw = r["twice.weight"]  # Linear's kaiming uniform_ overwritten by normal_: one dead pass
+    assert tw["source"] == "normal" and tw["rng_ops"] == 2 and tw["p1"] == pytest.approx(0.02)
+    assert r["const"]["source"] == "const"  # ones * 3 + 1 folded through ATen
+    s = r["scaled"]  # randn * 0.02 + 1.0
+    assert s["source"] == "normal" and s["n_epilogue"] == 2
+    assert r["int_fill"]["source"] == "const" and r["int_fill"]["dtype"] == "Long"
+    for name in ("mask", "steps"):  # tril / arange: replayed by ATen on the target device
+        assert r[name]["source"] == "opaque" and not r[name]["fusible"]
+    assert r["bn.num_batches_tracked"]["source"] == "real"  # torch.tensor(0) is never intercepted
+
+
+def test_llama_linear_chain_has_one_dead_uniform():
+    r = report(lambda: cases.build("tiny_llama", "bf16"))
+    w = r["model.layers.0.mlp.up_proj.weight"]
+    assert (w["source"], w["dtype"], w["rng_ops"], w["p0"], w["p1"]) == ("normal", "BFloat16", 2, 0.0, pytest.approx(0.02))
+    assert r["model.norm.weight"]["source"] == "const"
+
+
+def fusible_fraction(r):
+    total = sum(v["numel"] for v in r.values())
+    return sum(v["numel"] for v in r.values() if v["fusible"]) / total
+
+
+@pytest.mark.parametrize("case", ["tiny_llama", "tiny_gpt2", "torch_transformer", "mlp_stack", "clones"])
+def test_model_families_stay_on_the_fused_path(case):
+    assert fusible_fraction(report(lambda: cases.build(case, "fp32"))) > 0.999
+
+
+def test_more_hf_families_and_torch_modules():
+    import transformers as T
+
+    fams = {
+        "vit": lambda: T.ViTModel(T.ViTConfig(hidden_size=64, num_hidden_layers=1, num_attention_heads=4,
+                                              intermediate_size=128, image_size=32, patch_size=8)),
+        "t5": lambda: T.T5Model(T.T5Config(d_model=64, d_ff=128, num_layers=1, num_heads=4, vocab_size=512)),
+        "mixtral": lambda: T.MixtralForCausalLM(T.MixtralConfig(vocab_size=512, hidden_size=64, intermediate_size=128,
+                                                                num_hidden_layers=1, num_attention_heads=4,
+                                                                num_key_value_heads=2, num_local_experts=2)),
+        "lstm": lambda: nn.LSTM(32, 64, num_layers=2),
+        "conv_bn": lambda: nn.Sequential(nn.Conv2d(3, 16, 3), nn.BatchNorm2d(16), nn.Linear(10, 10)),
+    }
+    for name, fn in fams.items():
+        assert fusible_fraction(report(fn)) > 0.99, name
+
+
+def test_mid_history_reader_forces_generic_replay():
+    def build():
+        w = torch.empty(8, 8).uniform_()
+        snapshot = w * 2.0  # reads the uniform state ...
+        w.normal_()  # ... which is then overwritten
+        m = nn.Module()
+        m.w, m.s = nn.Parameter(w), nn.Parameter(snapshot)
+        return m
+
+    m = deferred_init(build)
+    r = plan_report(m)
+    assert r["w"]["source"] == "opaque"  # the reader must run at its own point in history
+    from torchdistx_b200.deferred_init import materialize_module
+    torch.manual_seed(0)
+    materialize_module(m)
+    torch.manual_seed(0)
+    e = build()
+    assert torch.equal(m.w, e.w) and torch.equal(m.s, e.s)

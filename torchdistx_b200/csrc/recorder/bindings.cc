@@ -221,6 +221,22 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("materialize_module", &py_materialize_module, py::arg("module"), py::arg("buffers_only") = false,
         py::arg("check_fn") = py::none(), py::arg("device") = py::none(), py::arg("shard") = py::none(),
         py::arg("fused") = true);
+  m.def("plan_info", [](const at::Tensor& t) {
+    const tdx::PlanInfo i = tdx::plan_info(t);
+    py::dict d;
+    d["deferred"] = i.deferred;
+    d["fusible"] = i.fusible;
+    d["source"] = i.source;
+    d["dtype"] = i.dtype;
+    d["numel"] = i.numel;
+    d["p0"] = i.p0;
+    d["p1"] = i.p1;
+    d["n_epilogue"] = i.n_epilogue;
+    d["rng_ops"] = i.rng_ops;
+    d["first_unfusable_op"] = i.first_unfusable_op;
+    return d;
+  });
+  m.def("storage_history", &tdx::storage_history);
   m.def("last_stats", &py_last_stats);
   m.def("last_descriptors", [] { return py::bytes(tdx::last_descriptors()); });
   m.def("kernel_abi_version", [] { return tdx_abi_version(); });

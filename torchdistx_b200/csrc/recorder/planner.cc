@@ -292,6 +292,7 @@ void transition(Tape& tape, uint32_t op_idx, uint32_t S, Sym& st) {
     case OpKind::ClampInplace:
     case OpKind::MulOut:
     case OpKind::AddOut:
+    case OpKind::CloneOut:
     case OpKind::CastOut: {
       const bool inplace = op.kind == OpKind::MulInplace || op.kind == OpKind::AddInplace ||
                            op.kind == OpKind::ErfinvInplace || op.kind == OpKind::ClampInplace;
@@ -301,6 +302,12 @@ void transition(Tape& tape, uint32_t op_idx, uint32_t S, Sym& st) {
         const ValueInfo& in = tape.values[op.inputs[0].value];
         if (!in.covers_storage || in.numel != out.numel || in.storage == S) { st = make_opaque(); return; }
         st = eval_storage(tape, in.storage, op_idx);
+      }
+      if (op.kind == OpKind::CloneOut) {
+        // a copy: same elements (an RNG state keeps its op, hence its Philox stream: the clone is
+        // bit-identical to its source, as deepcopy semantics require)
+        if (st.opaque() || !need_cover() || out.dtype != st.dtype) st = make_opaque();
+        return;
       }
       if (st.opaque() || st.src == Sym::Uninit || !need_cover()) { st = make_opaque(); return; }
       if (st.src == Sym::Const) {
@@ -349,11 +356,13 @@ Sym eval_storage(Tape& tape, uint32_t S, uint32_t upto) {
   const StorageInfo& si = tape.storages[S];
   Sym st;
   bool any = false;
-  // index of the last op (< upto) that writes S
+  // index of the last op (< upto) that changes the CONTENT of S (aliases only re-describe it)
   uint32_t last_writer = kNoValue;
   for (uint32_t oi : si.touching_ops) {
     if (oi >= upto) break;
-    for (uint32_t v : tape.ops[oi].outputs)
+    const TapeOp& op = tape.ops[oi];
+    if (op.kind == OpKind::Alias || op.kind == OpKind::HookVariableData) continue;
+    for (uint32_t v : op.outputs)
       if (v != kNoValue && tape.values[v].storage == S) last_writer = oi;
   }
   for (uint32_t oi : si.touching_ops) {
@@ -848,6 +857,66 @@ void add_wrap_time(double us) { g_stats.wrap_us += us; }
 at::Tensor materialize_one(const at::Tensor& fake, const MaterializeOptions& opts) {
   if (!can_materialize(fake)) return fake;
   return materialize_many({fake}, opts)[0];
+}
+
+PlanInfo plan_info(const at::Tensor& fake) {
+  PlanInfo info;
+  if (!can_materialize(fake)) {
+    info.source = "real";
+    return info;
+  }
+  info.deferred = true;
+  const auto rec = fake_impl(fake)->record();
+  Tape& tape = *rec->tape;
+  const ValueInfo& vi = tape.values[rec->value];
+  info.dtype = c10::toString(vi.dtype);
+  info.numel = vi.numel;
+  const StorageInfo& si = tape.storages[vi.storage];
+  if (vi.real.defined() || si.fused_done) {
+    info.source = "materialized";
+    return info;
+  }
+  Sym st = eval_storage(tape, vi.storage, static_cast<uint32_t>(tape.ops.size()));
+  static const char* names[] = {"opaque", "uninit", "const", "uniform", "normal"};
+  info.source = names[st.src];
+  info.fusible = !st.opaque();
+  if (st.src == Sym::Uniform || st.src == Sym::Normal) info.fusible = tdx_dtype_of(st.dtype) >= 0;
+  info.p0 = st.p0;
+  info.p1 = st.p1;
+  info.n_epilogue = static_cast<int>(st.epi.size());
+  info.rng_ops = static_cast<int>(st.rng_chain.size());
+  if (st.opaque()) {
+    // best effort: the first op on the storage the planner does not model
+    for (uint32_t oi : si.touching_ops) {
+      const TapeOp& op = tape.ops[oi];
+      if (op.kind == OpKind::Generic || op.kind == OpKind::HookSetData) {
+        info.first_unfusable_op = op.name();
+        break;
+      }
+    }
+  }
+  return info;
+}
+
+std::vector<std::string> storage_history(const at::Tensor& fake) {
+  std::vector<std::string> out;
+  if (!can_materialize(fake)) return out;
+  const auto rec = fake_impl(fake)->record();
+  Tape& tape = *rec->tape;
+  const StorageInfo& si = tape.storages[tape.values[rec->value].storage];
+  for (uint32_t oi : si.touching_ops) {
+    const TapeOp& op = tape.ops[oi];
+    std::string line = op.name();
+    bool writes = false, covers = true;
+    for (uint32_t v : op.outputs)
+      if (v != kNoValue && tape.values[v].storage == tape.values[rec->value].storage) {
+        writes = true;
+        covers = covers && tape.values[v].covers_storage;
+      }
+    line += writes ? (covers ? " [writes]" : " [writes part]") : " [reads]";
+    out.push_back(line);
+  }
+  return out;
 }
 
 MaterializeStats last_stats() { return g_stats; }

@@ -68,6 +68,23 @@ std::vector<double> last_subtimers();  // planner phases (eval, alloc, rng, desc
 // benchmarks and tests re-launch / inspect exactly what the engine ran.
 std::string last_descriptors();
 
+// Planner verdict for one tensor, without allocating or launching anything (works without a GPU:
+// used by CPU tests and by `torchdistx_b200.deferred_init.plan_report`).
+struct PlanInfo {
+  bool deferred = false;   // the tensor awaits materialisation
+  bool fusible = false;    // its program folds into one descriptor
+  std::string source;      // "uninit" | "const" | "uniform" | "normal" | "opaque" | "real"
+  std::string dtype;
+  int64_t numel = 0;
+  double p0 = 0, p1 = 0;
+  int n_epilogue = 0;
+  int rng_ops = 0;         // RNG passes on the chain, live + dead
+  std::string first_unfusable_op;  // for "opaque": the op that stopped the fold (best effort)
+};
+PlanInfo plan_info(const at::Tensor& fake);
+// Every recorded op touching the tensor's storage, in order (debug aid for unfusable programs).
+std::vector<std::string> storage_history(const at::Tensor& fake);
+
 // The tensor that a previous materialisation handed to Python for this fake tensor (keeps the
 // Python object identity stable), and the hook to store it.
 at::Tensor cached_python_tensor(const at::Tensor& fake);

@@ -53,6 +53,7 @@ OpKind kind_from_name(const std::string& name, const std::string& overload) {
   if (n == "clamp_" && overload.empty()) return OpKind::ClampInplace;
   if (n == "mul" && (overload == "Tensor" || overload == "Scalar")) return OpKind::MulOut;
   if (n == "add" && (overload == "Tensor" || overload == "Scalar")) return OpKind::AddOut;
+  if (n == "clone") return OpKind::CloneOut;
   if (n == "_to_copy" || (n == "to" && (overload == "dtype" || overload == "dtype_layout")))
     return OpKind::CastOut;
   return OpKind::Generic;
@@ -116,11 +117,16 @@ std::shared_ptr<const at::ThreadLocalState> current_tls_snapshot() {
              view_replay == o.view_replay && autocast == o.autocast;
     }
   };
-  thread_local Fingerprint last_fp;
+  // a handful of states alternate during module construction (grad mode on for constructors, off
+  // inside nn.init.*): keep one snapshot per state
+  struct Slot {
+    Fingerprint fp;
+    std::shared_ptr<const at::ThreadLocalState> tls;
+  };
+  thread_local std::vector<Slot> slots;
   thread_local uint64_t last_session = ~0ull;
-  thread_local std::shared_ptr<const at::ThreadLocalState> last;
   if (last_session != tls_session) {  // never carry a snapshot over from an earlier deferred_init
-    last.reset();
+    slots.clear();
     last_session = tls_session;
   }
   Fingerprint fp;
@@ -138,11 +144,11 @@ std::shared_ptr<const at::ThreadLocalState> current_tls_snapshot() {
     if (d == c10::kCPU || d == c10::kCUDA)
       fp.autocast = fp.autocast * 131 + (at::autocast::is_autocast_enabled(d) ? 1 + static_cast<int>(at::autocast::get_autocast_dtype(d)) : 0);
   }
-  if (!last || !(fp == last_fp)) {
-    last = std::make_shared<const at::ThreadLocalState>();
-    last_fp = fp;
-  }
-  return last;
+  for (const Slot& sl : slots)
+    if (sl.fp == fp) return sl.tls;
+  if (slots.size() >= 8) slots.erase(slots.begin());
+  slots.push_back(Slot{fp, std::make_shared<const at::ThreadLocalState>()});
+  return slots.back().tls;
 }
 
 // Call frames are replayed much later: deep-copy containers so that a caller mutating its list

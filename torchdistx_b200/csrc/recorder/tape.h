@@ -47,7 +47,7 @@ enum class OpKind : uint8_t {
   UniformInplace, NormalInplace, FillInplace, ZeroInplace,
   MulInplace, AddInplace, ErfinvInplace, ClampInplace,
   // out-of-place unary elementwise (new storage, same geometry)
-  MulOut, AddOut, CastOut,
+  MulOut, AddOut, CastOut, CloneOut,
   // autograd hook pseudo-ops
   HookVariableData, HookSetData,
 };

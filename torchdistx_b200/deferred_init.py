@@ -34,6 +34,7 @@ __all__ = [
     "materialize_module",
     "last_materialize_stats",
     "last_descriptors",
+    "plan_report",
 ]
 
 M = TypeVar("M", bound=Module)
@@ -104,6 +105,17 @@ def materialize_module(
         _C.materialize_module(module, buffers_only, check_fn, _device(device), shard)
     except ValueError as e:  # same wording as the reference (deferred_init.py:110-113)
         raise ValueError(f"{e} (a tensor of the module has already been materialized)") from None
+
+
+def plan_report(module: Module) -> Dict[str, Dict[str, object]]:
+    """What the planner will do with every parameter / buffer of a deferred module, without
+    allocating or launching anything (works on a machine without a GPU): per tensor name,
+    ``{"fusible", "source" (uninit|const|uniform|normal|opaque|real|materialized), "dtype", "numel",
+    "p0", "p1", "n_epilogue", "rng_ops", "first_unfusable_op"}``."""
+    out: Dict[str, Dict[str, object]] = {}
+    for name, t in list(module.named_parameters()) + list(module.named_buffers()):
+        out[name] = dict(_C.plan_info(t))
+    return out
 
 
 def last_descriptors():
