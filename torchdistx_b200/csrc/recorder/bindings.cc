@@ -234,6 +234,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     d["n_epilogue"] = i.n_epilogue;
     d["rng_ops"] = i.rng_ops;
     d["first_unfusable_op"] = i.first_unfusable_op;
+    d["sizes"] = i.sizes;
+    d["device"] = i.device;
+    d["requires_grad"] = i.requires_grad;
+    d["epilogue"] = i.epilogue;
+    d["const_bytes"] = py::bytes(i.const_bytes);
+    d["rng_numels"] = i.rng_numels;
     return d;
   });
   m.def("storage_history", &tdx::storage_history);

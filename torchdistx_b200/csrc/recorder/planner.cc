@@ -871,6 +871,9 @@ PlanInfo plan_info(const at::Tensor& fake) {
   const ValueInfo& vi = tape.values[rec->value];
   info.dtype = c10::toString(vi.dtype);
   info.numel = vi.numel;
+  info.sizes = vi.sizes;
+  info.device = vi.device.str();
+  info.requires_grad = fake.is_leaf() && fake.requires_grad();
   const StorageInfo& si = tape.storages[vi.storage];
   if (vi.real.defined() || si.fused_done) {
     info.source = "materialized";
@@ -885,6 +888,22 @@ PlanInfo plan_info(const at::Tensor& fake) {
   info.p1 = st.p1;
   info.n_epilogue = static_cast<int>(st.epi.size());
   info.rng_ops = static_cast<int>(st.rng_chain.size());
+  for (const TdxEpiStep& e : st.epi) info.epilogue.emplace_back(static_cast<int>(e.op), e.a, e.b);
+  {
+    const size_t isz = c10::elementSize(st.dtype == ScalarType::Undefined ? vi.dtype : st.dtype);
+    const int64_t storage_numel = isz ? static_cast<int64_t>(si.nbytes / isz) : vi.numel;
+    for (size_t i = 0; i < st.rng_chain.size(); ++i) info.rng_numels.push_back(storage_numel);
+    if (st.src == Sym::Const) {
+      unsigned char one[16];
+      size_t got = 0;
+      if (!(st.has_scalar && scalar_bits(st.cscalar, st.dtype, one, &got) && got == isz)) {
+        ensure_cval(st);
+        std::memcpy(one, st.cval.contiguous().data_ptr(), isz);
+      }
+      info.const_bytes.assign(reinterpret_cast<const char*>(one), isz);
+    }
+    if (!vi.covers_storage) info.fusible = false;  // a plan names whole tensors only
+  }
   if (st.opaque()) {
     // best effort: the first op on the storage the planner does not model
     for (uint32_t oi : si.touching_ops) {

@@ -21,6 +21,7 @@
 #include <cstdint>
 #include <optional>
 #include <string>
+#include <tuple>
 #include <vector>
 
 namespace tdx {
@@ -80,6 +81,13 @@ struct PlanInfo {
   int n_epilogue = 0;
   int rng_ops = 0;         // RNG passes on the chain, live + dead
   std::string first_unfusable_op;  // for "opaque": the op that stopped the fold (best effort)
+  // everything needed to rebuild the descriptor later without the recording (InitPlan)
+  std::vector<int64_t> sizes;
+  std::string device;
+  bool requires_grad = false;
+  std::vector<std::tuple<int, double, double>> epilogue;  // (TDX_EPI_*, a, b)
+  std::string const_bytes;                                 // "const": one element's bytes
+  std::vector<int64_t> rng_numels;  // global numel of every RNG pass on the chain, in order
 };
 PlanInfo plan_info(const at::Tensor& fake);
 // Every recorded op touching the tensor's storage, in order (debug aid for unfusable programs).

@@ -1,0 +1,260 @@
+"""Serialisable initialisation plans.
+
+The reference's recording cannot leave the process: every op holds a ``std::function`` over the
+dispatcher and an ``OperatorHandle&`` (reference src/cc/torchdistx/deferred_init.cc:159, 217-225),
+so re-materialising a model -- elastic restart, a new rank joining, another seed -- means
+re-running the Python constructor under ``deferred_init``.  Here the planner's verdict per tensor
+is plain data (source, parameters, epilogue, RNG passes on the chain), so it can be written to
+disk and replayed later with nothing but the C ABI:
+
+    plan = InitPlan.from_module(deferred_model)        # no allocation, works without a GPU
+    plan.save("llama3-8b.init.json")
+    ...
+    tensors = InitPlan.load("llama3-8b.init.json").materialize(device="cuda", shard=(rank, world))
+
+Under the same generator state ``InitPlan.materialize`` produces exactly the bits
+``materialize_module`` produces (tests/test_plan_gpu.py): same traversal order, same Philox
+offset bookkeeping, same kernels.  Tensors whose program is not fusible (tiny ``arange``-style
+buffers such as rotary ``inv_freq``) are evaluated once when the plan is built and stored by
+value (refused above ``max_embedded_bytes``).
+"""
+from __future__ import annotations
+
+import base64
+import json
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch.nn import Module
+
+from . import _C, _cabi
+
+_DTYPES = {
+    "Float": torch.float32, "BFloat16": torch.bfloat16, "Half": torch.float16, "Double": torch.float64,
+    "Long": torch.int64, "Int": torch.int32, "Short": torch.int16, "Char": torch.int8,
+    "Byte": torch.uint8, "Bool": torch.bool,
+}
+_TDX_DTYPE = {torch.float32: _cabi.TDX_F32, torch.bfloat16: _cabi.TDX_BF16, torch.float16: _cabi.TDX_F16}
+_RAW = {1: _cabi.TDX_RAW8, 2: _cabi.TDX_RAW16, 4: _cabi.TDX_RAW32, 8: _cabi.TDX_RAW64}
+_DTYPE_NAMES = {v: k for k, v in _DTYPES.items()}
+FORMAT = "torchdistx_b200.InitPlan/1"
+
+
+def offset_increment(numel: int) -> int:
+    """Generator offset one RNG pass over `numel` elements consumes (planner.cc assign_rng)."""
+    blocks = (numel + 3) // 4
+    return ((blocks + 3) // 4) * 4 + 4
+
+
+@dataclass
+class PlanEntry:
+    name: str
+    kind: str  # "param" | "buffer"
+    sizes: List[int]
+    dtype: str
+    source: str  # "const" | "uniform" | "normal" | "uninit" | "value"
+    p0: float = 0.0
+    p1: float = 0.0
+    epilogue: List[Tuple[int, float, float]] = field(default_factory=list)
+    const_bytes: str = ""  # base64, one element
+    value: str = ""  # base64 of the whole tensor for "value" entries
+    rng_numels: List[int] = field(default_factory=list)
+    requires_grad: bool = False
+    alias_of: Optional[str] = None  # tied parameters: same tensor as an earlier entry
+
+
+class InitPlan:
+    def __init__(self, entries: List[PlanEntry]):
+        self.entries = entries
+
+    # ------------------------------------------------------------------------------------- build
+    @classmethod
+    def from_module(cls, module: Module, max_embedded_bytes: int = 1 << 20) -> "InitPlan":
+        """Builds the plan of a module created by ``deferred_init``.  Traversal order is the one
+        ``materialize_module`` uses (children first, then own parameters, then own buffers)."""
+        from .deferred_init import materialize_tensor
+
+        entries: List[PlanEntry] = []
+        seen: Dict[int, str] = {}
+
+        def visit(mod: Module, prefix: str) -> None:
+            for cname, child in mod._modules.items():
+                if child is not None:
+                    visit(child, f"{prefix}{cname}.")
+            for kind, group in (("param", mod._parameters), ("buffer", mod._buffers)):
+                for key, t in group.items():
+                    if t is None:
+                        continue
+                    name = prefix + key
+                    if id(t) in seen:
+                        entries.append(PlanEntry(name, kind, list(t.shape), _DTYPE_NAMES[t.dtype], "alias", alias_of=seen[id(t)]))
+                        continue
+                    seen[id(t)] = name
+                    info = dict(_C.plan_info(t))
+                    if info["source"] in ("const", "uniform", "normal", "uninit") and info["fusible"]:
+                        entries.append(PlanEntry(
+                            name, kind, list(info["sizes"]), info["dtype"], info["source"], info["p0"], info["p1"],
+                            [tuple(e) for e in info["epilogue"]],
+                            base64.b64encode(info["const_bytes"]).decode(), "", list(info["rng_numels"]),
+                            bool(info["requires_grad"])))
+                        continue
+                    # not fusible (or already real): evaluate now and store by value
+                    real = materialize_tensor(t) if info["deferred"] else t
+                    nbytes = real.numel() * real.element_size()
+                    if nbytes > max_embedded_bytes:
+                        raise ValueError(
+                            f"'{name}' ({nbytes} bytes) has an initialisation program the planner cannot fold "
+                            f"(first unfusable op: {info['first_unfusable_op'] or 'n/a'}) and is too large to embed")
+                    raw = real.detach().cpu().contiguous().reshape(-1).view(torch.uint8).numpy().tobytes()
+                    entries.append(PlanEntry(name, kind, list(real.shape), _DTYPE_NAMES[real.dtype],
+                                             "value", value=base64.b64encode(raw).decode(),
+                                             requires_grad=bool(real.requires_grad)))
+
+        visit(module, "")
+        return cls(entries)
+
+    # --------------------------------------------------------------------------------------- io
+    def save(self, path: str) -> None:
+        with open(path, "w") as f:
+            json.dump({"format": FORMAT, "entries": [e.__dict__ for e in self.entries]}, f)
+
+    @classmethod
+    def load(cls, path: str) -> "InitPlan":
+        with open(path) as f:
+            doc = json.load(f)
+        if doc.get("format") != FORMAT:
+            raise ValueError(f"{path}: not an {FORMAT} file")
+        entries = []
+        for d in doc["entries"]:
+            d["epilogue"] = [tuple(e) for e in d.get("epilogue", [])]
+            entries.append(PlanEntry(**d))
+        return cls(entries)
+
+    @property
+    def num_params(self) -> int:
+        n = 0
+        for e in self.entries:
+            if e.kind == "param" and e.source != "alias":
+                k = 1
+                for s in e.sizes:
+                    k *= s
+                n += k
+        return n
+
+    # ------------------------------------------------------------------------------ materialise
+    def materialize(self, device="cuda", shard: Optional[Tuple[int, int]] = None,
+                    generator: Optional[torch.Generator] = None,
+                    into: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """Builds every tensor of the plan on `device` through libtdx_init and returns
+        ``{name: tensor}`` (parameters as ``torch.nn.Parameter``).  Consumes the CUDA generator
+        exactly like ``materialize_module`` would.
+
+        `into`: write into caller-owned CUDA buffers instead of allocating (``{name: tensor}``; each
+        must be contiguous, of the plan's dtype and hold at least this rank's elements).  This is
+        the FSDP hand-off of SURVEY 8f.1: after ``fully_shard(meta_model)`` / ``to_empty`` the
+        local shards FSDP owns are initialised in place, no unsharded tensor, no copy
+        (:func:`init_sharded_module`).
+        """
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise ValueError("InitPlan.materialize drives the CUDA kernels; there is no CPU path")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        gen = generator or torch.cuda.default_generators[device.index]
+        seed, offset = gen.initial_seed(), gen.get_offset()
+        out: Dict[str, torch.Tensor] = {}
+        descs = []
+        with torch.cuda.device(device):
+            for e in self.entries:
+                if e.source == "alias":
+                    out[e.name] = out[e.alias_of]
+                    continue
+                dtype = _DTYPES[e.dtype]
+                target = None if into is None else into.get(e.name)
+                if e.source == "value":
+                    raw = torch.frombuffer(bytearray(base64.b64decode(e.value)), dtype=torch.uint8)
+                    t = raw.view(dtype).reshape(e.sizes).to(device)
+                    if target is not None:
+                        target.copy_(t)
+                        t = target
+                    out[e.name] = t if target is not None else _wrap(t, e)
+                    continue
+                sizes, begin = list(e.sizes), 0
+                numel = 1
+                for s in sizes:
+                    numel *= s
+                count = numel
+                if shard is not None and shard[1] > 1 and e.kind == "param" and sizes:
+                    rank, world = shard
+                    d0 = sizes[0]
+                    inner = numel // d0 if d0 else 0
+                    per = -(-d0 // world)
+                    start = min(d0, rank * per)
+                    rows = min(per, d0 - start)
+                    begin, count, sizes = start * inner, rows * inner, [rows] + sizes[1:]
+                if target is not None:
+                    if not (target.is_cuda and target.is_contiguous() and target.dtype == dtype
+                            and target.numel() >= count):
+                        raise ValueError(f"'{e.name}': `into` buffer must be a contiguous CUDA {dtype} tensor "
+                                         f"with at least {count} elements")
+                    t = target
+                else:
+                    t = torch.empty(sizes, dtype=dtype, device=device)
+                # every RNG pass on the chain takes its slice of the stream; the last one is live
+                live_offset = offset
+                for n in e.rng_numels:
+                    live_offset = offset
+                    offset += offset_increment(n)
+                if e.source != "uninit" and count > 0:
+                    if e.source == "const":
+                        isz = t.element_size()
+                        descs.append(_cabi.make_desc(
+                            t.data_ptr(), dtype=_RAW[isz], src=_cabi.TDX_SRC_CONST, elem_count=count,
+                            fill_bits=int.from_bytes(base64.b64decode(e.const_bytes), "little"), fill_itemsize=isz))
+                    else:
+                        descs.append(_cabi.make_desc(
+                            t.data_ptr(), dtype=_TDX_DTYPE[dtype],
+                            src=_cabi.TDX_SRC_UNIFORM if e.source == "uniform" else _cabi.TDX_SRC_NORMAL,
+                            elem_begin=begin, elem_count=count, seed=seed, offset=live_offset, p0=e.p0, p1=e.p1,
+                            epi=e.epilogue))
+                out[e.name] = t if target is not None else _wrap(t, e)
+            if descs:
+                lib = _cabi.load()
+                ws_bytes = lib.tdx_init_workspace_bytes(len(descs))
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+                _cabi.launch(descs, ws.data_ptr(), ws_bytes, torch.cuda.current_stream(device).cuda_stream)
+            gen.set_offset(offset)
+        return out
+
+    def apply(self, module: Module, **kw) -> None:
+        """Materialises the plan into `module` (e.g. one built under ``torch.device("meta")``):
+        every parameter / buffer named in the plan is replaced."""
+        tensors = self.materialize(**kw)
+        for name, t in tensors.items():
+            owner, _, key = name.rpartition(".")
+            mod = module.get_submodule(owner) if owner else module
+            group = mod._parameters if key in mod._parameters else mod._buffers
+            group[key] = t
+
+
+def _wrap(t: torch.Tensor, e: PlanEntry) -> torch.Tensor:
+    if e.kind == "param":
+        return torch.nn.Parameter(t, requires_grad=e.requires_grad)
+    return t
+
+
+def init_sharded_module(module: Module, plan: InitPlan, rank: int, world: int, device="cuda") -> None:
+    """FSDP2 hand-off: `module` has been through ``fully_shard`` (its parameters are
+    ``DTensor``s sharded on dim 0 over `world` ranks, e.g. built on the meta device and
+    ``to_empty(device=...)``'d).  Every rank fills the local shards FSDP owns, in place, with its
+    slice of the plan -- no full tensor, no chunk/clone.  All ranks must hold the same generator
+    state (:func:`torchdistx_b200.parallel.sync_rng`)."""
+    into: Dict[str, torch.Tensor] = {}
+    for name, t in list(module.named_parameters()) + list(module.named_buffers()):
+        local = t.to_local() if hasattr(t, "to_local") else t
+        if hasattr(local, "data"):
+            local = local.data
+        into[name] = local
+    with torch.no_grad():
+        plan.materialize(device=device, shard=(rank, world), into=into)
