@@ -37,10 +37,13 @@
 
 namespace tdx {
 
+#ifndef TDX_VECS
+#define TDX_VECS 4
+#endif
 constexpr int kThreads = 256;
-constexpr int kVecsPerThread = 4;
+constexpr int kVecsPerThread = TDX_VECS;
 constexpr int kTileVecs = kThreads * kVecsPerThread;  // 1024 x 16 B = 16 KiB per tile
-constexpr int kTilesPerChunk = 16;                    // 256 KiB per work grab
+constexpr int kTilesPerChunk = 64 / TDX_VECS;          // 256 KiB per work grab
 
 // ---------------------------------------------------------------------------------------------
 // small device helpers
@@ -505,12 +508,12 @@ struct GroupArgs {
 };
 
 // Calls f(desc_index, first_tile_in_desc, n_tiles) for runs of consecutive tiles of one descriptor.
-template <int TILE_VECS = kTileVecs, class F>
+template <int TILES_PER_CHUNK = kTilesPerChunk, class F>
 __device__ __forceinline__ void for_each_tile_run(const GroupArgs& g, F&& f) {
-  // A work grab is 16 tiles: 256 KiB for the 256-thread kernels, 1 MiB for the 1024-thread table
-  // kernel.  (Measured: 256 KiB grabs for the table kernel cost 14 % -- two 32-warp barriers and an
-  // atomic per grab are not free.)
-  (void)TILE_VECS;
+  // A work grab is 256 KiB for the 256-thread kernels and 1 MiB for the 1024-thread table kernel.
+  // (Measured: 256 KiB grabs for the table kernel cost 14 % -- two 32-warp barriers and an atomic
+  // per grab are not free.)
+  constexpr int kTilesPerChunk = TILES_PER_CHUNK;
   __shared__ unsigned int s_chunk;
   for (;;) {
     __syncthreads();
@@ -535,12 +538,16 @@ __device__ __forceinline__ void for_each_tile_run(const GroupArgs& g, F&& f) {
   }
 }
 
-template <class Gen>
+// VECS = 16-byte vectors per thread and tile.  Measured (r1 sweep, 4 GiB): the fp32 generators gain
+// 3-5 % from 16 independent vectors in flight, the 16-bit ones (more registers per vector) lose.
+template <class Gen, int VECS = kVecsPerThread>
 __global__ void __launch_bounds__(kThreads) tdx_rng_kernel(const GroupArgs g) {
   using Out = typename Gen::OutT;
   using T = OutTraits<Out>;
   constexpr int EPV = Gen::kEpv;
-  for_each_tile_run(g, [&](uint32_t di, unsigned long long tile0, unsigned long long ntiles) {
+  constexpr int kVecsPerThread = VECS;
+  constexpr int kTileVecs = kThreads * VECS;
+  for_each_tile_run<(kThreads * tdx::kVecsPerThread * tdx::kTilesPerChunk) / (kThreads * VECS)>(g, [&](uint32_t di, unsigned long long tile0, unsigned long long ntiles) {
     const TdxInitDesc& d = g.descs[di];
     const typename Gen::Params P = Gen::setup(d);
     const uint64_t begin = d.elem_begin, count = d.elem_count;
@@ -631,9 +638,16 @@ __global__ void __launch_bounds__(kThreads) tdx_fill_kernel(const GroupArgs g) {
 #ifndef TDX_LUT_WORDS
 #define TDX_LUT_WORDS 4
 #endif
-constexpr int kLutThreads = 1024;
-constexpr int kLutVecsPerThread = 4;
-constexpr int kLutTileVecs = kLutThreads * kLutVecsPerThread;  // 64 KiB per tile
+#ifndef TDX_LUT_THREADS
+#define TDX_LUT_THREADS 1024
+#endif
+#ifndef TDX_LUT_VECS
+#define TDX_LUT_VECS 16
+#endif
+constexpr int kLutThreads = TDX_LUT_THREADS;
+constexpr int kLutVecsPerThread = TDX_LUT_VECS;
+constexpr int kLutTileVecs = kLutThreads * kLutVecsPerThread;  // bytes per tile = 16 x this
+constexpr int kLutTilesPerChunk = (1 << 20) / (kLutTileVecs * 16) > 0 ? (1 << 20) / (kLutTileVecs * 16) : 1;
 constexpr uint32_t kLutBytes = 65536u * 2u;
 constexpr unsigned short kLutSentinel = 0xffffu;  // a NaN pattern in bf16 and fp16: never a value
 
@@ -657,7 +671,7 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_normal16_lut_kernel(const 
   using T = OutTraits<Out>;
   extern __shared__ __align__(16) unsigned short lut[];
   float have_mean = 0.f, have_std = -1.f;  // table contents (uniform across the CTA)
-  for_each_tile_run<kLutTileVecs>(g, [&](uint32_t di, unsigned long long tile0, unsigned long long ntiles) {
+  for_each_tile_run<kLutTilesPerChunk>(g, [&](uint32_t di, unsigned long long tile0, unsigned long long ntiles) {
     const TdxInitDesc& d = g.descs[di];
     const typename Gen::Params P = Gen::setup(d);
     if (P.mean != have_mean || P.std != have_std) {
@@ -749,14 +763,19 @@ struct Family {
   int tile_vecs = kTileVecs;
   int dyn_smem = 0;
   bool lut = false;
+  int tiles_per_chunk = kTilesPerChunk;
 };
 
 #define TDX_FAM(src, dt, algo, rounds, epi, ...) \
   { src, dt, algo, rounds, epi, static_cast<KernelFn>(tdx_rng_kernel<__VA_ARGS__>), #__VA_ARGS__ }
+// fp32 generators: 16 vectors per thread (tile = 64 KiB, 4 tiles per 256 KiB grab)
+#define TDX_FAM_V16(src, dt, algo, rounds, epi, ...)                                               \
+  { src, dt, algo, rounds, epi, static_cast<KernelFn>(tdx_rng_kernel<__VA_ARGS__, 16>), #__VA_ARGS__, \
+    kThreads, kThreads * 16, 0, false, (kVecsPerThread * kTilesPerChunk) / 16 }
 #define TDX_FAM_LUT(dt, rounds, ...)                                                             \
   { TDX_SRC_NORMAL, dt, TDX_ALGO_ICDF16, rounds, 0,                                              \
     static_cast<KernelFn>(tdx_normal16_lut_kernel<__VA_ARGS__>), "lut<" #__VA_ARGS__ ">",        \
-    kLutThreads, kLutTileVecs, static_cast<int>(kLutBytes), true }
+    kLutThreads, kLutTileVecs, static_cast<int>(kLutBytes), true, kLutTilesPerChunk }
 
 using bf16 = __nv_bfloat16;
 using f16 = __half;
@@ -764,13 +783,13 @@ using f16 = __half;
 static const Family kFamilies[] = {
     {TDX_SRC_CONST, -1, 0, 0, 0, tdx_fill_kernel, "fill"},
     // shipped defaults
-    TDX_FAM(TDX_SRC_UNIFORM, TDX_F32, 0, 10, 0, GenUniform32<10, false>),
+    TDX_FAM_V16(TDX_SRC_UNIFORM, TDX_F32, 0, 10, 0, GenUniform32<10, false>),
     TDX_FAM(TDX_SRC_UNIFORM, TDX_F32, 0, 10, 1, GenUniform32<10, true>),
     TDX_FAM(TDX_SRC_UNIFORM, TDX_BF16, 0, 10, 0, GenUniform16<bf16, 10, false>),
     TDX_FAM(TDX_SRC_UNIFORM, TDX_BF16, 0, 10, 1, GenUniform16<bf16, 10, true>),
     TDX_FAM(TDX_SRC_UNIFORM, TDX_F16, 0, 10, 0, GenUniform16<f16, 10, false>),
     TDX_FAM(TDX_SRC_UNIFORM, TDX_F16, 0, 10, 1, GenUniform16<f16, 10, true>),
-    TDX_FAM(TDX_SRC_NORMAL, TDX_F32, TDX_ALGO_BM32, 10, 0, GenNormalBM32<float, 10, false>),
+    TDX_FAM_V16(TDX_SRC_NORMAL, TDX_F32, TDX_ALGO_BM32, 10, 0, GenNormalBM32<float, 10, false>),
     TDX_FAM(TDX_SRC_NORMAL, TDX_F32, TDX_ALGO_BM32, 10, 1, GenNormalBM32<float, 10, true>),
     TDX_FAM(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_ICDF16, 10, 0, GenNormalICDF16<bf16, 10, false>),
     TDX_FAM(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_ICDF16, 10, 1, GenNormalICDF16<bf16, 10, true>),
@@ -1032,7 +1051,8 @@ int launch_groups(const PlanHeader& hdr, void* workspace, cudaStream_t stream) {
     a.total_tiles = G.total_tiles;
     a.counter = &dev_hdr->counters[gi];
     a.n_desc = G.n_desc;
-    const unsigned long long chunks = (G.total_tiles + kTilesPerChunk - 1) / kTilesPerChunk;
+    const int tpc = kFamilies[G.family].tiles_per_chunk;
+    const unsigned long long chunks = (G.total_tiles + tpc - 1) / tpc;
     const unsigned long long resident =
         static_cast<unsigned long long>(info->sm_count) * info->blocks_per_sm[G.family];
     const unsigned int grid = static_cast<unsigned int>(std::min(chunks, resident));

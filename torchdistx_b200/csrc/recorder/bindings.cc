@@ -196,7 +196,6 @@ py::dict py_last_stats() {
   d["plan_us"] = s.plan_us;
   d["launch_us"] = s.launch_us;
   d["wrap_us"] = s.wrap_us;
-  d["plan_phases_us"] = tdx::last_subtimers();
   return d;
 }
 

@@ -30,7 +30,6 @@ using torch::jit::Stack;
 namespace {
 
 thread_local MaterializeStats g_stats;
-thread_local double g_sub[6] = {0, 0, 0, 0, 0, 0};  // eval, alloc, rng, desc, mark, alias (us)
 thread_local std::vector<TdxInitDesc> g_last_descs;  // what the last materialize call launched
 
 // Never record / fake anything we do while materialising.
@@ -679,9 +678,7 @@ struct Engine {
     const bool sharded = opts.shard && opts.shard->world > 1 && !vi.sizes.empty();
     if (sharded && !vi.covers_storage) return false;
 
-    double tq = now_us();
     Sym st = eval_storage(tape, S, static_cast<uint32_t>(tape.ops.size()));
-    g_sub[0] += now_us() - tq;
     if (st.opaque()) return false;
     const size_t isz = c10::elementSize(st.dtype);
     if (isz == 0 || si.nbytes % isz) return false;
@@ -708,10 +705,7 @@ struct Engine {
       batch.device = dev;
     }
     // straight to the caching allocator: no dispatcher round trip per tensor
-    tq = now_us();
     at::Tensor base = at::detail::empty_cuda(g.sizes, st.dtype, dev, std::nullopt);
-    g_sub[1] += now_us() - tq;
-    tq = now_us();
 
     // every RNG pass on the chain consumes its slice of the stream, live or dead
     for (uint32_t r : st.rng_chain) {
@@ -721,8 +715,6 @@ struct Engine {
       }
     }
 
-    g_sub[2] += now_us() - tq;
-    tq = now_us();
     if (st.src != Sym::Uninit && g.count > 0) {
       TdxInitDesc d;
       std::memset(&d, 0, sizeof(d));
@@ -757,8 +749,6 @@ struct Engine {
     }
     const int64_t submitted = (st.src != Sym::Uninit) ? g.count * static_cast<int64_t>(isz) : 0;
 
-    g_sub[3] += now_us() - tq;
-    tq = now_us();
     si.base = base;
     si.fused_done = true;
     for (uint32_t oi : si.touching_ops) {
@@ -771,7 +761,6 @@ struct Engine {
       }
     }
     g_stats.fused_tensors++;
-    g_sub[4] += now_us() - tq;
     batch.note(submitted);  // may submit what has accumulated so far
     return true;
   }
@@ -781,12 +770,7 @@ struct Engine {
     ValueInfo& vi = tape.values[v];
     if (vi.real.defined()) return vi.real;
     if (tape.storages[vi.storage].fused_done) return real_of(tape, v);
-    if (try_fused(tape, v)) {
-      const double tq = now_us();
-      at::Tensor r = real_of(tape, v);
-      g_sub[5] += now_us() - tq;
-      return r;
-    }
+    if (try_fused(tape, v)) return real_of(tape, v);
 
     // generic replay, in recorded order, of everything that determines this storage
     batch.flush();
@@ -825,7 +809,6 @@ std::vector<at::Tensor> materialize_many(const std::vector<at::Tensor>& fakes,
                                          const std::vector<uint8_t>* shard_mask) {
   g_stats = MaterializeStats{};
   g_last_descs.clear();
-  for (double& x : g_sub) x = 0;
   const double t_begin = now_us();
   std::vector<at::Tensor> out;
   out.reserve(fakes.size());
@@ -939,8 +922,6 @@ std::vector<std::string> storage_history(const at::Tensor& fake) {
 }
 
 MaterializeStats last_stats() { return g_stats; }
-
-std::vector<double> last_subtimers() { return std::vector<double>(g_sub, g_sub + 6); }
 
 std::string last_descriptors() {
   return std::string(reinterpret_cast<const char*>(g_last_descs.data()),

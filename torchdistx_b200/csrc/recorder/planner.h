@@ -64,7 +64,6 @@ std::vector<at::Tensor> materialize_many(const std::vector<at::Tensor>& fakes,
 
 MaterializeStats last_stats();
 void add_wrap_time(double us);
-std::vector<double> last_subtimers();  // planner phases (eval, alloc, rng, desc, mark, alias), us
 // The TdxInitDesc table (raw bytes) the last materialize call on this thread submitted; lets
 // benchmarks and tests re-launch / inspect exactly what the engine ran.
 std::string last_descriptors();
