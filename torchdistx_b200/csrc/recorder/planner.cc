@@ -405,8 +405,9 @@ struct Batch {
   static int64_t flush_start() {
     static const int64_t v = [] {
       const char* e = getenv("TDX_FLUSH_BYTES");  // 0 = submit once, at the end
-      // measured on Llama-3-8B (profiles/r1_e2e_submission_sweep.txt): 1 GiB start beats 128 MiB / 4 GiB
-      return e ? static_cast<int64_t>(strtoll(e, nullptr, 10)) : (int64_t{1} << 30);
+      // measured on Llama-3-8B (profiles/r1_e2e_submission_sweep.txt): 1 GiB start beats 128 MiB and
+      // 4 GiB on one GPU; 256 MiB keeps the first launch early when a rank only owns 1/8 of the model
+      return e ? static_cast<int64_t>(strtoll(e, nullptr, 10)) : (int64_t{256} << 20);
     }();
     return v;
   }
