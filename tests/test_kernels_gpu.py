@@ -213,3 +213,48 @@ def test_table_driven_normal_is_bit_identical_to_the_direct_kernel(dtype):
                C.make_desc(b.data_ptr(), dtype=dtype, src=C.TDX_SRC_NORMAL, elem_begin=cut, elem_count=n - cut, seed=5,
                            offset=8, p1=0.02)], [a, b])
     assert torch.equal(torch.cat([a, b]).view(torch.int16), full.view(torch.int16))
+
+
+@pytest.mark.parametrize("dtype,src", [(C.TDX_BF16, C.TDX_SRC_NORMAL), (C.TDX_F32, C.TDX_SRC_UNIFORM)])
+def test_beyond_2_to_32_elements(dtype, src):
+    """BASELINE config #5 reaches 16 GB tensors: global element indices above 2^32 must index the
+    Philox stream with 64 bits.  A shard that starts just below the 2^32 boundary of a (virtual)
+    2^33-element tensor is compared with the oracle element by element, and with the same region
+    produced inside a larger launch."""
+    base = (1 << 32) - 1000  # global index of the first element this launch writes
+    n = (1 << 21) + 7        # crosses 2^32 (and the table kernel's size threshold for bf16)
+    buf = torch.zeros(n, dtype=TORCH_DT[dtype], device="cuda")
+    d = C.make_desc(buf.data_ptr(), dtype=dtype, src=src, elem_begin=base, elem_count=n, seed=3, offset=16,
+                    p0=-1.0 if src == C.TDX_SRC_UNIFORM else 0.0, p1=1.0)
+    run_descs([d], [buf])
+    got = gpu_bits(buf, dtype)
+    for lo, cnt in ((0, 4096), (990, 64), (n - 4096, 4096)):  # around the boundary and at both ends
+        piece = C.make_desc(0, dtype=dtype, src=src, elem_begin=base + lo, elem_count=cnt, seed=3, offset=16,
+                            p0=-1.0 if src == C.TDX_SRC_UNIFORM else 0.0, p1=1.0)
+        diff = got[lo:lo + cnt].astype(np.int64) - O.generate(piece).astype(np.int64)
+        assert np.abs(diff).max() <= (0 if src == C.TDX_SRC_UNIFORM else 1)
+    # the stream is not periodic in 2^32: the same offsets 2^32 elements earlier differ
+    early = torch.zeros(4096, dtype=TORCH_DT[dtype], device="cuda")
+    run_descs([C.make_desc(early.data_ptr(), dtype=dtype, src=src, elem_begin=base - (1 << 32) + 1000, elem_count=4096,
+                           seed=3, offset=16, p0=-1.0 if src == C.TDX_SRC_UNIFORM else 0.0, p1=1.0)], [early])
+    assert (gpu_bits(early, dtype) != got[1000:1000 + 4096]).mean() > 0.9
+
+
+def test_sixteen_gigabyte_tensor_statistics():
+    """The largest sweep point: one 16 GiB bf16 normal tensor (8.6 G elements), written by one launch."""
+    n = 1 << 33
+    free, _ = torch.cuda.mem_get_info()
+    if free < (n * 2) + (4 << 30):
+        pytest.skip("not enough free HBM")
+    buf = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+    d = C.make_desc(buf.data_ptr(), dtype=C.TDX_BF16, src=C.TDX_SRC_NORMAL, elem_count=n, seed=11, offset=0, p0=0.0, p1=0.02)
+    run_descs([d], [buf])
+    for lo in (0, (1 << 32) - (1 << 20), n - (1 << 22)):
+        x = buf[lo:lo + (1 << 22)].float()
+        assert abs(x.mean().item()) < 5 * 0.02 / 2048 and abs(x.std().item() / 0.02 - 1) < 5e-3
+    tail = C.make_desc(0, dtype=C.TDX_BF16, src=C.TDX_SRC_NORMAL, elem_begin=n - 4096, elem_count=4096, seed=11,
+                       offset=0, p0=0.0, p1=0.02)
+    diff = gpu_bits(buf[n - 4096:], C.TDX_BF16).astype(np.int64) - O.generate(tail).astype(np.int64)
+    assert np.abs(diff).max() <= 1
+    del buf
+    torch.cuda.empty_cache()
