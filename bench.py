@@ -15,7 +15,8 @@ every parameter and buffer written to HBM once.  Recording (Python module constr
            inside the timed region.
   N > 1  : one model, dim-0 sharded across the ranks (each rank writes only its rows; the
            unsharded tensors never exist) => "scaling": "strong".  The only collective is the
-           16-byte seed/offset broadcast (torchdistx_b200.parallel.sync_rng), outside the kernels.
+           16-byte seed/offset broadcast (torchdistx_b200.parallel.sync_rng), once per step inside
+           the e2e timed region; there is none in or between the kernels.
   --impl reference : the reference's own CPU materialize (oracle/_ref = pytorch/torchdistx
            compiled from /root/reference) on a bounded sample of the same model, on the host cores.
 """
@@ -235,6 +236,8 @@ def run_ours(a):
     last_name = list(dict(fakes[0].named_parameters()))[-1]  # looked up outside the timed region
 
     def step(m):
+        if world > 1:
+            parallel.sync_rng(dev)  # the path's one collective, once per materialize_module (16 B)
         materialize_module(m, device=dev, shard=shard)
         last = m.get_parameter(last_name)
         probe.copy_(last.detach().flatten()[:32], non_blocking=True)  # D2H read of the step's result
