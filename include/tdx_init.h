@@ -76,6 +76,9 @@ enum {
   TDX_ALGO_DEFAULT = 0,
   TDX_ALGO_ICDF16 = 1, /* 16-bit dtypes: inverse-CDF on 16 random bits/element + tail refinement */
   TDX_ALGO_BM32 = 2,   /* Box-Muller on 32 random bits/element (f32 default) */
+  TDX_ALGO_WIDE32 = 2, /* same value: for 16-bit outputs of EITHER source, use the fp32 stream and
+                        * arithmetic (EPB = 4) and round once at the store -- the meaning of
+                        * `fp32_tensor.uniform_()/normal_()` followed by `.to(bf16/fp16)` */
   TDX_ALGO_BM16 = 3,   /* experimental: Box-Muller on 16-bit pairs, no tail refinement */
   TDX_ALGO_R7 = 0x10,  /* OR-able flag, experimental: Philox4x32-7 instead of -10 */
   TDX_ALGO_NOLUT = 0x20, /* OR-able flag: never use the shared-memory-table twin of ICDF16
@@ -145,7 +148,7 @@ TDX_C_API int tdx_init_launch(const TdxInitDesc* descs, int n, void* workspace,
  * kernels (plus one 4-byte memset per family for the work counter).
  */
 typedef struct TdxPlan {
-  uint64_t opaque[128]; /* host-side copy of the plan header; owned by the caller */
+  uint64_t opaque[256]; /* host-side copy of the plan header; owned by the caller */
 } TdxPlan;
 TDX_C_API int tdx_plan_upload(const TdxInitDesc* descs, int n, void* workspace,
                               size_t workspace_bytes, void* stream, TdxPlan* plan);

@@ -81,6 +81,26 @@ def clones():
     return Clones()
 
 
+class CastVariant(nn.Module):
+    """The `.to(dtype)` idiom: initialised in fp32, converted afterwards (Module.to rebinds
+    `param.data`), plus a tensor and its cast both kept alive."""
+
+    def __init__(self):
+        super().__init__()
+        self.body = nn.Sequential(nn.Linear(48, 40), nn.LayerNorm(40), nn.Embedding(32, 24)).to(torch.bfloat16)
+        self.head = nn.Linear(40, 16)
+        nn.init.trunc_normal_(self.head.weight, std=0.02, a=-0.05, b=0.05)
+        self.head.half()
+        self.a = nn.Parameter(torch.randn(64, 33) * 0.02)
+        self.b = nn.Parameter(self.a.detach().to(torch.bfloat16))
+        self.u = nn.Parameter(torch.empty(50, 20).uniform_(-0.3, 0.1))
+        self.v = nn.Parameter(self.u.detach().to(torch.float16))
+
+
+def cast_variant():
+    return CastVariant()
+
+
 def mlp_stack():
     return nn.Sequential(nn.Linear(64, 256), nn.GELU(), nn.Linear(256, 64), nn.LayerNorm(64))
 
@@ -93,6 +113,7 @@ CASES = {
     "mlp_stack": mlp_stack,
     "torch_transformer": torch_transformer,
     "clones": clones,
+    "cast_variant": cast_variant,
 }
 
 DTYPES = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}

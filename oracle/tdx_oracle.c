@@ -178,6 +178,7 @@ static void box_muller32(uint32_t x, uint32_t y, float* n0, float* n1) {
 static int resolve_algo(const TdxInitDesc* d) {
   const int a = d->algo & 0x0f;
   if (d->src == TDX_SRC_NORMAL) return a ? a : (d->dtype == TDX_F32 ? TDX_ALGO_BM32 : TDX_ALGO_ICDF16);
+  if (d->src == TDX_SRC_UNIFORM && d->dtype != TDX_F32 && a == TDX_ALGO_WIDE32) return TDX_ALGO_WIDE32;
   return 0;
 }
 
@@ -189,8 +190,10 @@ static float element(const TdxInitDesc* d, uint64_t g) {
   float v = 0.f;
   if (d->src == TDX_SRC_UNIFORM) {
     const float from = (float)d->p0, to = (float)d->p1;
-    const float to_prev = to > from ? prev_of(to, d->dtype) : to;
-    if (d->dtype == TDX_F32) {
+    /* the wide form of a 16-bit output keeps fp32 bounds (kernel: GenUniform32<Out>) */
+    const int wide = d->dtype == TDX_F32 || algo == TDX_ALGO_WIDE32;
+    const float to_prev = to > from ? prev_of(to, wide ? TDX_F32 : d->dtype) : to;
+    if (wide) {
       block_of(d, g / 4, 0, rounds, w);
       const float k = (float)(w[g % 4] >> 8);
       v = fminf(fmaf(k, (to - from) * 5.9604644775390625e-08f, from), to_prev);
@@ -247,9 +250,9 @@ int tdx_oracle_generate(const TdxInitDesc* d, void* out) {
   if (d->dtype != TDX_F32 && d->dtype != TDX_BF16 && d->dtype != TDX_F16) return -1;
   {
     const int algo = resolve_algo(d);
-    if (d->src == TDX_SRC_NORMAL && !(algo == TDX_ALGO_BM32 && d->dtype == TDX_F32) &&
-        !(algo == TDX_ALGO_ICDF16 && d->dtype != TDX_F32))
+    if (d->src == TDX_SRC_NORMAL && algo != TDX_ALGO_BM32 && !(algo == TDX_ALGO_ICDF16 && d->dtype != TDX_F32))
       return -1; /* experimental sweep variants are not part of the specification */
+    if (d->algo & TDX_ALGO_R7) return -1;
   }
   for (uint64_t i = 0; i < d->elem_count; ++i) {
     const float v = element(d, d->elem_begin + i);

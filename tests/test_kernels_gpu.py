@@ -258,3 +258,28 @@ def test_sixteen_gigabyte_tensor_statistics():
     assert np.abs(diff).max() <= 1
     del buf
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("dtype", [C.TDX_BF16, C.TDX_F16])
+@pytest.mark.parametrize("src", [C.TDX_SRC_UNIFORM, C.TDX_SRC_NORMAL])
+def test_wide_16bit_outputs_are_the_rounded_fp32_tensor(dtype, src):
+    """TDX_ALGO_WIDE32: a 16-bit tensor generated with the fp32 stream and arithmetic equals the
+    fp32 tensor of the same (seed, offset) cast to the dtype -- with and without fp32 epilogue
+    steps -- and matches the oracle."""
+    n = 100003
+    kw = dict(elem_count=n, seed=21, offset=64, p0=-0.25 if src == C.TDX_SRC_UNIFORM else 0.5, p1=0.75)
+    for epi32, epi16 in (((), ()), (((C.TDX_EPI_MUL, 0.02), (C.TDX_EPI_ADD, 1.0)),
+                                  ((C.TDX_EPI_MUL | C.TDX_EPI_NOROUND, 0.02), (C.TDX_EPI_ADD | C.TDX_EPI_NOROUND, 1.0)))):
+        f32 = torch.zeros(n, dtype=torch.float32, device="cuda")
+        t16 = torch.zeros(n, dtype=TORCH_DT[dtype], device="cuda")
+        d32 = C.make_desc(f32.data_ptr(), dtype=C.TDX_F32, src=src, epi=epi32, **kw)
+        d16 = C.make_desc(t16.data_ptr(), dtype=dtype, src=src, algo=C.TDX_ALGO_WIDE32, epi=epi16,
+                          flags=C.TDX_FLAG_SRC_NOROUND, **kw)
+        run_descs([d32, d16], [f32, t16])
+        assert torch.equal(t16, f32.to(TORCH_DT[dtype]))
+        exp = O.generate(d16)
+        diff = gpu_bits(t16, dtype).astype(np.int64) - exp.astype(np.int64)
+        if src == C.TDX_SRC_UNIFORM:
+            assert not diff.any()
+        else:
+            assert np.abs(diff).max() <= 1 and (diff != 0).mean() < 0.002

@@ -32,7 +32,7 @@ from torchdistx_b200.fake import is_fake
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CASES = [("init_zoo", "fp32"), ("init_zoo", "bf16"), ("tiny_llama", "fp32"), ("tiny_llama", "bf16"),
-         ("tiny_gpt2", "fp32"), ("mlp_stack", "fp32"), ("torch_transformer", "fp32"), ("clones", "fp32")]
+         ("tiny_gpt2", "fp32"), ("mlp_stack", "fp32"), ("torch_transformer", "fp32"), ("clones", "fp32"), ("cast_variant", "fp32")]
 
 
 @pytest.fixture(scope="module")
@@ -256,3 +256,16 @@ def test_clones_of_rng_tensors_are_bit_identical_to_their_source():
     assert torch.equal(m.a, m.b) and torch.equal(m.a, m.c)
     assert torch.equal(m.d, m.a * 2.0)
     assert m.a.data_ptr() != m.b.data_ptr()
+
+
+def test_cast_of_an_rng_tensor_equals_the_cast_of_its_materialised_source():
+    """`.to(bf16)` / `.half()` after an fp32 init is fused with the fp32 stream (TDX_ALGO_WIDE32):
+    the 16-bit tensor IS the rounded fp32 tensor, bit for bit, when both are kept."""
+    m = build_on_cuda("cast_variant", "fp32", seed=4)
+    st = last_materialize_stats()
+    assert st["generic_ops"] == 0 and st["fused_tensors"] == len(list(m.parameters()))
+    assert m.b.dtype == torch.bfloat16 and torch.equal(m.b, m.a.to(torch.bfloat16))
+    assert m.v.dtype == torch.float16 and torch.equal(m.v, m.u.to(torch.float16))
+    assert m.body[0].weight.dtype == torch.bfloat16 and m.head.weight.dtype == torch.float16
+    w = m.head.weight.float()
+    assert w.min() >= -0.05 and w.max() <= 0.05 and 0.012 < w.std() < 0.025

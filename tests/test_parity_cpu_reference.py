@@ -22,7 +22,7 @@ pytestmark = pytest.mark.skipif(
 CASES = [
     ("linear128", "fp32"), ("init_zoo", "fp32"), ("init_zoo", "bf16"), ("mlp_stack", "fp32"),
     ("tiny_llama", "fp32"), ("tiny_llama", "bf16"), ("tiny_gpt2", "fp32"),
-    ("torch_transformer", "fp32"), ("clones", "fp32"),
+    ("torch_transformer", "fp32"), ("clones", "fp32"), ("cast_variant", "fp32"),
 ]
 SEED = 5
 

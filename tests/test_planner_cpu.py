@@ -88,3 +88,14 @@ def test_mid_history_reader_forces_generic_replay():
     torch.manual_seed(0)
     e = build()
     assert torch.equal(m.w, e.w) and torch.equal(m.s, e.s)
+
+
+def test_to_dtype_variant_is_fused_with_the_fp32_stream():
+    r = report(lambda: cases.build("cast_variant", "fp32"))
+    assert fusible_fraction(r) == 1.0
+    w = r["body.0.weight"]  # Linear(fp32) -> Module.to(bf16): uniform_ -> _to_copy -> set_data
+    assert (w["source"], w["dtype"], w["wide"]) == ("uniform", "BFloat16", True)
+    h = r["head.weight"]  # kaiming (dead) -> trunc_normal_ chain -> half()
+    assert (h["source"], h["dtype"], h["wide"], h["n_epilogue"], h["rng_ops"]) == ("uniform", "Half", True, 4, 2)
+    assert r["body.1.weight"]["source"] == "const" and r["body.1.weight"]["dtype"] == "BFloat16"
+    assert r["a"]["wide"] is False and r["b"]["wide"] is True and r["b"]["n_epilogue"] == 1

@@ -23,10 +23,13 @@ TDX_F32, TDX_BF16, TDX_F16 = 0, 1, 2
 TDX_RAW8, TDX_RAW16, TDX_RAW32, TDX_RAW64 = 8, 9, 10, 11
 TDX_SRC_CONST, TDX_SRC_UNIFORM, TDX_SRC_NORMAL = 0, 1, 2
 TDX_ALGO_DEFAULT, TDX_ALGO_ICDF16, TDX_ALGO_BM32, TDX_ALGO_BM16 = 0, 1, 2, 3
+TDX_ALGO_WIDE32 = 2
 TDX_ALGO_R7 = 0x10
 TDX_ALGO_NOLUT = 0x20
 TDX_EPI_MUL, TDX_EPI_ADD, TDX_EPI_ERFINV, TDX_EPI_CLAMP = 1, 2, 3, 4
 TDX_MAX_EPI = 4
+TDX_EPI_NOROUND = 0x100
+TDX_FLAG_SRC_NOROUND = 0x1
 
 EXPORTED_SYMBOLS = (
     "tdx_init_workspace_bytes",
@@ -64,7 +67,7 @@ class TdxInitDesc(ctypes.Structure):
 
 
 class TdxPlan(ctypes.Structure):
-    _fields_ = [("opaque", ctypes.c_uint64 * 128)]
+    _fields_ = [("opaque", ctypes.c_uint64 * 256)]
 
 
 assert ctypes.sizeof(TdxInitDesc) == 128, ctypes.sizeof(TdxInitDesc)
@@ -118,7 +121,7 @@ def fill_pattern(value_bits: int, itemsize: int) -> Sequence[int]:
 def make_desc(dst: int, *, dtype: int, src: int, elem_count: int, elem_begin: int = 0,
               seed: int = 0, offset: int = 0, p0: float = 0.0, p1: float = 1.0, algo: int = 0,
               fill_bits: int = 0, fill_itemsize: int = 0,
-              epi: Iterable[tuple] = ()) -> TdxInitDesc:
+              epi: Iterable[tuple] = (), flags: int = 0) -> TdxInitDesc:
     d = TdxInitDesc()
     d.dst = dst
     d.elem_begin = elem_begin
@@ -127,6 +130,7 @@ def make_desc(dst: int, *, dtype: int, src: int, elem_count: int, elem_begin: in
     d.philox_offset = offset
     d.p0, d.p1 = p0, p1
     d.dtype, d.src, d.algo = dtype, src, algo
+    d.reserved = flags
     if src == TDX_SRC_CONST:
         lo, hi = fill_pattern(fill_bits, fill_itemsize)
         d.fill_bits[0], d.fill_bits[1] = lo, hi

@@ -299,11 +299,14 @@ struct GenUniform16 {
   }
 };
 
-// ---- uniform, 24-bit mantissa from 32 random bits per element (fp32 outputs) ----------------
-template <int R, bool EPI>
+// ---- uniform, 24-bit mantissa from 32 random bits per element -------------------------------
+// fp32 outputs, and the "wide" form of 16-bit outputs (TDX_ALGO_WIDE32): exactly what
+// `x.uniform_()` on an fp32 tensor followed by `.to(bf16)` produces -- fp32 arithmetic, fp32
+// bounds, one rounding at the store (epilogue steps flagged NOROUND stay in fp32 too).
+template <class Out, int R, bool EPI>
 struct GenUniform32 {
-  using OutT = float;
-  static constexpr int kEpv = 4;
+  using OutT = Out;
+  static constexpr int kEpv = OutTraits<Out>::kEpv;  // 4 (f32) or 8 (16-bit outputs: 2 blocks)
   struct Params {
     PhiloxCtx ph;
     float from, scale, to_prev;
@@ -319,14 +322,17 @@ struct GenUniform32 {
     if (EPI) p.epi = load_epi(d);
     return p;
   }
-  __device__ static __forceinline__ void gen(const Params& p, uint64_t gv, float (&v)[4]) {
-    const uint4 w = philox_block<R>(p.ph, gv);
-    const uint32_t x[4] = {w.x, w.y, w.z, w.w};
+  __device__ static __forceinline__ void gen(const Params& p, uint64_t gv, float (&v)[kEpv]) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float k = __uint2float_rn(x[e] >> 8);  // 24 bits, exact
-      float r = fminf(fmaf(k, p.scale, p.from), p.to_prev);
-      v[e] = EPI ? apply_epi<float>(p.epi, r) : r;
+    for (int b = 0; b < kEpv / 4; ++b) {
+      const uint4 w = philox_block<R>(p.ph, gv * (kEpv / 4) + b);
+      const uint32_t x[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float k = __uint2float_rn(x[e] >> 8);  // 24 bits, exact
+        float r = fminf(fmaf(k, p.scale, p.from), p.to_prev);
+        v[b * 4 + e] = EPI ? apply_epi<Out>(p.epi, r) : r;
+      }
     }
   }
 };
@@ -783,8 +789,8 @@ using f16 = __half;
 static const Family kFamilies[] = {
     {TDX_SRC_CONST, -1, 0, 0, 0, tdx_fill_kernel, "fill"},
     // shipped defaults
-    TDX_FAM_V16(TDX_SRC_UNIFORM, TDX_F32, 0, 10, 0, GenUniform32<10, false>),
-    TDX_FAM(TDX_SRC_UNIFORM, TDX_F32, 0, 10, 1, GenUniform32<10, true>),
+    TDX_FAM_V16(TDX_SRC_UNIFORM, TDX_F32, 0, 10, 0, GenUniform32<float, 10, false>),
+    TDX_FAM(TDX_SRC_UNIFORM, TDX_F32, 0, 10, 1, GenUniform32<float, 10, true>),
     TDX_FAM(TDX_SRC_UNIFORM, TDX_BF16, 0, 10, 0, GenUniform16<bf16, 10, false>),
     TDX_FAM(TDX_SRC_UNIFORM, TDX_BF16, 0, 10, 1, GenUniform16<bf16, 10, true>),
     TDX_FAM(TDX_SRC_UNIFORM, TDX_F16, 0, 10, 0, GenUniform16<f16, 10, false>),
@@ -795,6 +801,16 @@ static const Family kFamilies[] = {
     TDX_FAM(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_ICDF16, 10, 1, GenNormalICDF16<bf16, 10, true>),
     TDX_FAM(TDX_SRC_NORMAL, TDX_F16, TDX_ALGO_ICDF16, 10, 0, GenNormalICDF16<f16, 10, false>),
     TDX_FAM(TDX_SRC_NORMAL, TDX_F16, TDX_ALGO_ICDF16, 10, 1, GenNormalICDF16<f16, 10, true>),
+    // "wide" 16-bit outputs (TDX_ALGO_WIDE32): the fp32 stream and arithmetic, rounded once at the
+    // store -- what `t_fp32.uniform_()/normal_()` followed by `.to(bf16/fp16)` means
+    TDX_FAM(TDX_SRC_UNIFORM, TDX_BF16, TDX_ALGO_WIDE32, 10, 0, GenUniform32<bf16, 10, false>),
+    TDX_FAM(TDX_SRC_UNIFORM, TDX_BF16, TDX_ALGO_WIDE32, 10, 1, GenUniform32<bf16, 10, true>),
+    TDX_FAM(TDX_SRC_UNIFORM, TDX_F16, TDX_ALGO_WIDE32, 10, 0, GenUniform32<f16, 10, false>),
+    TDX_FAM(TDX_SRC_UNIFORM, TDX_F16, TDX_ALGO_WIDE32, 10, 1, GenUniform32<f16, 10, true>),
+    TDX_FAM(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_BM32, 10, 0, GenNormalBM32<bf16, 10, false>),
+    TDX_FAM(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_BM32, 10, 1, GenNormalBM32<bf16, 10, true>),
+    TDX_FAM(TDX_SRC_NORMAL, TDX_F16, TDX_ALGO_BM32, 10, 0, GenNormalBM32<f16, 10, false>),
+    TDX_FAM(TDX_SRC_NORMAL, TDX_F16, TDX_ALGO_BM32, 10, 1, GenNormalBM32<f16, 10, true>),
     // table-driven twins of the 16-bit normal for large descriptors (bit-identical output)
     TDX_FAM_LUT(TDX_BF16, 10, bf16, 10, TDX_LUT_WORDS),
     TDX_FAM_LUT(TDX_F16, 10, f16, 10, TDX_LUT_WORDS),
@@ -803,7 +819,6 @@ static const Family kFamilies[] = {
     TDX_FAM(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_ICDF16, 7, 0, GenNormalICDF16<bf16, 7, false>),
     TDX_FAM(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_BM16, 10, 0, GenNormalBM16<bf16, 10, false>),
     TDX_FAM(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_BM16, 7, 0, GenNormalBM16<bf16, 7, false>),
-    TDX_FAM(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_BM32, 10, 0, GenNormalBM32<bf16, 10, false>),
     TDX_FAM(TDX_SRC_NORMAL, TDX_F32, TDX_ALGO_BM32, 7, 0, GenNormalBM32<float, 7, false>),
 };
 constexpr int kNumFamilies = sizeof(kFamilies) / sizeof(kFamilies[0]);
@@ -836,6 +851,7 @@ int resolve_algo(const TdxInitDesc& d) {
     if (a != TDX_ALGO_DEFAULT) return a;
     return d.dtype == TDX_F32 ? TDX_ALGO_BM32 : TDX_ALGO_ICDF16;
   }
+  if (d.src == TDX_SRC_UNIFORM && d.dtype != TDX_F32 && a == TDX_ALGO_WIDE32) return TDX_ALGO_WIDE32;
   return 0;
 }
 
@@ -1125,7 +1141,7 @@ TDX_C_API int tdx_elems_per_block(int dtype, int src, int algo) {
   if (src == TDX_SRC_CONST) return 0;
   if (dtype == TDX_F32) return 4;
   if (dtype != TDX_BF16 && dtype != TDX_F16) return 0;
-  if (src == TDX_SRC_NORMAL && (algo & 0x0f) == TDX_ALGO_BM32) return 4;
+  if ((algo & 0x0f) == TDX_ALGO_WIDE32) return 4;  // BM32 == WIDE32
   return 8;
 }
 

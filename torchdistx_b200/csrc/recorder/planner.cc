@@ -52,6 +52,9 @@ struct Sym {
   uint32_t rng_op = kNoValue;                // the live RNG op
   std::vector<uint32_t> rng_chain;           // every RNG op met, live or dead, chronological
   std::vector<TdxEpiStep> epi;
+  // The RNG source ran on an fp32 tensor that was later cast to a 16-bit dtype: keep the fp32
+  // stream and arithmetic (TDX_ALGO_WIDE32) so that the result IS `fp32_tensor.to(dtype)`.
+  bool wide = false;
   bool opaque() const { return src == Opaque; }
 };
 
@@ -235,6 +238,7 @@ void transition(Tape& tape, uint32_t op_idx, uint32_t S, Sym& st) {
       return;
     case OpKind::Alias:
     case OpKind::HookVariableData:
+    case OpKind::HookSetData:  // `p.data = t`: p now names t's storage; its elements are t's
       return;  // same elements under another tensor object
     case OpKind::UniformInplace:
     case OpKind::NormalInplace: {
@@ -315,13 +319,18 @@ void transition(Tape& tape, uint32_t op_idx, uint32_t S, Sym& st) {
       }
       // RNG source followed by an elementwise op
       if (op.kind == OpKind::CastOut) {
-        if (!is_fused_float(out.dtype) || !st.epi.empty()) { st = make_opaque(); return; }
-        st.dtype = out.dtype;  // generate straight into the destination dtype
-        st.gen_dtype = out.dtype;
-        if (st.src == Sym::Uniform) {
-          st.p0 = round_to_dtype(st.p0, out.dtype);
-          st.p1 = round_to_dtype(st.p1, out.dtype);
+        if (out.dtype == st.dtype) return;  // a copy
+        // fp32 -> bf16/fp16: the values must be exactly `source.to(dtype)` (the fp32 source may be
+        // materialised too, e.g. `m.to(torch.bfloat16)` keeps both alive while recording), so the
+        // descriptor keeps the fp32 stream/arithmetic and rounds once, at this point of the chain
+        if (st.dtype != ScalarType::Float || !(out.dtype == ScalarType::BFloat16 || out.dtype == ScalarType::Half) ||
+            st.wide) {
+          st = make_opaque();
+          return;
         }
+        st.wide = true;
+        for (TdxEpiStep& e : st.epi) e.op |= TDX_EPI_NOROUND;  // steps so far ran in fp32
+        st.dtype = out.dtype;
         return;
       }
       if (out.dtype != st.dtype) { st = make_opaque(); return; }  // type promotion: not modelled
@@ -360,7 +369,8 @@ Sym eval_storage(Tape& tape, uint32_t S, uint32_t upto) {
   for (uint32_t oi : si.touching_ops) {
     if (oi >= upto) break;
     const TapeOp& op = tape.ops[oi];
-    if (op.kind == OpKind::Alias || op.kind == OpKind::HookVariableData) continue;
+    if (op.kind == OpKind::Alias || op.kind == OpKind::HookVariableData || op.kind == OpKind::HookSetData)
+      continue;
     for (uint32_t v : op.outputs)
       if (v != kNoValue && tape.values[v].storage == S) last_writer = oi;
   }
@@ -371,8 +381,10 @@ Sym eval_storage(Tape& tape, uint32_t S, uint32_t upto) {
     for (uint32_t v : op.outputs) writes |= (v != kNoValue && tape.values[v].storage == S);
     if (!writes) {
       // A reader that saw an intermediate state which a later op overwrote must run at its own
-      // point in history: only generic replay can do that.
-      if (!op.done && last_writer != kNoValue && oi < last_writer) return make_opaque();
+      // point in history: only generic replay can do that.  (`p.data = t` names p's old storage
+      // as an argument but never reads it.)
+      if (op.kind != OpKind::HookSetData && !op.done && last_writer != kNoValue && oi < last_writer)
+        return make_opaque();
       continue;
     }
     if (op.done && op.kind == OpKind::Generic) return make_opaque();
@@ -743,6 +755,10 @@ struct Engine {
         d.philox_offset = r.rng_offset;
         d.n_epi = static_cast<uint8_t>(st.epi.size());
         for (size_t i = 0; i < st.epi.size(); ++i) d.epi[i] = st.epi[i];
+        if (st.wide) {
+          d.algo = TDX_ALGO_WIDE32;
+          d.reserved |= TDX_FLAG_SRC_NOROUND;  // the source value stays fp32 until the cast
+        }
       }
       batch.descs.push_back(d);
       batch.keep_alive.push_back(base);
@@ -872,6 +888,7 @@ PlanInfo plan_info(const at::Tensor& fake) {
   info.p1 = st.p1;
   info.n_epilogue = static_cast<int>(st.epi.size());
   info.rng_ops = static_cast<int>(st.rng_chain.size());
+  info.wide = st.wide;
   for (const TdxEpiStep& e : st.epi) info.epilogue.emplace_back(static_cast<int>(e.op), e.a, e.b);
   {
     const size_t isz = c10::elementSize(st.dtype == ScalarType::Undefined ? vi.dtype : st.dtype);
