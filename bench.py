@@ -43,6 +43,10 @@ MODELS = {
     "llama3-70b": ("llama", dict(vocab_size=128256, hidden_size=8192, intermediate_size=28672,
                                  num_hidden_layers=80, num_attention_heads=64, num_key_value_heads=8,
                                  max_position_embeddings=8192, rope_theta=500000.0), "bf16"),
+    # SURVEY 8d cfg3 variant: constructed in fp32, converted with `.to(torch.bfloat16)` inside deferred_init
+    "llama3-8b-cast": ("llama", dict(vocab_size=128256, hidden_size=4096, intermediate_size=14336,
+                                     num_hidden_layers=32, num_attention_heads=32, num_key_value_heads=8,
+                                     max_position_embeddings=8192, rope_theta=500000.0), "fp32->bf16"),
     "gpt2-xl": ("gpt2", dict(n_layer=48, n_embd=1600, n_head=25, vocab_size=50257, n_positions=1024), "fp32"),
     "llama-tiny": ("llama", dict(vocab_size=4096, hidden_size=512, intermediate_size=1024,
                                  num_hidden_layers=4, num_attention_heads=8, num_key_value_heads=2), "bf16"),
@@ -59,11 +63,12 @@ def build_model(name: str, layers: int | None = None, vocab: int | None = None):
     if vocab is not None:
         kw["vocab_size"] = vocab
     prev = torch.get_default_dtype()
-    torch.set_default_dtype({"bf16": torch.bfloat16, "fp32": torch.float32}[dtype])
+    torch.set_default_dtype({"bf16": torch.bfloat16, "fp32": torch.float32, "fp32->bf16": torch.float32}[dtype])
     try:
         if family == "llama":
             from transformers import LlamaConfig, LlamaForCausalLM
-            return LlamaForCausalLM(LlamaConfig(**kw))
+            m = LlamaForCausalLM(LlamaConfig(**kw))
+            return m.to(torch.bfloat16) if dtype == "fp32->bf16" else m
         from transformers import GPT2Config, GPT2LMHeadModel
         return GPT2LMHeadModel(GPT2Config(**kw))
     finally:
@@ -124,7 +129,7 @@ import json, sys, time, torch
 sys.path.insert(0, {root!r})
 from oracle import ref_torchdistx as R
 import bench
-torch.set_default_dtype({{'bf16': torch.bfloat16, 'fp32': torch.float32}}[{dtype!r}])
+torch.set_default_dtype({{'bf16': torch.bfloat16, 'fp32': torch.float32, 'fp32->bf16': torch.float32}}[{dtype!r}])
 times, n = [], 0
 for i in range({reps}):
     m = R.deferred_init(lambda: bench.build_model({model!r}, layers={layers}, vocab={vocab}))
@@ -149,11 +154,11 @@ def reference_sample(model: str, layers: int, reps: int):
 # layer of the named model at full width (all seven Llama linears: dead uniform_ + live normal_,
 # exactly the chains of the full model) with the vocabulary cut to 2048 rows so that the two
 # vocab-sized matrices do not dominate; GPT-2 XL: 4 of its 48 blocks, full vocabulary.
-SAMPLE_VOCAB = {"llama3-8b": 2048, "llama3-70b": 2048}
+SAMPLE_VOCAB = {"llama3-8b": 2048, "llama3-8b-cast": 2048, "llama3-70b": 2048}
 
 
 def sample_layers(model: str) -> int:
-    return {"llama3-8b": 1, "llama3-70b": 1, "gpt2-xl": 4, "llama-tiny": 4}[model]
+    return {"llama3-8b": 1, "llama3-8b-cast": 1, "llama3-70b": 1, "gpt2-xl": 4, "llama-tiny": 4}[model]
 
 
 def run_reference_arm(a):
@@ -231,7 +236,7 @@ def run_ours(a):
     # ---- e2e: public API, H2D of descriptors + D2H of a result inside the timed region ---------
     torch.manual_seed(1234)
     parallel.sync_rng(dev)  # the one collective: 16 bytes, rank 0 -> all
-    probe = torch.empty(32, dtype=torch.bfloat16 if dtype == "bf16" else torch.float32).pin_memory()
+    probe = torch.empty(32, dtype=torch.float32 if dtype == "fp32" else torch.bfloat16).pin_memory()
 
     last_name = list(dict(fakes[0].named_parameters()))[-1]  # looked up outside the timed region
 
@@ -319,7 +324,8 @@ def run_ours(a):
     achieved = dom_bytes / dom_ms / 1e6
     kname = {C.TDX_SRC_CONST: "tdx_fill_kernel", C.TDX_SRC_UNIFORM: "tdx_rng_kernel<GenUniform*>",
              C.TDX_SRC_NORMAL: "tdx_normal16_lut_kernel<bf16> (+ tdx_rng_kernel<GenNormalICDF16<bf16>> for descriptors < 2^20 elements)"
-             if dtype == "bf16" else "tdx_rng_kernel<GenNormalBM32<float>>"}[dom_key[0]]
+             if dtype == "bf16" else "tdx_rng_kernel<GenNormalBM32<bf16>> (TDX_ALGO_WIDE32)" if dtype == "fp32->bf16"
+             else "tdx_rng_kernel<GenNormalBM32<float>>"}[dom_key[0]]
     if a.roofline_only:
         return
     traffic = None

@@ -285,6 +285,6 @@ def test_wide_16bit_outputs_are_the_rounded_fp32_tensor(dtype, src):
             # MUFU vs libm: an ABSOLUTE error ~1e-6 std on the fp32 value (see the fp32 normal test);
             # near x = 0 that is many ulps of the 16-bit result, so compare values, not ulps
             g, e = as_float(gpu_bits(t16, dtype), dtype), as_float(exp, dtype)
-            ulp = np.abs(e) * (2.0 ** -8 if dtype == C.TDX_BF16 else 2.0 ** -11)
+            ulp = np.abs(e) * (2.0 ** -7 if dtype == C.TDX_BF16 else 2.0 ** -10)  # spacing is at most this
             assert np.all(np.abs(g - e) <= ulp + 1e-5 * kw["p1"] * (1 + np.abs(e)))
             assert (diff != 0).mean() < 0.002
