@@ -95,6 +95,8 @@ class CastVariant(nn.Module):
         self.b = nn.Parameter(self.a.detach().to(torch.bfloat16))
         self.u = nn.Parameter(torch.empty(50, 20).uniform_(-0.3, 0.1))
         self.v = nn.Parameter(self.u.detach().to(torch.float16))
+        # fp32 steps, the cast, then more steps in the 16-bit dtype
+        self.w = nn.Parameter(self.a.detach().to(torch.bfloat16).mul_(3.0).add_(1.0))
 
 
 def cast_variant():

@@ -269,3 +269,6 @@ def test_cast_of_an_rng_tensor_equals_the_cast_of_its_materialised_source():
     assert m.body[0].weight.dtype == torch.bfloat16 and m.head.weight.dtype == torch.float16
     w = m.head.weight.float()
     assert w.min() >= -0.05 and w.max() <= 0.05 and 0.012 < w.std() < 0.025
+    # steps before the cast run in fp32, the cast rounds once, later steps round to bf16 one by one
+    assert m.w.dtype == torch.bfloat16
+    assert torch.equal(m.w, m.a.detach().to(torch.bfloat16).mul_(3.0).add_(1.0))

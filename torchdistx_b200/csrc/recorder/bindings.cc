@@ -233,6 +233,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     d["n_epilogue"] = i.n_epilogue;
     d["rng_ops"] = i.rng_ops;
     d["wide"] = i.wide;
+    d["src_noround"] = i.src_noround;
     d["first_unfusable_op"] = i.first_unfusable_op;
     d["sizes"] = i.sizes;
     d["device"] = i.device;

@@ -55,6 +55,7 @@ struct Sym {
   // The RNG source ran on an fp32 tensor that was later cast to a 16-bit dtype: keep the fp32
   // stream and arithmetic (TDX_ALGO_WIDE32) so that the result IS `fp32_tensor.to(dtype)`.
   bool wide = false;
+  bool src_noround = false;  // the generated value feeds fp32 epilogue steps before the cast
   bool opaque() const { return src == Opaque; }
 };
 
@@ -329,7 +330,10 @@ void transition(Tape& tape, uint32_t op_idx, uint32_t S, Sym& st) {
           return;
         }
         st.wide = true;
-        for (TdxEpiStep& e : st.epi) e.op |= TDX_EPI_NOROUND;  // steps so far ran in fp32
+        // everything before the cast ran in fp32; the cast itself is the rounding of the last
+        // pre-cast step (or of the generated value, if there was none)
+        st.src_noround = !st.epi.empty();
+        for (size_t i = 0; i + 1 < st.epi.size(); ++i) st.epi[i].op |= TDX_EPI_NOROUND;
         st.dtype = out.dtype;
         return;
       }
@@ -755,10 +759,8 @@ struct Engine {
         d.philox_offset = r.rng_offset;
         d.n_epi = static_cast<uint8_t>(st.epi.size());
         for (size_t i = 0; i < st.epi.size(); ++i) d.epi[i] = st.epi[i];
-        if (st.wide) {
-          d.algo = TDX_ALGO_WIDE32;
-          d.reserved |= TDX_FLAG_SRC_NOROUND;  // the source value stays fp32 until the cast
-        }
+        if (st.wide) d.algo = TDX_ALGO_WIDE32;
+        if (st.src_noround) d.reserved |= TDX_FLAG_SRC_NOROUND;
       }
       batch.descs.push_back(d);
       batch.keep_alive.push_back(base);
@@ -889,6 +891,7 @@ PlanInfo plan_info(const at::Tensor& fake) {
   info.n_epilogue = static_cast<int>(st.epi.size());
   info.rng_ops = static_cast<int>(st.rng_chain.size());
   info.wide = st.wide;
+  info.src_noround = st.src_noround;
   for (const TdxEpiStep& e : st.epi) info.epilogue.emplace_back(static_cast<int>(e.op), e.a, e.b);
   {
     const size_t isz = c10::elementSize(st.dtype == ScalarType::Undefined ? vi.dtype : st.dtype);

@@ -80,6 +80,7 @@ struct PlanInfo {
   int n_epilogue = 0;
   int rng_ops = 0;         // RNG passes on the chain, live + dead
   bool wide = false;       // fp32 source cast to a 16-bit dtype: TDX_ALGO_WIDE32
+  bool src_noround = false;  // TDX_FLAG_SRC_NOROUND
   std::string first_unfusable_op;  // for "opaque": the op that stopped the fold (best effort)
   // everything needed to rebuild the descriptor later without the recording (InitPlan)
   std::vector<int64_t> sizes;

@@ -63,6 +63,7 @@ class PlanEntry:
     requires_grad: bool = False
     alias_of: Optional[str] = None  # tied parameters: same tensor as an earlier entry
     wide: bool = False  # fp32 source cast to a 16-bit dtype (TDX_ALGO_WIDE32)
+    src_noround: bool = False  # TDX_FLAG_SRC_NOROUND
 
 
 class InitPlan:
@@ -98,7 +99,7 @@ class InitPlan:
                             name, kind, list(info["sizes"]), info["dtype"], info["source"], info["p0"], info["p1"],
                             [tuple(e) for e in info["epilogue"]],
                             base64.b64encode(info["const_bytes"]).decode(), "", list(info["rng_numels"]),
-                            bool(info["requires_grad"]), None, bool(info["wide"])))
+                            bool(info["requires_grad"]), None, bool(info["wide"]), bool(info["src_noround"])))
                         continue
                     # not fusible (or already real): evaluate now and store by value
                     real = materialize_tensor(t) if info["deferred"] else t
@@ -219,7 +220,7 @@ class InitPlan:
                             src=_cabi.TDX_SRC_UNIFORM if e.source == "uniform" else _cabi.TDX_SRC_NORMAL,
                             elem_begin=begin, elem_count=count, seed=seed, offset=live_offset, p0=e.p0, p1=e.p1,
                             epi=e.epilogue, algo=_cabi.TDX_ALGO_WIDE32 if e.wide else 0,
-                            flags=_cabi.TDX_FLAG_SRC_NOROUND if e.wide else 0))
+                            flags=_cabi.TDX_FLAG_SRC_NOROUND if e.src_noround else 0))
                 out[e.name] = t if target is not None else _wrap(t, e)
             if descs:
                 lib = _cabi.load()
