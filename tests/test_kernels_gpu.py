@@ -187,7 +187,8 @@ def test_determinism_and_seed_sensitivity():
 def test_table_driven_normal_is_bit_identical_to_the_direct_kernel(dtype):
     """Large descriptors take the shared-memory-table kernel; TDX_ALGO_NOLUT forces the direct one.
     Mixed sizes in one launch, two different (mean, std) so that CTAs rebuild their table."""
-    sizes = [(1 << 22) + 9, 1 << 20, (1 << 21) + 12345, 5000]
+    # the table kernel is used when a launch holds >= 2^27 table-eligible elements
+    sizes = [(1 << 27) + 9, 1 << 20, (1 << 21) + 12345, 5000]
     outs = {}
     for flag in (0, C.TDX_ALGO_NOLUT):
         bufs, descs = [], []
@@ -203,10 +204,10 @@ def test_table_driven_normal_is_bit_identical_to_the_direct_kernel(dtype):
     for a, b in zip(outs[0], outs[C.TDX_ALGO_NOLUT]):
         assert torch.equal(a.view(torch.int16), b.view(torch.int16))
     # and a table-kernel shard boundary in the middle of a vector
-    n = (1 << 21) + 3
+    n = (1 << 27) + (1 << 21) + 3
     full = torch.zeros(n, dtype=TORCH_DT[dtype], device="cuda")
     run_descs([C.make_desc(full.data_ptr(), dtype=dtype, src=C.TDX_SRC_NORMAL, elem_count=n, seed=5, offset=8, p1=0.02)], [full])
-    cut = (1 << 20) + 5
+    cut = (1 << 27) + 5
     a = torch.zeros(cut, dtype=TORCH_DT[dtype], device="cuda")
     b = torch.zeros(n - cut, dtype=TORCH_DT[dtype], device="cuda")
     run_descs([C.make_desc(a.data_ptr(), dtype=dtype, src=C.TDX_SRC_NORMAL, elem_count=cut, seed=5, offset=8, p1=0.02),

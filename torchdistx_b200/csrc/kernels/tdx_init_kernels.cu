@@ -655,6 +655,7 @@ constexpr int kLutVecsPerThread = TDX_LUT_VECS;
 constexpr int kLutTileVecs = kLutThreads * kLutVecsPerThread;  // bytes per tile = 16 x this
 constexpr int kLutTilesPerChunk = (1 << 20) / (kLutTileVecs * 16) > 0 ? (1 << 20) / (kLutTileVecs * 16) : 1;
 constexpr uint32_t kLutBytes = 65536u * 2u;
+constexpr uint64_t kLutMinLaunchElems = 1ull << 27;  // 256 MB of 16-bit output per launch (r1 sweep: break-even ~200 MB)
 constexpr unsigned short kLutSentinel = 0xffffu;  // a NaN pattern in bf16 and fp16: never a value
 
 // LUT_WORDS of the 4 Philox words of a vector (2 elements each) go through the table, the rest
@@ -967,6 +968,31 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
     fam[i] = family_of(d);
     if (fam[i] < 0) return fail(TDX_E_BADARG, "no kernel for (src, dtype, algo, epilogue)");
     per_family[fam[i]]++;
+  }
+  // The table kernel pays 65536 evaluations per CTA up front: worth it only if the launch as a
+  // whole has enough table-eligible work.  Otherwise its descriptors go to the direct twin
+  // (same bits either way).
+  {
+    uint64_t lut_elems[kNumFamilies] = {};
+    for (int i = 0; i < n; ++i)
+      if (kFamilies[fam[i]].lut) lut_elems[fam[i]] += descs[i].elem_count;
+    for (int f = 0; f < kNumFamilies; ++f) {
+      if (!kFamilies[f].lut || lut_elems[f] == 0 || lut_elems[f] >= kLutMinLaunchElems) continue;
+      int twin = -1;
+      for (int t = 1; t < kNumFamilies; ++t) {
+        const Family &A = kFamilies[f], &B = kFamilies[t];
+        if (!B.lut && B.src == A.src && B.dtype == A.dtype && B.algo == A.algo && B.rounds == A.rounds &&
+            B.epi == A.epi)
+          twin = t;
+      }
+      if (twin < 0) continue;
+      for (int i = 0; i < n; ++i)
+        if (fam[i] == f) {
+          fam[i] = twin;
+          per_family[f]--;
+          per_family[twin]++;
+        }
+    }
   }
   memset(&hdr, 0, sizeof(hdr));
   hdr.magic = kPlanMagic;
