@@ -187,7 +187,7 @@ def test_determinism_and_seed_sensitivity():
 def test_table_driven_normal_is_bit_identical_to_the_direct_kernel(dtype):
     """Large descriptors take the shared-memory-table kernel; TDX_ALGO_NOLUT forces the direct one.
     Mixed sizes in one launch, two different (mean, std) so that CTAs rebuild their table."""
-    # the table kernel is used when a launch holds >= 2^27 table-eligible elements
+    # the table kernel is used when a launch holds >= 2^26 table-eligible elements
     sizes = [(1 << 27) + 9, 1 << 20, (1 << 21) + 12345, 5000]
     outs = {}
     for flag in (0, C.TDX_ALGO_NOLUT):

@@ -655,7 +655,7 @@ constexpr int kLutVecsPerThread = TDX_LUT_VECS;
 constexpr int kLutTileVecs = kLutThreads * kLutVecsPerThread;  // bytes per tile = 16 x this
 constexpr int kLutTilesPerChunk = (1 << 20) / (kLutTileVecs * 16) > 0 ? (1 << 20) / (kLutTileVecs * 16) : 1;
 constexpr uint32_t kLutBytes = 65536u * 2u;
-constexpr uint64_t kLutMinLaunchElems = 1ull << 27;  // 256 MB of 16-bit output per launch (r1 sweep: break-even ~200 MB)
+constexpr uint64_t kLutMinLaunchElems = 1ull << 26;  // 128 MB of 16-bit output per launch (r1 sweep: break-even 130-200 MB)
 constexpr unsigned short kLutSentinel = 0xffffu;  // a NaN pattern in bf16 and fp16: never a value
 
 // LUT_WORDS of the 4 Philox words of a vector (2 elements each) go through the table, the rest
