@@ -26,7 +26,7 @@
  *   time the op was issued == unique id of this RNG op under that seed) and
  *   blk = floor(g / EPB) for GLOBAL linear element index g of the unsharded
  *   tensor.  EPB = 8 for 16-bit outputs (16 random bits per element), 4 for
- *   32-bit outputs.  Bit 31 of counter.w keeps the stream disjoint from
+ *   32-bit outputs and for 16-bit outputs generated "wide" (TDX_ALGO_WIDE32).  Bit 31 of counter.w keeps the stream disjoint from
  *   ATen's own (offset, thread-id) use of the same generator
  *   (ATen/native/cuda/DistributionTemplates.h:72-88); bits 30/29 of counter.w
  *   select the two tail-refinement blocks of the 16-bit normal.
