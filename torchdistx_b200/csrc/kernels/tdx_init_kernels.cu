@@ -700,6 +700,9 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_normal16_lut_kernel(const 
     const bool aligned = (begin % 8 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
     const uint64_t nfull = aligned ? count / 8 : 0;
     const char* const lut_bytes = reinterpret_cast<const char*>(lut);
+#ifdef TDX_LUT_CONFLICT_FREE_EXPERIMENT
+    const uint32_t lane4 = (threadIdx.x & 31u) * 4u;
+#endif
     for (unsigned long long tile = tile0; tile < tile0 + ntiles; ++tile) {
       const uint64_t base = tile * kLutTileVecs + threadIdx.x;
       if (base - threadIdx.x + kLutTileVecs <= nfull) {
@@ -716,8 +719,14 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_normal16_lut_kernel(const 
               // byte offsets 2*k of the two half-words: one PRMT (zero-extend) on the ALU pipe and
               // one multiply-by-2 on the FMA pipe each.  The ALU pipe (half rate) also carries
               // Philox's 20 LOP3, so everything that can be phrased otherwise stays off it.
+#ifdef TDX_LUT_CONFLICT_FREE_EXPERIMENT
+              // timing experiment only (wrong values): every lane reads its own bank
+              const uint32_t lo = ((ws[q] << 7) & 0x1ff80u) + lane4;
+              const uint32_t hi = ((ws[q] >> 9) & 0x1ff80u) + lane4;
+#else
               const uint32_t lo = __byte_perm(ws[q], 0u, 0x4410) * 2u;
               const uint32_t hi = __byte_perm(ws[q], 0u, 0x4432) * 2u;
+#endif
               const uint32_t a = *reinterpret_cast<const unsigned short*>(lut_bytes + lo);
               const uint32_t b = *reinterpret_cast<const unsigned short*>(lut_bytes + hi);
               r[q] = a | (b << 16);
