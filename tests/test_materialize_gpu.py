@@ -272,3 +272,73 @@ def test_cast_of_an_rng_tensor_equals_the_cast_of_its_materialised_source():
     # steps before the cast run in fp32, the cast rounds once, later steps round to bf16 one by one
     assert m.w.dtype == torch.bfloat16
     assert torch.equal(m.w, m.a.detach().to(torch.bfloat16).mul_(3.0).add_(1.0))
+
+
+def test_fused_constant_folding_equals_generic_replay_on_random_programs():
+    """Deterministic programs drawn at random (factories, fills, scalar arithmetic, clamps, casts,
+    clones, aliases): the fused path (constants folded through ATen on a 1-element tensor, one fill
+    kernel) must equal op-by-op ATen replay on the GPU bit for bit."""
+    import random
+
+    from torchdistx_b200 import _C
+
+    rng = random.Random(1234)
+    dtypes = [torch.float32, torch.bfloat16, torch.float16, torch.float64, torch.int64, torch.int32, torch.bool]
+
+    def program(seed):
+        r = random.Random(seed)
+        dt = r.choice(dtypes)
+        shape = r.choice([(7,), (33, 5), (4, 3, 2), (1,), (257,)])
+        steps = []
+        kind = r.choice(["zeros", "ones", "full", "empty_fill"])
+        for _ in range(r.randrange(0, 5)):
+            if dt in (torch.bool,):
+                steps.append(r.choice(["clone", "view", "detach"]))
+            elif dt in (torch.int64, torch.int32):
+                steps.append(r.choice([("mul_", r.randrange(-3, 4)), ("add_", r.randrange(-5, 6)), "clone", "view",
+                                       ("clamp_", -4, 9), ("to", torch.float32), ("to", torch.int64)]))
+            else:
+                steps.append(r.choice([("mul_", r.uniform(-2, 2)), ("add_", r.uniform(-1, 1)), ("mul", 1.5), ("add", -0.25),
+                                       "clone", "view", "detach", ("clamp_", -0.5, 0.75), ("fill_", r.uniform(-3, 3)),
+                                       "zero_", ("to", r.choice([torch.float32, torch.bfloat16, torch.float16]))]))
+
+        def build():
+            if kind == "zeros":
+                t = torch.zeros(shape, dtype=dt, device="cuda")
+            elif kind == "ones":
+                t = torch.ones(shape, dtype=dt, device="cuda")
+            elif kind == "full":
+                t = torch.full(shape, True if dt == torch.bool else 3, dtype=dt, device="cuda")
+            else:
+                t = torch.empty(shape, dtype=dt, device="cuda").fill_(True if dt == torch.bool else 2)
+            for s in steps:
+                if s == "clone":
+                    t = t.clone()
+                elif s == "view":
+                    t = t.view(-1).view(shape)
+                elif s == "detach":
+                    t = t.detach()
+                elif s == "zero_":
+                    t.zero_()
+                elif s[0] == "to":
+                    t = t.to(s[1])
+                elif s[0] in ("mul_", "add_", "fill_"):
+                    getattr(t, s[0])(s[1])
+                elif s[0] in ("mul", "add"):
+                    t = getattr(t, s[0])(s[1])
+                elif s[0] == "clamp_":
+                    t.clamp_(s[1], s[2])
+            return t
+
+        return build
+
+    fused_count = 0
+    for i in range(60):
+        build = program(rng.randrange(1 << 30))
+        a = _C.materialize_tensor(deferred_init(build), None, None, True)
+        fused_count += last_materialize_stats()["fused_tensors"]
+        b = _C.materialize_tensor(deferred_init(build), None, None, False)
+        assert last_materialize_stats()["fused_tensors"] == 0
+        assert a.dtype == b.dtype and a.shape == b.shape, i
+        assert torch.equal(a.reshape(-1).view(torch.uint8), b.reshape(-1).view(torch.uint8)), (i, a.dtype)
+    assert fused_count >= 50  # nearly all of these programs fold
