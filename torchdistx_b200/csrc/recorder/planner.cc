@@ -30,6 +30,12 @@ using torch::jit::Stack;
 namespace {
 
 thread_local MaterializeStats g_stats;
+// Where constant chains are folded.  ATen's CPU and CUDA kernels differ in the last bit for 16-bit
+// dtypes (the CPU kernels round a Python scalar to the tensor dtype first, the CUDA kernels keep it
+// in fp32), and a tensor recorded for CUDA must hold what the program computes on CUDA: so while
+// materialising onto a CUDA device the 1-element stand-in lives there.  (plan_info, which may run
+// on a machine without a GPU, folds on the CPU.)
+thread_local c10::Device g_fold_device = c10::Device(c10::kCPU);
 thread_local std::vector<TdxInitDesc> g_last_descs;  // what the last materialize call launched
 
 // Never record / fake anything we do while materialising.
@@ -85,7 +91,7 @@ void ensure_cval(Sym& st) {
   if (st.cval.defined() || !st.has_scalar) return;
   c10::impl::ExcludeDispatchKeyGuard a{c10::DispatchKey::DeferredInit};
   c10::impl::ExcludeDispatchKeyGuard b{c10::DispatchKey::Fake};
-  st.cval = at::full({1}, st.cscalar, at::TensorOptions().dtype(st.dtype).device(c10::kCPU));
+  st.cval = at::full({1}, st.cscalar, at::TensorOptions().dtype(st.dtype).device(g_fold_device));
 }
 
 bool is_fused_float(ScalarType t) {
@@ -149,6 +155,10 @@ bool fold_const(const TapeOp& op, Sym& st, bool inplace) {
       if (slot >= op.inputs.size()) return false;
       const InputRef& in = op.inputs[slot++];
       if (first_tensor) {
+        if (st.cval.device() != g_fold_device) {
+          NoInterception guard;
+          st.cval = st.cval.to(g_fold_device);
+        }
         stack.emplace_back(st.cval);
         first_tensor = false;
       } else if (in.real.defined() && in.real.numel() == 1 && in.real.is_cpu()) {
@@ -162,7 +172,7 @@ bool fold_const(const TapeOp& op, Sym& st, bool inplace) {
       for (const IValue& e : a.toListRef()) ok &= !e.isTensor();
       stack.push_back(a);
     } else if (a.isDevice()) {
-      stack.emplace_back(c10::Device(c10::kCPU));
+      stack.emplace_back(g_fold_device);
     } else {
       stack.push_back(a);
     }
@@ -695,6 +705,12 @@ struct Engine {
     const bool sharded = opts.shard && opts.shard->world > 1 && !vi.sizes.empty();
     if (sharded && !vi.covers_storage) return false;
 
+    struct FoldOn {  // constants fold with the target device's arithmetic
+      c10::Device prev = g_fold_device;
+      explicit FoldOn(c10::Device d) { g_fold_device = d; }
+      ~FoldOn() { g_fold_device = prev; }
+    } fold_on(dev);
+    c10::DeviceGuard fold_guard(dev);
     Sym st = eval_storage(tape, S, static_cast<uint32_t>(tape.ops.size()));
     if (st.opaque()) return false;
     const size_t isz = c10::elementSize(st.dtype);
@@ -745,7 +761,8 @@ struct Engine {
         size_t got = 0;
         if (!(st.has_scalar && scalar_bits(st.cscalar, st.dtype, one, &got) && got == isz)) {
           ensure_cval(st);
-          std::memcpy(one, st.cval.contiguous().data_ptr(), isz);
+          NoInterception guard;
+          std::memcpy(one, st.cval.cpu().contiguous().data_ptr(), isz);
         }
         for (size_t i = 0; i < 16; i += isz) std::memcpy(pat + i, one, isz);
         std::memcpy(d.fill_bits, pat, 16);
@@ -881,6 +898,13 @@ PlanInfo plan_info(const at::Tensor& fake) {
     info.source = "materialized";
     return info;
   }
+  // fold constants where the tensor will live, if that device exists here (a plan built on a
+  // machine without a GPU folds 16-bit constant arithmetic with the CPU kernels' rounding)
+  struct FoldOn {
+    c10::Device prev = g_fold_device;
+    explicit FoldOn(c10::Device d) { g_fold_device = d; }
+    ~FoldOn() { g_fold_device = prev; }
+  } fold_on(vi.device.is_cuda() && at::hasCUDA() ? vi.device : c10::Device(c10::kCPU));
   Sym st = eval_storage(tape, vi.storage, static_cast<uint32_t>(tape.ops.size()));
   static const char* names[] = {"opaque", "uninit", "const", "uniform", "normal"};
   info.source = names[st.src];
@@ -902,7 +926,8 @@ PlanInfo plan_info(const at::Tensor& fake) {
       size_t got = 0;
       if (!(st.has_scalar && scalar_bits(st.cscalar, st.dtype, one, &got) && got == isz)) {
         ensure_cval(st);
-        std::memcpy(one, st.cval.contiguous().data_ptr(), isz);
+        NoInterception guard;
+        std::memcpy(one, st.cval.cpu().contiguous().data_ptr(), isz);
       }
       info.const_bytes.assign(reinterpret_cast<const char*>(one), isz);
     }
