@@ -183,6 +183,46 @@ def test_determinism_and_seed_sensitivity():
     assert torch.equal(a, b) and (a != c).float().mean() > 0.9
 
 
+def test_table_kernel_with_mixed_seeds_and_across_a_2_32_block_boundary():
+    """The table kernel takes its Philox round keys from kernel parameters when the launch shares
+    one seed and from the descriptors otherwise; inside a tile it treats counter.y (block >> 32) as
+    uniform and leaves a tile that straddles a 2^32-block boundary to the generic path.  All of it
+    must give the bits of the direct kernel."""
+    dtype = C.TDX_BF16
+    n = (1 << 26) + 777
+    for seeds in ((11, 11, 11), (11, 12, 13)):
+        outs = {}
+        for flag in (0, C.TDX_ALGO_NOLUT):
+            bufs, descs = [], []
+            for i, seed in enumerate(seeds):
+                t = torch.zeros(n, dtype=torch.bfloat16, device="cuda")
+                bufs.append(t)
+                descs.append(C.make_desc(t.data_ptr(), dtype=dtype, src=C.TDX_SRC_NORMAL, elem_count=n, seed=seed,
+                                         offset=64 * i, p0=0.0, p1=0.02, algo=C.TDX_ALGO_ICDF16 | flag))
+            run_descs(descs, bufs)
+            outs[flag] = bufs
+        for a, b in zip(outs[0], outs[C.TDX_ALGO_NOLUT]):
+            assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+        if len(set(seeds)) > 1:
+            assert not torch.equal(outs[0][0], outs[0][1])
+    # a shard of a (virtual) 2^35+ element tensor: block indices cross 2^32 in the middle
+    m = 1 << 27
+    begin = (1 << 35) - (1 << 26) - 24
+    outs = []
+    for flag in (0, C.TDX_ALGO_NOLUT):
+        t = torch.zeros(m, dtype=torch.bfloat16, device="cuda")
+        run_descs([C.make_desc(t.data_ptr(), dtype=dtype, src=C.TDX_SRC_NORMAL, elem_begin=begin, elem_count=m,
+                               seed=3, offset=16, p1=1.0, algo=C.TDX_ALGO_ICDF16 | flag)], [t])
+        outs.append(t)
+    assert torch.equal(outs[0].view(torch.int16), outs[1].view(torch.int16))
+    # spot-check both sides of the boundary against the oracle
+    for off in (0, (1 << 26) + 24 - 64):
+        d = C.make_desc(0, dtype=dtype, src=C.TDX_SRC_NORMAL, elem_begin=begin + off, elem_count=4096, seed=3,
+                        offset=16, p1=1.0)
+        diff = gpu_bits(outs[0][off:off + 4096], dtype).astype(np.int64) - O.generate(d).astype(np.int64)
+        assert np.abs(diff).max() <= 1
+
+
 @pytest.mark.parametrize("dtype", [C.TDX_BF16, C.TDX_F16])
 def test_table_driven_normal_is_bit_identical_to_the_direct_kernel(dtype):
     """Large descriptors take the shared-memory-table kernel; TDX_ALGO_NOLUT forces the direct one.

@@ -430,16 +430,27 @@ struct GenNormalICDF16 {
     return icdf16_tail(s == 0 ? t.x : s == 1 ? t.y : s == 2 ? t.z : t.w);
   }
   // one element: `magic` = 2^23 + k as a float; returns the value, `t` = 1 - x^2 (0 iff k == 0)
-  __device__ static __forceinline__ float element(const Params& p, float magic, float& t) {
+  __device__ static __forceinline__ float element_l(const Params& p, float magic, float& t, float& l) {
     const float x = fmaf(magic, 3.0517578125e-05f, -257.0f);  // k/32768 - 1
     t = fmaf(-x, x, 1.0f);
-    const float l = mufu_lg2(t);
+    l = mufu_lg2(t);
     float q = fmaf(p.c5, l, p.c4);
     q = fmaf(q, l, p.c3);
     q = fmaf(q, l, p.c2);
     q = fmaf(q, l, p.c1);
     q = fmaf(q, l, p.c0);
     return fmaf(q, x, p.mean);
+  }
+  __device__ static __forceinline__ float element(const Params& p, float magic, float& t) {
+    float l;
+    return element_l(p, magic, t, l);
+  }
+  // the same value, except that k == 0 (t == 0, l == -inf) comes out as NaN -- what the table holds
+  // for that k.  One FMA-pipe instruction: l*0 is -0/+0 for finite l (v unchanged), NaN for -inf.
+  __device__ static __forceinline__ float element_nan(const Params& p, float magic) {
+    float t, l;
+    const float v = element_l(p, magic, t, l);
+    return fmaf(l, 0.0f, v);
   }
   __device__ static __forceinline__ void gen(const Params& p, uint64_t gv, float (&v)[8]) {
     const uint4 w = philox_block<R>(p.ph, gv);
@@ -511,6 +522,11 @@ struct GroupArgs {
   unsigned long long total_tiles;
   unsigned int* counter;  // chunk counter, zeroed before every launch
   uint32_t n_desc;
+  // Philox round keys of the group's seed when every descriptor of the group shares it
+  // (seed_shared != 0): kernel parameters live in the constant bank, so the 20 keys are operands of
+  // the Philox LOP3s directly -- no registers, no per-vector key arithmetic.
+  uint32_t seed_shared;
+  uint32_t rk[20];
 };
 
 // Calls f(desc_index, first_tile_in_desc, n_tiles) for runs of consecutive tiles of one descriptor.
@@ -541,6 +557,36 @@ __device__ __forceinline__ void for_each_tile_run(const GroupArgs& g, F&& f) {
       f(d, t - __ldg(g.tile_prefix + d), stop - t);
       t = stop;
     }
+  }
+}
+
+// Same contract, one barrier per grab instead of two: thread 0 fetches the NEXT chunk index at the
+// start of the current chunk (the atomic's round trip hides behind the chunk's work) and the single
+// barrier at the end of the chunk publishes it.  (ncu, table kernel: 6.5 % of the warp samples sat
+// in the two barriers of for_each_tile_run.)
+template <int TILES_PER_CHUNK, class F>
+__device__ __forceinline__ void for_each_tile_run_prefetch(const GroupArgs& g, unsigned int* s_next, F&& f) {
+  if (threadIdx.x == 0) s_next[0] = atomicAdd(g.counter, 1u);
+  __syncthreads();
+  for (unsigned int it = 0;; ++it) {
+    unsigned long long t = static_cast<unsigned long long>(s_next[it & 1u]) * TILES_PER_CHUNK;
+    if (t >= g.total_tiles) return;
+    if (threadIdx.x == 0) s_next[(it + 1u) & 1u] = atomicAdd(g.counter, 1u);
+    const unsigned long long last = min(t + TILES_PER_CHUNK, g.total_tiles);
+    uint32_t lo = 0, hi = g.n_desc;  // find d with prefix[d] <= t < prefix[d+1]
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (__ldg(g.tile_prefix + mid) <= t) lo = mid; else hi = mid;
+    }
+    uint32_t d = lo;
+    while (t < last) {
+      unsigned long long dend = __ldg(g.tile_prefix + d + 1);
+      while (dend <= t) dend = __ldg(g.tile_prefix + (++d) + 1);  // skip empty descriptors
+      const unsigned long long stop = min(dend, last);
+      f(d, t - __ldg(g.tile_prefix + d), stop - t);
+      t = stop;
+    }
+    __syncthreads();
   }
 }
 
@@ -767,6 +813,244 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_normal16_lut_kernel(const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// table kernel, second generation: the same table, a leaner instruction stream
+// ---------------------------------------------------------------------------------------------
+// ncu of the first table kernel (profiles/r1_ncu_bench_llama3_8b_lut_kernel.json): 93 instructions
+// per 8-element vector, ALU pipe (half rate) 82 of 149 cycles, LSU wavefronts 88 % of peak.  Changes:
+//  * byte address of a table entry = base + 2*k in ONE instruction: IDP.2A (dp2a.lo with the byte
+//    pair (2,0) or (0,2) selects a half-word, doubles it and adds the table base) on the FMA pipe
+//    instead of PRMT + IADD3 on the ALU pipe;
+//  * counter.y (blk >> 32) is uniform inside a tile, so Philox round 1's second product and round
+//    2's first product are loop-invariant: 18 IMAD.WIDE + 19 LOP3 per block instead of 20 + 20;
+//  * the k == 0 sentinel (NaN) is accumulated with 2 HFMA2 per vector (NaN survives a*b+c) and
+//    tested once per GROUP vectors; a hit re-derives the group's Philox blocks and repairs only
+//    the vectors that really contain a zero half-word;
+//  * LUT_ELEMS of the 8 elements of a vector go through the table, the others through the
+//    polynomial (same device function as the table builder => same bits): with the leaner stream
+//    the shared-memory wavefronts (3.56 per LDS on random indices) are the limit, and the FMA-lite
+//    and MUFU pipes are idle.
+#ifndef TDX_LUT2_ELEMS_A
+#define TDX_LUT2_ELEMS_A 7
+#endif
+#ifndef TDX_LUT2_ELEMS_B
+#define TDX_LUT2_ELEMS_B 7
+#endif
+#ifndef TDX_LUT2_GROUP
+#define TDX_LUT2_GROUP 4
+#endif
+#ifndef TDX_LUT2_PACK
+#define TDX_LUT2_PACK 0
+#endif
+
+__device__ __forceinline__ uint32_t lut_addr_lo(uint32_t w, uint32_t base) {
+  uint32_t a;
+  asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(w), "r"(0x00000002u), "r"(base));
+  return a;
+}
+__device__ __forceinline__ uint32_t lut_addr_hi(uint32_t w, uint32_t base) {
+  uint32_t a;
+  asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(w), "r"(0x00000200u), "r"(base));
+  return a;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return v;
+}
+// Dynamic shared memory of a kernel without static shared memory starts at this offset of the
+// shared window on sm_100 (the first KiB is reserved by the system).  The table kernel folds it
+// into the immediate field of its LDS instructions; it checks the assumption at run time and
+// takes the generic path if it ever does not hold.
+constexpr uint32_t kDynSmemBase = 1024;
+__device__ __forceinline__ uint32_t lds_u16_tab(uint32_t off) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1+1024];" : "=h"(v) : "r"(off));
+  return v;
+}
+__device__ __forceinline__ uint32_t pack_u16(uint32_t lo, uint32_t hi) {
+#if TDX_LUT2_PACK == 1
+  return __byte_perm(lo, hi, 0x5410);
+#elif TDX_LUT2_PACK == 2
+  return lo | (hi << 16);
+#else
+  uint32_t r;
+  asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(r) : "r"(hi), "r"(lo));
+  return r;
+#endif
+}
+// exact test for "some 16-bit half of w is zero"
+__device__ __forceinline__ bool has_zero_half(uint32_t w) {
+  return ((w - 0x00010001u) & ~w & 0x80008000u) != 0u;
+}
+
+template <int ROUNDS>
+__device__ __forceinline__ uint4 philox4x32_rk(uint4 c, const uint32_t (&rk)[20]) {
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    unsigned long long p0, p1;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p0) : "r"(c.x), "r"(kPhiloxM0));
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p1) : "r"(c.z), "r"(kPhiloxM1));
+    const uint32_t hi0 = static_cast<uint32_t>(p0 >> 32), lo0 = static_cast<uint32_t>(p0);
+    const uint32_t hi1 = static_cast<uint32_t>(p1 >> 32), lo1 = static_cast<uint32_t>(p1);
+    c = make_uint4(hi1 ^ c.y ^ rk[2 * r], lo1, hi0 ^ c.w ^ rk[2 * r + 1], lo0);
+  }
+  return c;
+}
+
+template <class Out>
+struct NanAcc;
+template <>
+struct NanAcc<__nv_bfloat16> {
+  uint32_t acc = 0;
+  __device__ __forceinline__ void add(uint32_t a, uint32_t b) {
+    asm("fma.rn.bf16x2 %0, %1, %2, %0;" : "+r"(acc) : "r"(a), "r"(b));
+  }
+  __device__ __forceinline__ bool any_nan() const {
+    const __nv_bfloat162 s = *reinterpret_cast<const __nv_bfloat162*>(&acc);
+    return !__hbeq2(s, s);
+  }
+};
+template <>
+struct NanAcc<__half> {
+  uint32_t acc = 0;
+  __device__ __forceinline__ void add(uint32_t a, uint32_t b) {
+    asm("fma.rn.f16x2 %0, %1, %2, %0;" : "+r"(acc) : "r"(a), "r"(b));
+  }
+  __device__ __forceinline__ bool any_nan() const {
+    const __half2 s = *reinterpret_cast<const __half2*>(&acc);
+    return !__hbeq2(s, s);
+  }
+};
+
+// Exponent-all-ones test of either half of a packed pair (inf or NaN).
+template <class Out>
+__device__ __forceinline__ bool any_nonfinite2(uint32_t v) {
+  constexpr uint32_t m = sizeof(Out) == 2 && OutTraits<Out>::kDtype == TDX_BF16 ? 0x7f80u : 0x7c00u;
+  return ((v & m) == m) || ((v & (m << 16)) == (m << 16));
+}
+
+// LUT_A / LUT_B: number of the 8 elements of an even / odd vector that go through the table (the
+// others through the polynomial).  PKEYS: Philox round keys are kernel parameters (the group's
+// descriptors share one seed).
+template <class Out, int R, bool PKEYS, int LUT_A = TDX_LUT2_ELEMS_A, int LUT_B = TDX_LUT2_ELEMS_B,
+          int GROUP = TDX_LUT2_GROUP>
+__global__ void __launch_bounds__(kLutThreads, 1) tdx_normal16_lut2_kernel(const GroupArgs g) {
+  using Gen = GenNormalICDF16<Out, R, false>;
+  using T = OutTraits<Out>;
+  static_assert(kLutVecsPerThread % GROUP == 0, "GROUP must divide the vectors per thread");
+  // The table is the first thing in shared memory (this kernel has no static shared memory; the
+  // scheduler's two slots follow the table), so the byte address of entry k is 2*k plus a constant
+  // that fits the LDS immediate, and the IDP that forms 2*k reads one vector register.
+  extern __shared__ __align__(16) unsigned short lut[];
+  unsigned int* const slots = reinterpret_cast<unsigned int*>(lut + 65536);
+  const bool base_ok = static_cast<uint32_t>(__cvta_generic_to_shared(lut)) == kDynSmemBase;
+  float have_mean = 0.f, have_std = -1.f;  // table contents (uniform across the CTA)
+  for_each_tile_run_prefetch<kLutTilesPerChunk>(g, slots, [&](uint32_t di, unsigned long long tile0,
+                                                              unsigned long long ntiles) {
+    const TdxInitDesc& d = g.descs[di];
+    typename Gen::Params P = Gen::setup(d);
+    // Loop-invariant scalars that come out of a global load: a warp reduction's result lives in a
+    // uniform register by construction, so the FFMAs / LOP3s that use them read two vector
+    // registers instead of three (measured: +2.5 %, fewer dispatch stalls).
+    P.mean = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(P.mean)));
+    P.c0 = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(P.c0)));
+    P.c1 = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(P.c1)));
+    P.c2 = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(P.c2)));
+    P.c3 = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(P.c3)));
+    P.c4 = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(P.c4)));
+    P.c5 = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(P.c5)));
+    if (P.mean != have_mean || P.std != have_std) {
+      __syncthreads();  // everyone is done reading the old table
+      for (uint32_t k = threadIdx.x; k < 65536u; k += kLutThreads) {
+        float t;
+        const float v = Gen::element(P, __uint_as_float(0x4b000000u | k), t);
+        const Out o = static_cast<Out>(v);
+        lut[k] = k == 0 ? kLutSentinel : *reinterpret_cast<const unsigned short*>(&o);
+      }
+      __syncthreads();
+      have_mean = P.mean;
+      have_std = P.std;
+    }
+    const uint64_t begin = d.elem_begin, count = d.elem_count;
+    const uint64_t gv0 = begin / 8;
+    const uint64_t nvec = (begin + count - 1) / 8 - gv0 + 1;
+    char* const dst = static_cast<char*>(d.dst);
+    const bool aligned = (begin % 8 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
+    const uint64_t nfull = aligned ? count / 8 : 0;
+    for (unsigned long long tile = tile0; tile < tile0 + ntiles; ++tile) {
+      const uint64_t tbase = tile * kLutTileVecs;  // first vector of the tile (descriptor-relative)
+      const uint64_t gfirst = gv0 + tbase;         // its global block index
+      const uint32_t blk_hi = static_cast<uint32_t>(gfirst >> 32);
+      const bool one_hi = static_cast<uint32_t>((gfirst + (kLutTileVecs - 1)) >> 32) == blk_hi;
+      if (tbase + kLutTileVecs <= nfull && one_hi && base_ok) {
+        const uint32_t lo0 = static_cast<uint32_t>(gfirst) + threadIdx.x;  // no carry: one_hi
+        char* const p0 = dst + (tbase + threadIdx.x) * 16;
+#pragma unroll
+        for (int i0 = 0; i0 < kLutVecsPerThread; i0 += GROUP) {
+          NanAcc<Out> nan;
+#pragma unroll
+          for (int i = i0; i < i0 + GROUP; ++i) {
+            const int LUT_ELEMS = (i & 1) ? LUT_B : LUT_A;
+            const uint4 c = make_uint4(lo0 + static_cast<uint32_t>(i) * kLutThreads, blk_hi, P.ph.cz, P.ph.cw);
+            const uint4 w = PKEYS ? philox4x32_rk<R>(c, g.rk) : philox4x32<R>(c, P.ph.k0, P.ph.k1);
+            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+            uint32_t r[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const bool lo_lut = 2 * q < LUT_ELEMS, hi_lut = 2 * q + 1 < LUT_ELEMS;
+              if (lo_lut && hi_lut) {
+                r[q] = pack_u16(lds_u16_tab(lut_addr_lo(ws[q], 0u)), lds_u16_tab(lut_addr_hi(ws[q], 0u)));
+              } else if (!lo_lut && !hi_lut) {
+                // k == 0 makes the polynomial +-inf (lg2(0) = -inf) or NaN; the group test below
+                // looks for either
+                float ta, tb;
+                r[q] = T::pack2(Gen::element(P, halfword_as_magic(w, 2 * q), ta),
+                                Gen::element(P, halfword_as_magic(w, 2 * q + 1), tb));
+              } else {  // low half from the table, high half computed
+                float tb;
+                const uint32_t hi16 = T::pack2(0.0f, Gen::element(P, halfword_as_magic(w, 2 * q + 1), tb));
+                r[q] = (hi16 & 0xffff0000u) | lds_u16_tab(lut_addr_lo(ws[q], 0u));
+              }
+            }
+            nan.add(r[0], r[1]);
+            nan.add(r[2], r[3]);
+            store_vec(p0 + static_cast<size_t>(i) * (kLutThreads * 16), make_uint4(r[0], r[1], r[2], r[3]));
+          }
+          // rare (2^-16 per element; also after an overflow of the accumulator, which only costs
+          // time): find the vector(s) that contain a zero half-word and redo them exactly
+          if (any_nonfinite2<Out>(nan.acc)) {
+#pragma unroll 1
+            for (int i = i0; i < i0 + GROUP; ++i) {
+              const uint64_t gv = gfirst + threadIdx.x + static_cast<uint64_t>(i) * kLutThreads;
+              const uint4 w = philox_block<R>(P.ph, gv);
+              if (has_zero_half(w.x) || has_zero_half(w.y) || has_zero_half(w.z) || has_zero_half(w.w))
+                store_vec(p0 + static_cast<size_t>(i) * (kLutThreads * 16), lut_slow_vector<Out, R>(&d, gv));
+            }
+          }
+        }
+      } else {
+        const uint64_t base = tbase + threadIdx.x;
+        for (int i = 0; i < kLutVecsPerThread; ++i) {
+          const uint64_t j = base + static_cast<uint64_t>(i) * kLutThreads;
+          if (j >= nvec) break;
+          float v[8];
+          Gen::gen(P, gv0 + j, v);
+          if (j < nfull) {
+            store_vec(dst + j * 16, T::pack(v));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const uint64_t gidx = (gv0 + j) * 8 + e;
+              if (gidx >= begin && gidx < begin + count) T::store_one(dst, gidx - begin, v[e]);
+            }
+          }
+        }
+      }
+    }
+  });
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side: validation, grouping into kernel families, plan upload, launch
 // ---------------------------------------------------------------------------------------------
 using KernelFn = void (*)(const GroupArgs);
@@ -780,6 +1064,7 @@ struct Family {
   int dyn_smem = 0;
   bool lut = false;
   int tiles_per_chunk = kTilesPerChunk;
+  KernelFn fn_any_seed = nullptr;  // twin of `fn` for groups whose descriptors do not share one seed
 };
 
 #define TDX_FAM(src, dt, algo, rounds, epi, ...) \
@@ -788,10 +1073,24 @@ struct Family {
 #define TDX_FAM_V16(src, dt, algo, rounds, epi, ...)                                               \
   { src, dt, algo, rounds, epi, static_cast<KernelFn>(tdx_rng_kernel<__VA_ARGS__, 16>), #__VA_ARGS__, \
     kThreads, kThreads * 16, 0, false, (kVecsPerThread * kTilesPerChunk) / 16 }
+#ifndef TDX_LUT_GEN
+#define TDX_LUT_GEN 2
+#endif
+#ifndef TDX_LUT2_PKEYS
+#define TDX_LUT2_PKEYS 1
+#endif
+#if TDX_LUT_GEN == 2
+#define TDX_LUT_KERNEL(out, rounds, words) tdx_normal16_lut2_kernel<out, rounds, TDX_LUT2_PKEYS != 0>
+#define TDX_LUT_KERNEL_ANY_SEED(out, rounds, words) tdx_normal16_lut2_kernel<out, rounds, false>
+#else
+#define TDX_LUT_KERNEL(out, rounds, words) tdx_normal16_lut_kernel<out, rounds, words>
+#define TDX_LUT_KERNEL_ANY_SEED(out, rounds, words) tdx_normal16_lut_kernel<out, rounds, words>
+#endif
 #define TDX_FAM_LUT(dt, rounds, ...)                                                             \
   { TDX_SRC_NORMAL, dt, TDX_ALGO_ICDF16, rounds, 0,                                              \
-    static_cast<KernelFn>(tdx_normal16_lut_kernel<__VA_ARGS__>), "lut<" #__VA_ARGS__ ">",        \
-    kLutThreads, kLutTileVecs, static_cast<int>(kLutBytes), true, kLutTilesPerChunk }
+    static_cast<KernelFn>(TDX_LUT_KERNEL(__VA_ARGS__)), "lut<" #__VA_ARGS__ ">",                 \
+    kLutThreads, kLutTileVecs, static_cast<int>(kLutBytes) + 16, true, kLutTilesPerChunk,         \
+    static_cast<KernelFn>(TDX_LUT_KERNEL_ANY_SEED(__VA_ARGS__)) }
 
 using bf16 = __nv_bfloat16;
 using f16 = __half;
@@ -913,6 +1212,9 @@ struct PlanGroup {
   unsigned long long desc_off;
   uint32_t n_desc;
   uint32_t family;
+  unsigned long long seed;  // seed of the group's descriptors if they all share one
+  uint32_t seed_shared;
+  uint32_t pad_;
 };
 struct PlanHeader {
   uint32_t magic;
@@ -946,6 +1248,11 @@ DeviceInfo* device_info() {
       int nb = 0;
       if (kFamilies[f].dyn_smem &&
           cudaFuncSetAttribute(reinterpret_cast<const void*>(kFamilies[f].fn),
+                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               kFamilies[f].dyn_smem) != cudaSuccess)
+        return nullptr;
+      if (kFamilies[f].dyn_smem && kFamilies[f].fn_any_seed &&
+          cudaFuncSetAttribute(reinterpret_cast<const void*>(kFamilies[f].fn_any_seed),
                                cudaFuncAttributeMaxDynamicSharedMemorySize,
                                kFamilies[f].dyn_smem) != cudaSuccess)
         return nullptr;
@@ -1021,8 +1328,11 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
     off += static_cast<size_t>(G.n_desc) * sizeof(TdxInitDesc);
     unsigned long long acc = 0;
     uint32_t k = 0;
+    G.seed_shared = 1;
     for (int i = 0; i < n; ++i) {
       if (fam[i] != f) continue;
+      if (k == 0) G.seed = descs[i].philox_seed;
+      else if (descs[i].philox_seed != G.seed) G.seed_shared = 0;
       prefix[k] = acc;
       out[k] = descs[i];
       acc += tiles_of(descs[i], kFamilies[f].tile_vecs);
@@ -1102,13 +1412,24 @@ int launch_groups(const PlanHeader& hdr, void* workspace, cudaStream_t stream) {
     a.total_tiles = G.total_tiles;
     a.counter = &dev_hdr->counters[gi];
     a.n_desc = G.n_desc;
+    a.seed_shared = G.seed_shared;
+    {
+      uint32_t k0 = static_cast<uint32_t>(G.seed), k1 = static_cast<uint32_t>(G.seed >> 32);
+      for (int r = 0; r < 10; ++r) {
+        a.rk[2 * r] = k0;
+        a.rk[2 * r + 1] = k1;
+        k0 += kPhiloxW0;
+        k1 += kPhiloxW1;
+      }
+    }
     const int tpc = kFamilies[G.family].tiles_per_chunk;
     const unsigned long long chunks = (G.total_tiles + tpc - 1) / tpc;
     const unsigned long long resident =
         static_cast<unsigned long long>(info->sm_count) * info->blocks_per_sm[G.family];
     const unsigned int grid = static_cast<unsigned int>(std::min(chunks, resident));
     const Family& F = kFamilies[G.family];
-    F.fn<<<grid, F.threads, F.dyn_smem, stream>>>(a);
+    const KernelFn fn = (F.fn_any_seed && !G.seed_shared) ? F.fn_any_seed : F.fn;
+    fn<<<grid, F.threads, F.dyn_smem, stream>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, kFamilies[G.family].name);
     ++launches;
