@@ -526,6 +526,7 @@ struct GroupArgs {
   // (seed_shared != 0): kernel parameters live in the constant bank, so the 20 keys are operands of
   // the Philox LOP3s directly -- no registers, no per-vector key arithmetic.
   uint32_t seed_shared;
+  uint32_t tiles_per_chunk;  // table kernel: tiles per work grab (host-chosen, see launch_groups)
   uint32_t rk[20];
 };
 
@@ -560,19 +561,23 @@ __device__ __forceinline__ void for_each_tile_run(const GroupArgs& g, F&& f) {
   }
 }
 
-// Same contract, one barrier per grab instead of two: thread 0 fetches the NEXT chunk index at the
-// start of the current chunk (the atomic's round trip hides behind the chunk's work) and the single
-// barrier at the end of the chunk publishes it.  (ncu, table kernel: 6.5 % of the warp samples sat
-// in the two barriers of for_each_tile_run.)
-template <int TILES_PER_CHUNK, class F>
+// Same contract, one barrier per grab instead of two, and a grab size chosen per launch by the
+// host (GroupArgs.tiles_per_chunk): thread 0 fetches the NEXT chunk index at the start of the
+// current chunk (the atomic's round trip hides behind the chunk's work) and the single barrier at
+// the end of the chunk publishes it.  Measured on the table kernel (4 GiB, one descriptor): every
+// grab costs ~2 us (32 warps drain into the barrier, then the descriptor is looked up and set up
+// again) -- 0.631 / 0.667 / 0.686 / 0.697 of the HBM roof with 0.5 / 1 / 2 / 4 MiB grabs -- so the
+// host makes grabs as large as load balance allows.
+template <class F>
 __device__ __forceinline__ void for_each_tile_run_prefetch(const GroupArgs& g, unsigned int* s_next, F&& f) {
+  const unsigned int tpc = g.tiles_per_chunk;
   if (threadIdx.x == 0) s_next[0] = atomicAdd(g.counter, 1u);
   __syncthreads();
   for (unsigned int it = 0;; ++it) {
-    unsigned long long t = static_cast<unsigned long long>(s_next[it & 1u]) * TILES_PER_CHUNK;
+    unsigned long long t = static_cast<unsigned long long>(s_next[it & 1u]) * tpc;
     if (t >= g.total_tiles) return;
     if (threadIdx.x == 0) s_next[(it + 1u) & 1u] = atomicAdd(g.counter, 1u);
-    const unsigned long long last = min(t + TILES_PER_CHUNK, g.total_tiles);
+    const unsigned long long last = min(t + tpc, g.total_tiles);
     uint32_t lo = 0, hi = g.n_desc;  // find d with prefix[d] <= t < prefix[d+1]
     while (hi - lo > 1) {
       const uint32_t mid = (lo + hi) >> 1;
@@ -700,6 +705,11 @@ constexpr int kLutThreads = TDX_LUT_THREADS;
 constexpr int kLutVecsPerThread = TDX_LUT_VECS;
 constexpr int kLutTileVecs = kLutThreads * kLutVecsPerThread;  // bytes per tile = 16 x this
 constexpr int kLutTilesPerChunk = (1 << 20) / (kLutTileVecs * 16) > 0 ? (1 << 20) / (kLutTileVecs * 16) : 1;
+#ifndef TDX_LUT_MAX_CHUNK_LOG2
+#define TDX_LUT_MAX_CHUNK_LOG2 22
+#endif
+constexpr unsigned long long kLutMaxTilesPerChunk =
+    (1ull << TDX_LUT_MAX_CHUNK_LOG2) / (kLutTileVecs * 16) > 0 ? (1ull << TDX_LUT_MAX_CHUNK_LOG2) / (kLutTileVecs * 16) : 1;
 constexpr uint32_t kLutBytes = 65536u * 2u;
 constexpr uint64_t kLutMinLaunchElems = 1ull << 26;  // 128 MB of 16-bit output per launch (r1 sweep: break-even 130-200 MB)
 constexpr unsigned short kLutSentinel = 0xffffu;  // a NaN pattern in bf16 and fp16: never a value
@@ -922,6 +932,39 @@ struct NanAcc<__half> {
   }
 };
 
+// Tiles that are not made of full, aligned vectors only (unaligned shards, ragged ends) or that
+// straddle a 2^32-block boundary: out of line and self-contained (everything is re-derived from the
+// descriptor), so that none of its state is live across the hot loop of the table kernel.
+template <class Out, int R>
+__device__ __noinline__ void lut_ragged_tile(const TdxInitDesc* dp, unsigned long long tile) {
+  using Gen = GenNormalICDF16<Out, R, false>;
+  using T = OutTraits<Out>;
+  const TdxInitDesc& d = *dp;
+  const typename Gen::Params P = Gen::setup(d);
+  const uint64_t begin = d.elem_begin, count = d.elem_count;
+  const uint64_t gv0 = begin / 8;
+  const uint64_t nvec = (begin + count - 1) / 8 - gv0 + 1;
+  char* const dst = static_cast<char*>(d.dst);
+  const bool aligned = (begin % 8 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
+  const uint64_t nfull = aligned ? count / 8 : 0;
+  const uint64_t base = tile * kLutTileVecs + threadIdx.x;
+  for (int i = 0; i < kLutVecsPerThread; ++i) {
+    const uint64_t j = base + static_cast<uint64_t>(i) * kLutThreads;
+    if (j >= nvec) break;
+    float v[8];
+    Gen::gen(P, gv0 + j, v);
+    if (j < nfull) {
+      store_vec(dst + j * 16, T::pack(v));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const uint64_t gidx = (gv0 + j) * 8 + e;
+        if (gidx >= begin && gidx < begin + count) T::store_one(dst, gidx - begin, v[e]);
+      }
+    }
+  }
+}
+
 // Exponent-all-ones test of either half of a packed pair (inf or NaN).
 template <class Out>
 __device__ __forceinline__ bool any_nonfinite2(uint32_t v) {
@@ -945,8 +988,7 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_normal16_lut2_kernel(const
   unsigned int* const slots = reinterpret_cast<unsigned int*>(lut + 65536);
   const bool base_ok = static_cast<uint32_t>(__cvta_generic_to_shared(lut)) == kDynSmemBase;
   float have_mean = 0.f, have_std = -1.f;  // table contents (uniform across the CTA)
-  for_each_tile_run_prefetch<kLutTilesPerChunk>(g, slots, [&](uint32_t di, unsigned long long tile0,
-                                                              unsigned long long ntiles) {
+  for_each_tile_run_prefetch(g, slots, [&](uint32_t di, unsigned long long tile0, unsigned long long ntiles) {
     const TdxInitDesc& d = g.descs[di];
     typename Gen::Params P = Gen::setup(d);
     // Loop-invariant scalars that come out of a global load: a warp reduction's result lives in a
@@ -959,6 +1001,8 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_normal16_lut2_kernel(const
     P.c3 = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(P.c3)));
     P.c4 = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(P.c4)));
     P.c5 = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(P.c5)));
+    P.ph.cz = __reduce_or_sync(0xffffffffu, P.ph.cz);
+    P.ph.cw = __reduce_or_sync(0xffffffffu, P.ph.cw);
     if (P.mean != have_mean || P.std != have_std) {
       __syncthreads();  // everyone is done reading the old table
       for (uint32_t k = threadIdx.x; k < 65536u; k += kLutThreads) {
@@ -971,12 +1015,11 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_normal16_lut2_kernel(const
       have_mean = P.mean;
       have_std = P.std;
     }
-    const uint64_t begin = d.elem_begin, count = d.elem_count;
+    const uint64_t begin = d.elem_begin;
     const uint64_t gv0 = begin / 8;
-    const uint64_t nvec = (begin + count - 1) / 8 - gv0 + 1;
     char* const dst = static_cast<char*>(d.dst);
     const bool aligned = (begin % 8 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
-    const uint64_t nfull = aligned ? count / 8 : 0;
+    const uint64_t nfull = aligned ? d.elem_count / 8 : 0;
     for (unsigned long long tile = tile0; tile < tile0 + ntiles; ++tile) {
       const uint64_t tbase = tile * kLutTileVecs;  // first vector of the tile (descriptor-relative)
       const uint64_t gfirst = gv0 + tbase;         // its global block index
@@ -1029,22 +1072,7 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_normal16_lut2_kernel(const
           }
         }
       } else {
-        const uint64_t base = tbase + threadIdx.x;
-        for (int i = 0; i < kLutVecsPerThread; ++i) {
-          const uint64_t j = base + static_cast<uint64_t>(i) * kLutThreads;
-          if (j >= nvec) break;
-          float v[8];
-          Gen::gen(P, gv0 + j, v);
-          if (j < nfull) {
-            store_vec(dst + j * 16, T::pack(v));
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const uint64_t gidx = (gv0 + j) * 8 + e;
-              if (gidx >= begin && gidx < begin + count) T::store_one(dst, gidx - begin, v[e]);
-            }
-          }
-        }
+        lut_ragged_tile<Out, R>(&d, tile);
       }
     }
   });
@@ -1089,7 +1117,7 @@ struct Family {
 #define TDX_FAM_LUT(dt, rounds, ...)                                                             \
   { TDX_SRC_NORMAL, dt, TDX_ALGO_ICDF16, rounds, 0,                                              \
     static_cast<KernelFn>(TDX_LUT_KERNEL(__VA_ARGS__)), "lut<" #__VA_ARGS__ ">",                 \
-    kLutThreads, kLutTileVecs, static_cast<int>(kLutBytes) + 16, true, kLutTilesPerChunk,         \
+    kLutThreads, kLutTileVecs, static_cast<int>(kLutBytes) + 128, true, kLutTilesPerChunk,         \
     static_cast<KernelFn>(TDX_LUT_KERNEL_ANY_SEED(__VA_ARGS__)) }
 
 using bf16 = __nv_bfloat16;
@@ -1422,10 +1450,17 @@ int launch_groups(const PlanHeader& hdr, void* workspace, cudaStream_t stream) {
         k1 += kPhiloxW1;
       }
     }
-    const int tpc = kFamilies[G.family].tiles_per_chunk;
-    const unsigned long long chunks = (G.total_tiles + tpc - 1) / tpc;
     const unsigned long long resident =
         static_cast<unsigned long long>(info->sm_count) * info->blocks_per_sm[G.family];
+    int tpc = kFamilies[G.family].tiles_per_chunk;
+    if (kFamilies[G.family].lut) {
+      // table kernel: grabs of 1..16 tiles (256 KiB .. 4 MiB), at least ~24 grabs per CTA so that the
+      // last round of grabs does not leave SMs idle for long
+      const unsigned long long want = G.total_tiles / (resident * 24ull);
+      tpc = static_cast<int>(std::min<unsigned long long>(std::max<unsigned long long>(want, 1ull), kLutMaxTilesPerChunk));
+    }
+    a.tiles_per_chunk = static_cast<uint32_t>(tpc);
+    const unsigned long long chunks = (G.total_tiles + tpc - 1) / tpc;
     const unsigned int grid = static_cast<unsigned int>(std::min(chunks, resident));
     const Family& F = kFamilies[G.family];
     const KernelFn fn = (F.fn_any_seed && !G.seed_shared) ? F.fn_any_seed : F.fn;
