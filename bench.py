@@ -240,13 +240,22 @@ def run_ours(a):
 
     last_name = list(dict(fakes[0].named_parameters()))[-1]  # looked up outside the timed region
 
+    host_split = {"api_return_ms": 0.0, "sync_ms": 0.0, "n": 0}
+
     def step(m):
+        t0 = time.perf_counter()
         if world > 1:
             parallel.sync_rng(dev)  # the path's one collective, once per materialize_module (16 B)
         materialize_module(m, device=dev, shard=shard)
+        t1 = time.perf_counter()
         last = m.get_parameter(last_name)
         probe.copy_(last.detach().flatten()[:32], non_blocking=True)  # D2H read of the step's result
         torch.cuda.current_stream().synchronize()
+        t2 = time.perf_counter()
+        # where the host was when the API returned vs when the GPU was done (diagnostic only)
+        host_split["api_return_ms"] += (t1 - t0) * 1e3
+        host_split["sync_ms"] += (t2 - t0) * 1e3
+        host_split["n"] += 1
 
     e2e_ms, h2d = 0.0, 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -255,7 +264,7 @@ def run_ours(a):
         step(fakes[i])
         fakes[i] = None
     st = last_materialize_stats() if not a.roofline_only else {"descriptors": 0}
-    h2d = lib.tdx_init_workspace_bytes(st["descriptors"])  # plan image copied H2D per step (upper bound)
+    h2d = int(st.get("upload_bytes", 0))  # plan images (descriptors, prefix sums, work lists) copied H2D per step
     barrier()
     if not a.roofline_only:
         # Each step is timed on its own (events on the launching stream, bracketed by a
@@ -365,7 +374,9 @@ def run_ours(a):
                    "params": n_params, "tensors": n_tensors, "descriptors_per_rank": len(descs),
                    "fused_tensors": st["fused_tensors"], "generic_ops": st["generic_ops"],
                    "elided_rng_ops": st["elided_rng_ops"], "record_s_per_model": record_s,
-                   "host_us": {k: round(st[k]) for k in ("plan_us", "launch_us", "wrap_us")},
+                   "host_us": {k: round(st[k]) for k in ("plan_us", "launch_us", "wrap_us", "first_submit_us", "last_submit_us", "submissions")},
+                   "e2e_host_split_ms": {"api_return": round(host_split["api_return_ms"] / max(host_split["n"], 1), 3),
+                                         "gpu_done": round(host_split["sync_ms"] / max(host_split["n"], 1), 3)},
                    "l2": "outputs per step (GBs) exceed the 126 MB L2; no flush needed",
                    "timed_region_value": "tdx_plan_launch only (plan resident in HBM)",
                    "timed_region_e2e": "per step: materialize_module (traversal, plan, alloc, H2D descriptors, kernels) + 64 B D2H + sync; model teardown between steps untimed"},

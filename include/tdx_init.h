@@ -158,6 +158,10 @@ TDX_C_API int tdx_plan_launch(const TdxPlan* plan, void* workspace, void* stream
  * thread issued (one per non-empty kernel family). */
 TDX_C_API int tdx_last_launch_count(void);
 
+/* Bytes of the plan image (descriptor table, prefix sums, work lists) the last
+ * tdx_plan_upload/tdx_init_launch on this thread copied host -> device. */
+TDX_C_API size_t tdx_last_upload_bytes(void);
+
 /* Elements of the global tensor covered by one Philox block for this dtype/algo
  * (the planner rounds RNG consumption with it). */
 TDX_C_API int tdx_elems_per_block(int dtype, int src, int algo);

@@ -239,6 +239,27 @@ def test_generic_replay_on_cuda_for_unfusable_programs():
     assert torch.allclose(out, out.t())
 
 
+def test_generic_replay_reads_a_fused_tensor_that_is_still_in_the_batch():
+    """Unfusable buffers no longer force a submission of the pending fused descriptors -- unless the
+    replayed program reads one of them; then the batch must reach the stream first."""
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = nn.Parameter(torch.full((1 << 12,), 0.5, device="cuda"))           # fused, pending
+            self.u = nn.Parameter(torch.empty(1 << 12, device="cuda").uniform_(1, 2))   # fused, pending
+            self.register_buffer("cs", torch.cumsum(self.w.detach() * 2, 0))            # generic, reads w
+            self.register_buffer("iv", 1.0 / torch.arange(1, 9, device="cuda"))         # generic, independent
+            self.register_buffer("us", torch.sort(self.u.detach())[0])                  # generic, reads u
+
+    m = deferred_init(M)
+    materialize_module(m)
+    st = last_materialize_stats()
+    assert st["fused_tensors"] == 2 and st["generic_ops"] >= 3
+    assert torch.equal(m.cs, torch.arange(1, (1 << 12) + 1, device="cuda", dtype=torch.float32))
+    assert torch.equal(m.iv, 1.0 / torch.arange(1, 9, device="cuda"))
+    assert torch.equal(m.us, torch.sort(m.u.detach())[0]) and float(m.us[0]) >= 1.0 and float(m.us[-1]) < 2.0
+
+
 def test_cfg1_linear128_on_cpu_still_bit_exact_with_cuda_present():
     torch.manual_seed(0)
     m = deferred_init(nn.Linear, 128, 128)

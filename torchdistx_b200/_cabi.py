@@ -37,6 +37,7 @@ EXPORTED_SYMBOLS = (
     "tdx_plan_upload",
     "tdx_plan_launch",
     "tdx_last_launch_count",
+    "tdx_last_upload_bytes",
     "tdx_elems_per_block",
     "tdx_abi_version",
     "tdx_last_error",
@@ -99,6 +100,7 @@ def load() -> ctypes.CDLL:
     lib.tdx_plan_launch.restype = ctypes.c_int
     lib.tdx_plan_launch.argtypes = [ctypes.POINTER(TdxPlan), ctypes.c_void_p, ctypes.c_void_p]
     lib.tdx_last_launch_count.restype = ctypes.c_int
+    lib.tdx_last_upload_bytes.restype = ctypes.c_size_t
     lib.tdx_elems_per_block.restype = ctypes.c_int
     lib.tdx_elems_per_block.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
     lib.tdx_abi_version.restype = ctypes.c_int

@@ -526,7 +526,8 @@ struct GroupArgs {
   // (seed_shared != 0): kernel parameters live in the constant bank, so the 20 keys are operands of
   // the Philox LOP3s directly -- no registers, no per-vector key arithmetic.
   uint32_t seed_shared;
-  uint32_t tiles_per_chunk;  // table kernel: tiles per work grab (host-chosen, see launch_groups)
+  uint32_t n_chunks;           // table kernel: host-built work list (see build_chunks)
+  const uint4* chunks;         // {descriptor, tiles, first tile in descriptor (lo, hi)}
   uint32_t rk[20];
 };
 
@@ -561,36 +562,26 @@ __device__ __forceinline__ void for_each_tile_run(const GroupArgs& g, F&& f) {
   }
 }
 
-// Same contract, one barrier per grab instead of two, and a grab size chosen per launch by the
-// host (GroupArgs.tiles_per_chunk): thread 0 fetches the NEXT chunk index at the start of the
-// current chunk (the atomic's round trip hides behind the chunk's work) and the single barrier at
-// the end of the chunk publishes it.  Measured on the table kernel (4 GiB, one descriptor): every
-// grab costs ~2 us (32 warps drain into the barrier, then the descriptor is looked up and set up
-// again) -- 0.631 / 0.667 / 0.686 / 0.697 of the HBM roof with 0.5 / 1 / 2 / 4 MiB grabs -- so the
-// host makes grabs as large as load balance allows.
+// Scheduler of the table kernel: a host-built work list instead of (chunk index -> binary search).
+// Measured on the table kernel (4 GiB, one descriptor): every grab costs ~2 us -- 32 warps drain
+// into the barrier, then the descriptor is found and set up again: 0.631 / 0.667 / 0.686 / 0.697 of
+// the HBM roof with 0.5 / 1 / 2 / 4 MiB grabs -- and a binary search over a module's few hundred
+// descriptors adds ~8 dependent L2 round trips to each.  So the host cuts every descriptor into
+// grabs of its own (guided sizes: up to 4 MiB while there is plenty of work left, down to one
+// 256 KiB tile at the end, for balance), and a grab is one 16-byte load.  Thread 0 fetches the
+// NEXT list index at the start of the current grab (the atomic's round trip hides behind the
+// grab's work); the single barrier at the end of the grab publishes it.
 template <class F>
-__device__ __forceinline__ void for_each_tile_run_prefetch(const GroupArgs& g, unsigned int* s_next, F&& f) {
-  const unsigned int tpc = g.tiles_per_chunk;
+__device__ __forceinline__ void for_each_listed_chunk(const GroupArgs& g, unsigned int* s_next, F&& f) {
   if (threadIdx.x == 0) s_next[0] = atomicAdd(g.counter, 1u);
   __syncthreads();
   for (unsigned int it = 0;; ++it) {
-    unsigned long long t = static_cast<unsigned long long>(s_next[it & 1u]) * tpc;
-    if (t >= g.total_tiles) return;
+    const unsigned int c = s_next[it & 1u];
+    if (c >= g.n_chunks) return;
     if (threadIdx.x == 0) s_next[(it + 1u) & 1u] = atomicAdd(g.counter, 1u);
-    const unsigned long long last = min(t + tpc, g.total_tiles);
-    uint32_t lo = 0, hi = g.n_desc;  // find d with prefix[d] <= t < prefix[d+1]
-    while (hi - lo > 1) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (__ldg(g.tile_prefix + mid) <= t) lo = mid; else hi = mid;
-    }
-    uint32_t d = lo;
-    while (t < last) {
-      unsigned long long dend = __ldg(g.tile_prefix + d + 1);
-      while (dend <= t) dend = __ldg(g.tile_prefix + (++d) + 1);  // skip empty descriptors
-      const unsigned long long stop = min(dend, last);
-      f(d, t - __ldg(g.tile_prefix + d), stop - t);
-      t = stop;
-    }
+    const uint4 e = __ldg(g.chunks + c);
+    f(e.x, static_cast<unsigned long long>(e.z) | (static_cast<unsigned long long>(e.w) << 32),
+      static_cast<unsigned long long>(e.y));
     __syncthreads();
   }
 }
@@ -988,7 +979,7 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_normal16_lut2_kernel(const
   unsigned int* const slots = reinterpret_cast<unsigned int*>(lut + 65536);
   const bool base_ok = static_cast<uint32_t>(__cvta_generic_to_shared(lut)) == kDynSmemBase;
   float have_mean = 0.f, have_std = -1.f;  // table contents (uniform across the CTA)
-  for_each_tile_run_prefetch(g, slots, [&](uint32_t di, unsigned long long tile0, unsigned long long ntiles) {
+  for_each_listed_chunk(g, slots, [&](uint32_t di, unsigned long long tile0, unsigned long long ntiles) {
     const TdxInitDesc& d = g.descs[di];
     typename Gen::Params P = Gen::setup(d);
     // Loop-invariant scalars that come out of a global load: a warp reduction's result lives in a
@@ -1162,6 +1153,7 @@ constexpr int kNumFamilies = sizeof(kFamilies) / sizeof(kFamilies[0]);
 
 thread_local char g_err[256] = "";
 thread_local int g_last_launches = 0;
+thread_local size_t g_last_upload_bytes = 0;
 
 int fail(int code, const char* msg) {
   snprintf(g_err, sizeof(g_err), "%s", msg);
@@ -1242,7 +1234,8 @@ struct PlanGroup {
   uint32_t family;
   unsigned long long seed;  // seed of the group's descriptors if they all share one
   uint32_t seed_shared;
-  uint32_t pad_;
+  uint32_t n_chunks;             // table kernel only: entries of the work list
+  unsigned long long chunk_off;  // and its byte offset
 };
 struct PlanHeader {
   uint32_t magic;
@@ -1253,10 +1246,15 @@ struct PlanHeader {
 constexpr uint32_t kPlanMagic = 0x58445431u;  // "TDX1"
 static_assert(kNumFamilies <= 32, "counter slots");
 
+// Work list of the table kernel: at most kMaxListChunks "large" grabs (the grab cap grows with the
+// launch so that this holds), a guided tail, and one partial grab per descriptor.
+constexpr size_t kMaxListChunks = 8192;
+constexpr size_t kMaxListTail = 4096;
 size_t plan_bytes(int n) {
-  // header + per-family prefix arrays (n + #families entries worst case) + descriptors
+  // header + per-family prefix arrays (n + #families entries worst case) + descriptors + work lists
   return sizeof(PlanHeader) + (static_cast<size_t>(n) + kNumFamilies) * sizeof(unsigned long long) +
-         static_cast<size_t>(n) * sizeof(TdxInitDesc) + 64;
+         static_cast<size_t>(n) * sizeof(TdxInitDesc) +
+         (2 * (kMaxListChunks + kMaxListTail) + static_cast<size_t>(n)) * sizeof(uint4) + 64;
 }
 
 struct DeviceInfo {
@@ -1341,6 +1339,8 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
   memset(&hdr, 0, sizeof(hdr));
   hdr.magic = kPlanMagic;
   img.assign(plan_bytes(n), 0);
+  int sm_count = 148;
+  if (DeviceInfo* info = device_info()) sm_count = info->sm_count;
   size_t off = (sizeof(PlanHeader) + 15) & ~static_cast<size_t>(15);
   for (int f = 0; f < kNumFamilies; ++f) {
     if (!per_family[f]) continue;
@@ -1368,6 +1368,32 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
     }
     prefix[k] = acc;
     G.total_tiles = acc;
+    if (kFamilies[f].lut) {
+      // guided work list: grab = remaining / (2 * CTAs), between 1 tile and the cap
+      off = (off + 15) & ~static_cast<size_t>(15);
+      G.chunk_off = off;
+      auto* list = reinterpret_cast<uint4*>(img.data() + off);
+      const unsigned long long ctas = static_cast<unsigned long long>(std::max(sm_count, 1));
+      const unsigned long long cap =
+          std::max<unsigned long long>(kLutMaxTilesPerChunk, (acc + kMaxListChunks - 1) / kMaxListChunks);
+      // below this many remaining tiles the sizes shrink; the tail is at most kMaxListTail entries
+      unsigned long long remaining = acc;
+      uint32_t nc = 0;
+      for (uint32_t di = 0; di < G.n_desc; ++di) {
+        unsigned long long t = 0;
+        const unsigned long long nt = prefix[di + 1] - prefix[di];
+        while (t < nt) {
+          unsigned long long sz = std::min(std::max(remaining / (2 * ctas), 1ull), cap);
+          sz = std::min(sz, nt - t);
+          list[nc++] = make_uint4(di, static_cast<uint32_t>(sz), static_cast<uint32_t>(t),
+                                  static_cast<uint32_t>(t >> 32));
+          t += sz;
+          remaining -= sz;
+        }
+      }
+      G.n_chunks = nc;
+      off += static_cast<size_t>(nc) * sizeof(uint4);
+    }
   }
   memcpy(img.data(), &hdr, sizeof(hdr));
   img.resize(off);
@@ -1452,15 +1478,11 @@ int launch_groups(const PlanHeader& hdr, void* workspace, cudaStream_t stream) {
     }
     const unsigned long long resident =
         static_cast<unsigned long long>(info->sm_count) * info->blocks_per_sm[G.family];
-    int tpc = kFamilies[G.family].tiles_per_chunk;
-    if (kFamilies[G.family].lut) {
-      // table kernel: grabs of 1..16 tiles (256 KiB .. 4 MiB), at least ~24 grabs per CTA so that the
-      // last round of grabs does not leave SMs idle for long
-      const unsigned long long want = G.total_tiles / (resident * 24ull);
-      tpc = static_cast<int>(std::min<unsigned long long>(std::max<unsigned long long>(want, 1ull), kLutMaxTilesPerChunk));
-    }
-    a.tiles_per_chunk = static_cast<uint32_t>(tpc);
-    const unsigned long long chunks = (G.total_tiles + tpc - 1) / tpc;
+    const int tpc = kFamilies[G.family].tiles_per_chunk;
+    a.n_chunks = G.n_chunks;
+    a.chunks = reinterpret_cast<const uint4*>(base + G.chunk_off);
+    const unsigned long long chunks =
+        kFamilies[G.family].lut ? G.n_chunks : (G.total_tiles + tpc - 1) / tpc;
     const unsigned int grid = static_cast<unsigned int>(std::min(chunks, resident));
     const Family& F = kFamilies[G.family];
     const KernelFn fn = (F.fn_any_seed && !G.seed_shared) ? F.fn_any_seed : F.fn;
@@ -1489,6 +1511,7 @@ TDX_C_API int tdx_plan_upload(const TdxInitDesc* descs, int n, void* workspace,
   memcpy(plan, &hdr, sizeof(hdr));
   if (workspace == nullptr || workspace_bytes < img.size())
     return tdx::fail(TDX_E_WORKSPACE, "workspace too small (see tdx_init_workspace_bytes)");
+  tdx::g_last_upload_bytes = img.size();
   cudaError_t e = cudaMemcpyAsync(workspace, img.data(), img.size(), cudaMemcpyHostToDevice,
                                   static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return tdx::cuda_fail(e, "cudaMemcpyAsync(plan)");
@@ -1520,6 +1543,7 @@ TDX_C_API int tdx_init_launch(const TdxInitDesc* descs, int n, void* workspace,
     return tdx::fail(TDX_E_WORKSPACE, "workspace too small (see tdx_init_workspace_bytes)");
   // The plan image goes through a small ring of pinned staging buffers so that the copy is truly
   // asynchronous: the host can go on planning the next batch while the GPU works on this one.
+  tdx::g_last_upload_bytes = img.size();
   void* pinned = nullptr;
   if (int rc = tdx::stage(img.data(), img.size(), static_cast<cudaStream_t>(stream), workspace, &pinned))
     return rc;
@@ -1527,6 +1551,7 @@ TDX_C_API int tdx_init_launch(const TdxInitDesc* descs, int n, void* workspace,
 }
 
 TDX_C_API int tdx_last_launch_count(void) { return tdx::g_last_launches; }
+TDX_C_API size_t tdx_last_upload_bytes(void) { return tdx::g_last_upload_bytes; }
 
 TDX_C_API int tdx_elems_per_block(int dtype, int src, int algo) {
   if (src == TDX_SRC_CONST) return 0;

@@ -417,6 +417,7 @@ Sym eval_storage(Tape& tape, uint32_t S, uint32_t upto) {
 // batched fused execution
 // ---------------------------------------------------------------------------------------------
 double now_us();
+thread_local double g_call_begin_us = 0;
 
 struct Batch {
   c10::Device device = c10::Device(c10::kCPU);
@@ -427,6 +428,7 @@ struct Batch {
   // writing while the host is still planning the rest of the module; the threshold quadruples after
   // every submission so that the launch count (each launch has a ~10-20 us tail) stays logarithmic.
   int64_t pending_bytes = 0;
+  uint64_t epoch = 1;  // bumped by every submission: a storage whose fused_epoch == epoch is not on the GPU yet
   int64_t flush_threshold = flush_start();
   static int64_t flush_start() {
     static const int64_t v = [] {
@@ -452,7 +454,10 @@ double now_us() {
 }
 
 void Batch::flush() {
-  if (descs.empty()) return;
+  if (descs.empty()) {
+    ++epoch;
+    return;
+  }
   const double t0 = now_us();
   NoInterception guard;
   c10::DeviceGuard dg(device);
@@ -465,10 +470,15 @@ void Batch::flush() {
   TORCH_CHECK(rc == 0, "libtdx_init: launch failed (", rc, "): ", tdx_last_error());
   g_stats.kernel_launches += tdx_last_launch_count();
   g_stats.descriptors += n;
+  g_stats.submissions++;
+  g_stats.upload_bytes += static_cast<int64_t>(tdx_last_upload_bytes());
+  if (g_stats.first_submit_us == 0) g_stats.first_submit_us = now_us() - g_call_begin_us;
+  g_stats.last_submit_us = now_us() - g_call_begin_us;
   g_last_descs.insert(g_last_descs.end(), descs.begin(), descs.end());
   descs.clear();
   keep_alive.clear();
   pending_bytes = 0;
+  ++epoch;
   g_stats.launch_us += now_us() - t0;
 }
 
@@ -648,6 +658,9 @@ struct Engine {
     for_each_tensor_mut(stack, nargs, [&](at::Tensor& t) {
       InputRef& in = op.inputs[slot++];
       if (in.value != kNoValue) {
+        // a fused result that is still sitting in the batch must reach the stream before ATen reads it
+        const StorageInfo& isi = tape.storages[tape.values[in.value].storage];
+        if (isi.fused_done && isi.fused_epoch == batch.epoch) batch.flush();
         t = real_of(tape, in.value);
       } else if (in.foreign) {
         t = materialize_value(in.foreign, in.foreign_value);
@@ -787,6 +800,7 @@ struct Engine {
 
     si.base = base;
     si.fused_done = true;
+    si.fused_epoch = batch.epoch;
     for (uint32_t oi : si.touching_ops) {
       TapeOp& op = tape.ops[oi];
       bool writes = false;
@@ -808,8 +822,9 @@ struct Engine {
     if (tape.storages[vi.storage].fused_done) return real_of(tape, v);
     if (try_fused(tape, v)) return real_of(tape, v);
 
-    // generic replay, in recorded order, of everything that determines this storage
-    batch.flush();
+    // generic replay, in recorded order, of everything that determines this storage.  Pending fused
+    // descriptors stay in the batch (replay() submits them first if one of its inputs is among them):
+    // a module's few unfusable buffers do not split the batch into extra launches.
     gens.write_back();  // ATen's own RNG kernels read the generators
     std::vector<uint8_t> mark(tape.ops.size(), 0);
     std::vector<uint32_t> visited(tape.storages.size(), 0);
@@ -846,6 +861,7 @@ std::vector<at::Tensor> materialize_many(const std::vector<at::Tensor>& fakes,
   g_stats = MaterializeStats{};
   g_last_descs.clear();
   const double t_begin = now_us();
+  g_call_begin_us = t_begin;
   std::vector<at::Tensor> out;
   out.reserve(fakes.size());
   Batch batch;

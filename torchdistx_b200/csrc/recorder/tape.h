@@ -76,6 +76,7 @@ struct StorageInfo {
   at::Tensor base;        // real backing tensor once the fused path materialised the storage
   bool fused_done = false;
   bool base_taken = false;  // `base` itself has been handed out as some value's tensor
+  uint64_t fused_epoch = 0;  // submission epoch of the batch that holds (held) its descriptor
 };
 
 // A tensor argument of a recorded op.
