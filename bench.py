@@ -332,7 +332,7 @@ def run_ours(a):
     peak, peak_src = peaks()
     achieved = dom_bytes / dom_ms / 1e6
     kname = {C.TDX_SRC_CONST: "tdx_fill_kernel", C.TDX_SRC_UNIFORM: "tdx_rng_kernel<GenUniform*>",
-             C.TDX_SRC_NORMAL: "tdx_normal16_lut_kernel<bf16> (+ tdx_rng_kernel<GenNormalICDF16<bf16>> for descriptors < 2^20 elements)"
+             C.TDX_SRC_NORMAL: "tdx_normal16_lut2_kernel<bf16> (+ tdx_rng_kernel<GenNormalICDF16<bf16>> for descriptors < 2^20 elements)"
              if dtype == "bf16" else "tdx_rng_kernel<GenNormalBM32<bf16>> (TDX_ALGO_WIDE32)" if dtype == "fp32->bf16"
              else "tdx_rng_kernel<GenNormalBM32<float>>"}[dom_key[0]]
     if a.roofline_only:

@@ -40,6 +40,9 @@ namespace tdx {
 #ifndef TDX_VECS
 #define TDX_VECS 4
 #endif
+#ifndef TDX_UNIFORM16_PACKED
+#define TDX_UNIFORM16_PACKED 1
+#endif
 constexpr int kThreads = 256;
 constexpr int kVecsPerThread = TDX_VECS;
 constexpr int kTileVecs = kThreads * kVecsPerThread;  // 1024 x 16 B = 16 KiB per tile
@@ -138,6 +141,11 @@ struct OutTraits<__nv_bfloat16> {
     __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&p);
   }
+  __device__ static __forceinline__ uint32_t min2(uint32_t a, uint32_t b) {
+    const __nv_bfloat162 m = __hmin2(*reinterpret_cast<const __nv_bfloat162*>(&a),
+                                     *reinterpret_cast<const __nv_bfloat162*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&m);
+  }
   __device__ static __forceinline__ bool any_nan4(const uint32_t (&r)[4]) {
     const __nv_bfloat162 s = __hadd2(__hadd2(*reinterpret_cast<const __nv_bfloat162*>(&r[0]),
                                              *reinterpret_cast<const __nv_bfloat162*>(&r[1])),
@@ -177,6 +185,10 @@ struct OutTraits<__half> {
   __device__ static __forceinline__ uint32_t pack2(float a, float b) {
     __half2 p = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&p);
+  }
+  __device__ static __forceinline__ uint32_t min2(uint32_t a, uint32_t b) {
+    const __half2 m = __hmin2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&m);
   }
   __device__ static __forceinline__ bool any_nan4(const uint32_t (&r)[4]) {
     const __half2 s = __hadd2(__hadd2(*reinterpret_cast<const __half2*>(&r[0]),
@@ -286,6 +298,13 @@ struct GenUniform16 {
     p.scale = (to - from) * 1.52587890625e-05f;  // * 2^-16, exact
     p.to_prev = (to > from) ? OutTraits<Out>::prev(to) : to;
     if (EPI) p.epi = load_epi(d);
+#if TDX_UNIFORM16_PACKED
+    // the three scalars are the same for every thread; out of a warp reduction they live in uniform
+    // registers and the per-element FFMA reads two vector registers instead of three
+    p.from = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(p.from)));
+    p.scale = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(p.scale)));
+    p.to_prev = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(p.to_prev)));
+#endif
     return p;
   }
   __device__ static __forceinline__ void gen(const Params& p, uint64_t gv, float (&v)[8]) {
@@ -297,7 +316,31 @@ struct GenUniform16 {
       v[e] = EPI ? apply_epi<Out>(p.epi, x) : x;
     }
   }
+  // Whole-vector form for the hot path (no epilogue): the clamp below `to` is applied to the packed
+  // pairs (4 packed mins instead of 8 scalar ones).  Rounding is monotone and to_prev is a value of
+  // the output type (checked by the caller: packed_ok), so min(round(x), to_prev) == round(min(x,
+  // to_prev)): the same bits as gen().
+  __device__ static __forceinline__ bool packed_ok(const Params& p) {
+    return !EPI && OutTraits<Out>::round_through(p.to_prev) == p.to_prev;
+  }
+  __device__ static __forceinline__ uint4 gen_vec(const Params& p, uint64_t gv) {
+    using T = OutTraits<Out>;
+    const uint4 w = philox_block<R>(p.ph, gv);
+    const uint32_t lim = T::pack2(p.to_prev, p.to_prev);
+    uint32_t r[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float a = fmaf(halfword_as_magic(w, 2 * q) - 8388608.0f, p.scale, p.from);
+      const float b = fmaf(halfword_as_magic(w, 2 * q + 1) - 8388608.0f, p.scale, p.from);
+      r[q] = T::min2(T::pack2(a, b), lim);
+    }
+    return make_uint4(r[0], r[1], r[2], r[3]);
+  }
 };
+template <class Gen>
+struct HasGenVec { static constexpr bool value = false; };
+template <class Out, int R>
+struct HasGenVec<GenUniform16<Out, R, false>> { static constexpr bool value = TDX_UNIFORM16_PACKED != 0; };
 
 // ---- uniform, 24-bit mantissa from 32 random bits per element -------------------------------
 // fp32 outputs, and the "wide" form of 16-bit outputs (TDX_ALGO_WIDE32): exactly what
@@ -608,6 +651,16 @@ __global__ void __launch_bounds__(kThreads) tdx_rng_kernel(const GroupArgs g) {
     for (unsigned long long tile = tile0; tile < tile0 + ntiles; ++tile) {
       const uint64_t base = tile * kTileVecs + threadIdx.x;
       if (base - threadIdx.x + kTileVecs <= nfull) {  // hot path: whole tile is full vectors
+        if constexpr (HasGenVec<Gen>::value) {
+          if (Gen::packed_ok(P)) {
+#pragma unroll
+            for (int i = 0; i < kVecsPerThread; ++i) {
+              const uint64_t j = base + static_cast<uint64_t>(i) * kThreads;
+              store_vec(dst + j * 16, Gen::gen_vec(P, gv0 + j));
+            }
+            continue;
+          }
+        }
 #pragma unroll
         for (int i = 0; i < kVecsPerThread; ++i) {
           const uint64_t j = base + static_cast<uint64_t>(i) * kThreads;
