@@ -30,6 +30,8 @@ VARIANTS = {
     "fill_bf16": (C.TDX_BF16, torch.bfloat16, C.TDX_SRC_CONST, 0, 0, 0),
     "fill_f32": (C.TDX_F32, torch.float32, C.TDX_SRC_CONST, 0, 0, 0),
     "uniform_bf16": (C.TDX_BF16, torch.bfloat16, C.TDX_SRC_UNIFORM, 0, -0.05, 0.05),
+    "uniform_bf16_nolut": (C.TDX_BF16, torch.bfloat16, C.TDX_SRC_UNIFORM, C.TDX_ALGO_NOLUT, -0.05, 0.05),
+    "uniform_f16": (C.TDX_F16, torch.float16, C.TDX_SRC_UNIFORM, 0, -0.05, 0.05),
     "uniform_bf16_r7": (C.TDX_BF16, torch.bfloat16, C.TDX_SRC_UNIFORM, C.TDX_ALGO_R7, -0.05, 0.05),
     "uniform_f32": (C.TDX_F32, torch.float32, C.TDX_SRC_UNIFORM, 0, -0.05, 0.05),
     "normal_bf16_icdf16": (C.TDX_BF16, torch.bfloat16, C.TDX_SRC_NORMAL, C.TDX_ALGO_ICDF16, 0.0, 0.02),

@@ -183,6 +183,34 @@ def test_determinism_and_seed_sensitivity():
     assert torch.equal(a, b) and (a != c).float().mean() > 0.9
 
 
+@pytest.mark.parametrize("dtype", [C.TDX_BF16, C.TDX_F16])
+def test_table_driven_uniform_is_bit_identical_to_the_direct_kernel_and_the_oracle(dtype):
+    """16-bit uniforms of large descriptors go through the same table kernel (table entry k =
+    the direct kernel's value for half-word k); different bounds force table rebuilds."""
+    sizes = [(1 << 26) + 9, (1 << 21) + 12345, 1 << 20, 5000]
+    bounds = [(-0.05, 0.05), (0.0, 1.0), (-3.0, -1.0), (2.0, 2.5)]
+    outs = {}
+    for flag in (0, C.TDX_ALGO_NOLUT):
+        bufs, descs = [], []
+        for i, (n, (lo, hi)) in enumerate(zip(sizes, bounds)):
+            t = torch.zeros(n, dtype=TORCH_DT[dtype], device="cuda")
+            bufs.append(t)
+            descs.append(C.make_desc(t.data_ptr(), dtype=dtype, src=C.TDX_SRC_UNIFORM, elem_count=n, seed=91,
+                                     offset=4096 * i, p0=lo, p1=hi, algo=flag))
+        launches = run_descs(descs, bufs)
+        assert launches == (2 if flag == 0 else 1)  # table kernel + direct kernel (small descriptor)
+        outs[flag] = (bufs, descs)
+    for a, b in zip(outs[0][0], outs[C.TDX_ALGO_NOLUT][0]):
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+    for t, d, (lo, hi) in zip(outs[0][0], outs[0][1], bounds):
+        head = C.make_desc(0, dtype=dtype, src=C.TDX_SRC_UNIFORM, elem_count=1 << 12, seed=91,
+                           offset=d.philox_offset, p0=lo, p1=hi)
+        assert np.array_equal(gpu_bits(t[:1 << 12], dtype), O.generate(head))
+        f = t.float()
+        lo_r, hi_r = (float(torch.tensor(v, dtype=TORCH_DT[dtype])) for v in (lo, hi))  # bounds as the dtype sees them
+        assert float(f.min()) >= lo_r and float(f.max()) <= hi_r
+
+
 def test_table_kernel_with_mixed_seeds_and_across_a_2_32_block_boundary():
     """The table kernel takes its Philox round keys from kernel parameters when the launch shares
     one seed and from the descriptors otherwise; inside a tile it treats counter.y (block >> 32) as

@@ -727,18 +727,14 @@ __global__ void __launch_bounds__(kThreads) tdx_fill_kernel(const GroupArgs g) {
 
 
 // ---------------------------------------------------------------------------------------------
-// 16-bit normal through a shared-memory table
+// 16-bit outputs through a shared-memory table
 // ---------------------------------------------------------------------------------------------
-// The 16-bit normal is a pure function of k in [0, 65535] once (mean, std) are fixed, so a CTA
-// can evaluate GenNormalICDF16::element once per k into a 128 KiB shared-memory table and then
-// turn every Philox half-word into an output with one LDS.U16 instead of 1 MUFU + 8 FMA-pipe
-// instructions.  The table is built by the SAME device function as the direct kernel, so the
-// two kernels are bit-identical (tests/test_kernels_gpu.py checks it); the host picks this
-// kernel for large descriptors only, because the table costs 65536 evaluations per CTA.
-// Per 8-element vector: Philox 40 slots + 12 address + 8 LDS + 4 pack + ~6 tail check.
-#ifndef TDX_LUT_WORDS
-#define TDX_LUT_WORDS 4
-#endif
+// A 16-bit normal or uniform is a pure function of the Philox half-word k in [0, 65535] once the
+// descriptor's parameters are fixed, so a CTA evaluates it once per k into a 128 KiB shared-memory
+// table and then turns most half-words into outputs with one LDS.U16 each.  The table is built by
+// the SAME device function as the direct kernel, so the two are bit-identical
+// (tests/test_kernels_gpu.py checks it); the host picks this kernel for large descriptors only,
+// because the table costs 65536 evaluations per CTA.
 #ifndef TDX_LUT_THREADS
 #define TDX_LUT_THREADS 1024
 #endif
@@ -758,9 +754,6 @@ constexpr uint32_t kLutBytes = 65536u * 2u;
 constexpr uint64_t kLutMinLaunchElems = 1ull << 26;  // 128 MB of 16-bit output per launch (r1 sweep: break-even 130-200 MB)
 constexpr unsigned short kLutSentinel = 0xffffu;  // a NaN pattern in bf16 and fp16: never a value
 
-// LUT_WORDS of the 4 Philox words of a vector (2 elements each) go through the table, the rest
-// through the polynomial: the table loads keep the LSU/shared-memory pipe busy, the polynomial the
-// otherwise idle FMA and MUFU pipes.
 // cold path of the table kernel (a vector that contains k == 0): out of line, to keep the hot loop
 // small enough for the instruction cache
 template <class Out, int R>
@@ -772,117 +765,25 @@ __device__ __noinline__ uint4 lut_slow_vector(const TdxInitDesc* d, uint64_t gv)
   return OutTraits<Out>::pack(v);
 }
 
-template <class Out, int R, int LUT_WORDS = 4>
-__global__ void __launch_bounds__(kLutThreads, 1) tdx_normal16_lut_kernel(const GroupArgs g) {
-  using Gen = GenNormalICDF16<Out, R, false>;
-  using T = OutTraits<Out>;
-  extern __shared__ __align__(16) unsigned short lut[];
-  float have_mean = 0.f, have_std = -1.f;  // table contents (uniform across the CTA)
-  for_each_tile_run<kLutTilesPerChunk>(g, [&](uint32_t di, unsigned long long tile0, unsigned long long ntiles) {
-    const TdxInitDesc& d = g.descs[di];
-    const typename Gen::Params P = Gen::setup(d);
-    if (P.mean != have_mean || P.std != have_std) {
-      __syncthreads();  // everyone is done reading the old table
-      for (uint32_t k = threadIdx.x; k < 65536u; k += kLutThreads) {
-        float t;
-        const float v = Gen::element(P, __uint_as_float(0x4b000000u | k), t);
-        const Out o = static_cast<Out>(v);
-        lut[k] = k == 0 ? kLutSentinel : *reinterpret_cast<const unsigned short*>(&o);
-      }
-      __syncthreads();
-      have_mean = P.mean;
-      have_std = P.std;
-    }
-    const uint64_t begin = d.elem_begin, count = d.elem_count;
-    const uint64_t gv0 = begin / 8;
-    const uint64_t nvec = (begin + count - 1) / 8 - gv0 + 1;
-    char* const dst = static_cast<char*>(d.dst);
-    const bool aligned = (begin % 8 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
-    const uint64_t nfull = aligned ? count / 8 : 0;
-    const char* const lut_bytes = reinterpret_cast<const char*>(lut);
-#ifdef TDX_LUT_CONFLICT_FREE_EXPERIMENT
-    const uint32_t lane4 = (threadIdx.x & 31u) * 4u;
-#endif
-    for (unsigned long long tile = tile0; tile < tile0 + ntiles; ++tile) {
-      const uint64_t base = tile * kLutTileVecs + threadIdx.x;
-      if (base - threadIdx.x + kLutTileVecs <= nfull) {
-#pragma unroll
-        for (int i = 0; i < kLutVecsPerThread; ++i) {
-          const uint64_t j = base + static_cast<uint64_t>(i) * kLutThreads;
-          const uint4 w = philox_block<R>(P.ph, gv0 + j);
-          const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-          uint32_t r[4];
-          float tmin = 1.0f;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (q < LUT_WORDS) {
-              // byte offsets 2*k of the two half-words: one PRMT (zero-extend) on the ALU pipe and
-              // one multiply-by-2 on the FMA pipe each.  The ALU pipe (half rate) also carries
-              // Philox's 20 LOP3, so everything that can be phrased otherwise stays off it.
-#ifdef TDX_LUT_CONFLICT_FREE_EXPERIMENT
-              // timing experiment only (wrong values): every lane reads its own bank
-              const uint32_t lo = ((ws[q] << 7) & 0x1ff80u) + lane4;
-              const uint32_t hi = ((ws[q] >> 9) & 0x1ff80u) + lane4;
-#else
-              const uint32_t lo = __byte_perm(ws[q], 0u, 0x4410) * 2u;
-              const uint32_t hi = __byte_perm(ws[q], 0u, 0x4432) * 2u;
-#endif
-              const uint32_t a = *reinterpret_cast<const unsigned short*>(lut_bytes + lo);
-              const uint32_t b = *reinterpret_cast<const unsigned short*>(lut_bytes + hi);
-              r[q] = a | (b << 16);
-            } else {
-              float ta, tb;
-              const float va = Gen::element(P, halfword_as_magic(w, 2 * q), ta);
-              const float vb = Gen::element(P, halfword_as_magic(w, 2 * q + 1), tb);
-              tmin = fminf(tmin, fminf(ta, tb));
-              r[q] = T::pack2(va, vb);
-            }
-          }
-          uint4 out = make_uint4(r[0], r[1], r[2], r[3]);
-          // k == 0 reads the NaN sentinel; a packed add of the four result words propagates it
-          // (3 HADD2 on the FMA pipe + 1 test instead of 8 integer mins on the ALU pipe)
-          if (T::any_nan4(r) || tmin <= 0.0f)  // rare: direct path for this vector
-            out = lut_slow_vector<Out, R>(&d, gv0 + j);
-          store_vec(dst + j * 16, out);
-        }
-      } else {
-        for (int i = 0; i < kLutVecsPerThread; ++i) {
-          const uint64_t j = base + static_cast<uint64_t>(i) * kLutThreads;
-          if (j >= nvec) break;
-          float v[8];
-          Gen::gen(P, gv0 + j, v);
-          if (j < nfull) {
-            store_vec(dst + j * 16, T::pack(v));
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const uint64_t gidx = (gv0 + j) * 8 + e;
-              if (gidx >= begin && gidx < begin + count) T::store_one(dst, gidx - begin, v[e]);
-            }
-          }
-        }
-      }
-    }
-  });
-}
-
 // ---------------------------------------------------------------------------------------------
-// table kernel, second generation: the same table, a leaner instruction stream
+// the table kernel
 // ---------------------------------------------------------------------------------------------
-// ncu of the first table kernel (profiles/r1_ncu_bench_llama3_8b_lut_kernel.json): 93 instructions
-// per 8-element vector, ALU pipe (half rate) 82 of 149 cycles, LSU wavefronts 88 % of peak.  Changes:
-//  * byte address of a table entry = base + 2*k in ONE instruction: IDP.2A (dp2a.lo with the byte
-//    pair (2,0) or (0,2) selects a half-word, doubles it and adds the table base) on the FMA pipe
-//    instead of PRMT + IADD3 on the ALU pipe;
+// What shaped it (ncu of its first version, profiles/r1_ncu_bench_llama3_8b_lut_kernel.json: 93
+// instructions per 8-element vector, LSU wavefronts 88 % of peak; and benchmarks/instr_rate.cu):
+//  * byte address of a table entry = 2*k in ONE instruction: IDP.2A (dp2a.lo with the byte pair
+//    (2,0) or (0,2) selects a half-word and doubles it) instead of PRMT + IADD3; the table's base
+//    is the LDS immediate;
 //  * counter.y (blk >> 32) is uniform inside a tile, so Philox round 1's second product and round
 //    2's first product are loop-invariant: 18 IMAD.WIDE + 19 LOP3 per block instead of 20 + 20;
-//  * the k == 0 sentinel (NaN) is accumulated with 2 HFMA2 per vector (NaN survives a*b+c) and
-//    tested once per GROUP vectors; a hit re-derives the group's Philox blocks and repairs only
-//    the vectors that really contain a zero half-word;
-//  * LUT_ELEMS of the 8 elements of a vector go through the table, the others through the
-//    polynomial (same device function as the table builder => same bits): with the leaner stream
-//    the shared-memory wavefronts (3.56 per LDS on random indices) are the limit, and the FMA-lite
-//    and MUFU pipes are idle.
+//    the round keys are kernel parameters (constant bank operands of the LOP3s);
+//  * the normal's k == 0 sentinel (NaN) is accumulated with 2 HFMA2 per vector (NaN survives
+//    a*b+c) and tested once per GROUP vectors; a hit re-derives the group's Philox blocks and
+//    repairs only the vectors that really contain a zero half-word;
+//  * LUT_ELEMS of the 8 elements of a vector go through the table, the others are computed (same
+//    device function as the table builder => same bits): random indices cost 3.56 shared-memory
+//    wavefronts per LDS and an SM delivers one wavefront per cycle, so a pure table kernel is
+//    LSU-bound at 0.63 of the HBM roof;
+//  * work comes from a host-built list of descriptor-pure grabs (for_each_listed_chunk).
 #ifndef TDX_LUT2_ELEMS_A
 #define TDX_LUT2_ELEMS_A 7
 #endif
@@ -976,12 +877,56 @@ struct NanAcc<__half> {
   }
 };
 
+// What the table kernel needs to know about a 16-bit generator: the value of half-word k (the table
+// entry and, for the elements that are not looked up, the directly computed value -- one device
+// function, hence the same bits), the parameters that identify a table, and whether some k needs the
+// exact out-of-line path (the normal's k == 0 tail).
+template <class Out, int R>
+struct TabNormal {
+  using Gen = GenNormalICDF16<Out, R, false>;
+  using Params = typename Gen::Params;
+  static constexpr bool kHasTail = true;
+  __device__ static __forceinline__ float value(const Params& p, float magic) {
+    float t;
+    return Gen::element(p, magic, t);  // k == 0: +-inf or NaN (lg2(0) = -inf)
+  }
+  __device__ static __forceinline__ void uniformize(Params& p) {
+    p.mean = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(p.mean)));
+    p.c0 = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(p.c0)));
+    p.c1 = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(p.c1)));
+    p.c2 = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(p.c2)));
+    p.c3 = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(p.c3)));
+    p.c4 = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(p.c4)));
+    p.c5 = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(p.c5)));
+  }
+  __device__ static __forceinline__ float key0(const Params& p) { return p.mean; }
+  __device__ static __forceinline__ float key1(const Params& p) { return p.std; }
+  __device__ static __forceinline__ float key2(const Params&) { return 0.f; }
+};
+template <class Out, int R>
+struct TabUniform {
+  using Gen = GenUniform16<Out, R, false>;
+  using Params = typename Gen::Params;
+  static constexpr bool kHasTail = false;
+  __device__ static __forceinline__ float value(const Params& p, float magic) {
+    return fminf(fmaf(magic - 8388608.0f, p.scale, p.from), p.to_prev);  // == Gen::gen, element by element
+  }
+  __device__ static __forceinline__ void uniformize(Params& p) {
+    p.from = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(p.from)));
+    p.scale = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(p.scale)));
+    p.to_prev = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(p.to_prev)));
+  }
+  __device__ static __forceinline__ float key0(const Params& p) { return p.from; }
+  __device__ static __forceinline__ float key1(const Params& p) { return p.scale; }
+  __device__ static __forceinline__ float key2(const Params& p) { return p.to_prev; }
+};
+
 // Tiles that are not made of full, aligned vectors only (unaligned shards, ragged ends) or that
 // straddle a 2^32-block boundary: out of line and self-contained (everything is re-derived from the
 // descriptor), so that none of its state is live across the hot loop of the table kernel.
-template <class Out, int R>
+template <class Gen>
 __device__ __noinline__ void lut_ragged_tile(const TdxInitDesc* dp, unsigned long long tile) {
-  using Gen = GenNormalICDF16<Out, R, false>;
+  using Out = typename Gen::OutT;
   using T = OutTraits<Out>;
   const TdxInitDesc& d = *dp;
   const typename Gen::Params P = Gen::setup(d);
@@ -1017,12 +962,15 @@ __device__ __forceinline__ bool any_nonfinite2(uint32_t v) {
 }
 
 // LUT_A / LUT_B: number of the 8 elements of an even / odd vector that go through the table (the
-// others through the polynomial).  PKEYS: Philox round keys are kernel parameters (the group's
-// descriptors share one seed).
-template <class Out, int R, bool PKEYS, int LUT_A = TDX_LUT2_ELEMS_A, int LUT_B = TDX_LUT2_ELEMS_B,
-          int GROUP = TDX_LUT2_GROUP>
-__global__ void __launch_bounds__(kLutThreads, 1) tdx_normal16_lut2_kernel(const GroupArgs g) {
-  using Gen = GenNormalICDF16<Out, R, false>;
+// others are computed).  PKEYS: Philox round keys are kernel parameters (the group's descriptors
+// share one seed).  Issue-cost model (benchmarks/instr_rate.cu: IMAD.WIDE, LOP3, PRMT, IDP, IMAD,
+// F2FP, HFMA2 hold the dispatch port 2 cycles, FFMA/FMNMX/LDS 1, and IMAD.WIDE its pipe 4):
+// Philox 74 of the ~126 cycles a vector takes, a table element 4 (IDP + LDS + half a pack), a
+// computed normal 14, a computed uniform 6 -- against 3.56 shared-memory wavefronts per looked-up
+// element, of which an SM delivers one per cycle.
+template <class Tab, class Out, int R, bool PKEYS, int LUT_A, int LUT_B, int GROUP = TDX_LUT2_GROUP>
+__global__ void __launch_bounds__(kLutThreads, 1) tdx_lut16_kernel(const GroupArgs g) {
+  using Gen = typename Tab::Gen;
   using T = OutTraits<Out>;
   static_assert(kLutVecsPerThread % GROUP == 0, "GROUP must divide the vectors per thread");
   // The table is the first thing in shared memory (this kernel has no static shared memory; the
@@ -1031,33 +979,28 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_normal16_lut2_kernel(const
   extern __shared__ __align__(16) unsigned short lut[];
   unsigned int* const slots = reinterpret_cast<unsigned int*>(lut + 65536);
   const bool base_ok = static_cast<uint32_t>(__cvta_generic_to_shared(lut)) == kDynSmemBase;
-  float have_mean = 0.f, have_std = -1.f;  // table contents (uniform across the CTA)
+  float have0 = 0.f, have1 = 0.f, have2 = 0.f;  // parameters of the table in shared memory
+  bool have = false;
   for_each_listed_chunk(g, slots, [&](uint32_t di, unsigned long long tile0, unsigned long long ntiles) {
     const TdxInitDesc& d = g.descs[di];
     typename Gen::Params P = Gen::setup(d);
     // Loop-invariant scalars that come out of a global load: a warp reduction's result lives in a
     // uniform register by construction, so the FFMAs / LOP3s that use them read two vector
     // registers instead of three (measured: +2.5 %, fewer dispatch stalls).
-    P.mean = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(P.mean)));
-    P.c0 = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(P.c0)));
-    P.c1 = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(P.c1)));
-    P.c2 = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(P.c2)));
-    P.c3 = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(P.c3)));
-    P.c4 = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(P.c4)));
-    P.c5 = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(P.c5)));
+    Tab::uniformize(P);
     P.ph.cz = __reduce_or_sync(0xffffffffu, P.ph.cz);
     P.ph.cw = __reduce_or_sync(0xffffffffu, P.ph.cw);
-    if (P.mean != have_mean || P.std != have_std) {
+    if (!have || Tab::key0(P) != have0 || Tab::key1(P) != have1 || Tab::key2(P) != have2) {
       __syncthreads();  // everyone is done reading the old table
       for (uint32_t k = threadIdx.x; k < 65536u; k += kLutThreads) {
-        float t;
-        const float v = Gen::element(P, __uint_as_float(0x4b000000u | k), t);
-        const Out o = static_cast<Out>(v);
-        lut[k] = k == 0 ? kLutSentinel : *reinterpret_cast<const unsigned short*>(&o);
+        const Out o = static_cast<Out>(Tab::value(P, __uint_as_float(0x4b000000u | k)));
+        lut[k] = (Tab::kHasTail && k == 0) ? kLutSentinel : *reinterpret_cast<const unsigned short*>(&o);
       }
       __syncthreads();
-      have_mean = P.mean;
-      have_std = P.std;
+      have = true;
+      have0 = Tab::key0(P);
+      have1 = Tab::key1(P);
+      have2 = Tab::key2(P);
     }
     const uint64_t begin = d.elem_begin;
     const uint64_t gv0 = begin / 8;
@@ -1088,24 +1031,24 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_normal16_lut2_kernel(const
               if (lo_lut && hi_lut) {
                 r[q] = pack_u16(lds_u16_tab(lut_addr_lo(ws[q], 0u)), lds_u16_tab(lut_addr_hi(ws[q], 0u)));
               } else if (!lo_lut && !hi_lut) {
-                // k == 0 makes the polynomial +-inf (lg2(0) = -inf) or NaN; the group test below
-                // looks for either
-                float ta, tb;
-                r[q] = T::pack2(Gen::element(P, halfword_as_magic(w, 2 * q), ta),
-                                Gen::element(P, halfword_as_magic(w, 2 * q + 1), tb));
+                r[q] = T::pack2(Tab::value(P, halfword_as_magic(w, 2 * q)),
+                                Tab::value(P, halfword_as_magic(w, 2 * q + 1)));
               } else {  // low half from the table, high half computed
-                float tb;
-                const uint32_t hi16 = T::pack2(0.0f, Gen::element(P, halfword_as_magic(w, 2 * q + 1), tb));
+                const uint32_t hi16 = T::pack2(0.0f, Tab::value(P, halfword_as_magic(w, 2 * q + 1)));
                 r[q] = (hi16 & 0xffff0000u) | lds_u16_tab(lut_addr_lo(ws[q], 0u));
               }
             }
-            nan.add(r[0], r[1]);
-            nan.add(r[2], r[3]);
+            if (Tab::kHasTail) {
+              nan.add(r[0], r[1]);
+              nan.add(r[2], r[3]);
+            }
             store_vec(p0 + static_cast<size_t>(i) * (kLutThreads * 16), make_uint4(r[0], r[1], r[2], r[3]));
           }
-          // rare (2^-16 per element; also after an overflow of the accumulator, which only costs
-          // time): find the vector(s) that contain a zero half-word and redo them exactly
-          if (any_nonfinite2<Out>(nan.acc)) {
+          // k == 0 reads the NaN sentinel from the table and makes a computed element +-inf or NaN;
+          // either survives the a*b+c accumulation.  Rare (2^-16 per element; also after an
+          // overflow of the accumulator, which only costs time): find the vector(s) that contain
+          // a zero half-word and redo them exactly.
+          if (Tab::kHasTail && any_nonfinite2<Out>(nan.acc)) {
 #pragma unroll 1
             for (int i = i0; i < i0 + GROUP; ++i) {
               const uint64_t gv = gfirst + threadIdx.x + static_cast<uint64_t>(i) * kLutThreads;
@@ -1116,7 +1059,7 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_normal16_lut2_kernel(const
           }
         }
       } else {
-        lut_ragged_tile<Out, R>(&d, tile);
+        lut_ragged_tile<Gen>(&d, tile);
       }
     }
   });
@@ -1145,24 +1088,19 @@ struct Family {
 #define TDX_FAM_V16(src, dt, algo, rounds, epi, ...)                                               \
   { src, dt, algo, rounds, epi, static_cast<KernelFn>(tdx_rng_kernel<__VA_ARGS__, 16>), #__VA_ARGS__, \
     kThreads, kThreads * 16, 0, false, (kVecsPerThread * kTilesPerChunk) / 16 }
-#ifndef TDX_LUT_GEN
-#define TDX_LUT_GEN 2
-#endif
 #ifndef TDX_LUT2_PKEYS
 #define TDX_LUT2_PKEYS 1
 #endif
-#if TDX_LUT_GEN == 2
-#define TDX_LUT_KERNEL(out, rounds, words) tdx_normal16_lut2_kernel<out, rounds, TDX_LUT2_PKEYS != 0>
-#define TDX_LUT_KERNEL_ANY_SEED(out, rounds, words) tdx_normal16_lut2_kernel<out, rounds, false>
-#else
-#define TDX_LUT_KERNEL(out, rounds, words) tdx_normal16_lut_kernel<out, rounds, words>
-#define TDX_LUT_KERNEL_ANY_SEED(out, rounds, words) tdx_normal16_lut_kernel<out, rounds, words>
+#ifndef TDX_LUT2_UNIFORM_ELEMS
+#define TDX_LUT2_UNIFORM_ELEMS 6  // measured at 4 GiB bf16: 8/7/6/5/4 -> 0.674/0.748/0.815/0.813/0.803 of the HBM roof
 #endif
-#define TDX_FAM_LUT(dt, rounds, ...)                                                             \
-  { TDX_SRC_NORMAL, dt, TDX_ALGO_ICDF16, rounds, 0,                                              \
-    static_cast<KernelFn>(TDX_LUT_KERNEL(__VA_ARGS__)), "lut<" #__VA_ARGS__ ">",                 \
-    kLutThreads, kLutTileVecs, static_cast<int>(kLutBytes) + 128, true, kLutTilesPerChunk,         \
-    static_cast<KernelFn>(TDX_LUT_KERNEL_ANY_SEED(__VA_ARGS__)) }
+// table-driven twins of the 16-bit generators: `fn` takes the Philox round keys from the kernel
+// parameters (groups that share one seed: the normal case), `fn_any_seed` from each descriptor
+#define TDX_FAM_LUT(src, dt, algo, name, tab, out, la, lb)                                              \
+  { src, dt, algo, 10, 0,                                                                             \
+    static_cast<KernelFn>(tdx_lut16_kernel<tab<out, 10>, out, 10, TDX_LUT2_PKEYS != 0, la, lb>), name,  \
+    kLutThreads, kLutTileVecs, static_cast<int>(kLutBytes) + 128, true, kLutTilesPerChunk,              \
+    static_cast<KernelFn>(tdx_lut16_kernel<tab<out, 10>, out, 10, false, la, lb>) }
 
 using bf16 = __nv_bfloat16;
 using f16 = __half;
@@ -1193,8 +1131,10 @@ static const Family kFamilies[] = {
     TDX_FAM(TDX_SRC_NORMAL, TDX_F16, TDX_ALGO_BM32, 10, 0, GenNormalBM32<f16, 10, false>),
     TDX_FAM(TDX_SRC_NORMAL, TDX_F16, TDX_ALGO_BM32, 10, 1, GenNormalBM32<f16, 10, true>),
     // table-driven twins of the 16-bit normal for large descriptors (bit-identical output)
-    TDX_FAM_LUT(TDX_BF16, 10, bf16, 10, TDX_LUT_WORDS),
-    TDX_FAM_LUT(TDX_F16, 10, f16, 10, TDX_LUT_WORDS),
+    TDX_FAM_LUT(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_ICDF16, "lut<normal, bf16>", TabNormal, bf16, TDX_LUT2_ELEMS_A, TDX_LUT2_ELEMS_B),
+    TDX_FAM_LUT(TDX_SRC_NORMAL, TDX_F16, TDX_ALGO_ICDF16, "lut<normal, f16>", TabNormal, f16, TDX_LUT2_ELEMS_A, TDX_LUT2_ELEMS_B),
+    TDX_FAM_LUT(TDX_SRC_UNIFORM, TDX_BF16, 0, "lut<uniform, bf16>", TabUniform, bf16, TDX_LUT2_UNIFORM_ELEMS, TDX_LUT2_UNIFORM_ELEMS),
+    TDX_FAM_LUT(TDX_SRC_UNIFORM, TDX_F16, 0, "lut<uniform, f16>", TabUniform, f16, TDX_LUT2_UNIFORM_ELEMS, TDX_LUT2_UNIFORM_ELEMS),
     // experimental variants, reachable only through an explicit TdxInitDesc.algo (bench sweeps)
     TDX_FAM(TDX_SRC_UNIFORM, TDX_BF16, 0, 7, 0, GenUniform16<bf16, 7, false>),
     TDX_FAM(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_ICDF16, 7, 0, GenNormalICDF16<bf16, 7, false>),
@@ -1252,9 +1192,10 @@ int family_of(const TdxInitDesc& d) {
   const int algo = resolve_algo(d);
   const int rounds = (d.algo & TDX_ALGO_R7) ? 7 : 10;
   const int epi = d.n_epi ? 1 : 0;
-  const bool want_lut = d.src == TDX_SRC_NORMAL && algo == TDX_ALGO_ICDF16 && !epi && rounds == 10 &&
-                        !(d.algo & TDX_ALGO_NOLUT) && lut_min_elems() != 0 &&
-                        d.elem_count >= lut_min_elems();
+  const bool lut_kind = (d.src == TDX_SRC_NORMAL && algo == TDX_ALGO_ICDF16) ||
+                        (d.src == TDX_SRC_UNIFORM && algo == 0 && d.dtype != TDX_F32);
+  const bool want_lut = lut_kind && !epi && rounds == 10 && !(d.algo & TDX_ALGO_NOLUT) &&
+                        lut_min_elems() != 0 && d.elem_count >= lut_min_elems();
   for (int f = 1; f < kNumFamilies; ++f) {
     const Family& F = kFamilies[f];
     if (F.src == d.src && F.dtype == d.dtype && F.algo == algo && F.rounds == rounds &&
