@@ -374,7 +374,7 @@ def run_ours(a):
                    "params": n_params, "tensors": n_tensors, "descriptors_per_rank": len(descs),
                    "fused_tensors": st["fused_tensors"], "generic_ops": st["generic_ops"],
                    "elided_rng_ops": st["elided_rng_ops"], "record_s_per_model": record_s,
-                   "host_us": {k: round(st[k]) for k in ("plan_us", "launch_us", "wrap_us", "first_submit_us", "last_submit_us", "submissions")},
+                   "host_us": {k: round(st[k]) for k in ("plan_us", "eval_us", "alloc_us", "launch_us", "wrap_us", "first_submit_us", "last_submit_us", "submissions")},
                    "e2e_host_split_ms": {"api_return": round(host_split["api_return_ms"] / max(host_split["n"], 1), 3),
                                          "gpu_done": round(host_split["sync_ms"] / max(host_split["n"], 1), 3)},
                    "l2": "outputs per step (GBs) exceed the 126 MB L2; no flush needed",

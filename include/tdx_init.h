@@ -145,7 +145,9 @@ TDX_C_API int tdx_init_launch(const TdxInitDesc* descs, int n, void* workspace,
  * Two-phase variant for callers that re-launch one plan (benchmarks, CUDA
  * graphs): upload once, launch many times.  `tdx_plan_upload` copies the
  * grouped descriptor table into `workspace`; `tdx_plan_launch` only issues the
- * kernels (plus one 4-byte memset per family for the work counter).
+ * kernels (the work counters in the workspace are uploaded as zero and every
+ * kernel puts its own back to zero when its last CTA leaves, so there is no
+ * memset between launches; one plan must not run on two streams at once).
  */
 typedef struct TdxPlan {
   uint64_t opaque[256]; /* host-side copy of the plan header; owned by the caller */

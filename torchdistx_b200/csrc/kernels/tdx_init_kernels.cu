@@ -563,32 +563,50 @@ struct GroupArgs {
   const unsigned long long* tile_prefix;  // [n_desc + 1], exclusive prefix sum of tiles per desc
   const TdxInitDesc* descs;               // [n_desc]
   unsigned long long total_tiles;
-  unsigned int* counter;  // chunk counter, zeroed before every launch
+  unsigned int* counter;  // chunk counter: zero at launch; the last CTA to leave zeroes it again
+  unsigned int* done;     // CTAs that have left
   uint32_t n_desc;
   // Philox round keys of the group's seed when every descriptor of the group shares it
   // (seed_shared != 0): kernel parameters live in the constant bank, so the 20 keys are operands of
   // the Philox LOP3s directly -- no registers, no per-vector key arithmetic.
   uint32_t seed_shared;
-  uint32_t n_chunks;           // table kernel: host-built work list (see build_chunks)
+  uint32_t tiles_per_chunk;    // 256-thread kernels: tiles per work grab (host-chosen per launch)
+  uint32_t n_chunks;           // table kernel: host-built work list (see build_plan)
   const uint4* chunks;         // {descriptor, tiles, first tile in descriptor (lo, hi)}
   uint32_t rk[20];
 };
 
+// Every CTA calls this once, after its last (failed) grab: the last one to arrive puts the two
+// counters back to zero, so a plan can be launched again without a memset in between.
+__device__ __forceinline__ void leave_grid(const GroupArgs& g) {
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(g.done, 1u) == gridDim.x - 1u) {
+      *g.counter = 0u;
+      *g.done = 0u;
+      __threadfence();
+    }
+  }
+}
+
 // Calls f(desc_index, first_tile_in_desc, n_tiles) for runs of consecutive tiles of one descriptor.
-template <int TILES_PER_CHUNK = kTilesPerChunk, class F>
+// A work grab is g.tiles_per_chunk tiles: 256 KiB for launches that fill the machine, down to one
+// 16 KiB tile for small ones (a 1 MB tensor is 64 single-tile grabs on 64 SMs, not 4 grabs of 16
+// tiles on 4).
+template <class F>
 __device__ __forceinline__ void for_each_tile_run(const GroupArgs& g, F&& f) {
-  // A work grab is 256 KiB for the 256-thread kernels and 1 MiB for the 1024-thread table kernel.
-  // (Measured: 256 KiB grabs for the table kernel cost 14 % -- two 32-warp barriers and an atomic
-  // per grab are not free.)
-  constexpr int kTilesPerChunk = TILES_PER_CHUNK;
+  const unsigned int tpc = g.tiles_per_chunk;
   __shared__ unsigned int s_chunk;
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) s_chunk = atomicAdd(g.counter, 1u);
     __syncthreads();
-    unsigned long long t = static_cast<unsigned long long>(s_chunk) * kTilesPerChunk;
-    if (t >= g.total_tiles) return;
-    const unsigned long long last = min(t + kTilesPerChunk, g.total_tiles);
+    unsigned long long t = static_cast<unsigned long long>(s_chunk) * tpc;
+    if (t >= g.total_tiles) {
+      leave_grid(g);
+      return;
+    }
+    const unsigned long long last = min(t + tpc, g.total_tiles);
     uint32_t lo = 0, hi = g.n_desc;  // find d with prefix[d] <= t < prefix[d+1]
     while (hi - lo > 1) {
       const uint32_t mid = (lo + hi) >> 1;
@@ -620,7 +638,10 @@ __device__ __forceinline__ void for_each_listed_chunk(const GroupArgs& g, unsign
   __syncthreads();
   for (unsigned int it = 0;; ++it) {
     const unsigned int c = s_next[it & 1u];
-    if (c >= g.n_chunks) return;
+    if (c >= g.n_chunks) {
+      leave_grid(g);
+      return;
+    }
     if (threadIdx.x == 0) s_next[(it + 1u) & 1u] = atomicAdd(g.counter, 1u);
     const uint4 e = __ldg(g.chunks + c);
     f(e.x, static_cast<unsigned long long>(e.z) | (static_cast<unsigned long long>(e.w) << 32),
@@ -638,7 +659,7 @@ __global__ void __launch_bounds__(kThreads) tdx_rng_kernel(const GroupArgs g) {
   constexpr int EPV = Gen::kEpv;
   constexpr int kVecsPerThread = VECS;
   constexpr int kTileVecs = kThreads * VECS;
-  for_each_tile_run<(kThreads * tdx::kVecsPerThread * tdx::kTilesPerChunk) / (kThreads * VECS)>(g, [&](uint32_t di, unsigned long long tile0, unsigned long long ntiles) {
+  for_each_tile_run(g, [&](uint32_t di, unsigned long long tile0, unsigned long long ntiles) {
     const TdxInitDesc& d = g.descs[di];
     const typename Gen::Params P = Gen::setup(d);
     const uint64_t begin = d.elem_begin, count = d.elem_count;
@@ -1235,6 +1256,7 @@ struct PlanHeader {
   uint32_t magic;
   uint32_t n_groups;
   unsigned int counters[32];
+  unsigned int done[32];
   PlanGroup groups[kNumFamilies];
 };
 constexpr uint32_t kPlanMagic = 0x58445431u;  // "TDX1"
@@ -1445,20 +1467,15 @@ int launch_groups(const PlanHeader& hdr, void* workspace, cudaStream_t stream) {
   auto* base = static_cast<unsigned char*>(workspace);
   auto* dev_hdr = reinterpret_cast<PlanHeader*>(base);
   int launches = 0;
-  bool zeroed = false;
   for (uint32_t gi = 0; gi < hdr.n_groups; ++gi) {
     const PlanGroup& G = hdr.groups[gi];
     if (G.total_tiles == 0) continue;
-    if (!zeroed) {
-      cudaError_t e = cudaMemsetAsync(dev_hdr->counters, 0, sizeof(dev_hdr->counters), stream);
-      if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(counters)");
-      zeroed = true;
-    }
     GroupArgs a;
     a.tile_prefix = reinterpret_cast<const unsigned long long*>(base + G.prefix_off);
     a.descs = reinterpret_cast<const TdxInitDesc*>(base + G.desc_off);
     a.total_tiles = G.total_tiles;
-    a.counter = &dev_hdr->counters[gi];
+    a.counter = &dev_hdr->counters[gi];  // zero: uploaded so, and put back by the kernel (leave_grid)
+    a.done = &dev_hdr->done[gi];
     a.n_desc = G.n_desc;
     a.seed_shared = G.seed_shared;
     {
@@ -1472,7 +1489,13 @@ int launch_groups(const PlanHeader& hdr, void* workspace, cudaStream_t stream) {
     }
     const unsigned long long resident =
         static_cast<unsigned long long>(info->sm_count) * info->blocks_per_sm[G.family];
-    const int tpc = kFamilies[G.family].tiles_per_chunk;
+    // 256-thread kernels: full-size grabs only when every resident CTA still gets a few of them
+    int tpc = kFamilies[G.family].tiles_per_chunk;
+    if (!kFamilies[G.family].lut) {
+      const unsigned long long want = G.total_tiles / (resident * 4ull);
+      tpc = static_cast<int>(std::min<unsigned long long>(std::max<unsigned long long>(want, 1ull), tpc));
+    }
+    a.tiles_per_chunk = static_cast<uint32_t>(tpc);
     a.n_chunks = G.n_chunks;
     a.chunks = reinterpret_cast<const uint4*>(base + G.chunk_off);
     const unsigned long long chunks =

@@ -196,6 +196,8 @@ py::dict py_last_stats() {
   d["plan_us"] = s.plan_us;
   d["launch_us"] = s.launch_us;
   d["wrap_us"] = s.wrap_us;
+  d["eval_us"] = s.eval_us;
+  d["alloc_us"] = s.alloc_us;
   d["submissions"] = s.submissions;
   d["upload_bytes"] = s.upload_bytes;
   d["first_submit_us"] = s.first_submit_us;

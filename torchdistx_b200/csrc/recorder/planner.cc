@@ -724,7 +724,9 @@ struct Engine {
       ~FoldOn() { g_fold_device = prev; }
     } fold_on(dev);
     c10::DeviceGuard fold_guard(dev);
+    const double t_eval = now_us();
     Sym st = eval_storage(tape, S, static_cast<uint32_t>(tape.ops.size()));
+    g_stats.eval_us += now_us() - t_eval;
     if (st.opaque()) return false;
     const size_t isz = c10::elementSize(st.dtype);
     if (isz == 0 || si.nbytes % isz) return false;
@@ -751,7 +753,9 @@ struct Engine {
       batch.device = dev;
     }
     // straight to the caching allocator: no dispatcher round trip per tensor
+    const double t_alloc = now_us();
     at::Tensor base = at::detail::empty_cuda(g.sizes, st.dtype, dev, std::nullopt);
+    g_stats.alloc_us += now_us() - t_alloc;
 
     // every RNG pass on the chain consumes its slice of the stream, live or dead
     for (uint32_t r : st.rng_chain) {

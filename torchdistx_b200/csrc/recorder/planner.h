@@ -50,6 +50,8 @@ struct MaterializeStats {
   double plan_us = 0;    // host time: slicing, symbolic evaluation, allocation, descriptor build
   double launch_us = 0;  // host time inside tdx_init_launch (plan image + H2D copy + launches)
   double wrap_us = 0;    // host time giving results their Python class / identity
+  double eval_us = 0;            // part of plan_us: symbolic evaluation of the recorded programs
+  double alloc_us = 0;           // part of plan_us: output allocations (caching allocator)
   int64_t upload_bytes = 0;      // plan images copied host -> device
   int64_t submissions = 0;       // tdx_init_launch calls (early submissions + the final one)
   double first_submit_us = 0;    // host time from the start of the call to the first submission
