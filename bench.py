@@ -332,7 +332,7 @@ def run_ours(a):
     peak, peak_src = peaks()
     achieved = dom_bytes / dom_ms / 1e6
     kname = {C.TDX_SRC_CONST: "tdx_fill_kernel", C.TDX_SRC_UNIFORM: "tdx_rng_kernel<GenUniform*>",
-             C.TDX_SRC_NORMAL: "tdx_normal16_lut2_kernel<bf16> (+ tdx_rng_kernel<GenNormalICDF16<bf16>> for descriptors < 2^20 elements)"
+             C.TDX_SRC_NORMAL: "tdx_lut16_kernel<TabNormal, bf16> (+ tdx_rng_kernel<GenNormalICDF16<bf16>> for descriptors < 2^20 elements)"
              if dtype == "bf16" else "tdx_rng_kernel<GenNormalBM32<bf16>> (TDX_ALGO_WIDE32)" if dtype == "fp32->bf16"
              else "tdx_rng_kernel<GenNormalBM32<float>>"}[dom_key[0]]
     if a.roofline_only:
@@ -387,7 +387,7 @@ def run_ours(a):
         "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
-                     "secondary_ceiling": "instruction issue (Philox4x32-10 + inverse-CDF): see DESIGN.md"},
+                     "secondary_ceiling": "dispatch port: Philox4x32-10 alone is 80 cycles per 16-byte vector = 7.0 TB/s-equivalent (benchmarks/philox_rate.cu); see DESIGN.md section 4"},
         "cpu_baseline": cpu,
         "clocks": {"sm_mhz": c1["sm_mhz"], "sm_max_mhz": c1["sm_max_mhz"], "reasons": c1["reasons"],
                    "e2e_sm_mhz": c2["sm_mhz"], "e2e_reasons": c2["reasons"]},

@@ -1357,6 +1357,8 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
   img.assign(plan_bytes(n), 0);
   int sm_count = 148;
   if (DeviceInfo* info = device_info()) sm_count = info->sm_count;
+  std::vector<int> order;
+  order.reserve(static_cast<size_t>(n));
   size_t off = (sizeof(PlanHeader) + 15) & ~static_cast<size_t>(15);
   for (int f = 0; f < kNumFamilies; ++f) {
     if (!per_family[f]) continue;
@@ -1373,8 +1375,19 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
     unsigned long long acc = 0;
     uint32_t k = 0;
     G.seed_shared = 1;
-    for (int i = 0; i < n; ++i) {
-      if (fam[i] != f) continue;
+    // Table kernel: a CTA rebuilds its 65536-entry table (~10 us) whenever the parameters change
+    // from one grab to the next, so descriptors with equal parameters are made neighbours (GPT-2's
+    // alternating std 0.02 / 0.02/sqrt(2L) would otherwise cost a rebuild per tensor).  The order
+    // inside a family is free: every descriptor is self-contained.
+    order.clear();
+    for (int i = 0; i < n; ++i)
+      if (fam[i] == f) order.push_back(i);
+    if (kFamilies[f].lut)
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        if (descs[a].p0 != descs[b].p0) return descs[a].p0 < descs[b].p0;
+        return descs[a].p1 < descs[b].p1;
+      });
+    for (int i : order) {
       if (k == 0) G.seed = descs[i].philox_seed;
       else if (descs[i].philox_seed != G.seed) G.seed_shared = 0;
       prefix[k] = acc;
@@ -1492,7 +1505,7 @@ int launch_groups(const PlanHeader& hdr, void* workspace, cudaStream_t stream) {
     // 256-thread kernels: full-size grabs only when every resident CTA still gets a few of them
     int tpc = kFamilies[G.family].tiles_per_chunk;
     if (!kFamilies[G.family].lut) {
-      const unsigned long long want = G.total_tiles / (resident * 4ull);
+      const unsigned long long want = G.total_tiles / (resident * 2ull);
       tpc = static_cast<int>(std::min<unsigned long long>(std::max<unsigned long long>(want, 1ull), tpc));
     }
     a.tiles_per_chunk = static_cast<uint32_t>(tpc);
