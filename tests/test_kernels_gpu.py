@@ -12,6 +12,7 @@ Bars (stated here, enforced below):
     then by exactly 1 ulp of the output dtype.
 """
 import ctypes
+import math
 
 import numpy as np
 import pytest
@@ -209,6 +210,40 @@ def test_table_driven_uniform_is_bit_identical_to_the_direct_kernel_and_the_orac
         f = t.float()
         lo_r, hi_r = (float(torch.tensor(v, dtype=TORCH_DT[dtype])) for v in (lo, hi))  # bounds as the dtype sees them
         assert float(f.min()) >= lo_r and float(f.max()) <= hi_r
+
+
+@pytest.mark.parametrize("dtype", [C.TDX_BF16, C.TDX_F16])
+def test_table_kernel_with_epilogues_is_bit_identical_to_the_direct_kernel(dtype):
+    """Descriptors with epilogue steps (trunc_normal_, randn * s + m) are table-driven too: the table
+    holds the final value of every half-word.  Same bits as the direct kernel, k == 0 tails included."""
+    std, mean, a, b = 0.02, 0.0, -0.04, 0.04
+    lo = math.erf((a - mean) / std / math.sqrt(2.0))
+    hi = math.erf((b - mean) / std / math.sqrt(2.0))
+    trunc = [(C.TDX_EPI_ERFINV,), (C.TDX_EPI_MUL, std * math.sqrt(2)), (C.TDX_EPI_ADD, mean), (C.TDX_EPI_CLAMP, a, b)]
+    affine = [(C.TDX_EPI_MUL, 0.02), (C.TDX_EPI_ADD, 1.0)]
+    specs = [  # (src, p0, p1, epilogue, elements)
+        (C.TDX_SRC_UNIFORM, lo, hi, trunc, (1 << 26) + 9),
+        (C.TDX_SRC_NORMAL, 0.0, 1.0, affine, (1 << 26) + 77),
+        (C.TDX_SRC_NORMAL, 0.0, 1.0, [(C.TDX_EPI_MUL, 0.5)], (1 << 21) + 3),   # same source, other epilogue: other table
+        (C.TDX_SRC_UNIFORM, lo, hi, trunc, 70001),                            # small: direct kernel either way
+    ]
+    outs = {}
+    for flag in (0, C.TDX_ALGO_NOLUT):
+        bufs, descs = [], []
+        for i, (src, p0, p1, epi, n) in enumerate(specs):
+            t = torch.zeros(n, dtype=TORCH_DT[dtype], device="cuda")
+            bufs.append(t)
+            descs.append(C.make_desc(t.data_ptr(), dtype=dtype, src=src, elem_count=n, seed=17, offset=10000 * i,
+                                     p0=p0, p1=p1, epi=epi, algo=flag))
+        launches = run_descs(descs, bufs)
+        assert launches == (4 if flag == 0 else 2)  # two table kernels + two direct ones / two direct ones
+        outs[flag] = bufs
+    for x, y in zip(outs[0], outs[C.TDX_ALGO_NOLUT]):
+        assert torch.equal(x.view(torch.int16), y.view(torch.int16))
+    t = outs[0][0].float()
+    assert float(t.min()) >= a - 1e-3 and float(t.max()) <= b + 1e-3 and abs(float(t.std()) - 0.0176) < 2e-3  # trunc at +-2 sigma
+    g = outs[0][1].float()
+    assert abs(float(g.mean()) - 1.0) < 1e-3 and abs(float(g.std()) - 0.02) < 2e-3 and torch.isfinite(g).all()
 
 
 def test_table_kernel_with_mixed_seeds_and_across_a_2_32_block_boundary():

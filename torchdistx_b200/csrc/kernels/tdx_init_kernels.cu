@@ -777,9 +777,9 @@ constexpr unsigned short kLutSentinel = 0xffffu;  // a NaN pattern in bf16 and f
 
 // cold path of the table kernel (a vector that contains k == 0): out of line, to keep the hot loop
 // small enough for the instruction cache
-template <class Out, int R>
+template <class Gen>
 __device__ __noinline__ uint4 lut_slow_vector(const TdxInitDesc* d, uint64_t gv) {
-  using Gen = GenNormalICDF16<Out, R, false>;
+  using Out = typename Gen::OutT;
   const typename Gen::Params P = Gen::setup(*d);
   float v[8];
   Gen::gen(P, gv, v);
@@ -902,14 +902,28 @@ struct NanAcc<__half> {
 // entry and, for the elements that are not looked up, the directly computed value -- one device
 // function, hence the same bits), the parameters that identify a table, and whether some k needs the
 // exact out-of-line path (the normal's k == 0 tail).
-template <class Out, int R>
+// Two descriptors of one table-kernel family share a table iff their generator parameters and
+// epilogues are equal (dtype, source and "has an epilogue" are the family's).
+__device__ __forceinline__ bool same_table(const TdxInitDesc& a, const TdxInitDesc& b) {
+  bool same = a.p0 == b.p0 && a.p1 == b.p1 && a.n_epi == b.n_epi && a.reserved == b.reserved;
+  for (int i = 0; i < TDX_MAX_EPI; ++i)
+    if (i < a.n_epi)
+      same = same && a.epi[i].op == b.epi[i].op && a.epi[i].a == b.epi[i].a && a.epi[i].b == b.epi[i].b;
+  return same;
+}
+
+// EPI: the descriptor carries epilogue steps (trunc_normal_, randn * s + m, ...).  The table then
+// holds the FINAL value for every half-word -- the epilogue is as elementwise as the source
+// transform -- so an erfinv costs the same as nothing once the table is built.
+template <class Out, int R, bool EPI = false>
 struct TabNormal {
-  using Gen = GenNormalICDF16<Out, R, false>;
+  using Gen = GenNormalICDF16<Out, R, EPI>;
   using Params = typename Gen::Params;
   static constexpr bool kHasTail = true;
   __device__ static __forceinline__ float value(const Params& p, float magic) {
     float t;
-    return Gen::element(p, magic, t);  // k == 0: +-inf or NaN (lg2(0) = -inf)
+    const float v = Gen::element(p, magic, t);  // k == 0: +-inf or NaN (lg2(0) = -inf)
+    return EPI ? apply_epi<Out>(p.epi, v) : v;
   }
   __device__ static __forceinline__ void uniformize(Params& p) {
     p.mean = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(p.mean)));
@@ -920,26 +934,21 @@ struct TabNormal {
     p.c4 = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(p.c4)));
     p.c5 = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(p.c5)));
   }
-  __device__ static __forceinline__ float key0(const Params& p) { return p.mean; }
-  __device__ static __forceinline__ float key1(const Params& p) { return p.std; }
-  __device__ static __forceinline__ float key2(const Params&) { return 0.f; }
 };
-template <class Out, int R>
+template <class Out, int R, bool EPI = false>
 struct TabUniform {
-  using Gen = GenUniform16<Out, R, false>;
+  using Gen = GenUniform16<Out, R, EPI>;
   using Params = typename Gen::Params;
   static constexpr bool kHasTail = false;
   __device__ static __forceinline__ float value(const Params& p, float magic) {
-    return fminf(fmaf(magic - 8388608.0f, p.scale, p.from), p.to_prev);  // == Gen::gen, element by element
+    const float x = fminf(fmaf(magic - 8388608.0f, p.scale, p.from), p.to_prev);  // == Gen::gen, element by element
+    return EPI ? apply_epi<Out>(p.epi, x) : x;
   }
   __device__ static __forceinline__ void uniformize(Params& p) {
     p.from = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(p.from)));
     p.scale = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(p.scale)));
     p.to_prev = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(p.to_prev)));
   }
-  __device__ static __forceinline__ float key0(const Params& p) { return p.from; }
-  __device__ static __forceinline__ float key1(const Params& p) { return p.scale; }
-  __device__ static __forceinline__ float key2(const Params& p) { return p.to_prev; }
 };
 
 // Tiles that are not made of full, aligned vectors only (unaligned shards, ragged ends) or that
@@ -1000,8 +1009,7 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_lut16_kernel(const GroupAr
   extern __shared__ __align__(16) unsigned short lut[];
   unsigned int* const slots = reinterpret_cast<unsigned int*>(lut + 65536);
   const bool base_ok = static_cast<uint32_t>(__cvta_generic_to_shared(lut)) == kDynSmemBase;
-  float have0 = 0.f, have1 = 0.f, have2 = 0.f;  // parameters of the table in shared memory
-  bool have = false;
+  uint32_t have_di = 0xffffffffu;  // descriptor the table in shared memory was built for
   for_each_listed_chunk(g, slots, [&](uint32_t di, unsigned long long tile0, unsigned long long ntiles) {
     const TdxInitDesc& d = g.descs[di];
     typename Gen::Params P = Gen::setup(d);
@@ -1011,18 +1019,15 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_lut16_kernel(const GroupAr
     Tab::uniformize(P);
     P.ph.cz = __reduce_or_sync(0xffffffffu, P.ph.cz);
     P.ph.cw = __reduce_or_sync(0xffffffffu, P.ph.cw);
-    if (!have || Tab::key0(P) != have0 || Tab::key1(P) != have1 || Tab::key2(P) != have2) {
+    if (have_di == 0xffffffffu || (di != have_di && !same_table(d, g.descs[have_di]))) {
       __syncthreads();  // everyone is done reading the old table
       for (uint32_t k = threadIdx.x; k < 65536u; k += kLutThreads) {
         const Out o = static_cast<Out>(Tab::value(P, __uint_as_float(0x4b000000u | k)));
         lut[k] = (Tab::kHasTail && k == 0) ? kLutSentinel : *reinterpret_cast<const unsigned short*>(&o);
       }
       __syncthreads();
-      have = true;
-      have0 = Tab::key0(P);
-      have1 = Tab::key1(P);
-      have2 = Tab::key2(P);
     }
+    have_di = di;
     const uint64_t begin = d.elem_begin;
     const uint64_t gv0 = begin / 8;
     char* const dst = static_cast<char*>(d.dst);
@@ -1075,7 +1080,7 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_lut16_kernel(const GroupAr
               const uint64_t gv = gfirst + threadIdx.x + static_cast<uint64_t>(i) * kLutThreads;
               const uint4 w = philox_block<R>(P.ph, gv);
               if (has_zero_half(w.x) || has_zero_half(w.y) || has_zero_half(w.z) || has_zero_half(w.w))
-                store_vec(p0 + static_cast<size_t>(i) * (kLutThreads * 16), lut_slow_vector<Out, R>(&d, gv));
+                store_vec(p0 + static_cast<size_t>(i) * (kLutThreads * 16), lut_slow_vector<Gen>(&d, gv));
             }
           }
         }
@@ -1117,11 +1122,11 @@ struct Family {
 #endif
 // table-driven twins of the 16-bit generators: `fn` takes the Philox round keys from the kernel
 // parameters (groups that share one seed: the normal case), `fn_any_seed` from each descriptor
-#define TDX_FAM_LUT(src, dt, algo, name, tab, out, la, lb)                                              \
-  { src, dt, algo, 10, 0,                                                                             \
-    static_cast<KernelFn>(tdx_lut16_kernel<tab<out, 10>, out, 10, TDX_LUT2_PKEYS != 0, la, lb>), name,  \
+#define TDX_FAM_LUT(src, dt, algo, epi, name, out, la, lb, ...)                                          \
+  { src, dt, algo, 10, epi,                                                                           \
+    static_cast<KernelFn>(tdx_lut16_kernel<__VA_ARGS__, out, 10, TDX_LUT2_PKEYS != 0, la, lb>), name,   \
     kLutThreads, kLutTileVecs, static_cast<int>(kLutBytes) + 128, true, kLutTilesPerChunk,              \
-    static_cast<KernelFn>(tdx_lut16_kernel<tab<out, 10>, out, 10, false, la, lb>) }
+    static_cast<KernelFn>(tdx_lut16_kernel<__VA_ARGS__, out, 10, false, la, lb>) }
 
 using bf16 = __nv_bfloat16;
 using f16 = __half;
@@ -1152,16 +1157,23 @@ static const Family kFamilies[] = {
     TDX_FAM(TDX_SRC_NORMAL, TDX_F16, TDX_ALGO_BM32, 10, 0, GenNormalBM32<f16, 10, false>),
     TDX_FAM(TDX_SRC_NORMAL, TDX_F16, TDX_ALGO_BM32, 10, 1, GenNormalBM32<f16, 10, true>),
     // table-driven twins of the 16-bit normal for large descriptors (bit-identical output)
-    TDX_FAM_LUT(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_ICDF16, "lut<normal, bf16>", TabNormal, bf16, TDX_LUT2_ELEMS_A, TDX_LUT2_ELEMS_B),
-    TDX_FAM_LUT(TDX_SRC_NORMAL, TDX_F16, TDX_ALGO_ICDF16, "lut<normal, f16>", TabNormal, f16, TDX_LUT2_ELEMS_A, TDX_LUT2_ELEMS_B),
-    TDX_FAM_LUT(TDX_SRC_UNIFORM, TDX_BF16, 0, "lut<uniform, bf16>", TabUniform, bf16, TDX_LUT2_UNIFORM_ELEMS, TDX_LUT2_UNIFORM_ELEMS),
-    TDX_FAM_LUT(TDX_SRC_UNIFORM, TDX_F16, 0, "lut<uniform, f16>", TabUniform, f16, TDX_LUT2_UNIFORM_ELEMS, TDX_LUT2_UNIFORM_ELEMS),
+    TDX_FAM_LUT(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_ICDF16, 0, "lut<normal, bf16>", bf16, TDX_LUT2_ELEMS_A, TDX_LUT2_ELEMS_B, TabNormal<bf16, 10>),
+    TDX_FAM_LUT(TDX_SRC_NORMAL, TDX_F16, TDX_ALGO_ICDF16, 0, "lut<normal, f16>", f16, TDX_LUT2_ELEMS_A, TDX_LUT2_ELEMS_B, TabNormal<f16, 10>),
+    TDX_FAM_LUT(TDX_SRC_UNIFORM, TDX_BF16, 0, 0, "lut<uniform, bf16>", bf16, TDX_LUT2_UNIFORM_ELEMS, TDX_LUT2_UNIFORM_ELEMS, TabUniform<bf16, 10>),
+    TDX_FAM_LUT(TDX_SRC_UNIFORM, TDX_F16, 0, 0, "lut<uniform, f16>", f16, TDX_LUT2_UNIFORM_ELEMS, TDX_LUT2_UNIFORM_ELEMS, TabUniform<f16, 10>),
+    // with an epilogue every element is looked up: the computed alternative may contain an erfinv
+    TDX_FAM_LUT(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_ICDF16, 1, "lut<normal+epilogue, bf16>", bf16, 8, 8, TabNormal<bf16, 10, true>),
+    TDX_FAM_LUT(TDX_SRC_NORMAL, TDX_F16, TDX_ALGO_ICDF16, 1, "lut<normal+epilogue, f16>", f16, 8, 8, TabNormal<f16, 10, true>),
+    TDX_FAM_LUT(TDX_SRC_UNIFORM, TDX_BF16, 0, 1, "lut<uniform+epilogue, bf16>", bf16, 8, 8, TabUniform<bf16, 10, true>),
+    TDX_FAM_LUT(TDX_SRC_UNIFORM, TDX_F16, 0, 1, "lut<uniform+epilogue, f16>", f16, 8, 8, TabUniform<f16, 10, true>),
+#ifdef TDX_EXPERIMENTAL_ALGOS
     // experimental variants, reachable only through an explicit TdxInitDesc.algo (bench sweeps)
     TDX_FAM(TDX_SRC_UNIFORM, TDX_BF16, 0, 7, 0, GenUniform16<bf16, 7, false>),
     TDX_FAM(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_ICDF16, 7, 0, GenNormalICDF16<bf16, 7, false>),
     TDX_FAM(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_BM16, 10, 0, GenNormalBM16<bf16, 10, false>),
     TDX_FAM(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_BM16, 7, 0, GenNormalBM16<bf16, 7, false>),
     TDX_FAM(TDX_SRC_NORMAL, TDX_F32, TDX_ALGO_BM32, 7, 0, GenNormalBM32<float, 7, false>),
+#endif
 };
 constexpr int kNumFamilies = sizeof(kFamilies) / sizeof(kFamilies[0]);
 
@@ -1215,7 +1227,7 @@ int family_of(const TdxInitDesc& d) {
   const int epi = d.n_epi ? 1 : 0;
   const bool lut_kind = (d.src == TDX_SRC_NORMAL && algo == TDX_ALGO_ICDF16) ||
                         (d.src == TDX_SRC_UNIFORM && algo == 0 && d.dtype != TDX_F32);
-  const bool want_lut = lut_kind && !epi && rounds == 10 && !(d.algo & TDX_ALGO_NOLUT) &&
+  const bool want_lut = lut_kind && rounds == 10 && !(d.algo & TDX_ALGO_NOLUT) &&
                         lut_min_elems() != 0 && d.elem_count >= lut_min_elems();
   for (int f = 1; f < kNumFamilies; ++f) {
     const Family& F = kFamilies[f];
@@ -1384,8 +1396,11 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
       if (fam[i] == f) order.push_back(i);
     if (kFamilies[f].lut)
       std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-        if (descs[a].p0 != descs[b].p0) return descs[a].p0 < descs[b].p0;
-        return descs[a].p1 < descs[b].p1;
+        const TdxInitDesc &x = descs[a], &y = descs[b];
+        if (x.p0 != y.p0) return x.p0 < y.p0;
+        if (x.p1 != y.p1) return x.p1 < y.p1;
+        if (x.n_epi != y.n_epi) return x.n_epi < y.n_epi;
+        return x.n_epi != 0 && memcmp(x.epi, y.epi, sizeof(TdxEpiStep) * x.n_epi) < 0;
       });
     for (int i : order) {
       if (k == 0) G.seed = descs[i].philox_seed;
