@@ -1210,12 +1210,15 @@ int resolve_algo(const TdxInitDesc& d) {
   return 0;
 }
 
-// Descriptors at least this large use the table-driven 16-bit normal (TDX_LUT_MIN_ELEMS overrides;
-// 0 disables).  Below it the 65536-entry table would cost more than it saves.
+// Descriptors at least this large (two tiles) use the table kernel when their launch does
+// (TDX_LUT_MIN_ELEMS overrides; 0 disables).  The table is paid per CTA and per distinct parameter
+// set, not per descriptor -- the host sorts a family's descriptors by parameters -- so the bound only
+// keeps descriptors out whose tiles would mostly take the ragged path (a sharded k_proj of
+// Llama-3-8B on 8 GPUs is 2^19 elements).
 uint64_t lut_min_elems() {
   static const uint64_t v = [] {
     const char* e = getenv("TDX_LUT_MIN_ELEMS");
-    return e ? strtoull(e, nullptr, 10) : (1ull << 20);
+    return e ? strtoull(e, nullptr, 10) : (1ull << 18);
   }();
   return v;
 }

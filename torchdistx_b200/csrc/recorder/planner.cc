@@ -30,6 +30,7 @@ using torch::jit::Stack;
 namespace {
 
 thread_local MaterializeStats g_stats;
+thread_local double g_pending_traverse_us = 0;  // see add_traverse_time
 // Where constant chains are folded.  ATen's CPU and CUDA kernels differ in the last bit for 16-bit
 // dtypes (the CPU kernels round a Python scalar to the tensor dtype first, the CUDA kernels keep it
 // in fp32), and a tensor recorded for CUDA must hold what the program computes on CUDA: so while
@@ -847,7 +848,7 @@ struct Engine {
   }
 };
 
-at::Tensor finish(const at::Tensor& fake, at::Tensor out) {
+at::Tensor finish_tensor(const at::Tensor& fake, at::Tensor out) {
   // requires_grad_() is not an operator and cannot be recorded: re-apply it on leaves
   // (same rule as reference deferred_init.cc:722-726)
   if (fake.is_leaf() && fake.requires_grad() && !out.requires_grad() &&
@@ -859,39 +860,71 @@ at::Tensor finish(const at::Tensor& fake, at::Tensor out) {
 
 }  // namespace
 
+struct MaterializeSession::Impl {
+  MaterializeOptions opts;
+  Batch batch;
+  Engine eng;
+  double t_begin;
+  double add_us = 0;
+  bool finished = false;
+  explicit Impl(const MaterializeOptions& o) : opts(o), eng{o, batch}, t_begin(now_us()) {}
+};
+
+MaterializeSession::MaterializeSession(const MaterializeOptions& opts) {
+  g_stats = MaterializeStats{};
+  g_stats.traverse_us = g_pending_traverse_us;
+  g_pending_traverse_us = 0;
+  g_last_descs.clear();
+  impl_ = std::make_unique<Impl>(opts);
+  g_call_begin_us = impl_->t_begin;
+}
+
+MaterializeSession::~MaterializeSession() {
+  // also on error paths: offsets already handed out must stay consumed
+  if (impl_ && !impl_->finished) {
+    try { impl_->eng.gens.write_back(); } catch (...) {}
+  }
+}
+
+at::Tensor MaterializeSession::add(const at::Tensor& t, bool apply_shard) {
+  g_stats.tensors++;
+  if (!can_materialize(t)) return t;
+  const double t0 = now_us();
+  impl_->eng.opts.shard = apply_shard ? impl_->opts.shard : std::nullopt;
+  const auto rec = fake_impl(t)->record();  // copy: keeps the tape alive while we work
+  at::Tensor out = finish_tensor(t, impl_->eng.materialize_value(rec->tape, rec->value));
+  impl_->add_us += now_us() - t0;
+  return out;
+}
+
+void MaterializeSession::finish() {
+  const double t0 = now_us();
+  impl_->batch.flush();
+  impl_->eng.gens.write_back();
+  impl_->finished = true;
+  impl_->add_us += now_us() - t0;
+  g_stats.plan_us = impl_->add_us - g_stats.launch_us;
+  // whatever else happened between the first add() and now was the caller walking its modules
+  g_stats.traverse_us += (now_us() - impl_->t_begin) - impl_->add_us;
+}
+
 std::vector<at::Tensor> materialize_many(const std::vector<at::Tensor>& fakes,
                                          const MaterializeOptions& opts,
                                          const std::vector<uint8_t>* shard_mask) {
-  g_stats = MaterializeStats{};
-  g_last_descs.clear();
-  const double t_begin = now_us();
-  g_call_begin_us = t_begin;
+  MaterializeSession session(opts);
   std::vector<at::Tensor> out;
   out.reserve(fakes.size());
-  Batch batch;
-  Engine eng{opts, batch};
-  struct WriteBack {  // also on error paths: offsets already handed out must stay consumed
-    GenCache& g;
-    ~WriteBack() { try { g.write_back(); } catch (...) {} }
-  } write_back{eng.gens};
-  for (size_t i = 0; i < fakes.size(); ++i) {
-    const at::Tensor& t = fakes[i];
-    g_stats.tensors++;
-    if (!can_materialize(t)) {
-      out.push_back(t);
-      continue;
-    }
-    eng.opts.shard = (shard_mask && !(*shard_mask)[i]) ? std::nullopt : opts.shard;
-    const auto rec = fake_impl(t)->record();  // copy: keeps the tape alive while we work
-    out.push_back(finish(t, eng.materialize_value(rec->tape, rec->value)));
-  }
-  batch.flush();
-  eng.gens.write_back();
-  g_stats.plan_us = now_us() - t_begin - g_stats.launch_us;
+  for (size_t i = 0; i < fakes.size(); ++i)
+    out.push_back(session.add(fakes[i], !(shard_mask && !(*shard_mask)[i])));
+  session.finish();
   return out;
 }
 
 void add_wrap_time(double us) { g_stats.wrap_us += us; }
+// (materialize_many resets the counters: the traversal that precedes it is reported through a
+// pending value that the next reset picks up)
+void add_traverse_time(double us) { g_pending_traverse_us += us; }
+void add_assign_time(double us) { g_stats.assign_us += us; }
 
 at::Tensor materialize_one(const at::Tensor& fake, const MaterializeOptions& opts) {
   if (!can_materialize(fake)) return fake;

@@ -19,6 +19,7 @@
 #include <ATen/Tensor.h>
 
 #include <cstdint>
+#include <memory>
 #include <optional>
 #include <string>
 #include <tuple>
@@ -50,6 +51,8 @@ struct MaterializeStats {
   double plan_us = 0;    // host time: slicing, symbolic evaluation, allocation, descriptor build
   double launch_us = 0;  // host time inside tdx_init_launch (plan image + H2D copy + launches)
   double wrap_us = 0;    // host time giving results their Python class / identity
+  double traverse_us = 0;  // host time walking the module tree and unpacking its tensors (before planning)
+  double assign_us = 0;    // host time putting the results back into the modules' dicts
   double eval_us = 0;            // part of plan_us: symbolic evaluation of the recorded programs
   double alloc_us = 0;           // part of plan_us: output allocations (caching allocator)
   int64_t upload_bytes = 0;      // plan images copied host -> device
@@ -68,8 +71,29 @@ std::vector<at::Tensor> materialize_many(const std::vector<at::Tensor>& fakes,
                                          const MaterializeOptions& opts,
                                          const std::vector<uint8_t>* shard_mask = nullptr);
 
+// The same, one tensor at a time: `materialize_module` walks the module tree and feeds tensors as it
+// finds them, so the first kernels are on the GPU while the walk is still going on (the walk of a
+// Llama-3-8B costs as much host time as planning a third of it).  add() order defines RNG
+// consumption; finish() submits what is left and writes the generators back (the destructor does
+// the latter on error paths too).
+class MaterializeSession {
+ public:
+  explicit MaterializeSession(const MaterializeOptions& opts);
+  ~MaterializeSession();
+  MaterializeSession(const MaterializeSession&) = delete;
+  MaterializeSession& operator=(const MaterializeSession&) = delete;
+  at::Tensor add(const at::Tensor& fake, bool apply_shard = true);
+  void finish();
+
+ private:
+  struct Impl;
+  std::unique_ptr<Impl> impl_;
+};
+
 MaterializeStats last_stats();
 void add_wrap_time(double us);
+void add_traverse_time(double us);
+void add_assign_time(double us);
 // The TdxInitDesc table (raw bytes) the last materialize call on this thread submitted; lets
 // benchmarks and tests re-launch / inspect exactly what the engine ran.
 std::string last_descriptors();
