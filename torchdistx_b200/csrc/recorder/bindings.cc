@@ -160,7 +160,12 @@ struct PendingSlot {
 
 void walk_and_feed(const py::handle& module, bool buffers_only, const py::object& check_fn, bool sharded,
                    tdx::MaterializeSession& session, std::vector<PendingSlot>& pending) {
-  py::dict children = py::reinterpret_borrow<py::dict>(module.attr("_modules"));
+  // interned once: attr("...") would build a Python string per call, three times per module
+  static PyObject* const k_modules = PyUnicode_InternFromString("_modules");
+  static PyObject* const k_groups[2] = {PyUnicode_InternFromString("_parameters"),
+                                        PyUnicode_InternFromString("_buffers")};
+  py::dict children = py::reinterpret_steal<py::dict>(PyObject_GetAttr(module.ptr(), k_modules));
+  if (!children) throw py::error_already_set();
   std::vector<PyObject*> seen;  // Module.children() yields each distinct child once
   for (auto item : children) {
     if (item.second.is_none()) continue;
@@ -169,10 +174,11 @@ void walk_and_feed(const py::handle& module, bool buffers_only, const py::object
     walk_and_feed(item.second, buffers_only, check_fn, sharded, session, pending);
   }
   if (!check_fn.is_none() && !py::cast<bool>(check_fn(module))) return;
-  for (const char* group : {"_parameters", "_buffers"}) {
-    const bool is_parameter = group[1] == 'p';
+  for (int gi = 0; gi < 2; ++gi) {
+    const bool is_parameter = gi == 0;
     if (buffers_only && is_parameter) continue;
-    py::dict d = py::reinterpret_borrow<py::dict>(module.attr(group));
+    py::dict d = py::reinterpret_steal<py::dict>(PyObject_GetAttr(module.ptr(), k_groups[gi]));
+    if (!d) throw py::error_already_set();
     for (auto item : d) {
       if (item.second.is_none()) continue;
       if (!THPVariable_Check(item.second.ptr()))
@@ -193,6 +199,7 @@ void py_materialize_module(const py::object& module, bool buffers_only, const py
                            const py::object& device, const py::object& shard, bool fused) {
   const tdx::MaterializeOptions opts = make_options(device, shard, fused);
   std::vector<PendingSlot> pending;
+  pending.reserve(512);
   {
     tdx::MaterializeSession session(opts);
     walk_and_feed(module, buffers_only, check_fn, !shard.is_none(), session, pending);
