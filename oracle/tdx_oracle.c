@@ -166,13 +166,12 @@ static float icdf16_tail(uint32_t word) {
 }
 
 /* kernel: box_muller32 */
-static void box_muller32(uint32_t x, uint32_t y, float* n0, float* n1) {
+static void box_muller32(uint32_t x, uint32_t y, float* r, float* c, float* s) {
   const float u1 = fmaf((float)x, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-  const float r = sqrtf(-1.3862943611198906f * log2f(u1));
-  const float t = bits_f((y >> 9) | 0x3f800000u);
-  const float ang = fmaf(t, 6.2831853071795865f, -9.4247779607693797f);
-  *n0 = r * cosf(ang);
-  *n1 = r * sinf(ang);
+  *r = sqrtf(-1.3862943611198906f * log2f(u1));
+  const float ang = (float)(int32_t)y * 1.4629180792671596e-09f; /* y signed, times pi / 2^31 */
+  *c = cosf(ang);
+  *s = sinf(ang);
 }
 
 static int resolve_algo(const TdxInitDesc* d) {
@@ -195,8 +194,8 @@ static float element(const TdxInitDesc* d, uint64_t g) {
     const float to_prev = to > from ? prev_of(to, wide ? TDX_F32 : d->dtype) : to;
     if (wide) {
       block_of(d, g / 4, 0, rounds, w);
-      const float k = (float)(w[g % 4] >> 8);
-      v = fminf(fmaf(k, (to - from) * 5.9604644775390625e-08f, from), to_prev);
+      const float k = (float)w[g % 4]; /* all 32 bits, round to nearest (kernel: I2FP) */
+      v = fminf(fmaf(k, (to - from) * 2.3283064365386963e-10f, from), to_prev);
     } else {
       block_of(d, g / 8, 0, rounds, w);
       const float k = (float)halfword(w, (int)(g % 8));
@@ -205,11 +204,11 @@ static float element(const TdxInitDesc* d, uint64_t g) {
   } else { /* TDX_SRC_NORMAL */
     const float mean = (float)d->p0, std = (float)d->p1;
     if (algo == TDX_ALGO_BM32) {
-      float n[4];
+      float r[2], dir[4];
       block_of(d, g / 4, 0, rounds, w);
-      box_muller32(w[0], w[1], &n[0], &n[1]);
-      box_muller32(w[2], w[3], &n[2], &n[3]);
-      v = fmaf(n[g % 4], std, mean);
+      box_muller32(w[0], w[1], &r[0], &dir[0], &dir[1]);
+      box_muller32(w[2], w[3], &r[1], &dir[2], &dir[3]);
+      v = fmaf(r[(g % 4) >> 1] * std, dir[g % 4], mean);
     } else { /* TDX_ALGO_ICDF16 */
       const int e = (int)(g % 8);
       block_of(d, g / 8, 0, rounds, w);

@@ -360,7 +360,7 @@ struct GenUniform32 {
     p.ph = load_philox(d);
     const float from = static_cast<float>(d.p0), to = static_cast<float>(d.p1);
     p.from = from;
-    p.scale = (to - from) * 5.9604644775390625e-08f;  // * 2^-24, exact
+    p.scale = (to - from) * 2.3283064365386963e-10f;  // * 2^-32, exact
     p.to_prev = (to > from) ? OutTraits<float>::prev(to) : to;
     if (EPI) p.epi = load_epi(d);
     return p;
@@ -372,7 +372,9 @@ struct GenUniform32 {
       const uint32_t x[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float k = __uint2float_rn(x[e] >> 8);  // 24 bits, exact
+        // all 32 bits, rounded to the nearest fp32 (one I2FP; a shift to 24 exact bits would cost as
+        // much again on the dispatch port); the top half-bin rounds to 2^32 and is clamped below `to`
+        const float k = __uint2float_rn(x[e]);
         float r = fminf(fmaf(k, p.scale, p.from), p.to_prev);
         v[b * 4 + e] = EPI ? apply_epi<Out>(p.epi, r) : r;
       }
@@ -382,14 +384,15 @@ struct GenUniform32 {
 
 // ---- normal: Box-Muller on 2 x 32 random bits per pair -------------------------------------
 // (x, y) -> radius from x (32-bit resolution, (0,1]), angle from the top 23 bits of y.
-__device__ __forceinline__ void box_muller32(uint32_t x, uint32_t y, float& n0, float& n1) {
+// Returns the two UNSCALED directions; the caller multiplies the radius by std once per pair.
+__device__ __forceinline__ void box_muller32(uint32_t x, uint32_t y, float& r, float& c, float& s) {
   const float u1 = fmaf(__uint2float_rn(x), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
   // r = sqrt(-2 ln u1) = sqrt(-2 ln2 * lg2 u1)
-  const float r = mufu_sqrt(-1.3862943611198906f * mufu_lg2(u1));
-  const float t = __uint_as_float((y >> 9) | 0x3f800000u);            // [1, 2)
-  const float ang = fmaf(t, 6.2831853071795865f, -9.4247779607693797f);  // [-pi, pi)
-  n0 = r * mufu_cos(ang);
-  n1 = r * mufu_sin(ang);
+  r = mufu_sqrt(-1.3862943611198906f * mufu_lg2(u1));
+  // angle: y as a SIGNED 32-bit integer times pi / 2^31, in [-pi, pi] (one I2FP + one FMUL)
+  const float ang = __int2float_rn(static_cast<int>(y)) * 1.4629180792671596e-09f;
+  c = mufu_cos(ang);
+  s = mufu_sin(ang);
 }
 
 template <class Out, int R, bool EPI>
@@ -413,12 +416,13 @@ struct GenNormalBM32 {
 #pragma unroll
     for (int b = 0; b < kEpv / 4; ++b) {
       const uint4 w = philox_block<R>(p.ph, gv * (kEpv / 4) + b);
-      float n[4];
-      box_muller32(w.x, w.y, n[0], n[1]);
-      box_muller32(w.z, w.w, n[2], n[3]);
+      float r0, r1, d[4];
+      box_muller32(w.x, w.y, r0, d[0], d[1]);
+      box_muller32(w.z, w.w, r1, d[2], d[3]);
+      const float rs[2] = {r0 * p.std, r1 * p.std};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        float r = fmaf(n[e], p.std, p.mean);
+        const float r = fmaf(rs[e >> 1], d[e], p.mean);
         v[b * 4 + e] = EPI ? apply_epi<Out>(p.epi, r) : r;
       }
     }
@@ -671,23 +675,33 @@ __global__ void __launch_bounds__(kThreads) tdx_rng_kernel(const GroupArgs g) {
     const uint64_t nfull = aligned ? count / EPV : 0;  // vectors [0, nfull) are full + aligned
     for (unsigned long long tile = tile0; tile < tile0 + ntiles; ++tile) {
       const uint64_t base = tile * kTileVecs + threadIdx.x;
-      if (base - threadIdx.x + kTileVecs <= nfull) {  // hot path: whole tile is full vectors
+      // Inside a tile the upper 32 bits of the vector index (= Philox counter.y for the one-block
+      // generators) are the same for every thread: handing them to the generator as a uniform value
+      // makes round 1's second product and round 2's first product loop-invariant (18 IMAD.WIDE + 19
+      // LOP3 per block instead of 20 + 20) and the per-vector index a 32-bit add.  A tile that
+      // straddles a 2^32 boundary takes the edge path.
+      const uint64_t gfirst = gv0 + (base - threadIdx.x);
+      const uint32_t hi = static_cast<uint32_t>(gfirst >> 32);
+      const bool one_hi = static_cast<uint32_t>((gfirst + (kTileVecs - 1)) >> 32) == hi;
+      if (base - threadIdx.x + kTileVecs <= nfull && one_hi) {  // hot path: whole tile is full vectors
+        const uint32_t lo0 = static_cast<uint32_t>(gfirst) + threadIdx.x;  // no carry: one_hi
+        char* const p0 = dst + base * 16;
         if constexpr (HasGenVec<Gen>::value) {
           if (Gen::packed_ok(P)) {
 #pragma unroll
             for (int i = 0; i < kVecsPerThread; ++i) {
-              const uint64_t j = base + static_cast<uint64_t>(i) * kThreads;
-              store_vec(dst + j * 16, Gen::gen_vec(P, gv0 + j));
+              const uint64_t gv = (static_cast<uint64_t>(hi) << 32) | (lo0 + static_cast<uint32_t>(i) * kThreads);
+              store_vec(p0 + static_cast<size_t>(i) * (kThreads * 16), Gen::gen_vec(P, gv));
             }
             continue;
           }
         }
 #pragma unroll
         for (int i = 0; i < kVecsPerThread; ++i) {
-          const uint64_t j = base + static_cast<uint64_t>(i) * kThreads;
+          const uint64_t gv = (static_cast<uint64_t>(hi) << 32) | (lo0 + static_cast<uint32_t>(i) * kThreads);
           float v[EPV];
-          Gen::gen(P, gv0 + j, v);
-          store_vec(dst + j * 16, T::pack(v));
+          Gen::gen(P, gv, v);
+          store_vec(p0 + static_cast<size_t>(i) * (kThreads * 16), T::pack(v));
         }
       } else {  // ragged edge: partial vectors, unaligned shards, last tile
         for (int i = 0; i < kVecsPerThread; ++i) {
