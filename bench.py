@@ -88,13 +88,15 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, index: int, period_ms: int = 100):
+        # rank 0 samples every 100 ms; the other ranks of a multi-GPU run every 500 ms (eight
+        # nvidia-smi loops at 10 Hz compete with the ranks' own driver calls inside the timed region)
+        self.rows, self.proc, self.index, self.period_ms = [], None, index, period_ms
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
                                          stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -260,7 +262,7 @@ def run_ours(a):
 
     e2e_ms, h2d = 0.0, 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    clk_e2e = ClockSampler(local)
+    clk_e2e = ClockSampler(local, 100 if rank == 0 else 500)
     for i in range(0 if a.roofline_only else a.warmup):
         step(fakes[i])
         fakes[i] = None
@@ -295,7 +297,7 @@ def run_ours(a):
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     plan = C.TdxPlan()
     C.check(lib.tdx_plan_upload(descs, len(descs), ws.data_ptr(), ws_bytes, stream, ctypes.byref(plan)))
-    clk = ClockSampler(local)
+    clk = ClockSampler(local, 100 if rank == 0 else 500)
     ms, launches_per_step = 1.0, 0
     if not a.roofline_only:
         for _ in range(max(a.warmup, 3)):

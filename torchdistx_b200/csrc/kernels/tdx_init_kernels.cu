@@ -9,18 +9,22 @@
 // persistent kernel streams it to HBM exactly once: Philox counter-based RNG in
 // registers, 128-bit coalesced stores, zero reads, no intermediates.
 //
-// Roofline: pure HBM write.  Algorithmic bytes = elem_count * itemsize per
-// descriptor.  The secondary ceiling is instruction issue: Philox4x32-10 costs
-// 40 slots per 128 random bits, so 16-bit outputs draw 16 random bits per
-// element (8 elements per Philox block) and the normal transform is a
-// branch-free inverse CDF (1 MUFU + 8 FMA-pipe ops per element) instead of
-// Box-Muller (2 MUFU per element, which caps below the HBM roof on B200's
-// 16 MUFU lanes/SM/clk).  See DESIGN.md "Kernels".
+// Roofline: pure HBM write.  Algorithmic bytes = elem_count * itemsize per descriptor.  What
+// actually bounds the RNG kernels on B200 is the dispatch port (benchmarks/instr_rate.cu):
+// IMAD.WIDE holds its pipe 4 cycles per warp instruction and, like every other half-rate
+// instruction (LOP3, PRMT, IMAD, IDP, F2FP, HFMA2), the dispatch port 2; Philox4x32-10 is 20 + 20 of
+// them = 80 cycles per 128 random bits, i.e. 7.0 TB/s-equivalent at one block per 16-byte vector
+// with nothing else in the loop (benchmarks/philox_rate.cu).  So 16-bit outputs draw 16 random bits
+// per element (8 elements per Philox block), large 16-bit descriptors turn half-words into outputs
+// through a shared-memory table (tdx_lut16_kernel), counter.y is hoisted per tile, and the fp32
+// generators spend one I2FP per element.  See DESIGN.md section 4.
 //
-// Scheduling: one kernel launch per kernel family (<= a handful per module, not
-// one per tensor).  Grid = #SM x resident CTAs; CTAs grab 256 KiB chunks of the
-// family's global tile space from an atomic counter, so small and large
-// tensors, shards and ragged tails balance across all 148 SMs.
+// Scheduling: one kernel launch per kernel family (<= a handful per module, not one per tensor).
+// 256-thread kernels: grid = #SM x resident CTAs, CTAs grab runs of tiles of the family's global
+// tile space from an atomic counter (grab size chosen per launch).  Table kernel: one 1024-thread
+// CTA per SM, grabs from a host-built, descriptor-pure work list.  Small and large tensors, shards
+// and ragged tails balance across all 148 SMs either way; every kernel zeroes its work counter
+// when its last CTA leaves.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -72,25 +76,11 @@ __device__ __forceinline__ float mufu_cos(float x) {
   return y;
 }
 // 128-bit streaming store: the data is written once and never re-read by this kernel.
-#ifndef TDX_STORE_MODE
-#define TDX_STORE_MODE 0
-#endif
 __device__ __forceinline__ void store_vec(void* p, uint4 v) {
-#if TDX_STORE_MODE == 0
+  // .cs (evict-first): measured 2 % ahead of the default, .wt and L1::no_allocate forms
   asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
                "r"(v.w)
                : "memory");
-#elif TDX_STORE_MODE == 1
-  *reinterpret_cast<uint4*>(p) = v;
-#elif TDX_STORE_MODE == 2
-  asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x),
-               "r"(v.y), "r"(v.z), "r"(v.w)
-               : "memory");
-#else
-  asm volatile("st.global.wt.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
-               "r"(v.w)
-               : "memory");
-#endif
 }
 
 template <class Out>
@@ -146,13 +136,6 @@ struct OutTraits<__nv_bfloat16> {
                                      *reinterpret_cast<const __nv_bfloat162*>(&b));
     return *reinterpret_cast<const uint32_t*>(&m);
   }
-  __device__ static __forceinline__ bool any_nan4(const uint32_t (&r)[4]) {
-    const __nv_bfloat162 s = __hadd2(__hadd2(*reinterpret_cast<const __nv_bfloat162*>(&r[0]),
-                                             *reinterpret_cast<const __nv_bfloat162*>(&r[1])),
-                                     __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&r[2]),
-                                             *reinterpret_cast<const __nv_bfloat162*>(&r[3])));
-    return !__hbeq2(s, s);  // all-equal test fails iff a half is NaN
-  }
   __device__ static __forceinline__ float prev(float to) {  // `to` is exactly a bf16 value
     uint32_t b = __float_as_uint(to);
     if (to > 0.f) return __uint_as_float(b - 0x10000u);
@@ -189,13 +172,6 @@ struct OutTraits<__half> {
   __device__ static __forceinline__ uint32_t min2(uint32_t a, uint32_t b) {
     const __half2 m = __hmin2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
     return *reinterpret_cast<const uint32_t*>(&m);
-  }
-  __device__ static __forceinline__ bool any_nan4(const uint32_t (&r)[4]) {
-    const __half2 s = __hadd2(__hadd2(*reinterpret_cast<const __half2*>(&r[0]),
-                                      *reinterpret_cast<const __half2*>(&r[1])),
-                              __hadd2(*reinterpret_cast<const __half2*>(&r[2]),
-                                      *reinterpret_cast<const __half2*>(&r[3])));
-    return !__hbeq2(s, s);
   }
   __device__ static __forceinline__ float prev(float to) {  // `to` is exactly an fp16 value
     unsigned short h = __half_as_ushort(__float2half_rn(to));
@@ -491,13 +467,6 @@ struct GenNormalICDF16 {
   __device__ static __forceinline__ float element(const Params& p, float magic, float& t) {
     float l;
     return element_l(p, magic, t, l);
-  }
-  // the same value, except that k == 0 (t == 0, l == -inf) comes out as NaN -- what the table holds
-  // for that k.  One FMA-pipe instruction: l*0 is -0/+0 for finite l (v unchanged), NaN for -inf.
-  __device__ static __forceinline__ float element_nan(const Params& p, float magic) {
-    float t, l;
-    const float v = element_l(p, magic, t, l);
-    return fmaf(l, 0.0f, v);
   }
   __device__ static __forceinline__ void gen(const Params& p, uint64_t gv, float (&v)[8]) {
     const uint4 w = philox_block<R>(p.ph, gv);
@@ -819,33 +788,29 @@ __device__ __noinline__ uint4 lut_slow_vector(const TdxInitDesc* d, uint64_t gv)
 //    wavefronts per LDS and an SM delivers one wavefront per cycle, so a pure table kernel is
 //    LSU-bound at 0.63 of the HBM roof;
 //  * work comes from a host-built list of descriptor-pure grabs (for_each_listed_chunk).
-#ifndef TDX_LUT2_ELEMS_A
-#define TDX_LUT2_ELEMS_A 7
+#ifndef TDX_LUT_ELEMS_A
+#define TDX_LUT_ELEMS_A 7
 #endif
-#ifndef TDX_LUT2_ELEMS_B
-#define TDX_LUT2_ELEMS_B 7
+#ifndef TDX_LUT_ELEMS_B
+#define TDX_LUT_ELEMS_B 7
 #endif
-#ifndef TDX_LUT2_GROUP
-#define TDX_LUT2_GROUP 4
+#ifndef TDX_LUT_GROUP
+#define TDX_LUT_GROUP 4
 #endif
-#ifndef TDX_LUT2_PACK
-#define TDX_LUT2_PACK 0
+#ifndef TDX_LUT_PACK
+#define TDX_LUT_PACK 0
 #endif
 
-__device__ __forceinline__ uint32_t lut_addr_lo(uint32_t w, uint32_t base) {
+// byte offset 2*k of the table entry of the low / high half-word of a Philox word, in one IDP.2A
+__device__ __forceinline__ uint32_t lut_off_lo(uint32_t w) {
   uint32_t a;
-  asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(w), "r"(0x00000002u), "r"(base));
+  asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(w), "r"(0x00000002u), "r"(0u));
   return a;
 }
-__device__ __forceinline__ uint32_t lut_addr_hi(uint32_t w, uint32_t base) {
+__device__ __forceinline__ uint32_t lut_off_hi(uint32_t w) {
   uint32_t a;
-  asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(w), "r"(0x00000200u), "r"(base));
+  asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(w), "r"(0x00000200u), "r"(0u));
   return a;
-}
-__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
-  unsigned short v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
-  return v;
 }
 // Dynamic shared memory of a kernel without static shared memory starts at this offset of the
 // shared window on sm_100 (the first KiB is reserved by the system).  The table kernel folds it
@@ -858,9 +823,9 @@ __device__ __forceinline__ uint32_t lds_u16_tab(uint32_t off) {
   return v;
 }
 __device__ __forceinline__ uint32_t pack_u16(uint32_t lo, uint32_t hi) {
-#if TDX_LUT2_PACK == 1
+#if TDX_LUT_PACK == 1
   return __byte_perm(lo, hi, 0x5410);
-#elif TDX_LUT2_PACK == 2
+#elif TDX_LUT_PACK == 2
   return lo | (hi << 16);
 #else
   uint32_t r;
@@ -895,20 +860,12 @@ struct NanAcc<__nv_bfloat16> {
   __device__ __forceinline__ void add(uint32_t a, uint32_t b) {
     asm("fma.rn.bf16x2 %0, %1, %2, %0;" : "+r"(acc) : "r"(a), "r"(b));
   }
-  __device__ __forceinline__ bool any_nan() const {
-    const __nv_bfloat162 s = *reinterpret_cast<const __nv_bfloat162*>(&acc);
-    return !__hbeq2(s, s);
-  }
 };
 template <>
 struct NanAcc<__half> {
   uint32_t acc = 0;
   __device__ __forceinline__ void add(uint32_t a, uint32_t b) {
     asm("fma.rn.f16x2 %0, %1, %2, %0;" : "+r"(acc) : "r"(a), "r"(b));
-  }
-  __device__ __forceinline__ bool any_nan() const {
-    const __half2 s = *reinterpret_cast<const __half2*>(&acc);
-    return !__hbeq2(s, s);
   }
 };
 
@@ -1012,7 +969,7 @@ __device__ __forceinline__ bool any_nonfinite2(uint32_t v) {
 // Philox 74 of the ~126 cycles a vector takes, a table element 4 (IDP + LDS + half a pack), a
 // computed normal 14, a computed uniform 6 -- against 3.56 shared-memory wavefronts per looked-up
 // element, of which an SM delivers one per cycle.
-template <class Tab, class Out, int R, bool PKEYS, int LUT_A, int LUT_B, int GROUP = TDX_LUT2_GROUP>
+template <class Tab, class Out, int R, bool PKEYS, int LUT_A, int LUT_B, int GROUP = TDX_LUT_GROUP>
 __global__ void __launch_bounds__(kLutThreads, 1) tdx_lut16_kernel(const GroupArgs g) {
   using Gen = typename Tab::Gen;
   using T = OutTraits<Out>;
@@ -1069,13 +1026,13 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_lut16_kernel(const GroupAr
             for (int q = 0; q < 4; ++q) {
               const bool lo_lut = 2 * q < LUT_ELEMS, hi_lut = 2 * q + 1 < LUT_ELEMS;
               if (lo_lut && hi_lut) {
-                r[q] = pack_u16(lds_u16_tab(lut_addr_lo(ws[q], 0u)), lds_u16_tab(lut_addr_hi(ws[q], 0u)));
+                r[q] = pack_u16(lds_u16_tab(lut_off_lo(ws[q])), lds_u16_tab(lut_off_hi(ws[q])));
               } else if (!lo_lut && !hi_lut) {
                 r[q] = T::pack2(Tab::value(P, halfword_as_magic(w, 2 * q)),
                                 Tab::value(P, halfword_as_magic(w, 2 * q + 1)));
               } else {  // low half from the table, high half computed
                 const uint32_t hi16 = T::pack2(0.0f, Tab::value(P, halfword_as_magic(w, 2 * q + 1)));
-                r[q] = (hi16 & 0xffff0000u) | lds_u16_tab(lut_addr_lo(ws[q], 0u));
+                r[q] = (hi16 & 0xffff0000u) | lds_u16_tab(lut_off_lo(ws[q]));
               }
             }
             if (Tab::kHasTail) {
@@ -1128,17 +1085,17 @@ struct Family {
 #define TDX_FAM_V16(src, dt, algo, rounds, epi, ...)                                               \
   { src, dt, algo, rounds, epi, static_cast<KernelFn>(tdx_rng_kernel<__VA_ARGS__, 16>), #__VA_ARGS__, \
     kThreads, kThreads * 16, 0, false, (kVecsPerThread * kTilesPerChunk) / 16 }
-#ifndef TDX_LUT2_PKEYS
-#define TDX_LUT2_PKEYS 1
+#ifndef TDX_LUT_PKEYS
+#define TDX_LUT_PKEYS 1
 #endif
-#ifndef TDX_LUT2_UNIFORM_ELEMS
-#define TDX_LUT2_UNIFORM_ELEMS 6  // measured at 4 GiB bf16: 8/7/6/5/4 -> 0.674/0.748/0.815/0.813/0.803 of the HBM roof
+#ifndef TDX_LUT_UNIFORM_ELEMS
+#define TDX_LUT_UNIFORM_ELEMS 6  // measured at 4 GiB bf16: 8/7/6/5/4 -> 0.674/0.748/0.815/0.813/0.803 of the HBM roof
 #endif
 // table-driven twins of the 16-bit generators: `fn` takes the Philox round keys from the kernel
 // parameters (groups that share one seed: the normal case), `fn_any_seed` from each descriptor
 #define TDX_FAM_LUT(src, dt, algo, epi, name, out, la, lb, ...)                                          \
   { src, dt, algo, 10, epi,                                                                           \
-    static_cast<KernelFn>(tdx_lut16_kernel<__VA_ARGS__, out, 10, TDX_LUT2_PKEYS != 0, la, lb>), name,   \
+    static_cast<KernelFn>(tdx_lut16_kernel<__VA_ARGS__, out, 10, TDX_LUT_PKEYS != 0, la, lb>), name,   \
     kLutThreads, kLutTileVecs, static_cast<int>(kLutBytes) + 128, true, kLutTilesPerChunk,              \
     static_cast<KernelFn>(tdx_lut16_kernel<__VA_ARGS__, out, 10, false, la, lb>) }
 
@@ -1171,10 +1128,10 @@ static const Family kFamilies[] = {
     TDX_FAM(TDX_SRC_NORMAL, TDX_F16, TDX_ALGO_BM32, 10, 0, GenNormalBM32<f16, 10, false>),
     TDX_FAM(TDX_SRC_NORMAL, TDX_F16, TDX_ALGO_BM32, 10, 1, GenNormalBM32<f16, 10, true>),
     // table-driven twins of the 16-bit normal for large descriptors (bit-identical output)
-    TDX_FAM_LUT(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_ICDF16, 0, "lut<normal, bf16>", bf16, TDX_LUT2_ELEMS_A, TDX_LUT2_ELEMS_B, TabNormal<bf16, 10>),
-    TDX_FAM_LUT(TDX_SRC_NORMAL, TDX_F16, TDX_ALGO_ICDF16, 0, "lut<normal, f16>", f16, TDX_LUT2_ELEMS_A, TDX_LUT2_ELEMS_B, TabNormal<f16, 10>),
-    TDX_FAM_LUT(TDX_SRC_UNIFORM, TDX_BF16, 0, 0, "lut<uniform, bf16>", bf16, TDX_LUT2_UNIFORM_ELEMS, TDX_LUT2_UNIFORM_ELEMS, TabUniform<bf16, 10>),
-    TDX_FAM_LUT(TDX_SRC_UNIFORM, TDX_F16, 0, 0, "lut<uniform, f16>", f16, TDX_LUT2_UNIFORM_ELEMS, TDX_LUT2_UNIFORM_ELEMS, TabUniform<f16, 10>),
+    TDX_FAM_LUT(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_ICDF16, 0, "lut<normal, bf16>", bf16, TDX_LUT_ELEMS_A, TDX_LUT_ELEMS_B, TabNormal<bf16, 10>),
+    TDX_FAM_LUT(TDX_SRC_NORMAL, TDX_F16, TDX_ALGO_ICDF16, 0, "lut<normal, f16>", f16, TDX_LUT_ELEMS_A, TDX_LUT_ELEMS_B, TabNormal<f16, 10>),
+    TDX_FAM_LUT(TDX_SRC_UNIFORM, TDX_BF16, 0, 0, "lut<uniform, bf16>", bf16, TDX_LUT_UNIFORM_ELEMS, TDX_LUT_UNIFORM_ELEMS, TabUniform<bf16, 10>),
+    TDX_FAM_LUT(TDX_SRC_UNIFORM, TDX_F16, 0, 0, "lut<uniform, f16>", f16, TDX_LUT_UNIFORM_ELEMS, TDX_LUT_UNIFORM_ELEMS, TabUniform<f16, 10>),
     // with an epilogue every element is looked up: the computed alternative may contain an erfinv
     TDX_FAM_LUT(TDX_SRC_NORMAL, TDX_BF16, TDX_ALGO_ICDF16, 1, "lut<normal+epilogue, bf16>", bf16, 8, 8, TabNormal<bf16, 10, true>),
     TDX_FAM_LUT(TDX_SRC_NORMAL, TDX_F16, TDX_ALGO_ICDF16, 1, "lut<normal+epilogue, f16>", f16, 8, 8, TabNormal<f16, 10, true>),

@@ -501,6 +501,15 @@ struct GenCache {
     bool dirty = false;
   };
   std::vector<Entry> entries;
+  // the default generator of a device, looked up once per materialize call (the global context's
+  // accessor takes a lock and re-validates the device on every call)
+  std::vector<std::pair<c10::Device, at::Generator>> defaults;
+  const at::Generator& default_generator(c10::Device device) {
+    for (const auto& d : defaults)
+      if (d.first == device) return d.second;
+    defaults.emplace_back(device, at::globalContext().defaultGenerator(device));
+    return defaults.back().second;
+  }
   Entry& get(const at::Generator& g) {
     for (auto& e : entries)
       if (e.gen.unsafeGetGeneratorImpl() == g.unsafeGetGeneratorImpl()) return e;
@@ -533,7 +542,7 @@ void assign_rng(TapeOp& op, int64_t numel, c10::Device device, GenCache& cache) 
     const size_t pos = find_arg(op, "generator");
     if (pos != static_cast<size_t>(-1) && op.args[pos].isGenerator()) gen = op.args[pos].toGenerator();
   }
-  if (!gen.defined()) gen = at::globalContext().defaultGenerator(device);
+  if (!gen.defined()) gen = cache.default_generator(device);
   TORCH_CHECK(gen.device().type() == device.type(), "Expected a '", device.type(),
               "' device type for generator but found '", gen.device().type(), "'");
   GenCache::Entry& e = cache.get(gen);
