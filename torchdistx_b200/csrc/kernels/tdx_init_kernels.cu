@@ -755,7 +755,9 @@ constexpr int kLutTilesPerChunk = (1 << 20) / (kLutTileVecs * 16) > 0 ? (1 << 20
 constexpr unsigned long long kLutMaxTilesPerChunk =
     (1ull << TDX_LUT_MAX_CHUNK_LOG2) / (kLutTileVecs * 16) > 0 ? (1ull << TDX_LUT_MAX_CHUNK_LOG2) / (kLutTileVecs * 16) : 1;
 constexpr uint32_t kLutBytes = 65536u * 2u;
-constexpr uint64_t kLutMinLaunchElems = 1ull << 26;  // 128 MB of 16-bit output per launch (r1 sweep: break-even 130-200 MB)
+// A launch uses the table kernel when it holds at least this many table-eligible elements
+// (TDX_LUT_MIN_LAUNCH_ELEMS overrides): the table costs every CTA ~4 us.
+constexpr uint64_t kLutMinLaunchElemsDefault = 1ull << 25;  // 64 MB of 16-bit output
 constexpr unsigned short kLutSentinel = 0xffffu;  // a NaN pattern in bf16 and fp16: never a value
 
 // cold path of the table kernel (a vector that contains k == 0): out of line, to keep the hot loop
@@ -1194,6 +1196,14 @@ uint64_t lut_min_elems() {
   return v;
 }
 
+uint64_t lut_min_launch_elems() {
+  static const uint64_t v = [] {
+    const char* e = getenv("TDX_LUT_MIN_LAUNCH_ELEMS");
+    return e ? strtoull(e, nullptr, 10) : kLutMinLaunchElemsDefault;
+  }();
+  return v;
+}
+
 int family_of(const TdxInitDesc& d) {
   if (d.src == TDX_SRC_CONST) return 0;
   const int algo = resolve_algo(d);
@@ -1321,7 +1331,7 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
     for (int i = 0; i < n; ++i)
       if (kFamilies[fam[i]].lut) lut_elems[fam[i]] += descs[i].elem_count;
     for (int f = 0; f < kNumFamilies; ++f) {
-      if (!kFamilies[f].lut || lut_elems[f] == 0 || lut_elems[f] >= kLutMinLaunchElems) continue;
+      if (!kFamilies[f].lut || lut_elems[f] == 0 || lut_elems[f] >= lut_min_launch_elems()) continue;
       int twin = -1;
       for (int t = 1; t < kNumFamilies; ++t) {
         const Family &A = kFamilies[f], &B = kFamilies[t];
