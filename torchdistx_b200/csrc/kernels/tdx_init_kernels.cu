@@ -757,7 +757,7 @@ constexpr unsigned long long kLutMaxTilesPerChunk =
 constexpr uint32_t kLutBytes = 65536u * 2u;
 // A launch uses the table kernel when it holds at least this many table-eligible elements
 // (TDX_LUT_MIN_LAUNCH_ELEMS overrides): the table costs every CTA ~4 us.
-constexpr uint64_t kLutMinLaunchElemsDefault = 1ull << 25;  // 64 MB of 16-bit output
+constexpr uint64_t kLutMinLaunchElemsDefault = 1ull << 25;  // 64 MB of 16-bit output (normal; x2 for the uniform)
 constexpr unsigned short kLutSentinel = 0xffffu;  // a NaN pattern in bf16 and fp16: never a value
 
 // cold path of the table kernel (a vector that contains k == 0): out of line, to keep the hot loop
@@ -1331,7 +1331,10 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
     for (int i = 0; i < n; ++i)
       if (kFamilies[fam[i]].lut) lut_elems[fam[i]] += descs[i].elem_count;
     for (int f = 0; f < kNumFamilies; ++f) {
-      if (!kFamilies[f].lut || lut_elems[f] == 0 || lut_elems[f] >= lut_min_launch_elems()) continue;
+      // measured break-even (profiles/r1_lut_launch_threshold.txt): ~64 MB for the normal, whose
+      // direct kernel is the slowest, ~128 MB for the uniform
+      const uint64_t need = lut_min_launch_elems() * (kFamilies[f].src == TDX_SRC_UNIFORM ? 2 : 1);
+      if (!kFamilies[f].lut || lut_elems[f] == 0 || lut_elems[f] >= need) continue;
       int twin = -1;
       for (int t = 1; t < kNumFamilies; ++t) {
         const Family &A = kFamilies[f], &B = kFamilies[t];
