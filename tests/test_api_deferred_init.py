@@ -197,3 +197,56 @@ def test_nested_deferred_init_and_cross_scope_inputs():
     out = materialize_tensor(p)
     w = materialize_tensor(emb.weight)
     assert torch.equal(out, w.detach() * 2.0)
+
+
+def test_materialize_module_error_leaves_the_module_untouched_and_does_not_hang():
+    """materialize_module plans on a helper thread; a failure there must surface as the same
+    exception on the calling thread, with no tensor assigned and the next call working."""
+    ext = torch.ones(4)
+
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = nn.Parameter(torch.zeros(3))
+            self.b = nn.Parameter(torch.full((4,), 2.0) + ext)   # replay needs `ext` unchanged
+            self.c = nn.Parameter(torch.ones(2))
+
+    m = deferred_init(M)
+    ext.add_(1)
+    with pytest.raises(RuntimeError, match="updated in-place"):
+        materialize_module(m)
+    assert is_fake(m.a) and is_fake(m.b) and is_fake(m.c)  # nothing was assigned
+    ok = deferred_init(nn.Linear, 3, 2)
+    materialize_module(ok)
+    assert not is_deferred(ok)
+
+
+def test_materialize_module_runs_under_the_callers_thread_local_state():
+    """The helper thread applies the caller's ThreadLocalState: results built under no_grad /
+    with another default dtype behave as if built inline."""
+    m = deferred_init(nn.Linear, 4, 4)
+    with torch.no_grad():
+        materialize_module(m)
+    assert m.weight.requires_grad and m.weight.grad_fn is None
+    torch.manual_seed(3)
+    a = deferred_init(nn.Linear, 8, 8)
+    materialize_module(a)
+    torch.manual_seed(3)
+    b = nn.Linear(8, 8)
+    assert torch.equal(a.weight, b.weight) and torch.equal(a.bias, b.bias)  # generator written back before return
+
+
+def test_materialize_module_in_a_forked_child():
+    """The helper thread does not survive fork(); the child must start its own."""
+    import os
+    materialize_module(deferred_init(nn.Linear, 2, 2))  # make sure the parent's helper exists
+    pid = os.fork()
+    if pid == 0:
+        try:
+            m = deferred_init(nn.Linear, 3, 3)
+            materialize_module(m)
+            os._exit(0 if not is_deferred(m) else 3)
+        except BaseException:
+            os._exit(4)
+    _, status = os.waitpid(pid, 0)
+    assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0

@@ -1262,11 +1262,21 @@ static_assert(kNumFamilies <= 32, "counter slots");
 // launch so that this holds), a guided tail, and one partial grab per descriptor.
 constexpr size_t kMaxListChunks = 8192;
 constexpr size_t kMaxListTail = 4096;
+size_t lut_family_count() {
+  static const size_t v = [] {
+    size_t c = 0;
+    for (int f = 0; f < kNumFamilies; ++f) c += kFamilies[f].lut ? 1 : 0;
+    return c;
+  }();
+  return v;
+}
 size_t plan_bytes(int n) {
-  // header + per-family prefix arrays (n + #families entries worst case) + descriptors + work lists
+  // header + per-family prefix arrays (n + #families entries worst case) + descriptors + one work
+  // list per table family (each at most kMaxListChunks + kMaxListTail grabs plus one per descriptor)
   return sizeof(PlanHeader) + (static_cast<size_t>(n) + kNumFamilies) * sizeof(unsigned long long) +
          static_cast<size_t>(n) * sizeof(TdxInitDesc) +
-         (2 * (kMaxListChunks + kMaxListTail) + static_cast<size_t>(n)) * sizeof(uint4) + 64;
+         (lut_family_count() * (kMaxListChunks + kMaxListTail) + static_cast<size_t>(n)) * sizeof(uint4) +
+         16 * static_cast<size_t>(kNumFamilies) + 64;
 }
 
 struct DeviceInfo {
@@ -1306,7 +1316,9 @@ DeviceInfo* device_info() {
 }
 
 // Builds the host image of the plan.  Returns 0 or an error code.
-int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img, PlanHeader& hdr) {
+// `img` is scratch that only grows (zero-filling 1.6 MB per call would cost more host time than the
+// planning of a small module); `used` = bytes of the image to copy to the device.
+int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img, PlanHeader& hdr, size_t& used) {
   if (n < 0 || (n > 0 && descs == nullptr)) return fail(TDX_E_BADARG, "descs == NULL or n < 0");
   std::vector<int> fam(static_cast<size_t>(n));
   int per_family[kNumFamilies] = {};
@@ -1353,7 +1365,7 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
   }
   memset(&hdr, 0, sizeof(hdr));
   hdr.magic = kPlanMagic;
-  img.assign(plan_bytes(n), 0);
+  if (img.size() < plan_bytes(n)) img.resize(plan_bytes(n));
   int sm_count = 148;
   if (DeviceInfo* info = device_info()) sm_count = info->sm_count;
   std::vector<int> order;
@@ -1416,6 +1428,8 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
         while (t < nt) {
           unsigned long long sz = std::min(std::max(remaining / (2 * ctas), 1ull), cap);
           sz = std::min(sz, nt - t);
+          if (off + (static_cast<size_t>(nc) + 1) * sizeof(uint4) > img.size())
+            return fail(TDX_E_WORKSPACE, "internal: work list exceeds its bound");
           list[nc++] = make_uint4(di, static_cast<uint32_t>(sz), static_cast<uint32_t>(t),
                                   static_cast<uint32_t>(t >> 32));
           t += sz;
@@ -1427,7 +1441,7 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
     }
   }
   memcpy(img.data(), &hdr, sizeof(hdr));
-  img.resize(off);
+  used = off;
   return 0;
 }
 
@@ -1539,12 +1553,13 @@ TDX_C_API int tdx_plan_upload(const TdxInitDesc* descs, int n, void* workspace,
   thread_local std::vector<unsigned char> img;
   tdx::PlanHeader hdr;
   if (plan == nullptr) return tdx::fail(TDX_E_BADARG, "plan == NULL");
-  if (int rc = tdx::build_plan(descs, n, img, hdr)) return rc;
+  size_t used = 0;
+  if (int rc = tdx::build_plan(descs, n, img, hdr, used)) return rc;
   memcpy(plan, &hdr, sizeof(hdr));
-  if (workspace == nullptr || workspace_bytes < img.size())
+  if (workspace == nullptr || workspace_bytes < used)
     return tdx::fail(TDX_E_WORKSPACE, "workspace too small (see tdx_init_workspace_bytes)");
-  tdx::g_last_upload_bytes = img.size();
-  cudaError_t e = cudaMemcpyAsync(workspace, img.data(), img.size(), cudaMemcpyHostToDevice,
+  tdx::g_last_upload_bytes = used;
+  cudaError_t e = cudaMemcpyAsync(workspace, img.data(), used, cudaMemcpyHostToDevice,
                                   static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return tdx::cuda_fail(e, "cudaMemcpyAsync(plan)");
   // the staging image is reused by the next call on this thread: make sure the copy has left it
@@ -1566,18 +1581,19 @@ TDX_C_API int tdx_init_launch(const TdxInitDesc* descs, int n, void* workspace,
                               size_t workspace_bytes, void* stream) {
   thread_local std::vector<unsigned char> img;
   tdx::PlanHeader hdr;
-  if (int rc = tdx::build_plan(descs, n, img, hdr)) return rc;
+  size_t used = 0;
+  if (int rc = tdx::build_plan(descs, n, img, hdr, used)) return rc;
   if (hdr.n_groups == 0) {
     tdx::g_last_launches = 0;
     return 0;
   }
-  if (workspace == nullptr || workspace_bytes < img.size())
+  if (workspace == nullptr || workspace_bytes < used)
     return tdx::fail(TDX_E_WORKSPACE, "workspace too small (see tdx_init_workspace_bytes)");
   // The plan image goes through a small ring of pinned staging buffers so that the copy is truly
   // asynchronous: the host can go on planning the next batch while the GPU works on this one.
-  tdx::g_last_upload_bytes = img.size();
+  tdx::g_last_upload_bytes = used;
   void* pinned = nullptr;
-  if (int rc = tdx::stage(img.data(), img.size(), static_cast<cudaStream_t>(stream), workspace, &pinned))
+  if (int rc = tdx::stage(img.data(), used, static_cast<cudaStream_t>(stream), workspace, &pinned))
     return rc;
   return tdx::launch_groups(hdr, workspace, static_cast<cudaStream_t>(stream));
 }

@@ -155,11 +155,12 @@ struct PendingSlot {
   py::object key;
   py::object var;  // the fake tensor object (its Python class is what the result must have)
   at::Tensor fake;
-  at::Tensor out;
+  size_t ticket;  // of the planner's result; kNoTicket: the tensor was handed out before
 };
+constexpr size_t kNoTicket = static_cast<size_t>(-1);
 
 void walk_and_feed(const py::handle& module, bool buffers_only, const py::object& check_fn, bool sharded,
-                   tdx::MaterializeSession& session, std::vector<PendingSlot>& pending) {
+                   tdx::PipelinedMaterialize& session, std::vector<PendingSlot>& pending) {
   // interned once: attr("...") would build a Python string per call, three times per module
   static PyObject* const k_modules = PyUnicode_InternFromString("_modules");
   static PyObject* const k_groups[2] = {PyUnicode_InternFromString("_parameters"),
@@ -186,10 +187,10 @@ void walk_and_feed(const py::handle& module, bool buffers_only, const py::object
       const at::Tensor& t = THPVariable_Unpack(item.second.ptr());
       if (!tdx::can_materialize(t)) continue;  // real tensors stay where they are
       PendingSlot p{d, py::reinterpret_borrow<py::object>(item.first),
-                    py::reinterpret_borrow<py::object>(item.second), t, at::Tensor()};
+                    py::reinterpret_borrow<py::object>(item.second), t, kNoTicket};
       // tensors that were already handed out keep their identity and are not touched again
       // (parameters are chunked, buffers replicated -- no isinstance(): which dict it came from says it)
-      if (!tdx::cached_python_tensor(t).defined()) p.out = session.add(t, /*apply_shard=*/!sharded || is_parameter);
+      if (!tdx::cached_python_tensor(t).defined()) p.ticket = session.add(t, /*apply_shard=*/!sharded || is_parameter);
       pending.push_back(std::move(p));
     }
   }
@@ -200,18 +201,56 @@ void py_materialize_module(const py::object& module, bool buffers_only, const py
   const tdx::MaterializeOptions opts = make_options(device, shard, fused);
   std::vector<PendingSlot> pending;
   pending.reserve(512);
-  {
-    tdx::MaterializeSession session(opts);
+  std::vector<py::object> wrapped;
+  double wrap_us = 0;
+  const auto t_walk = std::chrono::steady_clock::now();
+  // plans on a helper thread while this one keeps walking
+  auto session_ptr = std::make_unique<tdx::PipelinedMaterialize>(opts);
+  tdx::PipelinedMaterialize& session = *session_ptr;
+  try {
     walk_and_feed(module, buffers_only, check_fn, !shard.is_none(), session, pending);
     session.finish();
-  }
-  const auto t0 = std::chrono::steady_clock::now();
-  for (PendingSlot& p : pending) {
+    tdx::add_traverse_time(std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_walk).count());
+    // Results get their Python identity as they become ready.  Nothing is assigned before every
+    // tensor has been planned: a failure leaves the module as it was (the reference's per-tensor loop
+    // would leave it half-built).
+    wrapped.resize(pending.size());
+    for (size_t i = 0; i < pending.size(); ++i) {
+      PendingSlot& p = pending[i];
+      if (p.ticket == kNoTicket) {
+        wrapped[i] = py::cast(tdx::cached_python_tensor(p.fake));
+        continue;
+      }
+      at::Tensor out;
+      if (session.ready(p.ticket)) {
+        out = session.result(p.ticket);
+      } else {
+        py::gil_scoped_release nogil;  // the helper may need the GIL (Python-level dispatch during a replay)
+        out = session.result(p.ticket);
+      }
+      const auto t0 = std::chrono::steady_clock::now();
+      wrapped[i] = wrap_like(p.var, p.fake, out);
+      wrap_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+    }
+    {
+      py::gil_scoped_release nogil;
+      session.join();
+    }
+    const auto t0 = std::chrono::steady_clock::now();
     // (assignment through the dict, like Module.__setattr__ does for an existing entry)
-    if (p.out.defined()) p.dict[p.key] = wrap_like(p.var, p.fake, p.out);
-    else p.dict[p.key] = py::cast(tdx::cached_python_tensor(p.fake));
+    for (size_t i = 0; i < pending.size(); ++i) pending[i].dict[pending[i].key] = wrapped[i];
+    wrap_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+    tdx::add_wrap_time(wrap_us);
+  } catch (...) {
+    // the helper may be inside a replay that needs the GIL: never wait for it while holding it
+    py::gil_scoped_release nogil;
+    session_ptr.reset();
+    throw;
   }
-  tdx::add_wrap_time(std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
+  {
+    py::gil_scoped_release nogil;
+    session_ptr.reset();
+  }
 }
 
 py::dict py_last_stats() {

@@ -14,7 +14,17 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <mutex>
+#include <thread>
+
+#include <unistd.h>
+
+#include <ATen/ThreadLocalState.h>
+#include <c10/cuda/CUDAFunctions.h>
 
 #include "fake_tensor.h"
 #include "stack_walk.h"
@@ -927,6 +937,266 @@ std::vector<at::Tensor> materialize_many(const std::vector<at::Tensor>& fakes,
     out.push_back(session.add(fakes[i], !(shard_mask && !(*shard_mask)[i])));
   session.finish();
   return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the session on a helper thread
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+// One helper thread per process, started on first use (and again in a forked child).
+class HelperThread {
+ public:
+  static HelperThread& get() {
+    static std::mutex m;
+    static std::unique_ptr<HelperThread> inst;
+    std::lock_guard<std::mutex> lock(m);
+    if (!inst || inst->pid_ != getpid()) {
+      if (inst && inst->pid_ != getpid()) inst.release();  // forked child: the parent's thread is not ours to join
+      inst.reset(new HelperThread());
+    }
+    return *inst;
+  }
+  void post(std::function<void()> fn) {
+    {
+      std::lock_guard<std::mutex> lock(m_);
+      q_.push_back(std::move(fn));
+    }
+    cv_.notify_one();
+  }
+  ~HelperThread() {
+    {
+      std::lock_guard<std::mutex> lock(m_);
+      stop_ = true;
+    }
+    cv_.notify_one();
+    if (th_.joinable()) th_.join();
+  }
+
+ private:
+  HelperThread() : pid_(getpid()), th_([this] { run(); }) {}
+  void run() {
+    for (;;) {
+      std::function<void()> fn;
+      {
+        std::unique_lock<std::mutex> lock(m_);
+        cv_.wait(lock, [this] { return stop_ || !q_.empty(); });
+        if (q_.empty()) return;  // stop requested and nothing left
+        fn = std::move(q_.front());
+        q_.pop_front();
+      }
+      fn();
+    }
+  }
+  pid_t pid_;
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::deque<std::function<void()>> q_;
+  bool stop_ = false;
+  std::thread th_;
+};
+
+bool host_threads_enabled() {
+  static const bool v = [] {
+    const char* e = getenv("TDX_HOST_THREADS");
+    return !(e && e[0] == '0');
+  }();
+  return v;
+}
+
+}  // namespace
+
+struct PipelinedMaterialize::State {
+  struct Item {
+    at::Tensor fake;
+    bool apply_shard = true;
+    at::Tensor out;
+    std::atomic<uint8_t> done{0};
+  };
+  MaterializeOptions opts;
+  bool threaded = false;
+  at::ThreadLocalState tls;                    // the caller's, applied around the whole session
+  std::vector<c10::cuda::CUDAStream> streams;  // the caller's current stream of every device
+  std::unique_ptr<MaterializeSession> session;  // inline mode only (the helper keeps its own on its stack)
+  std::mutex m;
+  std::condition_variable cv_work, cv_done;
+  std::vector<std::unique_ptr<Item>> items;  // pushed by the caller, consumed in order by the helper
+  bool finish_requested = false;
+  bool helper_waiting = false;
+  std::atomic<bool> caller_waiting{false};
+  bool finished = false;
+  std::exception_ptr error;
+  MaterializeStats stats;
+  std::vector<TdxInitDesc> descs;
+
+  void record_error() {
+    std::lock_guard<std::mutex> lock(m);
+    if (!error) error = std::current_exception();
+  }
+  bool failed() {
+    std::lock_guard<std::mutex> lock(m);
+    return static_cast<bool>(error);
+  }
+  void process(MaterializeSession& s, Item& it) {
+    if (!failed()) {
+      try {
+        it.out = s.add(it.fake, it.apply_shard);
+      } catch (...) {
+        record_error();
+      }
+    }
+    it.done.store(1, std::memory_order_release);
+    if (caller_waiting.load(std::memory_order_acquire)) {
+      std::lock_guard<std::mutex> lock(m);
+      cv_done.notify_all();
+    }
+  }
+  // The helper's side of one session: one task, one ThreadLocalStateGuard, items in batches.
+  void run_on_helper() {
+    try {
+      at::ThreadLocalStateGuard g(tls);
+      for (const auto& st : streams) c10::cuda::setCurrentCUDAStream(st);  // (kept until the next call sets its own)
+      MaterializeSession s(opts);
+      size_t next = 0;
+      std::vector<Item*> batch;
+      for (;;) {
+        bool fin;
+        {
+          std::unique_lock<std::mutex> lock(m);
+          while (next == items.size() && !finish_requested) {
+            helper_waiting = true;
+            cv_work.wait(lock);
+            helper_waiting = false;
+          }
+          fin = finish_requested;
+          batch.clear();
+          for (size_t i = next; i < items.size(); ++i) batch.push_back(items[i].get());
+          next = items.size();
+        }
+        for (Item* it : batch) process(s, *it);
+        if (fin && batch.empty()) break;  // finish() was requested and nothing arrived after it
+      }
+      if (!failed()) {
+        try {
+          s.finish();
+        } catch (...) {
+          record_error();
+        }
+      }
+      stats = g_stats;  // the helper thread's counters of this session
+      descs = g_last_descs;
+    } catch (...) {  // (session construction / thread-local state)
+      record_error();
+    }
+    std::lock_guard<std::mutex> lock(m);
+    for (auto& it : items) it->done.store(1, std::memory_order_release);  // nobody waits for ever
+    finished = true;
+    cv_done.notify_all();
+  }
+};
+
+PipelinedMaterialize::PipelinedMaterialize(const MaterializeOptions& opts) : st_(std::make_shared<State>()) {
+  st_->opts = opts;
+  st_->threaded = host_threads_enabled();
+  st_->items.reserve(1024);
+  if (st_->threaded) {
+    if (at::hasCUDA()) {
+      const int n = static_cast<int>(c10::cuda::device_count());
+      for (int i = 0; i < n; ++i)
+        st_->streams.push_back(c10::cuda::getCurrentCUDAStream(static_cast<c10::DeviceIndex>(i)));
+    }
+    auto st = st_;
+    HelperThread::get().post([st] { st->run_on_helper(); });
+  } else {
+    st_->session = std::make_unique<MaterializeSession>(opts);
+  }
+}
+
+PipelinedMaterialize::~PipelinedMaterialize() {
+  if (!st_) return;
+  if (!st_->threaded) {
+    st_->session.reset();  // writes the generators back if finish() was never reached
+    return;
+  }
+  // the helper must be done with the caller's tensors and generators before the caller goes on
+  std::unique_lock<std::mutex> lock(st_->m);
+  if (!st_->finish_requested) {
+    st_->finish_requested = true;
+    if (!st_->error) st_->error = std::make_exception_ptr(std::runtime_error("materialize_module was abandoned"));
+    st_->cv_work.notify_one();
+  }
+  st_->cv_done.wait(lock, [&] { return st_->finished; });
+}
+
+size_t PipelinedMaterialize::add(const at::Tensor& fake, bool apply_shard) {
+  auto item = std::make_unique<State::Item>();
+  item->fake = fake;
+  item->apply_shard = apply_shard;
+  State::Item* raw = item.get();
+  size_t ticket;
+  bool wake;
+  {
+    std::lock_guard<std::mutex> lock(st_->m);
+    ticket = st_->items.size();
+    st_->items.push_back(std::move(item));
+    wake = st_->helper_waiting;
+  }
+  if (!st_->threaded) {
+    st_->process(*st_->session, *raw);
+  } else if (wake) {
+    st_->cv_work.notify_one();
+  }
+  return ticket;
+}
+
+void PipelinedMaterialize::finish() {
+  if (!st_->threaded) {
+    if (!st_->failed()) {
+      try {
+        st_->session->finish();
+      } catch (...) {
+        st_->record_error();
+      }
+    }
+    st_->session.reset();
+    std::lock_guard<std::mutex> lock(st_->m);
+    st_->finished = true;
+    return;
+  }
+  std::lock_guard<std::mutex> lock(st_->m);
+  st_->finish_requested = true;
+  st_->cv_work.notify_one();
+}
+
+bool PipelinedMaterialize::ready(size_t ticket) {
+  return st_->items[ticket]->done.load(std::memory_order_acquire) != 0;  // (items is only grown by this thread)
+}
+
+at::Tensor PipelinedMaterialize::result(size_t ticket) {
+  State::Item& it = *st_->items[ticket];
+  if (it.done.load(std::memory_order_acquire) == 0) {
+    std::unique_lock<std::mutex> lock(st_->m);
+    st_->caller_waiting.store(true, std::memory_order_release);
+    st_->cv_done.wait(lock, [&] { return it.done.load(std::memory_order_acquire) != 0; });
+    st_->caller_waiting.store(false, std::memory_order_release);
+  }
+  {
+    std::lock_guard<std::mutex> lock(st_->m);
+    if (st_->error) std::rethrow_exception(st_->error);
+  }
+  return it.out;
+}
+
+void PipelinedMaterialize::join() {
+  std::unique_lock<std::mutex> lock(st_->m);
+  st_->cv_done.wait(lock, [&] { return st_->finished; });
+  if (st_->threaded) {  // inline mode already counted on this thread
+    g_stats = st_->stats;
+    g_stats.traverse_us = g_pending_traverse_us;  // the caller's own measure of its walk
+    g_last_descs = st_->descs;
+  }
+  g_pending_traverse_us = 0;
+  if (st_->error) std::rethrow_exception(st_->error);
 }
 
 void add_wrap_time(double us) { g_stats.wrap_us += us; }
