@@ -142,6 +142,17 @@ TDX_C_API int tdx_init_launch(const TdxInitDesc* descs, int n, void* workspace,
                               size_t workspace_bytes, void* stream);
 
 /*
+ * The same in two steps, for callers that want to allocate exactly what a table
+ * needs instead of the upper bound of tdx_init_workspace_bytes(n) (which has to
+ * allow for the table kernels' work lists: ~1.6 MB): tdx_init_prepare validates
+ * and lays the plan out on the host and returns its size (0: nothing to launch);
+ * tdx_init_submit copies it into `workspace` and launches.  The prepared plan
+ * belongs to the calling thread and is consumed by the next tdx_init_submit.
+ */
+TDX_C_API int tdx_init_prepare(const TdxInitDesc* descs, int n, size_t* workspace_bytes);
+TDX_C_API int tdx_init_submit(void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Two-phase variant for callers that re-launch one plan (benchmarks, CUDA
  * graphs): upload once, launch many times.  `tdx_plan_upload` copies the
  * grouped descriptor table into `workspace`; `tdx_plan_launch` only issues the

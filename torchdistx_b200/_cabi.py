@@ -34,6 +34,8 @@ TDX_FLAG_SRC_NOROUND = 0x1
 EXPORTED_SYMBOLS = (
     "tdx_init_workspace_bytes",
     "tdx_init_launch",
+    "tdx_init_prepare",
+    "tdx_init_submit",
     "tdx_plan_upload",
     "tdx_plan_launch",
     "tdx_last_launch_count",
@@ -90,6 +92,10 @@ def load() -> ctypes.CDLL:
     lib = ctypes.CDLL(LIB_PATH)
     lib.tdx_init_workspace_bytes.restype = ctypes.c_size_t
     lib.tdx_init_workspace_bytes.argtypes = [ctypes.c_int]
+    lib.tdx_init_prepare.restype = ctypes.c_int
+    lib.tdx_init_prepare.argtypes = [ctypes.POINTER(TdxInitDesc), ctypes.c_int, ctypes.POINTER(ctypes.c_size_t)]
+    lib.tdx_init_submit.restype = ctypes.c_int
+    lib.tdx_init_submit.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
     lib.tdx_init_launch.restype = ctypes.c_int
     lib.tdx_init_launch.argtypes = [
         ctypes.POINTER(TdxInitDesc), ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
@@ -151,4 +157,21 @@ def launch(descs: Sequence[TdxInitDesc], workspace_ptr: int, workspace_bytes: in
     lib = load()
     arr = (TdxInitDesc * len(descs))(*descs)
     check(lib.tdx_init_launch(arr, len(descs), workspace_ptr, workspace_bytes, stream))
+    return lib.tdx_last_launch_count()
+
+
+def prepare(descs: Sequence[TdxInitDesc]) -> int:
+    """tdx_init_prepare: lays the plan out on the host; returns the exact workspace size it needs
+    (0: nothing to launch).  Follow with `submit` on the same thread."""
+    lib = load()
+    arr = (TdxInitDesc * len(descs))(*descs)
+    need = ctypes.c_size_t(0)
+    check(lib.tdx_init_prepare(arr, len(descs), ctypes.byref(need)))
+    return int(need.value)
+
+
+def submit(workspace_ptr: int, workspace_bytes: int, stream: int = 0) -> int:
+    """tdx_init_submit of the plan `prepare` built; returns the number of kernel launches."""
+    lib = load()
+    check(lib.tdx_init_submit(workspace_ptr, workspace_bytes, stream))
     return lib.tdx_last_launch_count()

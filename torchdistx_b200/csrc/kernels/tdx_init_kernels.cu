@@ -1577,25 +1577,57 @@ TDX_C_API int tdx_plan_launch(const TdxPlan* plan, void* workspace, void* stream
   return tdx::launch_groups(hdr, workspace, static_cast<cudaStream_t>(stream));
 }
 
-TDX_C_API int tdx_init_launch(const TdxInitDesc* descs, int n, void* workspace,
-                              size_t workspace_bytes, void* stream) {
-  thread_local std::vector<unsigned char> img;
-  tdx::PlanHeader hdr;
-  size_t used = 0;
-  if (int rc = tdx::build_plan(descs, n, img, hdr, used)) return rc;
+// The host image of the plan tdx_init_prepare() built on this thread, waiting for tdx_init_submit().
+namespace tdx {
+thread_local std::vector<unsigned char> g_prepared_img;
+thread_local PlanHeader g_prepared_hdr;
+thread_local size_t g_prepared_used = 0;
+thread_local bool g_prepared = false;
+}  // namespace tdx
+
+TDX_C_API int tdx_init_prepare(const TdxInitDesc* descs, int n, size_t* workspace_bytes) {
+  tdx::g_prepared = false;
+  if (workspace_bytes == nullptr) return tdx::fail(TDX_E_BADARG, "workspace_bytes == NULL");
+  if (int rc = tdx::build_plan(descs, n, tdx::g_prepared_img, tdx::g_prepared_hdr, tdx::g_prepared_used)) return rc;
+  *workspace_bytes = tdx::g_prepared_hdr.n_groups ? tdx::g_prepared_used : 0;
+  tdx::g_prepared = true;
+  return 0;
+}
+
+TDX_C_API int tdx_init_submit(void* workspace, size_t workspace_bytes, void* stream) {
+  if (!tdx::g_prepared) return tdx::fail(TDX_E_BADARG, "tdx_init_submit without tdx_init_prepare on this thread");
+  tdx::g_prepared = false;
+  const tdx::PlanHeader& hdr = tdx::g_prepared_hdr;
   if (hdr.n_groups == 0) {
     tdx::g_last_launches = 0;
     return 0;
   }
+  const size_t used = tdx::g_prepared_used;
   if (workspace == nullptr || workspace_bytes < used)
-    return tdx::fail(TDX_E_WORKSPACE, "workspace too small (see tdx_init_workspace_bytes)");
+    return tdx::fail(TDX_E_WORKSPACE, "workspace too small (see tdx_init_prepare)");
   // The plan image goes through a small ring of pinned staging buffers so that the copy is truly
   // asynchronous: the host can go on planning the next batch while the GPU works on this one.
   tdx::g_last_upload_bytes = used;
   void* pinned = nullptr;
-  if (int rc = tdx::stage(img.data(), used, static_cast<cudaStream_t>(stream), workspace, &pinned))
+  if (int rc = tdx::stage(tdx::g_prepared_img.data(), used, static_cast<cudaStream_t>(stream), workspace, &pinned))
     return rc;
   return tdx::launch_groups(hdr, workspace, static_cast<cudaStream_t>(stream));
+}
+
+TDX_C_API int tdx_init_launch(const TdxInitDesc* descs, int n, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  size_t need = 0;
+  if (int rc = tdx_init_prepare(descs, n, &need)) return rc;
+  if (need == 0) {
+    tdx::g_prepared = false;
+    tdx::g_last_launches = 0;
+    return 0;
+  }
+  if (workspace == nullptr || workspace_bytes < need) {
+    tdx::g_prepared = false;
+    return tdx::fail(TDX_E_WORKSPACE, "workspace too small (see tdx_init_workspace_bytes)");
+  }
+  return tdx_init_submit(workspace, workspace_bytes, stream);
 }
 
 TDX_C_API int tdx_last_launch_count(void) { return tdx::g_last_launches; }

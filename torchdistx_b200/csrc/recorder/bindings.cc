@@ -18,6 +18,8 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 #include "fake_tensor.h"
 #include "planner.h"
@@ -204,12 +206,17 @@ void py_materialize_module(const py::object& module, bool buffers_only, const py
   std::vector<py::object> wrapped;
   double wrap_us = 0;
   const auto t_walk = std::chrono::steady_clock::now();
+  static const bool trace = getenv("TDX_TRACE") != nullptr;  // timeline of the call on stderr (diagnostics)
+  auto since = [&] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_walk).count(); };
+  double t_created = 0, t_walked = 0, t_wrapped = 0, t_joined = 0, t_assigned = 0;
   // plans on a helper thread while this one keeps walking
   auto session_ptr = std::make_unique<tdx::PipelinedMaterialize>(opts);
   tdx::PipelinedMaterialize& session = *session_ptr;
+  t_created = since();
   try {
     walk_and_feed(module, buffers_only, check_fn, !shard.is_none(), session, pending);
     session.finish();
+    t_walked = since();
     tdx::add_traverse_time(std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_walk).count());
     // Results get their Python identity as they become ready.  Nothing is assigned before every
     // tensor has been planned: a failure leaves the module as it was (the reference's per-tensor loop
@@ -232,15 +239,18 @@ void py_materialize_module(const py::object& module, bool buffers_only, const py
       wrapped[i] = wrap_like(p.var, p.fake, out);
       wrap_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
     }
+    t_wrapped = since();
     {
       py::gil_scoped_release nogil;
       session.join();
     }
+    t_joined = since();
     const auto t0 = std::chrono::steady_clock::now();
     // (assignment through the dict, like Module.__setattr__ does for an existing entry)
     for (size_t i = 0; i < pending.size(); ++i) pending[i].dict[pending[i].key] = wrapped[i];
     wrap_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
     tdx::add_wrap_time(wrap_us);
+    t_assigned = since();
   } catch (...) {
     // the helper may be inside a replay that needs the GIL: never wait for it while holding it
     py::gil_scoped_release nogil;
@@ -251,6 +261,9 @@ void py_materialize_module(const py::object& module, bool buffers_only, const py
     py::gil_scoped_release nogil;
     session_ptr.reset();
   }
+  if (trace)
+    fprintf(stderr, "[tdx] materialize_module: session %.0f us, walked %.0f, wrapped %.0f, joined %.0f, assigned %.0f, "
+            "done %.0f (%zu tensors)\n", t_created, t_walked, t_wrapped, t_joined, t_assigned, since(), pending.size());
 }
 
 py::dict py_last_stats() {

@@ -473,11 +473,15 @@ void Batch::flush() {
   NoInterception guard;
   c10::DeviceGuard dg(device);
   const int n = static_cast<int>(descs.size());
-  const size_t ws_bytes = tdx_init_workspace_bytes(n);
-  at::Tensor ws = at::empty({static_cast<int64_t>(ws_bytes)},
+  // prepare: the plan is laid out on the host and says how much workspace it needs (descriptor table
+  // + prefix sums + work lists: tens of KB, not the upper bound of tdx_init_workspace_bytes)
+  size_t ws_bytes = 0;
+  int rc = tdx_init_prepare(descs.data(), n, &ws_bytes);
+  TORCH_CHECK(rc == 0, "libtdx_init: plan failed (", rc, "): ", tdx_last_error());
+  at::Tensor ws = at::empty({static_cast<int64_t>(std::max<size_t>(ws_bytes, 16))},
                             at::TensorOptions().dtype(at::kByte).device(device));
   auto stream = c10::cuda::getCurrentCUDAStream(device.index());
-  const int rc = tdx_init_launch(descs.data(), n, ws.data_ptr(), ws_bytes, stream.stream());
+  rc = tdx_init_submit(ws.data_ptr(), ws_bytes, stream.stream());
   TORCH_CHECK(rc == 0, "libtdx_init: launch failed (", rc, "): ", tdx_last_error());
   g_stats.kernel_launches += tdx_last_launch_count();
   g_stats.descriptors += n;
@@ -1100,10 +1104,12 @@ PipelinedMaterialize::PipelinedMaterialize(const MaterializeOptions& opts) : st_
   st_->threaded = host_threads_enabled();
   st_->items.reserve(1024);
   if (st_->threaded) {
-    if (at::hasCUDA()) {
-      const int n = static_cast<int>(c10::cuda::device_count());
-      for (int i = 0; i < n; ++i)
-        st_->streams.push_back(c10::cuda::getCurrentCUDAStream(static_cast<c10::DeviceIndex>(i)));
+    if (at::hasCUDA() && c10::cuda::device_count() > 0) {
+      // only devices this call can touch: asking for another device's stream would create a context there
+      const c10::DeviceIndex cur = c10::cuda::current_device();
+      st_->streams.push_back(c10::cuda::getCurrentCUDAStream(cur));
+      if (opts.device && opts.device->is_cuda() && opts.device->has_index() && opts.device->index() != cur)
+        st_->streams.push_back(c10::cuda::getCurrentCUDAStream(opts.device->index()));
     }
     auto st = st_;
     HelperThread::get().post([st] { st->run_on_helper(); });

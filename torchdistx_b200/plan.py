@@ -223,10 +223,10 @@ class InitPlan:
                             flags=_cabi.TDX_FLAG_SRC_NOROUND if e.src_noround else 0))
                 out[e.name] = t if target is not None else _wrap(t, e)
             if descs:
-                lib = _cabi.load()
-                ws_bytes = lib.tdx_init_workspace_bytes(len(descs))
-                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
-                _cabi.launch(descs, ws.data_ptr(), ws_bytes, torch.cuda.current_stream(device).cuda_stream)
+                ws_bytes = _cabi.prepare(descs)  # exactly what this table needs (not the ~1.6 MB upper bound)
+                if ws_bytes:
+                    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+                    _cabi.submit(ws.data_ptr(), ws_bytes, torch.cuda.current_stream(device).cuda_stream)
             gen.set_offset(offset)
         return out
 
