@@ -9,6 +9,7 @@ sharded materialise becomes host-bound -- without 8 ranks competing for the box'
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import sys
@@ -26,6 +27,7 @@ def main():
     ap.add_argument("--model", default="llama3-8b")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--worlds", default="1,2,4,8")
+    ap.add_argument("--gc", type=int, default=1, help="0: collect before and disable the Python GC inside every timed call (like timeit)")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
@@ -36,12 +38,17 @@ def main():
         ms, host, acc = [], [], {}
         for i, m in enumerate(fakes):
             torch.cuda.synchronize()
+            if not a.gc:
+                gc.collect()
+                gc.disable()
             t0 = time.perf_counter()
             e0.record()
             materialize_module(m, device=dev, shard=shard)
             t1 = time.perf_counter()
             e1.record()
             e1.synchronize()
+            if not a.gc:
+                gc.enable()
             if i >= 2:  # two warm-up steps (allocator, lazy module loading)
                 ms.append(e0.elapsed_time(e1))
                 host.append((t1 - t0) * 1e3)
@@ -52,7 +59,7 @@ def main():
         n = len(ms)
         keys = ("traverse_us", "plan_us", "eval_us", "alloc_us", "launch_us", "wrap_us", "first_submit_us",
                 "last_submit_us", "submissions", "kernel_launches", "bytes_written")
-        print(json.dumps({"model": a.model, "shard": [0, world], "e2e_ms": round(sum(ms) / n, 3),
+        print(json.dumps({"model": a.model, "shard": [0, world], "python_gc_inside_timed_call": bool(a.gc), "e2e_ms": round(sum(ms) / n, 3),
                           "api_return_ms": round(sum(host) / n, 3),
                           "host": {k: round(acc.get(k, 0) / n, 1) for k in keys}}), flush=True)
 
