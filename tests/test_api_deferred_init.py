@@ -250,3 +250,30 @@ def test_materialize_module_in_a_forked_child():
             os._exit(4)
     _, status = os.waitpid(pid, 0)
     assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0
+
+
+def test_materialize_module_from_two_python_threads():
+    """Two Python threads share the one helper thread: calls serialise there, neither deadlocks, and
+    each thread's recording (deferred_init state is thread-local) comes back complete."""
+    import threading
+
+    errors, done = [], []
+
+    def work(seed):
+        try:
+            for i in range(10):
+                m = deferred_init(lambda: nn.Sequential(nn.Linear(16, 16), nn.LayerNorm(16), nn.Linear(16, 4)))
+                materialize_module(m)
+                assert not is_deferred(m)
+                assert torch.equal(m[1].weight, torch.ones(16)) and m[0].weight.shape == (16, 16)
+            done.append(seed)
+        except BaseException as e:  # noqa: BLE001
+            errors.append(e)
+
+    ts = [threading.Thread(target=work, args=(s,)) for s in (1, 2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=120)
+    assert not errors, errors
+    assert sorted(done) == [1, 2]
