@@ -1,6 +1,11 @@
 #!/bin/sh
 # Builds A/B variants of libtdx_init.so (knobs of the table kernel) + the C++ harness.
 # usage: benchmarks/build_variants.sh "tag:-Dflags" ...
+# knobs (tdx_init_kernels.cu): TDX_LUT_ELEMS_A / _B (looked-up elements of even / odd vectors, normal),
+#   TDX_LUT_UNIFORM_ELEMS, TDX_LUT_GROUP (vectors per NaN test), TDX_LUT_PACK (0 IMAD, 1 PRMT),
+#   TDX_LUT_VECS (vectors per thread and tile), TDX_LUT_MAX_CHUNK_LOG2 (largest grab),
+#   TDX_LUT_PKEYS (round keys as kernel parameters), TDX_UNIFORM16_PACKED, TDX_VECS,
+#   TDX_EXPERIMENTAL_ALGOS (Philox-7 / Box-Muller-16 kernels for benchmarks/kernel_sweep.py)
 set -e
 cd "$(dirname "$0")/.."
 mkdir -p benchmarks/_variants
