@@ -24,6 +24,7 @@
 #include <unistd.h>
 
 #include <ATen/ThreadLocalState.h>
+#include <ATen/detail/CUDAHooksInterface.h>
 #include <c10/cuda/CUDAFunctions.h>
 
 #include "fake_tensor.h"
@@ -1020,7 +1021,8 @@ struct PipelinedMaterialize::State {
   MaterializeOptions opts;
   bool threaded = false;
   at::ThreadLocalState tls;                    // the caller's, applied around the whole session
-  std::vector<c10::cuda::CUDAStream> streams;  // the caller's current stream of every device
+  std::vector<c10::cuda::CUDAStream> streams;  // the caller's current streams (its device, the target device)
+  c10::DeviceIndex caller_device = -1;         // the caller's current CUDA device
   std::unique_ptr<MaterializeSession> session;  // inline mode only (the helper keeps its own on its stack)
   std::mutex m;
   std::condition_variable cv_work, cv_done;
@@ -1059,7 +1061,11 @@ struct PipelinedMaterialize::State {
   void run_on_helper() {
     try {
       at::ThreadLocalStateGuard g(tls);
-      for (const auto& st : streams) c10::cuda::setCurrentCUDAStream(st);  // (kept until the next call sets its own)
+      // The helper must sit on the caller's device: with another current device every DeviceGuard of
+      // the planner would switch devices twice per tensor (and create a context on device 0 in every
+      // rank of a multi-GPU job).  Device and streams stay until the next call sets its own.
+      if (caller_device >= 0) c10::cuda::set_device(caller_device);
+      for (const auto& st : streams) c10::cuda::setCurrentCUDAStream(st);
       MaterializeSession s(opts);
       size_t next = 0;
       std::vector<Item*> batch;
@@ -1105,11 +1111,20 @@ PipelinedMaterialize::PipelinedMaterialize(const MaterializeOptions& opts) : st_
   st_->items.reserve(1024);
   if (st_->threaded) {
     if (at::hasCUDA() && c10::cuda::device_count() > 0) {
-      // only devices this call can touch: asking for another device's stream would create a context there
+      // Only devices this call can touch, and only if they are in use already: asking for another
+      // device's stream, or sitting on a device the process never used, would create a CUDA context
+      // there (a CPU-only materialise on a GPU machine must not start CUDA at all).
+      const auto& hooks = at::detail::getCUDAHooks();
       const c10::DeviceIndex cur = c10::cuda::current_device();
-      st_->streams.push_back(c10::cuda::getCurrentCUDAStream(cur));
-      if (opts.device && opts.device->is_cuda() && opts.device->has_index() && opts.device->index() != cur)
-        st_->streams.push_back(c10::cuda::getCurrentCUDAStream(opts.device->index()));
+      const bool cur_live = hooks.hasPrimaryContext(cur);
+      if (cur_live) st_->streams.push_back(c10::cuda::getCurrentCUDAStream(cur));
+      if (opts.device && opts.device->is_cuda() && opts.device->has_index()) {
+        st_->caller_device = opts.device->index();  // the device every tensor of this call is built on
+        if (opts.device->index() != cur && hooks.hasPrimaryContext(opts.device->index()))
+          st_->streams.push_back(c10::cuda::getCurrentCUDAStream(opts.device->index()));
+      } else if (cur_live) {
+        st_->caller_device = cur;
+      }
     }
     auto st = st_;
     HelperThread::get().post([st] { st->run_on_helper(); });
