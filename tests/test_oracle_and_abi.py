@@ -108,3 +108,55 @@ def test_oracle_is_shard_invariant_and_offsets_disjoint():
     other = O.generate(C.make_desc(0, dtype=C.TDX_BF16, src=C.TDX_SRC_NORMAL, elem_count=1000, seed=9,
                                    offset=20, p1=0.02))
     assert (a != other).mean() > 0.9
+
+
+def test_prepare_lays_out_extreme_plans_within_the_workspace_bound():
+    """tdx_init_prepare is host-only: the plan image (descriptor table, prefix sums, the table
+    kernels' guided work lists) must fit tdx_init_workspace_bytes(n) for any mix -- one 180 GB tensor,
+    thousands of table-eligible descriptors in every table family at once, nothing at all."""
+    import ctypes
+
+    lib = C.load()
+
+    def prepare(descs):
+        arr = (C.TdxInitDesc * len(descs))(*descs)
+        need = ctypes.c_size_t(0)
+        rc = lib.tdx_init_prepare(arr, len(descs), ctypes.byref(need))
+        assert rc == 0, lib.tdx_last_error()
+        assert need.value <= lib.tdx_init_workspace_bytes(len(descs))
+        return need.value
+
+    base = 0x7F0000000000  # never dereferenced: prepare does not touch the device
+    # one huge tensor (90 G bf16 elements = 180 GB): the grab cap grows so that the list stays bounded
+    big = prepare([C.make_desc(base, dtype=C.TDX_BF16, src=C.TDX_SRC_NORMAL, elem_count=90 * (1 << 30), seed=1, offset=0,
+                               p0=0.0, p1=0.02)])
+    assert big < 400 << 10
+    # every table family at once (normal / uniform x bf16 / f16 x with / without epilogue), 700 descriptors each
+    epi = [(C.TDX_EPI_MUL, 0.5)]
+    descs = []
+    for dt in (C.TDX_BF16, C.TDX_F16):
+        for src in (C.TDX_SRC_NORMAL, C.TDX_SRC_UNIFORM):
+            for e in ([], epi):
+                for i in range(700):
+                    descs.append(C.make_desc(base + 4096 * len(descs), dtype=dt, src=src,
+                                             elem_count=(1 << 18) + 8 * (i % 5) + (1 << 20) * (i % 3), seed=7,
+                                             offset=16 * len(descs), p0=0.0 if src == C.TDX_SRC_NORMAL else -1.0,
+                                             p1=0.02 + 0.001 * (i % 7), epi=e))
+    many = prepare(descs)
+    assert many > len(descs) * 128  # the table is in there
+    # a Llama-3-8B-like mix: 291 descriptors, a few sizes
+    llama = []
+    for layer in range(32):
+        for n in (4096 * 4096, 1024 * 4096, 1024 * 4096, 4096 * 4096, 14336 * 4096, 14336 * 4096, 4096 * 14336):
+            llama.append(C.make_desc(base, dtype=C.TDX_BF16, src=C.TDX_SRC_NORMAL, elem_count=n, seed=3,
+                                     offset=64 * len(llama), p0=0.0, p1=0.02))
+    llama += [C.make_desc(base, dtype=C.TDX_BF16, src=C.TDX_SRC_NORMAL, elem_count=128256 * 4096, seed=3, offset=1 << 30,
+                          p0=0.0, p1=0.02)] * 2
+    assert 100 << 10 < prepare(llama) < 400 << 10
+    # nothing to do
+    assert prepare([C.make_desc(base, dtype=C.TDX_F32, src=C.TDX_SRC_NORMAL, elem_count=0, seed=1, offset=0)]) >= 0
+    # submit without a device must fail cleanly, not crash (there is no GPU in the CPU test run)
+    need = ctypes.c_size_t(0)
+    arr = (C.TdxInitDesc * 1)(llama[0])
+    assert lib.tdx_init_prepare(arr, 1, ctypes.byref(need)) == 0 and need.value > 0
+    assert lib.tdx_init_submit(None, 0, None) != 0
