@@ -90,8 +90,8 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int, period_ms: int = 100):
-        # rank 0 samples every 100 ms; the other ranks of a multi-GPU run every 500 ms (eight
-        # nvidia-smi loops at 10 Hz compete with the ranks' own driver calls inside the timed region)
+        # rank 0 samples every 20 ms; the other ranks of a multi-GPU run every 500 ms (eight fast
+        # nvidia-smi loops compete with the ranks' own driver calls inside the timed region)
         self.rows, self.proc, self.index, self.period_ms = [], None, index, period_ms
 
     def __enter__(self):
@@ -101,6 +101,11 @@ class ClockSampler:
                                          stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            # the timed regions are short (the kernels-only one is ~35 ms): do not start them before the
+            # sampler has delivered its first row, or every sample could fall after the region
+            t_end = time.time() + 1.5
+            while not self.rows and time.time() < t_end:
+                time.sleep(0.005)
         except Exception:
             self.proc = None
         return self
@@ -263,7 +268,7 @@ def run_ours(a):
 
     e2e_ms, h2d = 0.0, 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    clk_e2e = ClockSampler(local, 100 if rank == 0 else 500)
+    clk_e2e = ClockSampler(local, 20 if rank == 0 else 500)
     for i in range(0 if a.roofline_only else a.warmup):
         step(fakes[i])
         fakes[i] = None
@@ -304,7 +309,7 @@ def run_ours(a):
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     plan = C.TdxPlan()
     C.check(lib.tdx_plan_upload(descs, len(descs), ws.data_ptr(), ws_bytes, stream, ctypes.byref(plan)))
-    clk = ClockSampler(local, 100 if rank == 0 else 500)
+    clk = ClockSampler(local, 20 if rank == 0 else 500)
     ms, launches_per_step = 1.0, 0
     if not a.roofline_only:
         for _ in range(max(a.warmup, 3)):
