@@ -90,7 +90,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int, period_ms: int = 100):
-        # rank 0 samples every 20 ms; the other ranks of a multi-GPU run every 500 ms (eight fast
+        # rank 0 samples every 100 ms (20 ms around the short kernels-only region); the other ranks every 500 ms (eight fast
         # nvidia-smi loops compete with the ranks' own driver calls inside the timed region)
         self.rows, self.proc, self.index, self.period_ms = [], None, index, period_ms
 
@@ -268,7 +268,7 @@ def run_ours(a):
 
     e2e_ms, h2d = 0.0, 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    clk_e2e = ClockSampler(local, 20 if rank == 0 else 500)
+    clk_e2e = ClockSampler(local, 100 if rank == 0 else 500)
     for i in range(0 if a.roofline_only else a.warmup):
         step(fakes[i])
         fakes[i] = None
