@@ -107,8 +107,80 @@ def mlp_stack():
     return nn.Sequential(nn.Linear(64, 256), nn.GELU(), nn.Linear(256, 64), nn.LayerNorm(64))
 
 
+# ---- BASELINE-sized cases (tests/test_t1_fullsize_gpu.py; SURVEY.md section 8c tier T1) -----------------
+LLAMA8B_LAYER = dict(vocab_size=2048, hidden_size=4096, intermediate_size=14336, num_hidden_layers=1,
+                     num_attention_heads=32, num_key_value_heads=8, max_position_embeddings=8192,
+                     rope_theta=500000.0)
+
+
+def llama8b_layer():
+    """The bounded sample bench.py times the reference on: one full-width Llama-3-8B decoder layer
+    (all seven linears at their real sizes, 4096x14336 included), vocabulary cut to 2048 rows:
+    234,893,312 parameters."""
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    return LlamaForCausalLM(LlamaConfig(**LLAMA8B_LAYER))
+
+
+def llama8b_layer_cast():
+    """SURVEY 8d cfg3 variant: built in fp32, converted with `.to(torch.bfloat16)`."""
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float32)
+    try:
+        return llama8b_layer().to(torch.bfloat16)
+    finally:
+        torch.set_default_dtype(prev)
+
+
+BIG = 4096  # 4096 x 4096 = 2^24 elements per tensor
+
+
+class BigInits(nn.Module):
+    """One 2^24-element tensor per RNG idiom of BASELINE config 5 (+ the two epilogue chains)."""
+
+    def __init__(self):
+        super().__init__()
+        self.normal = nn.Parameter(torch.empty(BIG, BIG).normal_(0.0, 0.02))
+        self.uniform = nn.Parameter(torch.empty(BIG, BIG).uniform_(-0.05, 0.03))
+        self.kaiming = nn.Parameter(torch.empty(BIG, BIG))
+        nn.init.kaiming_uniform_(self.kaiming, a=math.sqrt(5))  # bound = 1/sqrt(fan_in) = 1/64
+        self.trunc = nn.Parameter(torch.empty(BIG, BIG))
+        nn.init.trunc_normal_(self.trunc, mean=0.0, std=0.02, a=-0.04, b=0.04)
+        self.scaled = nn.Parameter(torch.randn(BIG, BIG) * 0.02 + 1.0)
+
+
+def big_inits():
+    return BigInits()
+
+
+class PaddedEmbeddings(nn.Module):
+    """`padding_idx` embeddings: normal_ then one row zeroed through a view (nn.Embedding itself,
+    and the HF `_init_weights` idiom of BERT / OPT / Gemma / Phi-3)."""
+
+    def __init__(self):
+        super().__init__()
+        self.torch_style = nn.Embedding(512, 64, padding_idx=3)
+        self.hf_style = nn.Embedding(300, 48, padding_idx=0)
+        self.hf_style.weight.data.normal_(mean=0.0, std=0.02)
+        self.hf_style.weight.data[self.hf_style.padding_idx].zero_()
+        self.last_row = nn.Embedding(257, 40, padding_idx=256)
+        self.halves = nn.Parameter(torch.empty(64, 32))
+        with torch.no_grad():
+            self.halves[:32].normal_(0.0, 0.1)
+            self.halves[32:].fill_(0.5)
+            self.halves[:16].mul_(2.0)
+
+
+def padded_embeddings():
+    return PaddedEmbeddings()
+
+
 CASES = {
     "linear128": linear128,
+    "llama8b_layer": llama8b_layer,
+    "llama8b_layer_cast": llama8b_layer_cast,
+    "big_inits": big_inits,
+    "padded_embeddings": padded_embeddings,
     "init_zoo": init_zoo,
     "tiny_llama": tiny_llama,
     "tiny_gpt2": tiny_gpt2,

@@ -32,7 +32,13 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--stats", action="store_true",
+                    help="large tensors (> 2^20 elements) are saved as float64 moments + min/max + an evenly "
+                         "strided 2^20-element subsample instead of whole (BASELINE-sized cases)")
+    ap.add_argument("--round-to", default="", help="round every floating matrix (dim >= 2) to this dtype first (bf16/fp16)")
     a = ap.parse_args()
+    global STATS, ROUND_TO
+    STATS, ROUND_TO = a.stats, a.round_to
     if a.threads:
         torch.set_num_threads(a.threads)
     if a.cases:
@@ -41,6 +47,26 @@ def main():
             run(case, dtype, a.device, a.seed, os.path.join(a.outdir, f"{case}_{dtype}.pt"), False)
         return
     run(a.case, a.dtype, a.device, a.seed, a.out, a.time)
+
+
+STATS, ROUND_TO = False, ""
+SUBSAMPLE = 1 << 20
+
+
+def summarize(t: torch.Tensor):
+    """What the full-size parity tests need of a tensor too large to ship whole."""
+    if ROUND_TO and t.is_floating_point() and t.dim() >= 2:  # (matrices: the RNG-initialised tensors)
+        t = t.to(cases.DTYPES[ROUND_TO])
+    n = t.numel()
+    if not STATS or n <= SUBSAMPLE or not t.is_floating_point():
+        return t
+    flat = t.reshape(-1)
+    d = flat.double()
+    stride = n // SUBSAMPLE
+    return {"numel": n, "dtype": str(t.dtype), "shape": tuple(t.shape), "mean": d.mean().item(),
+            "std": d.std().item(), "min": d.min().item(), "max": d.max().item(),
+            "finite": bool(torch.isfinite(d).all()), "stride": stride,
+            "sample": flat[: stride * SUBSAMPLE : stride].clone()}
 
 
 def run(case, dtype, device, seed, out, timed):
@@ -62,7 +88,7 @@ def run(case, dtype, device, seed, out, timed):
     torch.set_default_dtype(prev)
     assert not R.is_deferred(m)
     if a.out:
-        sd = {k: v.detach().cpu() for k, v in list(m.named_parameters()) + list(m.named_buffers())}
+        sd = {k: summarize(v.detach().cpu()) for k, v in list(m.named_parameters()) + list(m.named_buffers())}
         torch.save(sd, a.out)
     if a.time:
         n = sum(p.numel() for p in m.parameters())

@@ -64,6 +64,13 @@ py::object wrap_like(const py::handle& like, const at::Tensor& fake, const at::T
   PyTypeObject* type = Py_TYPE(like.ptr());
   if (reinterpret_cast<PyObject*>(type) == reinterpret_cast<PyObject*>(THPVariableClass)) {
     result = py::cast(out);
+  } else if (reinterpret_cast<PyObject*>(type) == ParameterClass && out.use_count() > 0 &&
+             out.unsafeGetTensorImpl()->pyobj_slot()->load_pyobj() == nullptr && !out.grad_fn()) {
+    // A fresh leaf that Python has never seen: it can be born a Parameter (what
+    // Tensor._make_subclass does, minus the detach() and the trip through the argument parser --
+    // a microsecond per tensor, hundreds of tensors per call).
+    result = py::reinterpret_steal<py::object>(THPVariable_Wrap(out, type));
+    if (!result) throw py::error_already_set();
   } else {
     static py::object make_subclass = py::module_::import("torch").attr("Tensor").attr("_make_subclass");
     result = make_subclass(py::reinterpret_borrow<py::object>(reinterpret_cast<PyObject*>(type)),
@@ -251,6 +258,19 @@ void py_materialize_module(const py::object& module, bool buffers_only, const py
     wrap_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
     tdx::add_wrap_time(wrap_us);
     t_assigned = since();
+  } catch (const c10::ValueError&) {
+    // Same wording as the reference's loop (deferred_init.py:104-113), which turns the ValueError of
+    // `_C.materialize_tensor(tensor)` into "'<key>' has already been materialized.".
+    const size_t bad = session.failed_ticket();
+    std::string key;
+    for (const PendingSlot& p : pending)
+      if (p.ticket == bad && bad != kNoTicket) key = py::cast<std::string>(py::str(p.key));
+    {
+      py::gil_scoped_release nogil;
+      session_ptr.reset();
+    }
+    if (key.empty()) throw;
+    throw py::value_error("'" + key + "' has already been materialized.");
   } catch (...) {
     // the helper may be inside a replay that needs the GIL: never wait for it while holding it
     py::gil_scoped_release nogil;
@@ -287,6 +307,7 @@ py::dict py_last_stats() {
   d["upload_bytes"] = s.upload_bytes;
   d["first_submit_us"] = s.first_submit_us;
   d["last_submit_us"] = s.last_submit_us;
+  d["template_hits"] = s.template_hits;
   return d;
 }
 
@@ -332,6 +353,24 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     d["epilogue"] = i.epilogue;
     d["const_bytes"] = py::bytes(i.const_bytes);
     d["rng_numels"] = i.rng_numels;
+    d["rng_op_ids"] = i.rng_op_ids;
+    py::list segs;
+    for (const tdx::PlanSegment& g : i.segments) {
+      py::dict sd;
+      sd["begin"] = g.begin;
+      sd["end"] = g.end;
+      sd["origin"] = g.origin;
+      sd["source"] = g.source;
+      sd["p0"] = g.p0;
+      sd["p1"] = g.p1;
+      sd["wide"] = g.wide;
+      sd["src_noround"] = g.src_noround;
+      sd["epilogue"] = g.epilogue;
+      sd["const_bytes"] = py::bytes(g.const_bytes);
+      sd["rng_pass"] = g.rng_pass;
+      segs.append(sd);
+    }
+    d["segments"] = segs;
     return d;
   });
   m.def("storage_history", &tdx::storage_history);

@@ -6,6 +6,7 @@
 #include <ATen/cuda/EmptyTensor.h>
 #include <c10/core/DeviceGuard.h>
 #include <c10/core/impl/LocalDispatchKeySet.h>
+#include <c10/cuda/CUDACachingAllocator.h>
 #include <c10/cuda/CUDAStream.h>
 
 #include <algorithm>
@@ -59,25 +60,46 @@ struct NoInterception {
 // ---------------------------------------------------------------------------------------------
 // symbolic state of a storage: what its elements are, as a function of the element index
 // ---------------------------------------------------------------------------------------------
+// A storage is a list of disjoint SEGMENTS [begin, end) (element indices of the storage, in the
+// dtype it currently holds), each with one simple content description.  A tensor initialised as a
+// whole is one segment; `weight.normal_(); weight[padding_idx].zero_()` (nn.Embedding, BERT, Gemma,
+// OPT, Phi-3) is three; an in-place op through a contiguous view splits the segments it crosses.
 struct Sym {
-  enum Src { Opaque, Uninit, Const, Uniform, Normal } src = Opaque;
-  ScalarType dtype = ScalarType::Undefined;  // dtype of the tensor currently holding the state
-  ScalarType gen_dtype = ScalarType::Undefined;  // dtype the RNG source op ran in
-  at::Tensor cval;                           // Const: a 1-element CPU tensor of `dtype` (built lazily)
+  enum Src { Uninit, Const, Uniform, Normal } src = Uninit;
+  at::Tensor cval;                           // Const: a 1-element tensor of the state's dtype (built lazily)
   c10::Scalar cscalar;                       // Const: the value, while no folding has needed a tensor
   bool has_scalar = false;
   double p0 = 0, p1 = 1;                     // Uniform: from,to   Normal: mean,std
   uint32_t rng_op = kNoValue;                // the live RNG op
-  std::vector<uint32_t> rng_chain;           // every RNG op met, live or dead, chronological
-  std::vector<TdxEpiStep> epi;
+  c10::SmallVector<TdxEpiStep, TDX_MAX_EPI> epi;
   // The RNG source ran on an fp32 tensor that was later cast to a 16-bit dtype: keep the fp32
   // stream and arithmetic (TDX_ALGO_WIDE32) so that the result IS `fp32_tensor.to(dtype)`.
   bool wide = false;
   bool src_noround = false;  // the generated value feeds fp32 epilogue steps before the cast
-  bool opaque() const { return src == Opaque; }
+  bool rng() const { return src == Uniform || src == Normal; }
 };
 
-Sym make_opaque() { return Sym{}; }
+struct Seg {
+  int64_t begin = 0, end = 0;
+  // Storage index of element 0 of the tensor the segment's source op ran on: an RNG op on a view
+  // numbers its elements from the view's first element (global Philox index = index - origin).
+  int64_t origin = 0;
+  Sym st;
+};
+
+struct RngPass {
+  uint32_t op;     // tape op
+  int64_t numel;   // of the tensor it ran on: what it consumes of the generator's offset
+};
+
+struct State {
+  bool opaque = true;
+  ScalarType dtype = ScalarType::Undefined;  // dtype of the tensor currently holding the state
+  std::vector<Seg> segs;                     // sorted, disjoint, covering [0, numel)
+  std::vector<RngPass> rng_chain;            // every RNG pass met, live or dead, chronological
+};
+
+State make_opaque() { return State{}; }
 
 // Element bits of `v` converted to `dtype` (the conversion at::full performs), without building a
 // tensor.  Returns false for dtypes that are not handled here.
@@ -98,12 +120,20 @@ bool scalar_bits(const c10::Scalar& v, ScalarType dtype, unsigned char* out, siz
   }
 }
 
+// While a tape is analysed at the end of its recording (analyze_tape) the target device is not
+// known yet, and a constant chain must be folded with the target device's arithmetic: such
+// storages are evaluated when they are materialised instead.  The same holds for programs that
+// read a real tensor's value (it may be mutated before the materialisation: the version check
+// must see that).
+thread_local bool g_analysis_only = false;
+thread_local bool g_analysis_deferred = false;  // the last evaluation met one of those
+
 // The 1-element tensor form of a constant state (needed to fold further ops through ATen).
-void ensure_cval(Sym& st) {
+void ensure_cval(Sym& st, ScalarType dtype) {
   if (st.cval.defined() || !st.has_scalar) return;
   c10::impl::ExcludeDispatchKeyGuard a{c10::DispatchKey::DeferredInit};
   c10::impl::ExcludeDispatchKeyGuard b{c10::DispatchKey::Fake};
-  st.cval = at::full({1}, st.cscalar, at::TensorOptions().dtype(st.dtype).device(g_fold_device));
+  st.cval = at::full({1}, st.cscalar, at::TensorOptions().dtype(dtype).device(g_fold_device));
 }
 
 bool is_fused_float(ScalarType t) {
@@ -128,6 +158,10 @@ std::optional<double> scalar_arg(const TapeOp& op, size_t pos) {
     if (slot >= op.inputs.size()) return std::nullopt;
     const at::Tensor& t = op.inputs[slot].real;
     if (!t.defined() || t.numel() != 1 || !t.is_cpu() || t.is_complex()) return std::nullopt;
+    if (g_analysis_only) {  // its value is read when the storage is materialised, not now
+      g_analysis_deferred = true;
+      return std::nullopt;
+    }
     if (!t.is_inference() && static_cast<int64_t>(t._version()) != op.inputs[slot].real_version)
       return std::nullopt;  // mutated since recording: let generic replay raise the error
     return t.item<double>();
@@ -153,10 +187,15 @@ size_t find_arg(const TapeOp& op, const char* name) {
   return static_cast<size_t>(-1);
 }
 
-// Runs the recorded operator on `self` (a 1-element CPU tensor standing for a constant tensor),
-// with the recorded scalar arguments: exact ATen semantics for constant folding.
-bool fold_const(const TapeOp& op, Sym& st, bool inplace) {
-  ensure_cval(st);
+// Runs the recorded operator on `self` (a 1-element tensor standing for a constant segment), with
+// the recorded scalar arguments: exact ATen semantics for constant folding.  `dtype` is the
+// segment's dtype before the op; on success it is the result's.
+bool fold_const(const TapeOp& op, Sym& st, ScalarType& dtype, bool inplace) {
+  if (g_analysis_only) {
+    g_analysis_deferred = true;
+    return false;
+  }
+  ensure_cval(st, dtype);
   st.has_scalar = false;
   if (!op.handle || !st.cval.defined()) return false;
   Stack stack;
@@ -196,207 +235,331 @@ bool fold_const(const TapeOp& op, Sym& st, bool inplace) {
   at::Tensor out = stack.back().toTensor();
   if (out.numel() != 1) return false;
   st.cval = inplace ? st.cval : out;
-  st.dtype = st.cval.scalar_type();
+  dtype = st.cval.scalar_type();
   return true;
 }
 
-Sym eval_storage(Tape& tape, uint32_t S, uint32_t upto);
+// ---- segment bookkeeping ------------------------------------------------------------------------
+// The elements of the storage a value names, if they are one contiguous run.
+bool range_of(const ValueInfo& v, int64_t& begin, int64_t& end) {
+  int64_t expect = 1;
+  for (int64_t d = static_cast<int64_t>(v.sizes.size()) - 1; d >= 0; --d) {
+    if (v.sizes[d] == 1) continue;
+    if (v.strides[d] != expect) return false;
+    expect *= v.sizes[d];
+  }
+  begin = v.storage_offset;
+  end = v.storage_offset + v.numel;
+  return true;
+}
+
+// Cuts the segments at `at` so that none straddles it.
+void split_at(std::vector<Seg>& segs, int64_t at) {
+  for (size_t i = 0; i < segs.size(); ++i) {
+    if (segs[i].begin < at && at < segs[i].end) {
+      Seg right = segs[i];
+      right.begin = at;
+      segs[i].end = at;
+      segs.insert(segs.begin() + static_cast<std::ptrdiff_t>(i) + 1, std::move(right));
+      return;
+    }
+  }
+}
+
+// [b, e) now holds `st` (an op that overwrites what was there).
+void overwrite(State& s, int64_t b, int64_t e, Sym st, int64_t origin) {
+  if (b >= e) return;
+  split_at(s.segs, b);
+  split_at(s.segs, e);
+  std::vector<Seg> out;
+  out.reserve(s.segs.size() + 1);
+  bool placed = false;
+  for (Seg& g : s.segs) {
+    if (g.begin >= b && g.end <= e) {
+      if (!placed) {
+        Seg n;
+        n.begin = b;
+        n.end = e;
+        n.origin = origin;
+        n.st = std::move(st);
+        out.push_back(std::move(n));
+        placed = true;
+      }
+      continue;
+    }
+    out.push_back(std::move(g));
+  }
+  s.segs = std::move(out);
+}
+
+State eval_storage(Tape& tape, uint32_t S, uint32_t upto);
 
 // Applies one recorded op whose output lives on the storage being evaluated.
-void transition(Tape& tape, uint32_t op_idx, uint32_t S, Sym& st) {
+void transition(Tape& tape, uint32_t op_idx, uint32_t S, State& st) {
   TapeOp& op = tape.ops[op_idx];
   // the output of this op on S
   uint32_t out_v = kNoValue;
   for (uint32_t v : op.outputs)
     if (v != kNoValue && tape.values[v].storage == S) out_v = v;
   const ValueInfo& out = tape.values[out_v];
-  auto need_cover = [&] { return out.covers_storage; };
-  auto push_epi = [&](uint32_t code, double a, double b = 0) {
-    if (st.epi.size() >= TDX_MAX_EPI) { st = make_opaque(); return; }
+  auto push_epi = [&](Sym& sy, uint32_t code, double a, double b = 0) {
+    if (sy.epi.size() >= TDX_MAX_EPI) return false;
     TdxEpiStep s;
     s.op = code;  // every step rounds to the tensor dtype, like the in-place ATen op it stands for
     s.a = static_cast<float>(a);
     s.b = static_cast<float>(b);
-    st.epi.push_back(s);
+    sy.epi.push_back(s);
+    return true;
+  };
+  auto fresh = [&](Sym sy) {  // a factory: one segment over the whole (new) storage
+    std::vector<RngPass> chain = std::move(st.rng_chain);
+    st = State{};
+    st.opaque = false;
+    st.dtype = out.dtype;
+    st.rng_chain = std::move(chain);
+    Seg g;
+    g.begin = 0;
+    g.end = out.numel;
+    g.st = std::move(sy);
+    st.segs.push_back(std::move(g));
   };
 
   switch (op.kind) {
     case OpKind::Empty:
-      if (!need_cover()) { st = make_opaque(); return; }
-      st = Sym{};
-      st.src = Sym::Uninit;
-      st.dtype = out.dtype;
+      if (!out.covers_storage) { st = make_opaque(); return; }
+      st.rng_chain.clear();
+      fresh(Sym{});
       return;
     case OpKind::Zeros:
     case OpKind::Ones:
     case OpKind::Full: {
-      if (!need_cover()) { st = make_opaque(); return; }
-      st = Sym{};
-      st.src = Sym::Const;
-      st.dtype = out.dtype;
-      st.has_scalar = true;
-      if (op.kind == OpKind::Zeros) st.cscalar = 0;
-      else if (op.kind == OpKind::Ones) st.cscalar = 1;
+      if (!out.covers_storage) { st = make_opaque(); return; }
+      Sym sy;
+      sy.src = Sym::Const;
+      sy.has_scalar = true;
+      if (op.kind == OpKind::Zeros) sy.cscalar = 0;
+      else if (op.kind == OpKind::Ones) sy.cscalar = 1;
       else {
         const size_t pos = find_arg(op, "fill_value");
         if (pos == static_cast<size_t>(-1) || !op.args[pos].isScalar()) { st = make_opaque(); return; }
-        st.cscalar = op.args[pos].toScalar();
+        sy.cscalar = op.args[pos].toScalar();
       }
+      st.rng_chain.clear();
+      fresh(std::move(sy));
       return;
     }
     case OpKind::Randn:
-    case OpKind::Rand:
-      if (!need_cover() || !is_fused_float(out.dtype)) { st = make_opaque(); return; }
-      {
-        std::vector<uint32_t> chain = std::move(st.rng_chain);
-        st = Sym{};
-        st.rng_chain = std::move(chain);
-      }
-      st.src = op.kind == OpKind::Randn ? Sym::Normal : Sym::Uniform;
-      st.dtype = st.gen_dtype = out.dtype;
-      st.p0 = 0.0;
-      st.p1 = 1.0;
-      st.rng_op = op_idx;
-      st.rng_chain.push_back(op_idx);
+    case OpKind::Rand: {
+      if (!out.covers_storage || !is_fused_float(out.dtype)) { st = make_opaque(); return; }
+      Sym sy;
+      sy.src = op.kind == OpKind::Randn ? Sym::Normal : Sym::Uniform;
+      sy.p0 = 0.0;
+      sy.p1 = 1.0;
+      sy.rng_op = op_idx;
+      st.rng_chain.clear();
+      fresh(std::move(sy));
+      st.rng_chain.push_back(RngPass{op_idx, out.numel});
       return;
+    }
     case OpKind::Alias:
+    case OpKind::View:
     case OpKind::HookVariableData:
     case OpKind::HookSetData:  // `p.data = t`: p now names t's storage; its elements are t's
       return;  // same elements under another tensor object
-    case OpKind::UniformInplace:
-    case OpKind::NormalInplace: {
-      if (!need_cover() || !is_fused_float(out.dtype) || st.opaque()) { st = make_opaque(); return; }
-      const bool uni = op.kind == OpKind::UniformInplace;
-      const auto a = scalar_arg(op, 1), b = scalar_arg(op, 2);
-      if (!a || !b) { st = make_opaque(); return; }
-      std::vector<uint32_t> chain = std::move(st.rng_chain);
-      st = Sym{};
-      st.rng_chain = std::move(chain);
-      st.src = uni ? Sym::Uniform : Sym::Normal;
-      st.dtype = st.gen_dtype = out.dtype;
-      if (uni) {
-        TORCH_CHECK(*a <= *b, "uniform_ expects to return a [from, to) range, but found from=", *a,
-                    " > to=", *b);
-        st.p0 = round_to_dtype(*a, out.dtype);
-        st.p1 = round_to_dtype(*b, out.dtype);
-      } else {
-        TORCH_CHECK(*b >= 0.0, "normal expects std >= 0.0, but found std ", *b);
-        st.p0 = *a;
-        st.p1 = *b;
-      }
-      st.rng_op = op_idx;
-      st.rng_chain.push_back(op_idx);
+    default:
+      break;
+  }
+
+  // ---- in-place writers through `out` (the whole tensor or a contiguous view of part of it) ----
+  const bool inplace = op.kind == OpKind::UniformInplace || op.kind == OpKind::NormalInplace ||
+                       op.kind == OpKind::FillInplace || op.kind == OpKind::ZeroInplace ||
+                       op.kind == OpKind::MulInplace || op.kind == OpKind::AddInplace ||
+                       op.kind == OpKind::ErfinvInplace || op.kind == OpKind::ClampInplace;
+  if (inplace) {
+    int64_t b = 0, e = 0;
+    if (st.opaque || out.dtype != st.dtype || !range_of(out, b, e) || st.segs.empty() ||
+        b < 0 || e > st.segs.back().end) {
+      st = make_opaque();
       return;
     }
-    case OpKind::FillInplace:
-    case OpKind::ZeroInplace: {
-      if (!need_cover() || st.opaque()) { st = make_opaque(); return; }
-      std::vector<uint32_t> chain = std::move(st.rng_chain);
-      const ScalarType dt = out.dtype;
-      st = Sym{};
-      st.rng_chain = std::move(chain);
-      st.src = Sym::Const;
-      st.dtype = dt;
+    if (op.kind == OpKind::UniformInplace || op.kind == OpKind::NormalInplace) {
+      if (!is_fused_float(out.dtype)) { st = make_opaque(); return; }
+      const bool uni = op.kind == OpKind::UniformInplace;
+      const auto a = scalar_arg(op, 1), c = scalar_arg(op, 2);
+      if (!a || !c) { st = make_opaque(); return; }
+      Sym sy;
+      sy.src = uni ? Sym::Uniform : Sym::Normal;
+      if (uni) {
+        TORCH_CHECK(*a <= *c, "uniform_ expects to return a [from, to) range, but found from=", *a,
+                    " > to=", *c);
+        sy.p0 = round_to_dtype(*a, out.dtype);
+        sy.p1 = round_to_dtype(*c, out.dtype);
+      } else {
+        TORCH_CHECK(*c >= 0.0, "normal expects std >= 0.0, but found std ", *c);
+        sy.p0 = *a;
+        sy.p1 = *c;
+      }
+      sy.rng_op = op_idx;
+      overwrite(st, b, e, std::move(sy), b);
+      st.rng_chain.push_back(RngPass{op_idx, out.numel});
+      return;
+    }
+    if (op.kind == OpKind::FillInplace || op.kind == OpKind::ZeroInplace) {
+      Sym sy;
+      sy.src = Sym::Const;
       if (op.kind == OpKind::ZeroInplace) {
-        st.cscalar = 0;
-        st.has_scalar = true;
+        sy.cscalar = 0;
+        sy.has_scalar = true;
       } else if (op.args.size() > 1 && op.args[1].isScalar()) {
-        st.cscalar = op.args[1].toScalar();
-        st.has_scalar = true;
+        sy.cscalar = op.args[1].toScalar();
+        sy.has_scalar = true;
       } else if (op.inputs.size() > 1 && op.inputs[1].real.defined() &&
                  op.inputs[1].real.numel() == 1 && op.inputs[1].real.is_cpu()) {
+        if (g_analysis_only) {
+          g_analysis_deferred = true;
+          st = make_opaque();
+          return;
+        }
         NoInterception guard;
-        st.cval = op.inputs[1].real.detach().to(dt).reshape({1}).clone();
+        sy.cval = op.inputs[1].real.detach().to(out.dtype).reshape({1}).clone();
       } else {
         st = make_opaque();
+        return;
       }
+      overwrite(st, b, e, std::move(sy), b);
       return;
     }
-    case OpKind::MulInplace:
-    case OpKind::AddInplace:
-    case OpKind::ErfinvInplace:
-    case OpKind::ClampInplace:
-    case OpKind::MulOut:
-    case OpKind::AddOut:
-    case OpKind::CloneOut:
-    case OpKind::CastOut: {
-      const bool inplace = op.kind == OpKind::MulInplace || op.kind == OpKind::AddInplace ||
-                           op.kind == OpKind::ErfinvInplace || op.kind == OpKind::ClampInplace;
-      if (!inplace) {
-        // state comes from the (other) storage of the first tensor argument, as of this op
-        if (op.inputs.empty() || op.inputs[0].value == kNoValue) { st = make_opaque(); return; }
-        const ValueInfo& in = tape.values[op.inputs[0].value];
-        if (!in.covers_storage || in.numel != out.numel || in.storage == S) { st = make_opaque(); return; }
-        st = eval_storage(tape, in.storage, op_idx);
+    // elementwise: applies to every segment inside [b, e)
+    split_at(st.segs, b);
+    split_at(st.segs, e);
+    for (Seg& g : st.segs) {
+      if (g.begin < b || g.end > e) continue;
+      Sym& sy = g.st;
+      if (sy.src == Sym::Uninit) { st = make_opaque(); return; }
+      if (sy.src == Sym::Const) {
+        ScalarType dt = st.dtype;
+        if (!fold_const(op, sy, dt, /*inplace=*/true) || dt != st.dtype) { st = make_opaque(); return; }
+        continue;
       }
-      if (op.kind == OpKind::CloneOut) {
-        // a copy: same elements (an RNG state keeps its op, hence its Philox stream: the clone is
-        // bit-identical to its source, as deepcopy semantics require)
-        if (st.opaque() || !need_cover() || out.dtype != st.dtype) st = make_opaque();
-        return;
+      bool ok = true;
+      if (op.kind == OpKind::MulInplace) {
+        const auto c = scalar_arg(op, 1);
+        ok = c && push_epi(sy, TDX_EPI_MUL, *c);
+      } else if (op.kind == OpKind::AddInplace) {
+        const auto c = scalar_arg(op, 1), alpha = scalar_arg(op, 2);
+        ok = c && alpha && push_epi(sy, TDX_EPI_ADD, *c * *alpha);
+      } else if (op.kind == OpKind::ErfinvInplace) {
+        ok = push_epi(sy, TDX_EPI_ERFINV, 0);
+      } else {  // clamp_(min, max), either may be None
+        const bool has_min = !op.args[1].isNone(), has_max = !op.args[2].isNone();
+        const auto lo = scalar_arg(op, 1), hi = scalar_arg(op, 2);
+        ok = !((has_min && !lo) || (has_max && !hi)) &&
+             push_epi(sy, TDX_EPI_CLAMP, has_min ? *lo : -std::numeric_limits<double>::infinity(),
+                      has_max ? *hi : std::numeric_limits<double>::infinity());
       }
-      if (st.opaque() || st.src == Sym::Uninit || !need_cover()) { st = make_opaque(); return; }
-      if (st.src == Sym::Const) {
-        if (!fold_const(op, st, inplace)) st = make_opaque();
-        return;
+      if (!ok) { st = make_opaque(); return; }
+    }
+    return;
+  }
+
+  // ---- out-of-place unary ops: a new storage whose state derives from the argument's -------------
+  if (op.kind == OpKind::MulOut || op.kind == OpKind::AddOut || op.kind == OpKind::CloneOut ||
+      op.kind == OpKind::CastOut) {
+    if (op.inputs.empty() || op.inputs[0].value == kNoValue || !out.covers_storage) { st = make_opaque(); return; }
+    const ValueInfo& in = tape.values[op.inputs[0].value];
+    int64_t b = 0, e = 0;
+    if (in.numel != out.numel || in.storage == S || !range_of(in, b, e)) { st = make_opaque(); return; }
+    State src = eval_storage(tape, in.storage, op_idx);
+    if (src.opaque || src.dtype != in.dtype || src.segs.empty() || b < 0 || e > src.segs.back().end) {
+      st = make_opaque();
+      return;
+    }
+    // restrict to the argument's elements and renumber from 0
+    st = State{};
+    st.opaque = false;
+    st.dtype = src.dtype;
+    st.rng_chain = std::move(src.rng_chain);
+    for (Seg& g : src.segs) {
+      const int64_t gb = std::max(g.begin, b), ge = std::min(g.end, e);
+      if (gb >= ge) continue;
+      Seg n = std::move(g);
+      n.begin = gb - b;
+      n.end = ge - b;
+      n.origin -= b;
+      st.segs.push_back(std::move(n));
+    }
+    if (op.kind == OpKind::CloneOut) {
+      // a copy: same elements (an RNG segment keeps its op, hence its Philox stream: the clone is
+      // bit-identical to its source, as deepcopy semantics require)
+      if (out.dtype != st.dtype) st = make_opaque();
+      return;
+    }
+    ScalarType new_dtype = st.dtype;
+    for (Seg& g : st.segs) {
+      Sym& sy = g.st;
+      if (sy.src == Sym::Uninit) {
+        if (op.kind != OpKind::CastOut) { st = make_opaque(); return; }
+        new_dtype = out.dtype;
+        continue;
+      }
+      if (sy.src == Sym::Const) {
+        ScalarType dt = st.dtype;
+        if (!fold_const(op, sy, dt, /*inplace=*/false) || dt != out.dtype) { st = make_opaque(); return; }
+        new_dtype = out.dtype;
+        continue;
       }
       // RNG source followed by an elementwise op
       if (op.kind == OpKind::CastOut) {
-        if (out.dtype == st.dtype) return;  // a copy
+        if (out.dtype == st.dtype) continue;  // a copy
         // fp32 -> bf16/fp16: the values must be exactly `source.to(dtype)` (the fp32 source may be
         // materialised too, e.g. `m.to(torch.bfloat16)` keeps both alive while recording), so the
         // descriptor keeps the fp32 stream/arithmetic and rounds once, at this point of the chain
         if (st.dtype != ScalarType::Float || !(out.dtype == ScalarType::BFloat16 || out.dtype == ScalarType::Half) ||
-            st.wide) {
+            sy.wide) {
           st = make_opaque();
           return;
         }
-        st.wide = true;
+        sy.wide = true;
         // everything before the cast ran in fp32; the cast itself is the rounding of the last
         // pre-cast step (or of the generated value, if there was none)
-        st.src_noround = !st.epi.empty();
-        for (size_t i = 0; i + 1 < st.epi.size(); ++i) st.epi[i].op |= TDX_EPI_NOROUND;
-        st.dtype = out.dtype;
-        return;
+        sy.src_noround = !sy.epi.empty();
+        for (size_t i = 0; i + 1 < sy.epi.size(); ++i) sy.epi[i].op |= TDX_EPI_NOROUND;
+        new_dtype = out.dtype;
+        continue;
       }
       if (out.dtype != st.dtype) { st = make_opaque(); return; }  // type promotion: not modelled
-      if (op.kind == OpKind::MulInplace || op.kind == OpKind::MulOut) {
+      bool ok;
+      if (op.kind == OpKind::MulOut) {
         const auto c = scalar_arg(op, 1);
-        if (!c) { st = make_opaque(); return; }
-        push_epi(TDX_EPI_MUL, *c);
-      } else if (op.kind == OpKind::AddInplace || op.kind == OpKind::AddOut) {
+        ok = c && push_epi(sy, TDX_EPI_MUL, *c);
+      } else {
         const auto c = scalar_arg(op, 1), alpha = scalar_arg(op, 2);
-        if (!c || !alpha) { st = make_opaque(); return; }
-        push_epi(TDX_EPI_ADD, *c * *alpha);
-      } else if (op.kind == OpKind::ErfinvInplace) {
-        push_epi(TDX_EPI_ERFINV, 0);
-      } else {  // clamp_(min, max), either may be None
-        const bool has_min = !op.args[1].isNone(), has_max = !op.args[2].isNone();
-        const auto lo = scalar_arg(op, 1), hi = scalar_arg(op, 2);
-        if ((has_min && !lo) || (has_max && !hi)) { st = make_opaque(); return; }
-        push_epi(TDX_EPI_CLAMP, has_min ? *lo : -std::numeric_limits<double>::infinity(),
-                 has_max ? *hi : std::numeric_limits<double>::infinity());
+        ok = c && alpha && push_epi(sy, TDX_EPI_ADD, *c * *alpha);
       }
-      return;
+      if (!ok) { st = make_opaque(); return; }
     }
-    default:
-      st = make_opaque();
-      return;
+    if (new_dtype != out.dtype) { st = make_opaque(); return; }
+    st.dtype = new_dtype;
+    return;
   }
+  st = make_opaque();
+}
+
+bool is_pure_alias(OpKind k) {
+  return k == OpKind::Alias || k == OpKind::View || k == OpKind::HookVariableData || k == OpKind::HookSetData;
 }
 
 // State of storage S after every recorded op with index < upto.
-Sym eval_storage(Tape& tape, uint32_t S, uint32_t upto) {
+State eval_storage(Tape& tape, uint32_t S, uint32_t upto) {
   const StorageInfo& si = tape.storages[S];
-  Sym st;
+  State st;
   bool any = false;
   // index of the last op (< upto) that changes the CONTENT of S (aliases only re-describe it)
   uint32_t last_writer = kNoValue;
   for (uint32_t oi : si.touching_ops) {
     if (oi >= upto) break;
     const TapeOp& op = tape.ops[oi];
-    if (op.kind == OpKind::Alias || op.kind == OpKind::HookVariableData || op.kind == OpKind::HookSetData)
-      continue;
+    if (is_pure_alias(op.kind)) continue;
     for (uint32_t v : op.outputs)
       if (v != kNoValue && tape.values[v].storage == S) last_writer = oi;
   }
@@ -414,16 +577,22 @@ Sym eval_storage(Tape& tape, uint32_t S, uint32_t upto) {
       continue;
     }
     if (op.done && op.kind == OpKind::Generic) return make_opaque();
-    if (!any) {
-      // the first writer must be a factory (or an out-of-place op producing this storage)
-      any = true;
-    }
+    any = true;
     transition(tape, oi, S, st);
-    if (st.opaque()) return st;
+    if (st.opaque) return st;
   }
   if (!any) return make_opaque();
   return st;
 }
+
+}  // namespace
+
+// What analyze_tape leaves on a storage.
+struct StorageTemplate {
+  State st;
+};
+
+namespace {
 
 // ---------------------------------------------------------------------------------------------
 // batched fused execution
@@ -431,16 +600,46 @@ Sym eval_storage(Tape& tape, uint32_t S, uint32_t upto) {
 double now_us();
 thread_local double g_call_begin_us = 0;
 
+// Memory of the fused outputs.  A call's tensors are carved out of ONE allocation per submission
+// (a "slab"): one trip to the caching allocator -- and, on a cold allocator, one cudaMalloc instead
+// of one per tensor (226 of them for Llama-3-8B: ~0.6 s) -- while every tensor still gets a
+// StorageImpl of its own (no aliasing is visible through storage identity, `torch.save` writes
+// them separately, `untyped_storage().resize_()` works).  The slab goes back to the allocator
+// when the last tensor carved from it dies.  TDX_SLAB=0: one allocation per tensor instead
+// (memory is then released tensor by tensor).
+struct Slab {
+  c10::DataPtr block;
+};
+void slab_ref_delete(void* ctx) { delete static_cast<std::shared_ptr<Slab>*>(ctx); }
+
+bool slab_enabled() {
+  static const bool v = [] {
+    const char* e = getenv("TDX_SLAB");
+    return !(e && e[0] == '0');
+  }();
+  return v;
+}
+
+std::atomic<uint64_t> g_epoch{1};  // process-wide: storages remember the epoch across sessions
+
 struct Batch {
   c10::Device device = c10::Device(c10::kCPU);
   std::vector<TdxInitDesc> descs;
-  std::vector<at::Tensor> keep_alive;
+  // Outputs whose memory is assigned at the next submission: the tensor object exists as soon as
+  // its program has been planned (the caller can give it its Python identity meanwhile), its
+  // storage gets its address when the slab is allocated.
+  struct Pending {
+    c10::intrusive_ptr<c10::StorageImpl> storage;
+    size_t nbytes = 0;
+    uint32_t first_desc = 0, n_desc = 0;  // descriptors whose dst is relative to this tensor's base
+  };
+  std::vector<Pending> pending;
   // Early submission: the first descriptors are launched as soon as a modest amount of work has
-  // accumulated and the threshold doubles after every submission, so the GPU starts
-  // writing while the host is still planning the rest of the module; the threshold quadruples after
-  // every submission so that the launch count (each launch has a ~10-20 us tail) stays logarithmic.
+  // accumulated, so the GPU starts writing while the host is still planning the rest of the
+  // module; the threshold quadruples after every submission so that the launch count (each launch
+  // has a ~10-20 us tail) stays logarithmic.
   int64_t pending_bytes = 0;
-  uint64_t epoch = 1;  // bumped by every submission: a storage whose fused_epoch == epoch is not on the GPU yet
+  uint64_t epoch = g_epoch.fetch_add(1);  // bumped by every submission: a storage whose fused_epoch == epoch is not on the GPU yet
   int64_t flush_threshold = flush_start();
   static int64_t flush_start() {
     static const int64_t v = [] {
@@ -458,6 +657,7 @@ struct Batch {
       flush_threshold = std::min<int64_t>(flush_threshold * 4, int64_t{16} << 30);
     }
   }
+  void assign_memory();
   void flush();
 };
 
@@ -465,22 +665,76 @@ double now_us() {
   return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// An output tensor without memory yet (see Batch::Pending).  Built like at::detail::empty_generic
+// does, minus the allocation.
+at::Tensor make_output(c10::IntArrayRef sizes, ScalarType dtype, c10::Device dev, size_t nbytes,
+                       c10::intrusive_ptr<c10::StorageImpl>& storage_out) {
+  c10::Allocator* alloc = c10::cuda::CUDACachingAllocator::get();
+  storage_out = c10::make_intrusive<c10::StorageImpl>(c10::StorageImpl::use_byte_size_t(),
+                                                      static_cast<int64_t>(nbytes),
+                                                      c10::DataPtr(nullptr, dev), alloc, /*resizable=*/true);
+  at::Tensor t = at::detail::make_tensor<c10::TensorImpl>(
+      c10::Storage(storage_out), c10::DispatchKeySet(c10::DispatchKey::CUDA), c10::scalarTypeToTypeMeta(dtype));
+  t.unsafeGetTensorImpl()->generic_set_sizes_contiguous(sizes);
+  return t;
+}
+
+void Batch::assign_memory() {
+  if (pending.empty()) return;
+  const double t0 = now_us();
+  c10::Allocator* alloc = c10::cuda::CUDACachingAllocator::get();
+  constexpr size_t kAlign = 256;  // vector stores need 16; 256 keeps every tensor on its own L2 lines
+  if (slab_enabled() && pending.size() > 1) {
+    size_t total = 0;
+    for (const Pending& p : pending) total += (p.nbytes + kAlign - 1) & ~(kAlign - 1);
+    if (total) {
+      auto slab = std::make_shared<Slab>();
+      slab->block = alloc->allocate(total);
+      char* base = static_cast<char*>(slab->block.get());
+      size_t off = 0;
+      for (Pending& p : pending) {
+        if (p.nbytes == 0) continue;
+        char* ptr = base + off;
+        off += (p.nbytes + kAlign - 1) & ~(kAlign - 1);
+        p.storage->set_data_ptr_noswap(
+            c10::DataPtr(ptr, new std::shared_ptr<Slab>(slab), &slab_ref_delete, device));
+        for (uint32_t k = p.first_desc; k < p.first_desc + p.n_desc; ++k)
+          descs[k].dst = ptr + reinterpret_cast<uintptr_t>(descs[k].dst);
+      }
+    }
+  } else {
+    for (Pending& p : pending) {
+      if (p.nbytes == 0) continue;
+      c10::DataPtr d = alloc->allocate(p.nbytes);
+      char* ptr = static_cast<char*>(d.get());
+      p.storage->set_data_ptr_noswap(std::move(d));
+      for (uint32_t k = p.first_desc; k < p.first_desc + p.n_desc; ++k)
+        descs[k].dst = ptr + reinterpret_cast<uintptr_t>(descs[k].dst);
+    }
+  }
+  pending.clear();
+  g_stats.alloc_us += now_us() - t0;
+}
+
 void Batch::flush() {
+  NoInterception guard;
+  c10::DeviceGuard dg(device.is_cuda() ? device : c10::Device(c10::kCPU));
+  assign_memory();
   if (descs.empty()) {
-    ++epoch;
+    epoch = g_epoch.fetch_add(1);
+    pending_bytes = 0;
     return;
   }
   const double t0 = now_us();
-  NoInterception guard;
-  c10::DeviceGuard dg(device);
   const int n = static_cast<int>(descs.size());
   // prepare: the plan is laid out on the host and says how much workspace it needs (descriptor table
   // + prefix sums + work lists: tens of KB, not the upper bound of tdx_init_workspace_bytes)
   size_t ws_bytes = 0;
   int rc = tdx_init_prepare(descs.data(), n, &ws_bytes);
   TORCH_CHECK(rc == 0, "libtdx_init: plan failed (", rc, "): ", tdx_last_error());
-  at::Tensor ws = at::empty({static_cast<int64_t>(std::max<size_t>(ws_bytes, 16))},
-                            at::TensorOptions().dtype(at::kByte).device(device));
+  // (straight from the caching allocator: freed at the end of this scope, reused in stream order)
+  at::Tensor ws = at::detail::empty_cuda({static_cast<int64_t>(std::max<size_t>(ws_bytes, 16))}, at::kByte,
+                                         device, std::nullopt);
   auto stream = c10::cuda::getCurrentCUDAStream(device.index());
   rc = tdx_init_submit(ws.data_ptr(), ws_bytes, stream.stream());
   TORCH_CHECK(rc == 0, "libtdx_init: launch failed (", rc, "): ", tdx_last_error());
@@ -492,9 +746,8 @@ void Batch::flush() {
   g_stats.last_submit_us = now_us() - g_call_begin_us;
   g_last_descs.insert(g_last_descs.end(), descs.begin(), descs.end());
   descs.clear();
-  keep_alive.clear();
   pending_bytes = 0;
-  ++epoch;
+  epoch = g_epoch.fetch_add(1);
   g_stats.launch_us += now_us() - t0;
 }
 
@@ -611,19 +864,33 @@ struct Engine {
   Batch& batch;
   GenCache gens;
 
+  bool sharding(const ValueInfo& vi) const { return opts.shard && opts.shard->world > 1 && !vi.sizes.empty(); }
+
   at::Tensor real_of(Tape& tape, uint32_t v) {
     ValueInfo& vi = tape.values[v];
-    if (vi.real.defined()) return vi.real;
     StorageInfo& si = tape.storages[vi.storage];
+    if (vi.real.defined() && !(si.fused_done && si.base_is_shard && !sharding(vi))) return vi.real;
     TORCH_INTERNAL_ASSERT(si.fused_done, "value of `", tape.ops[vi.op].name(),
                           "` requested before it was materialised");
-    if (opts.shard && opts.shard->world > 1 && !vi.sizes.empty()) {
-      // the backing tensor is this rank's dim-0 chunk; only whole-storage tensors can name it
-      TORCH_CHECK(vi.covers_storage,
-                  "sharded materialisation only supports tensors that cover their whole storage");
-      vi.real = si.base_taken ? [&] { NoInterception guard; return si.base.detach(); }() : si.base;
-      si.base_taken = true;
-      return vi.real;
+    if (si.base_is_shard) {
+      if (sharding(vi)) {
+        // the backing tensor is this rank's dim-0 chunk; only whole-storage tensors can name it
+        TORCH_CHECK(vi.covers_storage,
+                    "sharded materialisation only supports tensors that cover their whole storage");
+        vi.real = si.base_taken ? [&] { NoInterception guard; return si.base.detach(); }() : si.base;
+        si.base_taken = true;
+        return vi.real;
+      }
+      // A reader (a buffer computed from a parameter, say) needs the unsharded tensor of a storage
+      // whose backing tensor is one rank's chunk: every element is a function of (seed, offset,
+      // index), so the full tensor is generated beside the chunk -- same bits, no communication.
+      if (!si.full_base.defined()) {
+        int64_t bytes = 0;
+        TORCH_INTERNAL_ASSERT(emit_fused(tape, vi.storage, vi, std::nullopt, si.full_base, bytes),
+                              "a fused storage stopped being fusible");
+        si.fused_epoch = batch.epoch;
+      }
+      return alias_of(si.full_base, vi, false);  // (not cached in vi.real: that names this rank's view)
     }
     vi.real = alias_of(si.base, vi, !si.base_taken);
     si.base_taken = true;
@@ -683,12 +950,15 @@ struct Engine {
     for_each_tensor_mut(stack, nargs, [&](at::Tensor& t) {
       InputRef& in = op.inputs[slot++];
       if (in.value != kNoValue) {
+        t = real_of(tape, in.value);
         // a fused result that is still sitting in the batch must reach the stream before ATen reads it
         const StorageInfo& isi = tape.storages[tape.values[in.value].storage];
         if (isi.fused_done && isi.fused_epoch == batch.epoch) batch.flush();
-        t = real_of(tape, in.value);
       } else if (in.foreign) {
+        // (recorded by an earlier deferred_init: same rule -- its descriptor may still be in the batch)
         t = materialize_value(in.foreign, in.foreign_value);
+        const StorageInfo& fsi = in.foreign->storages[in.foreign->values[in.foreign_value].storage];
+        if (fsi.fused_done && fsi.fused_epoch == batch.epoch) batch.flush();
       } else if (in.real.defined()) {
         TORCH_CHECK(!in.real.is_inference(), "A `Tensor` argument required for the materialization of `",
                     op.name(), "` was created in inference mode. Materialization cannot be performed "
@@ -722,7 +992,11 @@ struct Engine {
     }
     size_t k = 0;
     for_each_tensor(stack, op.num_returns, [&](const at::Tensor& t) {
-      if (k < op.outputs.size() && op.outputs[k] != kNoValue) tape.values[op.outputs[k]].real = t;
+      if (k < op.outputs.size() && op.outputs[k] != kNoValue) {
+        ValueInfo& ov = tape.values[op.outputs[k]];
+        ov.real = t;
+        tape.storages[ov.storage].replayed = true;  // its content now comes from ATen: never fuse it later
+      }
       ++k;
     });
     op.results = std::move(stack);
@@ -732,17 +1006,13 @@ struct Engine {
     g_stats.generic_ops++;
   }
 
-  // Fused path for the storage of value `v`.  Returns false if the program is not fusible.
-  bool try_fused(Tape& tape, uint32_t v) {
-    ValueInfo& vi = tape.values[v];
-    const uint32_t S = vi.storage;
-    StorageInfo& si = tape.storages[S];
-    if (!opts.fused) return false;
-    const c10::Device dev = target_device(vi.device);
-    if (!dev.is_cuda()) return false;
-    const bool sharded = opts.shard && opts.shard->world > 1 && !vi.sizes.empty();
-    if (sharded && !vi.covers_storage) return false;
-
+  // Symbolic state of a storage: what analyze_tape left on it, or a fresh evaluation.
+  const State* state_of(Tape& tape, uint32_t S, c10::Device dev, State& scratch) {
+    const StorageInfo& si = tape.storages[S];
+    if (si.tmpl) {
+      g_stats.template_hits++;
+      return &si.tmpl->st;
+    }
     struct FoldOn {  // constants fold with the target device's arithmetic
       c10::Device prev = g_fold_device;
       explicit FoldOn(c10::Device d) { g_fold_device = d; }
@@ -750,23 +1020,35 @@ struct Engine {
     } fold_on(dev);
     c10::DeviceGuard fold_guard(dev);
     const double t_eval = now_us();
-    Sym st = eval_storage(tape, S, static_cast<uint32_t>(tape.ops.size()));
+    scratch = eval_storage(tape, S, static_cast<uint32_t>(tape.ops.size()));
     g_stats.eval_us += now_us() - t_eval;
-    if (st.opaque()) return false;
+    return &scratch;
+  }
+
+  // Builds the descriptors of storage S (or of one rank's dim-0 chunk of it) and the tensor they
+  // write; `vi` is the value whose geometry the tensor takes (the parameter itself, normally).
+  // Returns false if the program is not fusible.  `bytes_out`: algorithmic bytes of the descriptors.
+  bool emit_fused(Tape& tape, uint32_t S, const ValueInfo& vi, const std::optional<ShardSpec>& shard,
+                  at::Tensor& base_out, int64_t& bytes_out) {
+    StorageInfo& si = tape.storages[S];
+    const c10::Device dev = target_device(vi.device);
+    State scratch;
+    const State* stp = state_of(tape, S, dev, scratch);
+    if (stp->opaque) return false;
+    const State& st = *stp;
     const size_t isz = c10::elementSize(st.dtype);
     if (isz == 0 || si.nbytes % isz) return false;
     const int64_t numel = static_cast<int64_t>(si.nbytes / isz);
-    if (numel == 0) return false;
-    if (st.src == Sym::Uniform || st.src == Sym::Normal) {
-      if (tdx_dtype_of(st.dtype) < 0) return false;
-    } else if (st.src == Sym::Const) {
-      if (!(isz == 1 || isz == 2 || isz == 4 || isz == 8)) return false;
+    if (numel == 0 || st.segs.empty() || st.segs.back().end != numel) return false;
+    for (const Seg& g : st.segs) {
+      if (g.st.rng() && tdx_dtype_of(st.dtype) < 0) return false;
+      if (g.st.src == Sym::Const && !(isz == 1 || isz == 2 || isz == 4 || isz == 8)) return false;
     }
 
     // geometry of what this rank writes
     ShardGeom g;
-    if (vi.covers_storage) {
-      g = shard_of(vi, opts.shard);
+    if (vi.covers_storage && vi.dtype == st.dtype) {
+      g = shard_of(vi, shard);
     } else {
       g.begin = 0;
       g.count = numel;
@@ -777,78 +1059,120 @@ struct Engine {
       batch.flush();
       batch.device = dev;
     }
-    // straight to the caching allocator: no dispatcher round trip per tensor
-    const double t_alloc = now_us();
-    at::Tensor base = at::detail::empty_cuda(g.sizes, st.dtype, dev, std::nullopt);
-    g_stats.alloc_us += now_us() - t_alloc;
+    Batch::Pending pend;
+    pend.nbytes = static_cast<size_t>(g.count) * isz;
+    at::Tensor base = make_output(g.sizes, st.dtype, dev, pend.nbytes, pend.storage);
 
     // every RNG pass on the chain consumes its slice of the stream, live or dead
-    for (uint32_t r : st.rng_chain) {
-      if (!tape.ops[r].rng_assigned) {
-        assign_rng(tape.ops[r], numel, dev, gens);
-        if (r != st.rng_op) g_stats.elided_rng_ops++;
-      }
+    for (const RngPass& r : st.rng_chain) {
+      TapeOp& rop = tape.ops[r.op];
+      if (rop.rng_assigned) continue;
+      assign_rng(rop, r.numel, dev, gens);
+      bool live = false;
+      for (const Seg& sg : st.segs) live |= sg.st.rng() && sg.st.rng_op == r.op;
+      if (!live) g_stats.elided_rng_ops++;
     }
 
-    if (st.src != Sym::Uninit && g.count > 0) {
+    pend.first_desc = static_cast<uint32_t>(batch.descs.size());
+    int64_t bytes = 0;
+    for (const Seg& sg : st.segs) {
+      const int64_t lo = std::max(sg.begin, g.begin), hi = std::min(sg.end, g.begin + g.count);
+      if (lo >= hi || sg.st.src == Sym::Uninit) continue;
+      const Sym& sy = sg.st;
       TdxInitDesc d;
       std::memset(&d, 0, sizeof(d));
-      d.dst = base.data_ptr();
-      d.elem_begin = static_cast<uint64_t>(g.begin);
-      d.elem_count = static_cast<uint64_t>(g.count);
-      if (st.src == Sym::Const) {
+      // byte offset inside the output until the submission gives the output its address
+      d.dst = reinterpret_cast<void*>(static_cast<uintptr_t>(lo - g.begin) * isz);
+      d.elem_count = static_cast<uint64_t>(hi - lo);
+      if (sy.src == Sym::Const) {
         d.src = TDX_SRC_CONST;
         d.dtype = isz == 1 ? TDX_RAW8 : isz == 2 ? TDX_RAW16 : isz == 4 ? TDX_RAW32 : TDX_RAW64;
         unsigned char pat[16], one[16];
         size_t got = 0;
-        if (!(st.has_scalar && scalar_bits(st.cscalar, st.dtype, one, &got) && got == isz)) {
-          ensure_cval(st);
+        if (!(sy.has_scalar && scalar_bits(sy.cscalar, st.dtype, one, &got) && got == isz)) {
+          Sym tmp = sy;
+          ensure_cval(tmp, st.dtype);
           NoInterception guard;
-          std::memcpy(one, st.cval.cpu().contiguous().data_ptr(), isz);
+          std::memcpy(one, tmp.cval.cpu().contiguous().data_ptr(), isz);
         }
         for (size_t i = 0; i < 16; i += isz) std::memcpy(pat + i, one, isz);
         std::memcpy(d.fill_bits, pat, 16);
       } else {
-        d.src = st.src == Sym::Uniform ? TDX_SRC_UNIFORM : TDX_SRC_NORMAL;
+        d.src = sy.src == Sym::Uniform ? TDX_SRC_UNIFORM : TDX_SRC_NORMAL;
         d.dtype = static_cast<uint8_t>(tdx_dtype_of(st.dtype));
-        d.p0 = st.p0;
-        d.p1 = st.p1;
-        const TapeOp& r = tape.ops[st.rng_op];
+        d.elem_begin = static_cast<uint64_t>(lo - sg.origin);  // index in the tensor the RNG op ran on
+        d.p0 = sy.p0;
+        d.p1 = sy.p1;
+        const TapeOp& r = tape.ops[sy.rng_op];
         d.philox_seed = r.rng_seed;
         d.philox_offset = r.rng_offset;
-        d.n_epi = static_cast<uint8_t>(st.epi.size());
-        for (size_t i = 0; i < st.epi.size(); ++i) d.epi[i] = st.epi[i];
-        if (st.wide) d.algo = TDX_ALGO_WIDE32;
-        if (st.src_noround) d.reserved |= TDX_FLAG_SRC_NOROUND;
+        d.n_epi = static_cast<uint8_t>(sy.epi.size());
+        for (size_t i = 0; i < sy.epi.size(); ++i) d.epi[i] = sy.epi[i];
+        if (sy.wide) d.algo = TDX_ALGO_WIDE32;
+        if (sy.src_noround) d.reserved |= TDX_FLAG_SRC_NOROUND;
       }
       batch.descs.push_back(d);
-      batch.keep_alive.push_back(base);
-      g_stats.bytes_written += g.count * static_cast<int64_t>(isz);
+      bytes += (hi - lo) * static_cast<int64_t>(isz);
     }
-    const int64_t submitted = (st.src != Sym::Uninit) ? g.count * static_cast<int64_t>(isz) : 0;
+    pend.n_desc = static_cast<uint32_t>(batch.descs.size()) - pend.first_desc;
+    batch.pending.push_back(std::move(pend));
+    g_stats.bytes_written += bytes;
+    bytes_out = bytes;
+    base_out = std::move(base);
+    return true;
+  }
 
-    si.base = base;
+  // Fused path for the storage of value `v`.  Returns false if the program is not fusible.
+  bool try_fused(Tape& tape, uint32_t v) {
+    ValueInfo& vi = tape.values[v];
+    const uint32_t S = vi.storage;
+    StorageInfo& si = tape.storages[S];
+    if (!opts.fused || si.replayed) return false;
+    if (!target_device(vi.device).is_cuda()) return false;
+    const bool sharded = sharding(vi);
+    if (sharded && !vi.covers_storage) return false;
+    at::Tensor base;
+    int64_t bytes = 0;
+    if (!emit_fused(tape, S, vi, sharded ? opts.shard : std::nullopt, base, bytes)) return false;
+    si.base = std::move(base);
+    si.base_is_shard = sharded;
     si.fused_done = true;
     si.fused_epoch = batch.epoch;
     for (uint32_t oi : si.touching_ops) {
       TapeOp& op = tape.ops[oi];
+      if (op.done) continue;
       bool writes = false;
       for (uint32_t ov : op.outputs) writes |= (ov != kNoValue && tape.values[ov].storage == S);
-      if (writes && !op.done) {
+      if (writes) {
         op.done = true;
         op.tls.reset();
       }
     }
     g_stats.fused_tensors++;
-    batch.note(submitted);  // may submit what has accumulated so far
+    batch.note(bytes);  // may submit what has accumulated so far
     return true;
+  }
+
+  // This rank's dim-0 chunk of a fully materialised tensor (generic replay always builds the whole
+  // tensor: its ops are recorded on whole tensors).
+  at::Tensor chunk_of(const ValueInfo& vi, const at::Tensor& full) {
+    NoInterception guard;
+    const ShardGeom g = shard_of(vi, opts.shard);
+    const int64_t inner = vi.sizes[0] ? vi.numel / vi.sizes[0] : 0;
+    const int64_t start = inner ? g.begin / inner : 0;
+    return full.narrow(0, start, g.sizes[0]).clone();
   }
 
   at::Tensor materialize_value(const std::shared_ptr<Tape>& tape_ptr, uint32_t v) {
     Tape& tape = *tape_ptr;
     ValueInfo& vi = tape.values[v];
-    if (vi.real.defined()) return vi.real;
-    if (tape.storages[vi.storage].fused_done) return real_of(tape, v);
+    StorageInfo& si = tape.storages[vi.storage];
+    if (si.fused_done) {
+      at::Tensor t = real_of(tape, v);
+      // (materialised whole earlier -- as a dependency, or by an unsharded call -- and asked for as a chunk now)
+      return (sharding(vi) && !si.base_is_shard) ? chunk_of(vi, t) : t;
+    }
+    if (vi.real.defined()) return sharding(vi) ? chunk_of(vi, vi.real) : vi.real;
     if (try_fused(tape, v)) return real_of(tape, v);
 
     // generic replay, in recorded order, of everything that determines this storage.  Pending fused
@@ -861,14 +1185,7 @@ struct Engine {
     for (uint32_t oi = 0; oi < mark.size(); ++oi)
       if (mark[oi]) replay(tape, oi);
     TORCH_INTERNAL_ASSERT(vi.real.defined(), "replay did not produce `", tape.ops[vi.op].name(), "`");
-    if (opts.shard && opts.shard->world > 1 && !vi.sizes.empty()) {
-      NoInterception guard;
-      const ShardGeom g = shard_of(vi, opts.shard);
-      const int64_t inner = vi.sizes[0] ? vi.numel / vi.sizes[0] : 0;
-      const int64_t start = inner ? g.begin / inner : 0;
-      return vi.real.narrow(0, start, g.sizes[0]).clone();
-    }
-    return vi.real;
+    return sharding(vi) ? chunk_of(vi, vi.real) : vi.real;
   }
 };
 
@@ -904,8 +1221,10 @@ MaterializeSession::MaterializeSession(const MaterializeOptions& opts) {
 }
 
 MaterializeSession::~MaterializeSession() {
-  // also on error paths: offsets already handed out must stay consumed
+  // also on error paths: tensors planned so far are part of the recording's state (a later call
+  // returns them), so their descriptors must run; offsets already handed out must stay consumed
   if (impl_ && !impl_->finished) {
+    try { impl_->batch.flush(); } catch (...) {}
     try { impl_->eng.gens.write_back(); } catch (...) {}
   }
 }
@@ -1032,23 +1351,27 @@ struct PipelinedMaterialize::State {
   std::atomic<bool> caller_waiting{false};
   bool finished = false;
   std::exception_ptr error;
+  size_t error_ticket = static_cast<size_t>(-1);  // the tensor whose materialisation raised `error`
   MaterializeStats stats;
   std::vector<TdxInitDesc> descs;
 
-  void record_error() {
+  void record_error(size_t ticket = static_cast<size_t>(-1)) {
     std::lock_guard<std::mutex> lock(m);
-    if (!error) error = std::current_exception();
+    if (!error) {
+      error = std::current_exception();
+      error_ticket = ticket;
+    }
   }
   bool failed() {
     std::lock_guard<std::mutex> lock(m);
     return static_cast<bool>(error);
   }
-  void process(MaterializeSession& s, Item& it) {
+  void process(MaterializeSession& s, Item& it, size_t ticket) {
     if (!failed()) {
       try {
         it.out = s.add(it.fake, it.apply_shard);
       } catch (...) {
-        record_error();
+        record_error(ticket);
       }
     }
     it.done.store(1, std::memory_order_release);
@@ -1067,7 +1390,7 @@ struct PipelinedMaterialize::State {
       if (caller_device >= 0) c10::cuda::set_device(caller_device);
       for (const auto& st : streams) c10::cuda::setCurrentCUDAStream(st);
       MaterializeSession s(opts);
-      size_t next = 0;
+      size_t next = 0, first = 0;
       std::vector<Item*> batch;
       for (;;) {
         bool fin;
@@ -1081,9 +1404,10 @@ struct PipelinedMaterialize::State {
           fin = finish_requested;
           batch.clear();
           for (size_t i = next; i < items.size(); ++i) batch.push_back(items[i].get());
+          first = next;
           next = items.size();
         }
-        for (Item* it : batch) process(s, *it);
+        for (size_t i = 0; i < batch.size(); ++i) process(s, *batch[i], first + i);
         if (fin && batch.empty()) break;  // finish() was requested and nothing arrived after it
       }
       if (!failed()) {
@@ -1163,7 +1487,7 @@ size_t PipelinedMaterialize::add(const at::Tensor& fake, bool apply_shard) {
     wake = st_->helper_waiting;
   }
   if (!st_->threaded) {
-    st_->process(*st_->session, *raw);
+    st_->process(*st_->session, *raw, ticket);
   } else if (wake) {
     st_->cv_work.notify_one();
   }
@@ -1206,6 +1530,11 @@ at::Tensor PipelinedMaterialize::result(size_t ticket) {
     if (st_->error) std::rethrow_exception(st_->error);
   }
   return it.out;
+}
+
+size_t PipelinedMaterialize::failed_ticket() {
+  std::lock_guard<std::mutex> lock(st_->m);
+  return st_->error ? st_->error_ticket : static_cast<size_t>(-1);
 }
 
 void PipelinedMaterialize::join() {
@@ -1258,45 +1587,98 @@ PlanInfo plan_info(const at::Tensor& fake) {
     explicit FoldOn(c10::Device d) { g_fold_device = d; }
     ~FoldOn() { g_fold_device = prev; }
   } fold_on(vi.device.is_cuda() && at::hasCUDA() ? vi.device : c10::Device(c10::kCPU));
-  Sym st = eval_storage(tape, vi.storage, static_cast<uint32_t>(tape.ops.size()));
-  static const char* names[] = {"opaque", "uninit", "const", "uniform", "normal"};
-  info.source = names[st.src];
-  info.fusible = !st.opaque();
-  if (st.src == Sym::Uniform || st.src == Sym::Normal) info.fusible = tdx_dtype_of(st.dtype) >= 0;
-  info.p0 = st.p0;
-  info.p1 = st.p1;
-  info.n_epilogue = static_cast<int>(st.epi.size());
-  info.rng_ops = static_cast<int>(st.rng_chain.size());
-  info.wide = st.wide;
-  info.src_noround = st.src_noround;
-  for (const TdxEpiStep& e : st.epi) info.epilogue.emplace_back(static_cast<int>(e.op), e.a, e.b);
-  {
-    const size_t isz = c10::elementSize(st.dtype == ScalarType::Undefined ? vi.dtype : st.dtype);
-    const int64_t storage_numel = isz ? static_cast<int64_t>(si.nbytes / isz) : vi.numel;
-    for (size_t i = 0; i < st.rng_chain.size(); ++i) info.rng_numels.push_back(storage_numel);
-    if (st.src == Sym::Const) {
-      unsigned char one[16];
-      size_t got = 0;
-      if (!(st.has_scalar && scalar_bits(st.cscalar, st.dtype, one, &got) && got == isz)) {
-        ensure_cval(st);
-        NoInterception guard;
-        std::memcpy(one, st.cval.cpu().contiguous().data_ptr(), isz);
-      }
-      info.const_bytes.assign(reinterpret_cast<const char*>(one), isz);
-    }
-    if (!vi.covers_storage) info.fusible = false;  // a plan names whole tensors only
-  }
-  if (st.opaque()) {
+  State fresh;
+  if (!si.tmpl) fresh = eval_storage(tape, vi.storage, static_cast<uint32_t>(tape.ops.size()));
+  const State& st = si.tmpl ? si.tmpl->st : fresh;
+  static const char* names[] = {"uninit", "const", "uniform", "normal"};
+  if (st.opaque || st.segs.empty()) {
+    info.source = "opaque";
     // best effort: the first op on the storage the planner does not model
     for (uint32_t oi : si.touching_ops) {
       const TapeOp& op = tape.ops[oi];
-      if (op.kind == OpKind::Generic || op.kind == OpKind::HookSetData) {
+      if (op.kind == OpKind::Generic) {
         info.first_unfusable_op = op.name();
         break;
       }
     }
+    return info;
   }
+  const size_t isz = c10::elementSize(st.dtype);
+  // the segment that writes the most elements names the tensor's source
+  const Seg* main = &st.segs.front();
+  for (const Seg& g : st.segs)
+    if (g.end - g.begin > main->end - main->begin) main = &g;
+  info.source = names[main->st.src];
+  info.fusible = si.replayed ? false : true;
+  info.p0 = main->st.p0;
+  info.p1 = main->st.p1;
+  info.n_epilogue = static_cast<int>(main->st.epi.size());
+  info.rng_ops = static_cast<int>(st.rng_chain.size());
+  info.wide = main->st.wide;
+  info.src_noround = main->st.src_noround;
+  for (const TdxEpiStep& e : main->st.epi) info.epilogue.emplace_back(static_cast<int>(e.op), e.a, e.b);
+  for (const RngPass& r : st.rng_chain) {
+    info.rng_numels.push_back(r.numel);
+    info.rng_op_ids.push_back(static_cast<int64_t>(r.op));
+  }
+  for (const Seg& g : st.segs) {
+    PlanSegment ps;
+    ps.begin = g.begin;
+    ps.end = g.end;
+    ps.origin = g.origin;
+    ps.source = names[g.st.src];
+    ps.p0 = g.st.p0;
+    ps.p1 = g.st.p1;
+    ps.wide = g.st.wide;
+    ps.src_noround = g.st.src_noround;
+    for (const TdxEpiStep& e : g.st.epi) ps.epilogue.emplace_back(static_cast<int>(e.op), e.a, e.b);
+    if (g.st.rng()) {
+      if (tdx_dtype_of(st.dtype) < 0) info.fusible = false;
+      for (size_t i = 0; i < st.rng_chain.size(); ++i)
+        if (st.rng_chain[i].op == g.st.rng_op) ps.rng_pass = static_cast<int>(i);
+    }
+    if (g.st.src == Sym::Const) {
+      unsigned char one[16];
+      size_t got = 0;
+      if (!(g.st.has_scalar && scalar_bits(g.st.cscalar, st.dtype, one, &got) && got == isz)) {
+        Sym tmp = g.st;
+        ensure_cval(tmp, st.dtype);
+        NoInterception guard;
+        std::memcpy(one, tmp.cval.cpu().contiguous().data_ptr(), isz);
+      }
+      ps.const_bytes.assign(reinterpret_cast<const char*>(one), isz);
+      if (!(isz == 1 || isz == 2 || isz == 4 || isz == 8)) info.fusible = false;
+      if (&g == main) info.const_bytes = ps.const_bytes;
+    }
+    info.segments.push_back(std::move(ps));
+  }
+  if (!vi.covers_storage || vi.dtype != st.dtype) info.fusible = false;  // a plan names whole tensors only
   return info;
+}
+
+void analyze_tape(Tape& tape) noexcept {
+  struct Flag {
+    Flag() { g_analysis_only = true; }
+    ~Flag() { g_analysis_only = false; }
+  } flag;
+  const uint32_t n_ops = static_cast<uint32_t>(tape.ops.size());
+  for (uint32_t S = 0; S < tape.storages.size(); ++S) {
+    StorageInfo& si = tape.storages[S];
+    if (si.tmpl || si.fused_done) continue;
+    g_analysis_deferred = false;
+    try {
+      NoInterception guard;
+      State st = eval_storage(tape, S, n_ops);
+      // constant chains fold with the TARGET device's arithmetic and programs that read a real
+      // tensor see its value at materialisation time: both are evaluated then
+      if (g_analysis_deferred) continue;
+      auto t = std::make_shared<StorageTemplate>();
+      t->st = std::move(st);
+      si.tmpl = std::move(t);
+    } catch (...) {
+      // (e.g. uniform_ with from > to: the error is raised when the tensor is materialised)
+    }
+  }
 }
 
 std::vector<std::string> storage_history(const at::Tensor& fake) {
@@ -1314,7 +1696,8 @@ std::vector<std::string> storage_history(const at::Tensor& fake) {
         writes = true;
         covers = covers && tape.values[v].covers_storage;
       }
-    line += writes ? (covers ? " [writes]" : " [writes part]") : " [reads]";
+    if (is_pure_alias(op.kind)) line += covers ? " [alias]" : " [view]";
+    else line += writes ? (covers ? " [writes]" : " [writes part]") : " [reads]";
     out.push_back(line);
   }
   return out;

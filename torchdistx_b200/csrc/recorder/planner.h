@@ -59,6 +59,7 @@ struct MaterializeStats {
   int64_t submissions = 0;       // tdx_init_launch calls (early submissions + the final one)
   double first_submit_us = 0;    // host time from the start of the call to the first submission
   double last_submit_us = 0;     // ... and to the last one
+  int64_t template_hits = 0;     // storages whose analysis was done when the recording ended
 };
 
 // Materialises `fake` (a no-op returning `fake` itself for real tensors).
@@ -109,6 +110,9 @@ class PipelinedMaterialize {
   void finish();
   at::Tensor result(size_t ticket);
   bool ready(size_t ticket);  // result(ticket) would not block
+  // After result()/join() threw: the ticket of the tensor whose materialisation failed (or -1 if the
+  // failure was not a tensor's: session set-up, the final submission).
+  size_t failed_ticket();
   void join();
 
  private:
@@ -126,6 +130,17 @@ std::string last_descriptors();
 
 // Planner verdict for one tensor, without allocating or launching anything (works without a GPU:
 // used by CPU tests and by `torchdistx_b200.deferred_init.plan_report`).
+struct PlanSegment {
+  int64_t begin = 0, end = 0;  // elements of the tensor
+  int64_t origin = 0;          // element of the tensor that is element 0 of the source op's tensor
+  std::string source;          // "uninit" | "const" | "uniform" | "normal"
+  double p0 = 0, p1 = 0;
+  bool wide = false, src_noround = false;
+  std::vector<std::tuple<int, double, double>> epilogue;
+  std::string const_bytes;
+  int rng_pass = -1;           // index into PlanInfo::rng_numels of the live RNG pass
+};
+
 struct PlanInfo {
   bool deferred = false;   // the tensor awaits materialisation
   bool fusible = false;    // its program folds into one descriptor
@@ -145,6 +160,12 @@ struct PlanInfo {
   std::vector<std::tuple<int, double, double>> epilogue;  // (TDX_EPI_*, a, b)
   std::string const_bytes;                                 // "const": one element's bytes
   std::vector<int64_t> rng_numels;  // global numel of every RNG pass on the chain, in order
+  // identity of every RNG pass (stable inside one recording): a clone shares its source's passes,
+  // so a pass met again under another tensor consumes nothing and yields the same stream
+  std::vector<int64_t> rng_op_ids;
+  // the tensor as a list of disjoint segments (one for a tensor initialised as a whole; three for
+  // `w.normal_(); w[padding_idx].zero_()`); the scalar fields above describe the largest one
+  std::vector<PlanSegment> segments;
 };
 PlanInfo plan_info(const at::Tensor& fake);
 // Every recorded op touching the tensor's storage, in order (debug aid for unfusable programs).

@@ -253,8 +253,10 @@ void append(std::optional<OperatorHandle> handle, OpKind kind, Stack frame, size
     impl->record()->value = vid;
   });
 
-  // A generic op whose single fake result re-describes exactly the elements of its first fake
-  // argument (view/reshape/flatten/unsqueeze of a contiguous tensor) is a plain alias.
+  // A generic, non-mutating op whose single fake result lives on the storage of its first fake
+  // argument is a view.  If it re-describes exactly the argument's elements (view / reshape /
+  // flatten / unsqueeze of a contiguous tensor) it is a plain alias; otherwise (select / narrow /
+  // slice / a[i] / t() ...) it names part of the storage -- nothing is read or written either way.
   if (kind == OpKind::Generic && op->outputs.size() == 1 && op->outputs[0] != kNoValue &&
       !op->inputs.empty() && op->inputs[0].value != kNoValue) {
     const ValueInfo& out = tape.values[op->outputs[0]];
@@ -263,10 +265,9 @@ void append(std::optional<OperatorHandle> handle, OpKind kind, Stack frame, size
     for (size_t i = 1; i < op->inputs.size(); ++i)
       only_one_tensor_input &= !(op->inputs[i].value != kNoValue || op->inputs[i].foreign ||
                                  op->inputs[i].real.defined());
-    if (only_one_tensor_input && out.storage == in.storage && out.covers_storage &&
-        in.covers_storage && out.dtype == in.dtype && op->handle &&
+    if (only_one_tensor_input && out.storage == in.storage && out.dtype == in.dtype && op->handle &&
         op->handle->schema().is_mutable() == false) {
-      op->kind = OpKind::Alias;
+      op->kind = (out.covers_storage && in.covers_storage) ? OpKind::Alias : OpKind::View;
     }
   }
 }
@@ -451,6 +452,7 @@ void leave_deferred_init() noexcept {
   if (--tls_level == 0) {
     c10::impl::tls_set_dispatch_key_included(DispatchKey::DeferredInit, false);
     uninstall_hooks();
+    if (tls_tape) analyze_tape(*tls_tape);
     tls_tape.reset();
   }
 }

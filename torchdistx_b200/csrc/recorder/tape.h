@@ -43,6 +43,9 @@ enum class OpKind : uint8_t {
   Empty, Zeros, Ones, Full, Randn, Rand,
   // full aliases of the input (same storage, same elements)
   Alias,  // detach, alias, view-like ops are classified Alias only when they cover the storage
+  // a view of PART of the input's storage (select / narrow / slice / a[i]): same memory, nothing
+  // written; later in-place ops through it are partial writes of the storage
+  View,
   // in-place writers
   UniformInplace, NormalInplace, FillInplace, ZeroInplace,
   MulInplace, AddInplace, ErfinvInplace, ClampInplace,
@@ -69,6 +72,8 @@ struct ValueInfo {
   at::Tensor py_wrapped;  // what the Python binding returned for it (keeps object identity stable)
 };
 
+struct StorageTemplate;  // planner.cc: what the analysis at the end of the recording found
+
 struct StorageInfo {
   c10::Storage meta;      // keeps the meta StorageImpl (our identity key) alive
   size_t nbytes = 0;
@@ -76,7 +81,13 @@ struct StorageInfo {
   at::Tensor base;        // real backing tensor once the fused path materialised the storage
   bool fused_done = false;
   bool base_taken = false;  // `base` itself has been handed out as some value's tensor
+  bool base_is_shard = false;  // `base` holds one rank's dim-0 chunk only (shard=(r, W), W > 1)
+  bool replayed = false;    // an op writing this storage went through generic replay: never fuse it afterwards
   uint64_t fused_epoch = 0;  // submission epoch of the batch that holds (held) its descriptor
+  at::Tensor full_base;   // unsharded copy built for a reader of a storage whose `base` is a shard
+  // Symbolic state of the storage, computed once when the outermost deferred_init scope ends
+  // (analyze_tape): materialising is then allocation + descriptor fill, not program analysis.
+  std::shared_ptr<const StorageTemplate> tmpl;
 };
 
 // A tensor argument of a recorded op.
@@ -131,5 +142,10 @@ struct NoDeferredInit {
 };
 
 OpKind classify(const c10::OperatorHandle& op);
+
+// planner.cc: evaluates every storage of a finished tape symbolically and caches the result on it
+// (called by leave_deferred_init; never throws -- a storage whose analysis fails is analysed again,
+// and reports its error, when it is materialised).
+void analyze_tape(Tape& tape) noexcept;
 
 }  // namespace tdx

@@ -101,10 +101,9 @@ def materialize_module(
             every parameter (buffers and 0-dim tensors are replicated).  All ranks must hold the
             same generator state; see :func:`torchdistx_b200.parallel.sync_rng`.
     """
-    try:
-        _C.materialize_module(module, buffers_only, check_fn, _device(device), shard)
-    except ValueError as e:  # same wording as the reference (deferred_init.py:110-113)
-        raise ValueError(f"{e} (a tensor of the module has already been materialized)") from None
+    # (a ValueError raised while a tensor is materialised comes back as the reference words it,
+    # deferred_init.py:110-113: "'<key>' has already been materialized."; others pass unchanged)
+    _C.materialize_module(module, buffers_only, check_fn, _device(device), shard)
 
 
 def plan_report(module: Module) -> Dict[str, Dict[str, object]]:
