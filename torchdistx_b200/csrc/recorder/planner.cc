@@ -76,6 +76,12 @@ struct Sym {
   // stream and arithmetic (TDX_ALGO_WIDE32) so that the result IS `fp32_tensor.to(dtype)`.
   bool wide = false;
   bool src_noround = false;  // the generated value feeds fp32 epilogue steps before the cast
+  // `wide` exists to keep the 16-bit tensor equal to `fp32_source.to(dtype)` when BOTH get
+  // materialised.  If nothing can ever ask for the fp32 source (`module.to(torch.bfloat16)` rebinds
+  // every parameter to its cast and drops the fp32 tensor), the equality is unobservable and the
+  // tensor takes the native 16-bit stream -- same distribution, the fast kernel (wide_observable()).
+  uint32_t wide_src_storage = kNoValue;  // the storage the RNG op wrote (and the cast read), if that simple
+  uint32_t wide_cast_op = kNoValue;
   bool rng() const { return src == Uniform || src == Normal; }
 };
 
@@ -90,7 +96,26 @@ struct Seg {
 struct RngPass {
   uint32_t op;     // tape op
   int64_t numel;   // of the tensor it ran on: what it consumes of the generator's offset
+  uint32_t slot;   // Tape::rng entry of the op
 };
+
+size_t find_arg(const TapeOp& op, const char* name);
+
+// The Tape::rng entry of an RNG op (made on first sight).
+uint32_t rng_slot_of(Tape& tape, uint32_t op_idx) {
+  TapeOp& op = tape.ops[op_idx];
+  if (op.rng_slot == kNoValue) {
+    RngSlot s;
+    s.op = op_idx;
+    if (op.handle) {
+      const size_t pos = find_arg(op, "generator");
+      s.explicit_generator = pos != static_cast<size_t>(-1) && pos < op.args.size() && op.args[pos].isGenerator();
+    }
+    op.rng_slot = static_cast<uint32_t>(tape.rng.size());
+    tape.rng.push_back(s);
+  }
+  return op.rng_slot;
+}
 
 struct State {
   bool opaque = true;
@@ -358,7 +383,7 @@ void transition(Tape& tape, uint32_t op_idx, uint32_t S, State& st) {
       sy.rng_op = op_idx;
       st.rng_chain.clear();
       fresh(std::move(sy));
-      st.rng_chain.push_back(RngPass{op_idx, out.numel});
+      st.rng_chain.push_back(RngPass{op_idx, out.numel, rng_slot_of(tape, op_idx)});
       return;
     }
     case OpKind::Alias:
@@ -401,7 +426,7 @@ void transition(Tape& tape, uint32_t op_idx, uint32_t S, State& st) {
       }
       sy.rng_op = op_idx;
       overwrite(st, b, e, std::move(sy), b);
-      st.rng_chain.push_back(RngPass{op_idx, out.numel});
+      st.rng_chain.push_back(RngPass{op_idx, out.numel, rng_slot_of(tape, op_idx)});
       return;
     }
     if (op.kind == OpKind::FillInplace || op.kind == OpKind::ZeroInplace) {
@@ -520,6 +545,15 @@ void transition(Tape& tape, uint32_t op_idx, uint32_t S, State& st) {
           return;
         }
         sy.wide = true;
+        {
+          bool direct = false;  // did the RNG op write the very storage this cast reads?
+          for (uint32_t ov : tape.ops[sy.rng_op].outputs)
+            direct |= ov != kNoValue && tape.values[ov].storage == in.storage;
+          if (direct) {
+            sy.wide_src_storage = in.storage;
+            sy.wide_cast_op = op_idx;
+          }
+        }
         // everything before the cast ran in fp32; the cast itself is the rounding of the last
         // pre-cast step (or of the generated value, if there was none)
         sy.src_noround = !sy.epi.empty();
@@ -543,6 +577,27 @@ void transition(Tape& tape, uint32_t op_idx, uint32_t S, State& st) {
     return;
   }
   st = make_opaque();
+}
+
+// Can anything still observe the fp32 tensor a `wide` segment was cast from?  Not if no fake tensor
+// names its storage any more, nothing of it has been materialised, and the only ops that ever
+// touched it are its own writers and the cast.
+bool wide_observable(const Tape& tape, const Sym& sy) {
+  if (!sy.wide) return false;
+  if (sy.wide_src_storage == kNoValue) return true;
+  const StorageInfo& a = tape.storages[sy.wide_src_storage];
+  if (a.live > 0 || a.fused_done || a.replayed) return true;
+  for (uint32_t oi : a.touching_ops) {
+    if (oi == sy.wide_cast_op) continue;
+    const TapeOp& op = tape.ops[oi];
+    if (op.kind == OpKind::HookSetData) continue;  // `p.data = cast`: names the old storage, never reads it
+    bool writes = false;
+    for (uint32_t v : op.outputs) writes |= v != kNoValue && tape.values[v].storage == sy.wide_src_storage;
+    bool produces = false;  // (metadata queries such as _has_compatible_shallow_copy_type yield no tensor)
+    for (uint32_t v : op.outputs) produces |= v != kNoValue;
+    if (!writes && produces) return true;  // another reader whose result could be asked for
+  }
+  return false;
 }
 
 bool is_pure_alias(OpKind k) {
@@ -587,9 +642,23 @@ State eval_storage(Tape& tape, uint32_t S, uint32_t upto) {
 
 }  // namespace
 
-// What analyze_tape leaves on a storage.
+// What analyze_tape leaves on a storage: the symbolic state, and -- for the states the kernels can
+// run -- the same thing laid out for the materialise call, which then touches this block, the
+// value's geometry and two RNG slots per tensor and nothing else of the recording (the recording is
+// cold in the caches by the time a model is materialised: every line touched is ~100 ns).
+struct FastSeg {
+  int64_t begin = 0, end = 0, origin = 0;
+  uint32_t rng_slot = kNoValue;  // kNoValue: a constant segment
+  bool wide = false;
+  const Sym* sym = nullptr;      // (into StorageTemplate::st) for the rare questions: wide_observable
+  TdxInitDesc proto;             // everything but dst / elem_begin / elem_count / seed / offset
+};
 struct StorageTemplate {
   State st;
+  bool fast = false;
+  uint8_t isz = 0;
+  int64_t numel = 0;
+  c10::SmallVector<FastSeg, 1> segs;  // Uninit segments are left out
 };
 
 namespace {
@@ -803,10 +872,11 @@ struct GenCache {
 
 // Gives an RNG op its Philox stream id (once) and advances the generator, so that replaying in
 // the same order with the same seed reproduces the same tensors, dead passes included.
-void assign_rng(TapeOp& op, int64_t numel, c10::Device device, GenCache& cache) {
-  if (op.rng_assigned) return;
+void assign_rng(Tape& tape, RngSlot& slot, int64_t numel, c10::Device device, GenCache& cache) {
+  if (slot.assigned) return;
   at::Generator gen;
-  if (op.handle) {
+  if (slot.explicit_generator) {
+    const TapeOp& op = tape.ops[slot.op];
     const size_t pos = find_arg(op, "generator");
     if (pos != static_cast<size_t>(-1) && op.args[pos].isGenerator()) gen = op.args[pos].toGenerator();
   }
@@ -814,18 +884,18 @@ void assign_rng(TapeOp& op, int64_t numel, c10::Device device, GenCache& cache) 
   TORCH_CHECK(gen.device().type() == device.type(), "Expected a '", device.type(),
               "' device type for generator but found '", gen.device().type(), "'");
   GenCache::Entry& e = cache.get(gen);
-  op.rng_seed = e.seed;
-  op.rng_offset = e.offset;
+  slot.seed = e.seed;
+  slot.offset = e.offset;
   // consumption is a function of the GLOBAL element count only: shard-invariant by construction
   const uint64_t blocks = (static_cast<uint64_t>(numel) + 3) / 4;
   e.offset += ((blocks + 3) / 4) * 4 + 4;
   e.dirty = true;
-  op.rng_assigned = true;
+  slot.assigned = true;
 }
 
 struct ShardGeom {
   int64_t begin = 0, count = 0;
-  std::vector<int64_t> sizes;
+  c10::SmallVector<int64_t, 4> sizes;
 };
 
 ShardGeom shard_of(const ValueInfo& v, const std::optional<ShardSpec>& shard) {
@@ -854,6 +924,68 @@ at::Tensor alias_of(const at::Tensor& base, const ValueInfo& v, bool first) {
   at::Tensor t = base.detach();
   if (!same) t.as_strided_(v.sizes, v.strides, v.storage_offset);
   return t;
+}
+
+// Lays a state out for emission (StorageTemplate's fast form).  false: some segment is not
+// expressible as a descriptor.  `may_sync`: a constant that only exists as a (device) tensor may be
+// read back (the materialise path; never the analysis at the end of the recording).
+bool build_fast(const Tape& tape, const StorageInfo& si, StorageTemplate& t, bool may_sync) {
+  (void)tape;
+  t.fast = false;
+  t.segs.clear();
+  const State& st = t.st;
+  if (st.opaque) return false;
+  const size_t isz = c10::elementSize(st.dtype);
+  if (isz == 0 || si.nbytes % isz) return false;
+  const int64_t numel = static_cast<int64_t>(si.nbytes / isz);
+  if (numel == 0 || st.segs.empty() || st.segs.back().end != numel) return false;
+  for (const Seg& sg : st.segs) {
+    const Sym& sy = sg.st;
+    if (sy.src == Sym::Uninit) continue;
+    FastSeg f;
+    f.begin = sg.begin;
+    f.end = sg.end;
+    f.origin = sg.origin;
+    f.sym = &sy;
+    TdxInitDesc& d = f.proto;
+    std::memset(&d, 0, sizeof(d));
+    if (sy.src == Sym::Const) {
+      if (!(isz == 1 || isz == 2 || isz == 4 || isz == 8)) return false;
+      d.src = TDX_SRC_CONST;
+      d.dtype = isz == 1 ? TDX_RAW8 : isz == 2 ? TDX_RAW16 : isz == 4 ? TDX_RAW32 : TDX_RAW64;
+      unsigned char pat[16], one[16];
+      size_t got = 0;
+      if (!(sy.has_scalar && scalar_bits(sy.cscalar, st.dtype, one, &got) && got == isz)) {
+        if (!may_sync) return false;
+        Sym tmp = sy;
+        ensure_cval(tmp, st.dtype);
+        if (!tmp.cval.defined()) return false;
+        NoInterception guard;
+        std::memcpy(one, tmp.cval.cpu().contiguous().data_ptr(), isz);
+      }
+      for (size_t i = 0; i < 16; i += isz) std::memcpy(pat + i, one, isz);
+      std::memcpy(d.fill_bits, pat, 16);
+    } else {
+      if (tdx_dtype_of(st.dtype) < 0) return false;
+      d.src = sy.src == Sym::Uniform ? TDX_SRC_UNIFORM : TDX_SRC_NORMAL;
+      d.dtype = static_cast<uint8_t>(tdx_dtype_of(st.dtype));
+      d.p0 = sy.p0;
+      d.p1 = sy.p1;
+      d.n_epi = static_cast<uint8_t>(sy.epi.size());
+      for (size_t i = 0; i < sy.epi.size(); ++i) d.epi[i] = sy.epi[i];
+      if (sy.src_noround) d.reserved |= TDX_FLAG_SRC_NOROUND;
+      f.wide = sy.wide;
+      f.rng_slot = kNoValue;
+      for (const RngPass& r : st.rng_chain)
+        if (r.op == sy.rng_op) f.rng_slot = r.slot;
+      if (f.rng_slot == kNoValue) return false;
+    }
+    t.segs.push_back(std::move(f));
+  }
+  t.isz = static_cast<uint8_t>(isz);
+  t.numel = numel;
+  t.fast = true;
+  return true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -897,12 +1029,21 @@ struct Engine {
     return vi.real;
   }
 
-  c10::Device target_device(c10::Device recorded) const { return opts.device ? *opts.device : recorded; }
+  c10::Device target_device(c10::Device recorded) {
+    c10::Device d = opts.device ? *opts.device : recorded;
+    if (d.is_cuda() && !d.has_index()) {  // "cuda" = the current device, asked for once per call
+      if (current_cuda < 0) current_cuda = c10::cuda::current_device();
+      d = c10::Device(c10::kCUDA, current_cuda);
+    }
+    return d;
+  }
+  c10::DeviceIndex current_cuda = -1;
 
   void collect_storage(Tape& tape, uint32_t S, uint32_t upto, std::vector<uint8_t>& mark,
                        std::vector<uint32_t>& visited_upto) {
     if (visited_upto[S] >= upto) return;
     visited_upto[S] = upto;
+    if (tape.storages[S].fused_done) return;  // its content comes from the kernels (real_of): nothing to replay
     const auto& touching = tape.storages[S].touching_ops;
     uint32_t last_writer = kNoValue;
     for (uint32_t oi : touching) {
@@ -1006,55 +1147,49 @@ struct Engine {
     g_stats.generic_ops++;
   }
 
-  // Symbolic state of a storage: what analyze_tape left on it, or a fresh evaluation.
-  const State* state_of(Tape& tape, uint32_t S, c10::Device dev, State& scratch) {
-    const StorageInfo& si = tape.storages[S];
-    if (si.tmpl) {
-      g_stats.template_hits++;
-      return &si.tmpl->st;
-    }
-    struct FoldOn {  // constants fold with the target device's arithmetic
-      c10::Device prev = g_fold_device;
-      explicit FoldOn(c10::Device d) { g_fold_device = d; }
-      ~FoldOn() { g_fold_device = prev; }
-    } fold_on(dev);
-    c10::DeviceGuard fold_guard(dev);
-    const double t_eval = now_us();
-    scratch = eval_storage(tape, S, static_cast<uint32_t>(tape.ops.size()));
-    g_stats.eval_us += now_us() - t_eval;
-    return &scratch;
-  }
-
   // Builds the descriptors of storage S (or of one rank's dim-0 chunk of it) and the tensor they
   // write; `vi` is the value whose geometry the tensor takes (the parameter itself, normally).
   // Returns false if the program is not fusible.  `bytes_out`: algorithmic bytes of the descriptors.
   bool emit_fused(Tape& tape, uint32_t S, const ValueInfo& vi, const std::optional<ShardSpec>& shard,
                   at::Tensor& base_out, int64_t& bytes_out) {
-    StorageInfo& si = tape.storages[S];
+    const StorageInfo& si = tape.storages[S];
     const c10::Device dev = target_device(vi.device);
-    State scratch;
-    const State* stp = state_of(tape, S, dev, scratch);
-    if (stp->opaque) return false;
-    const State& st = *stp;
-    const size_t isz = c10::elementSize(st.dtype);
-    if (isz == 0 || si.nbytes % isz) return false;
-    const int64_t numel = static_cast<int64_t>(si.nbytes / isz);
-    if (numel == 0 || st.segs.empty() || st.segs.back().end != numel) return false;
-    for (const Seg& g : st.segs) {
-      if (g.st.rng() && tdx_dtype_of(st.dtype) < 0) return false;
-      if (g.st.src == Sym::Const && !(isz == 1 || isz == 2 || isz == 4 || isz == 8)) return false;
+    if (si.tmpl && si.tmpl->fast) {  // analysed when the recording ended: nothing to evaluate
+      g_stats.template_hits++;
+      return emit_from(tape, *si.tmpl, vi, shard, dev, base_out, bytes_out);
     }
+    if (si.tmpl && si.tmpl->st.opaque) return false;
+    StorageTemplate tmp;
+    if (si.tmpl) {
+      tmp.st = si.tmpl->st;  // (a constant whose bits need a tensor: rare)
+    } else {
+      struct FoldOn {  // constants fold with the target device's arithmetic
+        c10::Device prev = g_fold_device;
+        explicit FoldOn(c10::Device d) { g_fold_device = d; }
+        ~FoldOn() { g_fold_device = prev; }
+      } fold_on(dev);
+      c10::DeviceGuard fold_guard(dev);
+      const double t_eval = now_us();
+      tmp.st = eval_storage(tape, S, static_cast<uint32_t>(tape.ops.size()));
+      g_stats.eval_us += now_us() - t_eval;
+    }
+    if (!build_fast(tape, si, tmp, /*may_sync=*/true)) return false;
+    return emit_from(tape, tmp, vi, shard, dev, base_out, bytes_out);
+  }
 
+  bool emit_from(Tape& tape, const StorageTemplate& t, const ValueInfo& vi, const std::optional<ShardSpec>& shard,
+                 c10::Device dev, at::Tensor& base_out, int64_t& bytes_out) {
+    const State& st = t.st;
+    const size_t isz = t.isz;
     // geometry of what this rank writes
     ShardGeom g;
     if (vi.covers_storage && vi.dtype == st.dtype) {
       g = shard_of(vi, shard);
     } else {
       g.begin = 0;
-      g.count = numel;
-      g.sizes = {numel};
+      g.count = t.numel;
+      g.sizes.assign(1, t.numel);
     }
-
     if (batch.device != dev) {
       batch.flush();
       batch.device = dev;
@@ -1065,53 +1200,31 @@ struct Engine {
 
     // every RNG pass on the chain consumes its slice of the stream, live or dead
     for (const RngPass& r : st.rng_chain) {
-      TapeOp& rop = tape.ops[r.op];
-      if (rop.rng_assigned) continue;
-      assign_rng(rop, r.numel, dev, gens);
+      RngSlot& slot = tape.rng[r.slot];
+      if (slot.assigned) continue;
+      assign_rng(tape, slot, r.numel, dev, gens);
       bool live = false;
-      for (const Seg& sg : st.segs) live |= sg.st.rng() && sg.st.rng_op == r.op;
+      for (const FastSeg& sg : t.segs) live |= sg.rng_slot == r.slot;
       if (!live) g_stats.elided_rng_ops++;
     }
 
     pend.first_desc = static_cast<uint32_t>(batch.descs.size());
     int64_t bytes = 0;
-    for (const Seg& sg : st.segs) {
+    for (const FastSeg& sg : t.segs) {
       const int64_t lo = std::max(sg.begin, g.begin), hi = std::min(sg.end, g.begin + g.count);
-      if (lo >= hi || sg.st.src == Sym::Uninit) continue;
-      const Sym& sy = sg.st;
-      TdxInitDesc d;
-      std::memset(&d, 0, sizeof(d));
+      if (lo >= hi) continue;
+      batch.descs.push_back(sg.proto);
+      TdxInitDesc& d = batch.descs.back();
       // byte offset inside the output until the submission gives the output its address
       d.dst = reinterpret_cast<void*>(static_cast<uintptr_t>(lo - g.begin) * isz);
       d.elem_count = static_cast<uint64_t>(hi - lo);
-      if (sy.src == Sym::Const) {
-        d.src = TDX_SRC_CONST;
-        d.dtype = isz == 1 ? TDX_RAW8 : isz == 2 ? TDX_RAW16 : isz == 4 ? TDX_RAW32 : TDX_RAW64;
-        unsigned char pat[16], one[16];
-        size_t got = 0;
-        if (!(sy.has_scalar && scalar_bits(sy.cscalar, st.dtype, one, &got) && got == isz)) {
-          Sym tmp = sy;
-          ensure_cval(tmp, st.dtype);
-          NoInterception guard;
-          std::memcpy(one, tmp.cval.cpu().contiguous().data_ptr(), isz);
-        }
-        for (size_t i = 0; i < 16; i += isz) std::memcpy(pat + i, one, isz);
-        std::memcpy(d.fill_bits, pat, 16);
-      } else {
-        d.src = sy.src == Sym::Uniform ? TDX_SRC_UNIFORM : TDX_SRC_NORMAL;
-        d.dtype = static_cast<uint8_t>(tdx_dtype_of(st.dtype));
+      if (sg.rng_slot != kNoValue) {
         d.elem_begin = static_cast<uint64_t>(lo - sg.origin);  // index in the tensor the RNG op ran on
-        d.p0 = sy.p0;
-        d.p1 = sy.p1;
-        const TapeOp& r = tape.ops[sy.rng_op];
-        d.philox_seed = r.rng_seed;
-        d.philox_offset = r.rng_offset;
-        d.n_epi = static_cast<uint8_t>(sy.epi.size());
-        for (size_t i = 0; i < sy.epi.size(); ++i) d.epi[i] = sy.epi[i];
-        if (sy.wide) d.algo = TDX_ALGO_WIDE32;
-        if (sy.src_noround) d.reserved |= TDX_FLAG_SRC_NOROUND;
+        const RngSlot& r = tape.rng[sg.rng_slot];
+        d.philox_seed = r.seed;
+        d.philox_offset = r.offset;
+        if (sg.wide && wide_observable(tape, *sg.sym)) d.algo = TDX_ALGO_WIDE32;
       }
-      batch.descs.push_back(d);
       bytes += (hi - lo) * static_cast<int64_t>(isz);
     }
     pend.n_desc = static_cast<uint32_t>(batch.descs.size()) - pend.first_desc;
@@ -1138,16 +1251,8 @@ struct Engine {
     si.base_is_shard = sharded;
     si.fused_done = true;
     si.fused_epoch = batch.epoch;
-    for (uint32_t oi : si.touching_ops) {
-      TapeOp& op = tape.ops[oi];
-      if (op.done) continue;
-      bool writes = false;
-      for (uint32_t ov : op.outputs) writes |= (ov != kNoValue && tape.values[ov].storage == S);
-      if (writes) {
-        op.done = true;
-        op.tls.reset();
-      }
-    }
+    // (the storage's writer ops are not marked done one by one: `fused_done` stops every walk over
+    // them -- collect_storage, eval_storage's callers -- and costs no cache line per op)
     g_stats.fused_tensors++;
     batch.note(bytes);  // may submit what has accumulated so far
     return true;
@@ -1572,7 +1677,7 @@ PlanInfo plan_info(const at::Tensor& fake) {
   const ValueInfo& vi = tape.values[rec->value];
   info.dtype = c10::toString(vi.dtype);
   info.numel = vi.numel;
-  info.sizes = vi.sizes;
+  info.sizes.assign(vi.sizes.begin(), vi.sizes.end());
   info.device = vi.device.str();
   info.requires_grad = fake.is_leaf() && fake.requires_grad();
   const StorageInfo& si = tape.storages[vi.storage];
@@ -1614,12 +1719,12 @@ PlanInfo plan_info(const at::Tensor& fake) {
   info.p1 = main->st.p1;
   info.n_epilogue = static_cast<int>(main->st.epi.size());
   info.rng_ops = static_cast<int>(st.rng_chain.size());
-  info.wide = main->st.wide;
+  info.wide = wide_observable(tape, main->st);
   info.src_noround = main->st.src_noround;
   for (const TdxEpiStep& e : main->st.epi) info.epilogue.emplace_back(static_cast<int>(e.op), e.a, e.b);
   for (const RngPass& r : st.rng_chain) {
     info.rng_numels.push_back(r.numel);
-    info.rng_op_ids.push_back(static_cast<int64_t>(r.op));
+    info.rng_op_ids.push_back(static_cast<int64_t>((tape.uid << 32) | r.op));
   }
   for (const Seg& g : st.segs) {
     PlanSegment ps;
@@ -1629,7 +1734,7 @@ PlanInfo plan_info(const at::Tensor& fake) {
     ps.source = names[g.st.src];
     ps.p0 = g.st.p0;
     ps.p1 = g.st.p1;
-    ps.wide = g.st.wide;
+    ps.wide = wide_observable(tape, g.st);
     ps.src_noround = g.st.src_noround;
     for (const TdxEpiStep& e : g.st.epi) ps.epilogue.emplace_back(static_cast<int>(e.op), e.a, e.b);
     if (g.st.rng()) {
@@ -1674,6 +1779,7 @@ void analyze_tape(Tape& tape) noexcept {
       if (g_analysis_deferred) continue;
       auto t = std::make_shared<StorageTemplate>();
       t->st = std::move(st);
+      build_fast(tape, si, *t, /*may_sync=*/false);
       si.tmpl = std::move(t);
     } catch (...) {
       // (e.g. uniform_ with from > to: the error is raised when the tensor is materialised)

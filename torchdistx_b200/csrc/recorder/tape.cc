@@ -6,6 +6,7 @@
 #include <c10/core/impl/LocalDispatchKeySet.h>
 #include <torch/library.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "fake_tensor.h"
@@ -186,8 +187,8 @@ ValueInfo describe(const at::Tensor& fake, uint32_t op, uint32_t storage, size_t
   v.storage = storage;
   v.dtype = fake.scalar_type();
   v.device = fake.device();
-  v.sizes = fake.sizes().vec();
-  v.strides = fake.strides().vec();
+  v.sizes.assign(fake.sizes().begin(), fake.sizes().end());
+  v.strides.assign(fake.strides().begin(), fake.strides().end());
   v.storage_offset = fake.storage_offset();
   v.numel = fake.numel();
   v.covers_storage = fake.is_contiguous() && v.storage_offset == 0 &&
@@ -203,7 +204,11 @@ void touch(Tape& tape, uint32_t storage, uint32_t op) {
 // Appends one record.  `frame` is the frozen argument frame, `outputs` the live result stack.
 void append(std::optional<OperatorHandle> handle, OpKind kind, Stack frame, size_t nargs,
             Stack& outputs, size_t nret) {
-  if (!tls_tape) tls_tape = std::make_shared<Tape>();
+  if (!tls_tape) {
+    static std::atomic<uint64_t> next_uid{1};
+    tls_tape = std::make_shared<Tape>();
+    tls_tape->uid = next_uid.fetch_add(1);
+  }
   Tape& tape = *tls_tape;
   const uint32_t op_idx = static_cast<uint32_t>(tape.ops.size());
   tape.ops.emplace_back();
@@ -249,8 +254,7 @@ void append(std::optional<OperatorHandle> handle, OpKind kind, Stack frame, size
     auto* impl = fake_impl(t);
     if (!impl->record()) impl->set_record(std::make_shared<TensorRecord>());
     // in-place results keep their tensor (and record); the record now names the new value
-    impl->record()->tape = tls_tape;
-    impl->record()->value = vid;
+    impl->record()->point_at(tls_tape, vid);
   });
 
   // A generic, non-mutating op whose single fake result lives on the storage of its first fake

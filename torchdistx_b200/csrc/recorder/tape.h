@@ -24,6 +24,7 @@
 #include <ATen/core/dispatch/Dispatcher.h>
 #include <ATen/core/ivalue.h>
 #include <c10/core/Storage.h>
+#include <c10/util/SmallVector.h>
 
 #include <cstdint>
 #include <memory>
@@ -63,7 +64,7 @@ struct ValueInfo {
   uint32_t storage = 0;   // index into Tape::storages
   c10::ScalarType dtype = c10::ScalarType::Undefined;
   c10::Device device = c10::Device(c10::kCPU);
-  std::vector<int64_t> sizes, strides;
+  c10::SmallVector<int64_t, 4> sizes, strides;  // inline: materialising reads them on a cold cache
   int64_t storage_offset = 0;
   int64_t numel = 0;
   bool covers_storage = false;  // contiguous, offset 0, numel*itemsize == storage bytes
@@ -83,6 +84,7 @@ struct StorageInfo {
   bool base_taken = false;  // `base` itself has been handed out as some value's tensor
   bool base_is_shard = false;  // `base` holds one rank's dim-0 chunk only (shard=(r, W), W > 1)
   bool replayed = false;    // an op writing this storage went through generic replay: never fuse it afterwards
+  int32_t live = 0;         // fake tensors (TensorRecords) that currently name a value on this storage
   uint64_t fused_epoch = 0;  // submission epoch of the batch that holds (held) its descriptor
   at::Tensor full_base;   // unsharded copy built for a reader of a storage whose `base` is a shard
   // Symbolic state of the storage, computed once when the outermost deferred_init scope ends
@@ -112,13 +114,23 @@ struct TapeOp {
   std::shared_ptr<const at::ThreadLocalState> tls;
   std::vector<c10::IValue> results;     // real outputs after generic replay
   bool done = false;
-  // RNG ops on the fused path: the Philox stream id they were given (once, in materialise order)
-  bool rng_assigned = false;
-  uint64_t rng_seed = 0, rng_offset = 0;
+  uint32_t rng_slot = kNoValue;  // RNG ops the planner has met: index into Tape::rng
   const char* name() const;
 };
 
+// RNG ops on the fused path: the Philox stream id they were given (once, in materialise order).
+// Kept in a dense array of its own: a materialise call touches two of these per tensor and nothing
+// else of the ops.
+struct RngSlot {
+  uint32_t op = kNoValue;
+  bool assigned = false;
+  bool explicit_generator = false;  // the op was recorded with a `generator=` argument
+  uint64_t seed = 0, offset = 0;
+};
+
 struct Tape : std::enable_shared_from_this<Tape> {
+  uint64_t uid = 0;  // process-wide number of the recording (makes op ids unique across recordings)
+  std::vector<RngSlot> rng;
   std::vector<TapeOp> ops;
   std::vector<ValueInfo> values;
   std::vector<StorageInfo> storages;
@@ -130,6 +142,20 @@ struct Tape : std::enable_shared_from_this<Tape> {
 struct TensorRecord {
   std::shared_ptr<Tape> tape;
   uint32_t value = kNoValue;  // the tensor's CURRENT value (updated by in-place ops)
+  // Re-points the record; keeps StorageInfo::live (how many fake tensors can still ask for a
+  // storage's content) in step.
+  void point_at(std::shared_ptr<Tape> t, uint32_t v) {
+    if (tape && value != kNoValue) tape->storages[tape->values[value].storage].live--;
+    tape = std::move(t);
+    value = v;
+    if (tape && value != kNoValue) tape->storages[tape->values[value].storage].live++;
+  }
+  TensorRecord() = default;
+  TensorRecord(const TensorRecord&) = delete;
+  TensorRecord& operator=(const TensorRecord&) = delete;
+  ~TensorRecord() {
+    if (tape && value != kNoValue) tape->storages[tape->values[value].storage].live--;
+  }
 };
 
 // ---- runtime API (mirrors reference src/cc/torchdistx/deferred_init.h:25-37) -----------------

@@ -7,7 +7,7 @@ re-running the Python constructor under ``deferred_init``.  Here the planner's v
 is plain data (source, parameters, epilogue, RNG passes on the chain), so it can be written to
 disk and replayed later with nothing but the C ABI:
 
-    plan = InitPlan.from_module(deferred_model)        # no allocation, works without a GPU
+    plan = InitPlan.from_module(deferred_model)        # works without a GPU
     plan.save("llama3-8b.init.json")
     ...
     tensors = InitPlan.load("llama3-8b.init.json").materialize(device="cuda", shard=(rank, world))
@@ -16,7 +16,10 @@ Under the same generator state ``InitPlan.materialize`` produces exactly the bit
 ``materialize_module`` produces (tests/test_plan_gpu.py): same traversal order, same Philox
 offset bookkeeping, same kernels.  Tensors whose program is not fusible (tiny ``arange``-style
 buffers such as rotary ``inv_freq``) are evaluated once when the plan is built and stored by
-value (refused above ``max_embedded_bytes``).
+value (refused above ``max_embedded_bytes``).  Building a plan therefore MATERIALISES those few
+tensors on the recording (on their recorded device); it does so under a forked RNG state, so the
+caller's generators are left as they were, and it refuses programs that draw random numbers
+(embedding one sample would freeze it).
 """
 from __future__ import annotations
 
@@ -38,7 +41,7 @@ _DTYPES = {
 _TDX_DTYPE = {torch.float32: _cabi.TDX_F32, torch.bfloat16: _cabi.TDX_BF16, torch.float16: _cabi.TDX_F16}
 _RAW = {1: _cabi.TDX_RAW8, 2: _cabi.TDX_RAW16, 4: _cabi.TDX_RAW32, 8: _cabi.TDX_RAW64}
 _DTYPE_NAMES = {v: k for k, v in _DTYPES.items()}
-FORMAT = "torchdistx_b200.InitPlan/1"
+FORMAT = "torchdistx_b200.InitPlan/2"
 
 
 def offset_increment(numel: int) -> int:
@@ -64,6 +67,24 @@ class PlanEntry:
     alias_of: Optional[str] = None  # tied parameters: same tensor as an earlier entry
     wide: bool = False  # fp32 source cast to a 16-bit dtype (TDX_ALGO_WIDE32)
     src_noround: bool = False  # TDX_FLAG_SRC_NOROUND
+    # Identity of every RNG pass of `rng_numels` inside the plan: a deepcopy / clone shares its
+    # source's passes (the copy is bit-identical and consumes nothing of the generator).
+    rng_ids: List[int] = field(default_factory=list)
+    # The tensor as disjoint element ranges, each with its own source (`w.normal_();
+    # w[padding_idx].zero_()` is three); empty = one segment described by the fields above.
+    # {"begin", "end", "origin", "source", "p0", "p1", "epilogue", "const_bytes", "wide",
+    #  "src_noround", "rng_pass" (index into rng_numels, -1: none)}
+    segments: List[dict] = field(default_factory=list)
+
+    def segment_list(self) -> List[dict]:
+        if self.segments:
+            return self.segments
+        numel = 1
+        for d in self.sizes:
+            numel *= d
+        return [dict(begin=0, end=numel, origin=0, source=self.source, p0=self.p0, p1=self.p1,
+                     epilogue=self.epilogue, const_bytes=self.const_bytes, wide=self.wide,
+                     src_noround=self.src_noround, rng_pass=len(self.rng_numels) - 1)]
 
 
 class InitPlan:
@@ -95,14 +116,32 @@ class InitPlan:
                     seen[id(t)] = name
                     info = dict(_C.plan_info(t))
                     if info["source"] in ("const", "uniform", "normal", "uninit") and info["fusible"]:
+                        segs = [dict(begin=g["begin"], end=g["end"], origin=g["origin"], source=g["source"],
+                                     p0=g["p0"], p1=g["p1"], epilogue=[tuple(e) for e in g["epilogue"]],
+                                     const_bytes=base64.b64encode(g["const_bytes"]).decode(),
+                                     wide=bool(g["wide"]), src_noround=bool(g["src_noround"]),
+                                     rng_pass=int(g["rng_pass"])) for g in info["segments"]]
                         entries.append(PlanEntry(
                             name, kind, list(info["sizes"]), info["dtype"], info["source"], info["p0"], info["p1"],
                             [tuple(e) for e in info["epilogue"]],
                             base64.b64encode(info["const_bytes"]).decode(), "", list(info["rng_numels"]),
-                            bool(info["requires_grad"]), None, bool(info["wide"]), bool(info["src_noround"])))
+                            bool(info["requires_grad"]), None, bool(info["wide"]), bool(info["src_noround"]),
+                            [int(i) for i in info["rng_op_ids"]], segs if len(segs) > 1 else []))
                         continue
-                    # not fusible (or already real): evaluate now and store by value
-                    real = materialize_tensor(t) if info["deferred"] else t
+                    # not fusible (or already real): evaluate now and store by value -- under a forked
+                    # RNG state, and never a program that draws random numbers (one frozen sample)
+                    if info["deferred"]:
+                        if any(n.startswith(("aten::rand", "aten::normal", "aten::uniform", "aten::bernoulli",
+                                             "aten::multinomial", "aten::dropout"))
+                               for n in (h.split(" ")[0] for h in _C.storage_history(t))):
+                            raise ValueError(
+                                f"'{name}' has a random initialisation program the planner cannot fold "
+                                f"(first unfusable op: {info['first_unfusable_op'] or 'n/a'}); a plan cannot embed it")
+                        devs = [torch.device(info["device"])] if info["device"].startswith("cuda") and torch.cuda.is_available() else []
+                        with torch.random.fork_rng(devices=devs):
+                            real = materialize_tensor(t)
+                    else:
+                        real = t
                     nbytes = real.numel() * real.element_size()
                     if nbytes > max_embedded_bytes:
                         raise ValueError(
@@ -125,11 +164,13 @@ class InitPlan:
     def load(cls, path: str) -> "InitPlan":
         with open(path) as f:
             doc = json.load(f)
-        if doc.get("format") != FORMAT:
+        if doc.get("format") not in (FORMAT, "torchdistx_b200.InitPlan/1"):
             raise ValueError(f"{path}: not an {FORMAT} file")
         entries = []
         for d in doc["entries"]:
             d["epilogue"] = [tuple(e) for e in d.get("epilogue", [])]
+            for g in d.get("segments", []):
+                g["epilogue"] = [tuple(e) for e in g.get("epilogue", [])]
             entries.append(PlanEntry(**d))
         return cls(entries)
 
@@ -167,6 +208,7 @@ class InitPlan:
         seed, offset = gen.initial_seed(), gen.get_offset()
         out: Dict[str, torch.Tensor] = {}
         descs = []
+        assigned: Dict[int, int] = {}  # RNG pass identity -> the offset it was given
         with torch.cuda.device(device):
             for e in self.entries:
                 if e.source == "alias":
@@ -203,24 +245,36 @@ class InitPlan:
                     t = target
                 else:
                     t = torch.empty(sizes, dtype=dtype, device=device)
-                # every RNG pass on the chain takes its slice of the stream; the last one is live
-                live_offset = offset
-                for n in e.rng_numels:
-                    live_offset = offset
+                # every RNG pass on the chain takes its slice of the stream, once per pass identity (a
+                # clone names its source's passes again: same stream, nothing consumed)
+                ids = e.rng_ids if e.rng_ids else [None] * len(e.rng_numels)
+                pass_offset = []
+                for pid, n in zip(ids, e.rng_numels):
+                    if pid is not None and pid in assigned:
+                        pass_offset.append(assigned[pid])
+                        continue
+                    pass_offset.append(offset)
+                    if pid is not None:
+                        assigned[pid] = offset
                     offset += offset_increment(n)
-                if e.source != "uninit" and count > 0:
-                    if e.source == "const":
-                        isz = t.element_size()
+                isz = t.element_size()
+                for g in e.segment_list():
+                    lo, hi = max(g["begin"], begin), min(g["end"], begin + count)
+                    if lo >= hi or g["source"] == "uninit":
+                        continue
+                    dst = t.data_ptr() + (lo - begin) * isz
+                    if g["source"] == "const":
                         descs.append(_cabi.make_desc(
-                            t.data_ptr(), dtype=_RAW[isz], src=_cabi.TDX_SRC_CONST, elem_count=count,
-                            fill_bits=int.from_bytes(base64.b64decode(e.const_bytes), "little"), fill_itemsize=isz))
+                            dst, dtype=_RAW[isz], src=_cabi.TDX_SRC_CONST, elem_count=hi - lo,
+                            fill_bits=int.from_bytes(base64.b64decode(g["const_bytes"]), "little"), fill_itemsize=isz))
                     else:
                         descs.append(_cabi.make_desc(
-                            t.data_ptr(), dtype=_TDX_DTYPE[dtype],
-                            src=_cabi.TDX_SRC_UNIFORM if e.source == "uniform" else _cabi.TDX_SRC_NORMAL,
-                            elem_begin=begin, elem_count=count, seed=seed, offset=live_offset, p0=e.p0, p1=e.p1,
-                            epi=e.epilogue, algo=_cabi.TDX_ALGO_WIDE32 if e.wide else 0,
-                            flags=_cabi.TDX_FLAG_SRC_NOROUND if e.src_noround else 0))
+                            dst, dtype=_TDX_DTYPE[dtype],
+                            src=_cabi.TDX_SRC_UNIFORM if g["source"] == "uniform" else _cabi.TDX_SRC_NORMAL,
+                            elem_begin=lo - g["origin"], elem_count=hi - lo, seed=seed,
+                            offset=pass_offset[g["rng_pass"]], p0=g["p0"], p1=g["p1"],
+                            epi=g["epilogue"], algo=_cabi.TDX_ALGO_WIDE32 if g["wide"] else 0,
+                            flags=_cabi.TDX_FLAG_SRC_NOROUND if g["src_noround"] else 0))
                 out[e.name] = t if target is not None else _wrap(t, e)
             if descs:
                 ws_bytes = _cabi.prepare(descs)  # exactly what this table needs (not the ~1.6 MB upper bound)
