@@ -195,9 +195,49 @@ def run_reference_arm(a):
 
 
 # ---------------------------------------------------------------------------------------------
+# baseline B: the reference itself replaying on the GPU with stock ATen kernels
+# ---------------------------------------------------------------------------------------------
+GPU_REF_SNIPPET = r"""
+import json, sys, time, torch
+sys.path.insert(0, {root!r})
+from oracle import ref_torchdistx as R
+import bench
+torch.cuda.set_device({index})
+times, n = [], 0
+for i in range({reps}):
+    with torch.device('cuda:{index}'):
+        m = R.deferred_init(lambda: bench.build_model({model!r}))
+    n = sum(p.numel() for p in m.parameters())
+    torch.manual_seed(i); torch.cuda.synchronize()
+    t0 = time.perf_counter(); R.materialize_module(m); torch.cuda.synchronize(); times.append(time.perf_counter() - t0)
+    del m
+print(json.dumps({{"times": times, "params": n}}))
+"""
+
+
+def reference_on_gpu(model: str, index: int, reps: int = 3):
+    """`oracle/_ref` (the reference's own engine) with the model recorded for cuda: one dispatcher
+    call and one stock ATen kernel per recorded op, dead ops included (deferred_init.cc:218-220)."""
+    code = GPU_REF_SNIPPET.format(root=ROOT, model=model, index=index, reps=reps)
+    out = subprocess.run([sys.executable, "-c", code], check=True, capture_output=True, text=True, cwd=ROOT)
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+# ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
-def run_ours(a):
+def desc_bytes(C, d):
+    return d.elem_count * (4 if d.dtype in (C.TDX_F32, C.TDX_RAW32) else 8 if d.dtype == C.TDX_RAW64
+                           else 1 if d.dtype == C.TDX_RAW8 else 2)
+
+
+class Ctx:
+    """What every measurement of one run shares."""
+
+
+def measure_model(cx, model: str, steps: int, warmup: int, first_call: bool = False, roofline_only: bool = False):
+    """value / e2e / roofline of one model, the procedure of the module docstring.
+    `roofline_only` (for ncu): one materialize, then 3 + steps launches of the dominant kernel's plan."""
     import torch
     import torch.distributed as dist
 
@@ -206,27 +246,17 @@ def run_ours(a):
     from torchdistx_b200.deferred_init import (deferred_init, last_descriptors, last_materialize_stats,
                                                materialize_module)
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+    dev, world, rank, local, lib, stream = cx.dev, cx.world, cx.rank, cx.local, cx.lib, cx.stream
     shard = (rank, world) if world > 1 else None
-    lib = C.load()
-    stream = torch.cuda.current_stream().cuda_stream
-    dtype = MODELS[a.model][2]
+    dtype = MODELS[model][2]
+    res = {"model": model, "dtype": dtype}
 
     # ---- record K+W+1 zero-storage models (untimed) -----------------------------------------
     t0 = time.perf_counter()
-    n_models = 1 if a.roofline_only else a.warmup + a.steps + 1
-    fakes = [deferred_init(build_model, a.model) for _ in range(n_models)]
-    record_s = (time.perf_counter() - t0) / len(fakes)
-    n_params = sum(p.numel() for p in fakes[0].parameters())
-    n_tensors = len(list(fakes[0].parameters())) + len(list(fakes[0].buffers()))
+    fakes = [deferred_init(build_model, model) for _ in range(1 if roofline_only else warmup + steps + 1)]
+    res["record_s_per_model"] = (time.perf_counter() - t0) / len(fakes)
+    n_params = res["params"] = sum(p.numel() for p in fakes[0].parameters())
+    res["tensors"] = len(list(fakes[0].parameters())) + len(list(fakes[0].buffers()))
 
     def barrier():
         torch.cuda.synchronize()
@@ -242,97 +272,105 @@ def run_ours(a):
         return float(t.item())
 
     # ---- e2e: public API, H2D of descriptors + D2H of a result inside the timed region ---------
-    torch.manual_seed(1234)
-    parallel.sync_rng(dev)  # the one collective: 16 bytes, rank 0 -> all
     probe = torch.empty(32, dtype=torch.float32 if dtype == "fp32" else torch.bfloat16).pin_memory()
-
     last_name = list(dict(fakes[0].named_parameters()))[-1]  # looked up outside the timed region
-
     host_split = {"api_return_ms": 0.0, "sync_ms": 0.0, "n": 0, "on": False}
 
     def step(m):
         t0 = time.perf_counter()
         if world > 1:
-            parallel.sync_rng(dev)  # the path's one collective, once per materialize_module (16 B)
+            # the path's one collective (16 B broadcast) on the first call; afterwards the ranks'
+            # generators advance in lock step and the call returns without communicating
+            parallel.sync_rng(dev)
         materialize_module(m, device=dev, shard=shard)
         t1 = time.perf_counter()
         last = m.get_parameter(last_name)
         probe.copy_(last.detach().flatten()[:32], non_blocking=True)  # D2H read of the step's result
         torch.cuda.current_stream().synchronize()
         t2 = time.perf_counter()
-        # where the host was when the API returned vs when the GPU was done (diagnostic only)
         if host_split["on"]:
             host_split["api_return_ms"] += (t1 - t0) * 1e3
             host_split["sync_ms"] += (t2 - t0) * 1e3
             host_split["n"] += 1
 
-    e2e_ms, h2d = 0.0, 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    clk_e2e = ClockSampler(local, 100 if rank == 0 else 500)
-    for i in range(0 if a.roofline_only else a.warmup):
-        step(fakes[i])
+    for i in range(0 if roofline_only else warmup):
+        if i == 0 and first_call:
+            # the very first materialize_module of the process: CUDA module load, cold caching
+            # allocator (cudaMalloc), pinned staging buffers -- what a user who calls it once pays
+            barrier()
+            t0 = time.perf_counter()
+            step(fakes[i])
+            res["e2e_cold_ms"] = max_over_ranks((time.perf_counter() - t0) * 1e3)
+            res["cold_alloc_ms"] = last_materialize_stats().get("alloc_us", 0) / 1e3
+        else:
+            step(fakes[i])
         fakes[i] = None
-    st = last_materialize_stats() if not a.roofline_only else {"descriptors": 0}
-    h2d = int(st.get("upload_bytes", 0))  # plan images (descriptors, prefix sums, work lists) copied H2D per step
-    barrier()
-    if not a.roofline_only:
-        # Each step is timed on its own (events on the launching stream, bracketed by a
-        # synchronize); tearing down the previous step's model -- Python GC of ~500 modules and
-        # the recording, hundreds of allocator frees -- happens between the timed regions: it is
-        # not part of the API under test and would otherwise dominate small models.
-        total = 0.0
-        host_split["on"] = True
-        with clk_e2e:
-            for i in range(a.warmup, a.warmup + a.steps):
-                # Python's cyclic GC is collected before and switched off inside the timed step, as
-                # `timeit` does: a collection triggered by the ~600 objects a step creates walks the
-                # whole heap of THIS harness (a dozen recorded models), which is not the API's cost.
-                gc.collect()
-                gc.disable()
-                barrier()
-                e0.record()
-                step(fakes[i])
-                e1.record()
-                e1.synchronize()
-                gc.enable()
-                total += e0.elapsed_time(e1)
-                fakes[i] = None  # untimed: release the model before the next step allocates
-        e2e_ms = max_over_ranks(total / a.steps)
-    # ---- value: plan resident in HBM, kernels only ----------------------------------------------
-    model = fakes[-1]
-    materialize_module(model, device=dev, shard=shard)  # allocates the outputs we re-launch into
-    descs = last_descriptors()
     st = last_materialize_stats()
-    my_bytes = sum(d.elem_count * (4 if d.dtype in (C.TDX_F32, C.TDX_RAW32) else 8 if d.dtype == C.TDX_RAW64
-                                   else 1 if d.dtype == C.TDX_RAW8 else 2) for d in descs)
+    res["h2d"] = int(st.get("upload_bytes", 0))  # plan images (descriptors, prefix sums, work lists) per step
+    barrier()
+    # Each step is timed on its own (events on the launching stream, bracketed by a synchronize);
+    # tearing down the previous step's model -- Python GC of ~500 modules, hundreds of allocator
+    # frees -- happens between the timed regions: it is not part of the API under test.
+    total = 0.0
+    host_split["on"] = True
+    clk_e2e = ClockSampler(local, 100 if rank == 0 else 500)
+    with clk_e2e:
+        for i in range(*((0, 0) if roofline_only else (warmup, warmup + steps))):
+            # Python's cyclic GC is collected before and switched off inside the timed step, as
+            # `timeit` does: a collection triggered by the ~600 objects a step creates walks the
+            # whole heap of THIS harness (a dozen recorded models), which is not the API's cost.
+            gc.collect()
+            gc.disable()
+            barrier()
+            e0.record()
+            step(fakes[i])
+            e1.record()
+            e1.synchronize()
+            gc.enable()
+            total += e0.elapsed_time(e1)
+            fakes[i] = None  # untimed: release the model before the next step allocates
+    res["e2e_ms"] = max_over_ranks(total / steps) if not roofline_only else 0.0
+    res["clk_e2e"] = clk_e2e.summary()
+    res["host_split"] = {"api_return": round(host_split["api_return_ms"] / max(host_split["n"], 1), 3),
+                         "gpu_done": round(host_split["sync_ms"] / max(host_split["n"], 1), 3)}
+    if world > 1:
+        assert parallel.check_agreement(dev), "ranks disagree on the generator state after the timed steps"
+
+    # ---- value: plan resident in HBM, kernels only ----------------------------------------------
+    keep = fakes[-1]
+    materialize_module(keep, device=dev, shard=shard)  # allocates the outputs we re-launch into
+    descs = last_descriptors()
+    st = res["stats"] = last_materialize_stats()
+    res["descs"] = len(descs)
+    my_bytes = res["my_bytes"] = sum(desc_bytes(C, d) for d in descs)
     ws_bytes = lib.tdx_init_workspace_bytes(len(descs))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     plan = C.TdxPlan()
     C.check(lib.tdx_plan_upload(descs, len(descs), ws.data_ptr(), ws_bytes, stream, ctypes.byref(plan)))
     clk = ClockSampler(local, 20 if rank == 0 else 500)
-    ms, launches_per_step = 1.0, 0
-    if not a.roofline_only:
-        for _ in range(max(a.warmup, 3)):
+    res["ms"], res["launches_per_step"] = 1.0, 0
+    if not roofline_only:
+        for _ in range(max(warmup, 3)):
             C.check(lib.tdx_plan_launch(ctypes.byref(plan), ws.data_ptr(), stream))
-        launches_per_step = lib.tdx_last_launch_count()
+        res["launches_per_step"] = lib.tdx_last_launch_count()
         barrier()
         with clk:
             e0.record()
-            for _ in range(a.steps):
+            for _ in range(steps):
                 C.check(lib.tdx_plan_launch(ctypes.byref(plan), ws.data_ptr(), stream))
             e1.record()
             barrier()
-        ms = max_over_ranks(e0.elapsed_time(e1) / a.steps)
+        res["ms"] = max_over_ranks(e0.elapsed_time(e1) / steps)
+    res["clk"] = clk.summary()
 
     # ---- roofline of the dominant kernel (most bytes), timed alone with the same events ----------
     fam = {}
     for d in descs:
-        key = (d.src, d.dtype if d.src != C.TDX_SRC_CONST else -1)
-        fam.setdefault(key, []).append(d)
-    isz = lambda d: 4 if d.dtype in (C.TDX_F32, C.TDX_RAW32) else 8 if d.dtype == C.TDX_RAW64 else 1 if d.dtype == C.TDX_RAW8 else 2
-    dom_key = max(fam, key=lambda k: sum(d.elem_count * isz(d) for d in fam[k]))
+        fam.setdefault((d.src, d.dtype if d.src != C.TDX_SRC_CONST else -1), []).append(d)
+    dom_key = max(fam, key=lambda k: sum(desc_bytes(C, d) for d in fam[k]))
     dom = (C.TdxInitDesc * len(fam[dom_key]))(*fam[dom_key])
-    dom_bytes = sum(d.elem_count * isz(d) for d in dom)
+    dom_bytes = sum(desc_bytes(C, d) for d in dom)
     ws2 = torch.empty(lib.tdx_init_workspace_bytes(len(dom)), dtype=torch.uint8, device=dev)
     plan2 = C.TdxPlan()
     C.check(lib.tdx_plan_upload(dom, len(dom), ws2.data_ptr(), ws2.numel(), stream, ctypes.byref(plan2)))
@@ -340,31 +378,185 @@ def run_ours(a):
         C.check(lib.tdx_plan_launch(ctypes.byref(plan2), ws2.data_ptr(), stream))
     torch.cuda.synchronize()
     e0.record()
-    for _ in range(a.steps):
+    for _ in range(steps):
         C.check(lib.tdx_plan_launch(ctypes.byref(plan2), ws2.data_ptr(), stream))
     e1.record()
     torch.cuda.synchronize()
-    dom_ms = e0.elapsed_time(e1) / a.steps
+    dom_ms = e0.elapsed_time(e1) / steps
+    wide = any(d.algo & 0x0f == C.TDX_ALGO_WIDE32 for d in dom) and dom_key[1] != C.TDX_F32
+    kname = {C.TDX_SRC_CONST: "tdx_fill_kernel", C.TDX_SRC_UNIFORM: "tdx_rng_kernel<GenUniform*> / tdx_lut16_kernel<TabUniform>",
+             C.TDX_SRC_NORMAL: ("tdx_rng_kernel<GenNormalBM32<float>>" if dom_key[1] == C.TDX_F32 else
+                                "tdx_rng_kernel<GenNormalBM32<16-bit>> (TDX_ALGO_WIDE32)" if wide else
+                                "tdx_lut16_kernel<TabNormal, 16-bit> (+ tdx_rng_kernel<GenNormalICDF16> for descriptors < 2^18 elements)")}[dom_key[0]]
     peak, peak_src = peaks()
     achieved = dom_bytes / dom_ms / 1e6
-    kname = {C.TDX_SRC_CONST: "tdx_fill_kernel", C.TDX_SRC_UNIFORM: "tdx_rng_kernel<GenUniform*>",
-             C.TDX_SRC_NORMAL: "tdx_lut16_kernel<TabNormal, bf16> (+ tdx_rng_kernel<GenNormalICDF16<bf16>> for descriptors < 2^18 elements)"
-             if dtype == "bf16" else "tdx_rng_kernel<GenNormalBM32<bf16>> (TDX_ALGO_WIDE32)" if dtype == "fp32->bf16"
-             else "tdx_rng_kernel<GenNormalBM32<float>>"}[dom_key[0]]
-    if a.roofline_only:
+    res["roofline"] = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                       "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                       "bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms}
+    del keep, ws, ws2, fakes
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res
+
+
+def kernel_sweep(cx, max_bytes: int):
+    """BASELINE config 5 at this run's N: one tensor of 1 MB .. 16 GB (x4 steps), each rank writing
+    bytes / N of it (its dim-0 chunk: elem_begin = rank * n / N), normal_ / uniform_ /
+    kaiming_uniform_ (= uniform_ with bound 1/sqrt(fan_in)) in bf16 and fp32; GB/s of the slowest
+    rank x N, L2 flushed before every timed launch below 256 MB per rank."""
+    import torch
+    import torch.distributed as dist
+
+    from torchdistx_b200 import _cabi as C
+
+    dev, world, rank, lib, stream = cx.dev, cx.world, cx.rank, cx.lib, cx.stream
+    peak, _ = peaks()
+    ws = torch.empty(lib.tdx_init_workspace_bytes(1), dtype=torch.uint8, device=dev)
+    flush = torch.empty(192 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    kinds = {"normal_bf16": (C.TDX_BF16, C.TDX_SRC_NORMAL, 0.0, 0.02), "uniform_bf16": (C.TDX_BF16, C.TDX_SRC_UNIFORM, -0.05, 0.05),
+             "kaiming_uniform_bf16": (C.TDX_BF16, C.TDX_SRC_UNIFORM, -1 / 64, 1 / 64),
+             "normal_f32": (C.TDX_F32, C.TDX_SRC_NORMAL, 0.0, 0.02), "uniform_f32": (C.TDX_F32, C.TDX_SRC_UNIFORM, -0.05, 0.05),
+             "kaiming_uniform_f32": (C.TDX_F32, C.TDX_SRC_UNIFORM, -1 / 64, 1 / 64)}
+    rows = []
+    nbytes = 1 << 20
+    while nbytes <= max_bytes:
+        mine = nbytes // world
+        buf = torch.empty(max(mine, 16), dtype=torch.uint8, device=dev)
+        row = {"bytes": nbytes}
+        for name, (dt, src, p0, p1) in kinds.items():
+            isz = 4 if dt == C.TDX_F32 else 2
+            n = mine // isz
+            d = C.make_desc(buf.data_ptr(), dtype=dt, src=src, elem_begin=rank * n, elem_count=n, seed=1234, offset=8,
+                            p0=p0, p1=p1)
+            arr = (C.TdxInitDesc * 1)(d)
+            plan = C.TdxPlan()
+            C.check(lib.tdx_plan_upload(arr, 1, ws.data_ptr(), ws.numel(), stream, ctypes.byref(plan)))
+            for _ in range(3):
+                C.check(lib.tdx_plan_launch(ctypes.byref(plan), ws.data_ptr(), stream))
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(5):
+                if mine < (256 << 20):
+                    flush.zero_()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                C.check(lib.tdx_plan_launch(ctypes.byref(plan), ws.data_ptr(), stream))
+                e.record()
+                e.synchronize()
+                ts.append(s.elapsed_time(e))
+            ms = sorted(ts)[len(ts) // 2]
+            if world > 1:
+                t = torch.tensor([ms], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            row[name] = {"gbs": round(nbytes / ms / 1e6, 1), "frac_per_gpu": round(nbytes / world / ms / 1e6 / peak, 3)}
+        rows.append(row)
+        del buf
+        nbytes *= 4
+    del flush
+    torch.cuda.empty_cache()
+    return rows
+
+
+def fsdp2_handoff_check(cx):
+    """SURVEY 8f.1, asserted where the driver has >= 2 GPUs: after `fully_shard` on the meta device
+    every rank fills the local shards FSDP owns IN PLACE from an InitPlan; the gathered parameters
+    must equal the unsharded materialisation bit for bit."""
+    import torch
+    import torch.distributed as dist
+    from torch.distributed.fsdp import fully_shard
+
+    from torchdistx_b200 import parallel
+    from torchdistx_b200.deferred_init import deferred_init, materialize_module
+    from torchdistx_b200.plan import InitPlan, init_sharded_module
+
+    plan = InitPlan.from_module(deferred_init(build_model, "llama-tiny"))
+    with torch.device("meta"):
+        model = build_model("llama-tiny")
+    for layer in model.model.layers:
+        fully_shard(layer)
+    fully_shard(model)
+    model.to_empty(device=cx.dev)
+    torch.manual_seed(77)
+    parallel.sync_rng(cx.dev, force=True)
+    init_sharded_module(model, plan, cx.rank, cx.world, device=cx.dev)
+    got = {n: p.full_tensor() for n, p in model.named_parameters()}
+    ref = deferred_init(build_model, "llama-tiny")
+    torch.manual_seed(77)
+    parallel.sync_rng(cx.dev, force=True)
+    materialize_module(ref, device=cx.dev)
+    bad = [n for n, p in ref.named_parameters() if not torch.equal(got[n], p.detach())]
+    flag = torch.tensor([len(bad)], device=cx.dev)
+    dist.all_reduce(flag)
+    assert int(flag.item()) == 0, f"FSDP2 hand-off mismatch on {bad[:3]}"
+    return "ok: llama-tiny, fully_shard on meta -> init_sharded_module in place -> full_tensor() == unsharded materialize_module, bit for bit"
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    from torchdistx_b200 import _cabi as C
+    from torchdistx_b200 import parallel
+
+    cx = Ctx()
+    world = cx.world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = cx.rank = int(os.environ.get("RANK", "0"))
+    local = cx.local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
+    torch.cuda.set_device(local)
+    dev = cx.dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+    cx.lib = C.load()
+    cx.stream = torch.cuda.current_stream().cuda_stream
+    dtype = MODELS[a.model][2]
+
+    if a.roofline_only:  # for ncu: one materialize, then launches of the dominant kernel's plan only
+        measure_model(cx, a.model, a.steps, 0, roofline_only=True)
         return
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_bench_summary.json"))).get(a.model, {}).get("dram_bytes_per_launch")
-    except Exception:
-        pass
+
+    torch.manual_seed(1234)
+    parallel.sync_rng(dev)  # the one collective: 16 bytes, rank 0 -> all
+    main = measure_model(cx, a.model, a.steps, a.warmup, first_call=True)
+
+    # ---- the other BASELINE configs, measured in the same run (smaller step counts) ----------------
+    extra = {}
+    if not a.no_extra:
+        side = []
+        if a.model == "llama3-8b":
+            side = ["gpt2-xl", "llama3-8b-cast"] if world == 1 else ["llama3-70b"] if world == 8 else []
+        for name in side:
+            try:
+                r = measure_model(cx, name, max(3, a.steps // 2), 3)
+                extra[name] = {"params": r["params"], "dtype": r["dtype"], "value": r["params"] / (r["ms"] / 1e3),
+                               "ms_per_step": r["ms"], "hbm_gbs_per_gpu": r["my_bytes"] / (r["ms"] / 1e3) / 1e9,
+                               "e2e": {"value": r["params"] / (r["e2e_ms"] / 1e3), "ms_per_step": r["e2e_ms"],
+                                       "api_return_ms": r["host_split"]["api_return"]},
+                               "roofline": r["roofline"], "fused_tensors": r["stats"]["fused_tensors"],
+                               "generic_ops": r["stats"]["generic_ops"], "descriptors_per_rank": r["descs"]}
+            except Exception as e:  # a side measurement must not cost the headline
+                extra[name] = {"error": f"{type(e).__name__}: {str(e)[-300:]}"}
+        try:
+            extra["kernel_sweep"] = {"what": kernel_sweep.__doc__.split("\n\n")[0].replace("\n    ", " "),
+                                     "rows": kernel_sweep(cx, 16 << 30)}
+        except Exception as e:
+            extra["kernel_sweep"] = {"error": f"{type(e).__name__}: {str(e)[-300:]}"}
+        if world > 1:
+            try:
+                extra["fsdp2_handoff_check"] = fsdp2_handoff_check(cx)
+            except Exception as e:
+                extra["fsdp2_handoff_check"] = f"FAILED: {type(e).__name__}: {str(e)[-300:]}"
 
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
-    # ---- CPU baseline: the reference itself on a bounded sample (rank 0, N = 1 only) ---------------
+    # ---- baselines on rank 0 at N = 1: the reference on the host cores (bounded sample), and the
+    # reference replaying on the GPU with stock ATen kernels (baseline B, whole model) --------------
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
         try:
@@ -378,38 +570,60 @@ def run_ours(a):
         except Exception as e:  # the oracle is test infrastructure: report, do not hide
             cpu = {"value": None, "unit": "params/s", "cores": os.cpu_count(), "kind": "reference",
                    "sample": f"unavailable: {type(e).__name__}: {str(e)[-200:]}"}
+        if not a.no_extra:
+            try:
+                torch.cuda.empty_cache()
+                g = reference_on_gpu(a.model, local)
+                best = min(g["times"][1:])
+                extra["gpu_baseline"] = {"what": "the reference's own engine (oracle/_ref) with the model recorded for cuda: "
+                                                 "materialize_module replays every recorded op through stock ATen kernels "
+                                                 "(baseline B of SURVEY 8d); wall clock incl. synchronize, best of 2 after a warm-up call",
+                                         "model": a.model, "value": g["params"] / best, "unit": "params/s",
+                                         "ms_per_step": best * 1e3, "first_call_ms": g["times"][0] * 1e3}
+            except Exception as e:
+                extra["gpu_baseline"] = {"error": f"{type(e).__name__}: {str(e)[-300:]}"}
 
-    c1, c2 = clk.summary(), clk_e2e.summary()
+    c1, c2, st = main["clk"], main["clk_e2e"], main["stats"]
+    ms, e2e_ms, n_params, my_bytes = main["ms"], main["e2e_ms"], main["params"], main["my_bytes"]
     total_bytes = my_bytes * world if world > 1 else my_bytes
+    rf = main["roofline"]
+    if world == 1 and a.model == "llama3-8b":
+        try:  # DRAM bytes of one launch of the dominant kernel, from the committed ncu capture (N = 1 only)
+            rf["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "ncu_bench_summary.json"))).get(a.model, {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    rf["secondary_ceiling"] = ("dispatch port: Philox4x32-10 alone is ~74 of the ~120 cycles a 16-byte vector takes "
+                               "(benchmarks/philox_rate.cu); see DESIGN.md section 4")
     line = {
         "metric": "materialize_module params/s", "value": n_params / (ms / 1e3), "unit": "params/s",
         "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": dtype, "data": "synthetic (random init of the named architecture, HF config; no checkpoint)",
         "config": {"workload": f"{a.model} deferred_init -> materialize_module on cuda, dim-0 sharded over {world} GPU(s)",
-                   "params": n_params, "tensors": n_tensors, "descriptors_per_rank": len(descs),
+                   "params": n_params, "tensors": main["tensors"], "descriptors_per_rank": main["descs"],
                    "fused_tensors": st["fused_tensors"], "generic_ops": st["generic_ops"],
-                   "elided_rng_ops": st["elided_rng_ops"], "record_s_per_model": record_s,
-                   "host_us": {k: round(st[k]) for k in ("traverse_us", "plan_us", "eval_us", "alloc_us", "launch_us", "wrap_us", "assign_us", "first_submit_us", "last_submit_us", "submissions")},
-                   "e2e_host_split_ms": {"api_return": round(host_split["api_return_ms"] / max(host_split["n"], 1), 3),
-                                         "gpu_done": round(host_split["sync_ms"] / max(host_split["n"], 1), 3)},
+                   "elided_rng_ops": st["elided_rng_ops"], "record_s_per_model": main["record_s_per_model"],
+                   "host_us": {k: round(st[k]) for k in ("traverse_us", "plan_us", "eval_us", "alloc_us", "launch_us", "wrap_us", "assign_us", "first_submit_us", "last_submit_us", "submissions", "template_hits")},
+                   "e2e_host_split_ms": main["host_split"],
                    "l2": "outputs per step (GBs) exceed the 126 MB L2; no flush needed",
+                   "collective": "one 16-byte broadcast of (seed, offset) before the first step; later steps derive their offsets locally (parallel.sync_rng), agreement asserted after the timed region",
                    "timed_region_value": "tdx_plan_launch only (plan resident in HBM)",
-                   "timed_region_e2e": "per step: materialize_module (traversal, plan, alloc, H2D descriptors, kernels) + 64 B D2H + sync; model teardown between steps untimed; Python GC collected before and disabled inside each timed step (as timeit does)"},
+                   "timed_region_e2e": "per step: sync_rng + materialize_module (traversal, plan, alloc, H2D descriptors, kernels) + 64 B D2H + sync; model teardown between steps untimed; Python GC collected before and disabled inside each timed step (as timeit does)"},
         "hbm_gbs": total_bytes / (ms / 1e3) / 1e9, "hbm_gbs_per_gpu": my_bytes / (ms / 1e3) / 1e9,
         "e2e": {"value": n_params / (e2e_ms / 1e3), "unit": "params/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": probe.numel() * probe.element_size()},
-        "gpu_launches": launches_per_step * a.steps,
-        "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
-                     "secondary_ceiling": "dispatch port: Philox4x32-10 alone is 80 cycles per 16-byte vector = 7.0 TB/s-equivalent (benchmarks/philox_rate.cu); see DESIGN.md section 4"},
+                "h2d_bytes_per_step": main["h2d"], "d2h_bytes_per_step": 64,
+                "cold_first_call_ms": main.get("e2e_cold_ms"), "cold_first_call_alloc_ms": main.get("cold_alloc_ms"),
+                "cold_note": "first materialize_module of the process: CUDA module load + cold caching allocator (one cudaMalloc per submission slab) + pinned staging; every later number is warm"},
+        "gpu_launches": main["launches_per_step"] * a.steps,
+        "roofline": rf,
         "cpu_baseline": cpu,
         "clocks": {"sm_mhz": c1["sm_mhz"], "sm_max_mhz": c1["sm_max_mhz"], "reasons": c1["reasons"],
                    "e2e_sm_mhz": c2["sm_mhz"], "e2e_reasons": c2["reasons"]},
+        "extra": extra,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -421,6 +635,8 @@ def main():
     ap.add_argument("--model", default="llama3-8b", choices=sorted(MODELS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the side measurements (the other BASELINE configs, the kernel sweep, baseline B)")
     ap.add_argument("--roofline-only", action="store_true",
                     help="for ncu: one materialize (1 launch per family), then 3+steps launches of the "
                          "dominant kernel's plan only; prints nothing")

@@ -21,15 +21,18 @@
  * oracle/tdx_oracle.c and pinned by tests/golden):
  *
  *   Philox4x32-R (R = 10 unless TDX_ALGO_*_R7), key = (seed_lo, seed_hi),
- *   counter = (blk_lo, blk_hi, off_lo, off_hi | 0x80000000)
+ *   counter = (off_lo, blk_hi, off_hi | 0x80000000, blk_lo)
  *   where off = TdxInitDesc.philox_offset (the torch generator offset at the
  *   time the op was issued == unique id of this RNG op under that seed) and
  *   blk = floor(g / EPB) for GLOBAL linear element index g of the unsharded
  *   tensor.  EPB = 8 for 16-bit outputs (16 random bits per element), 4 for
- *   32-bit outputs and for 16-bit outputs generated "wide" (TDX_ALGO_WIDE32).  Bit 31 of counter.w keeps the stream disjoint from
- *   ATen's own (offset, thread-id) use of the same generator
- *   (ATen/native/cuda/DistributionTemplates.h:72-88); bits 30/29 of counter.w
- *   select the two tail-refinement blocks of the 16-bit normal.
+ *   32-bit outputs and for 16-bit outputs generated "wide" (TDX_ALGO_WIDE32).  Bit 31 of counter.z
+ *   keeps the stream disjoint from ATen's own (offset, thread-id) use of the same generator
+ *   (ATen/native/cuda/DistributionTemplates.h:72-88: ATen's third counter word is the high half of a
+ *   thread index, far below 2^31); bits 30/29 of counter.z select the two tail-refinement blocks of
+ *   the 16-bit normal.  The per-element word blk_lo is the LAST counter word: a Philox round only
+ *   XORs and moves it, so the first multiplications of a block are per-tile constants (see
+ *   tdx_init_kernels.cu philox_block); every bit of it still passes nine multiplying rounds.
  *   Because the value of element g depends only on (seed, off, g), any
  *   partition of [0, numel) over ranks reproduces the unsharded tensor
  *   bit-for-bit.

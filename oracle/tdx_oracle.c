@@ -51,8 +51,8 @@ void tdx_oracle_philox4x32(const uint32_t ctr[4], const uint32_t key[2], int rou
 
 /* the engine's counter layout (include/tdx_init.h "Random stream specification") */
 static void block_of(const TdxInitDesc* d, uint64_t blk, uint32_t wflag, int rounds, uint32_t out[4]) {
-  const uint32_t ctr[4] = {(uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)d->philox_offset,
-                           (uint32_t)(d->philox_offset >> 32) | 0x80000000u | wflag};
+  const uint32_t ctr[4] = {(uint32_t)d->philox_offset, (uint32_t)(blk >> 32),
+                           (uint32_t)(d->philox_offset >> 32) | 0x80000000u | wflag, (uint32_t)blk};
   const uint32_t key[2] = {(uint32_t)d->philox_seed, (uint32_t)(d->philox_seed >> 32)};
   tdx_oracle_philox4x32(ctr, key, rounds, out);
 }

@@ -187,7 +187,7 @@ def test_buffer_computed_from_a_sharded_parameter_sees_the_whole_parameter():
 
 
 def _on_cuda(cls):
-    with torch.device("cuda"):
+    with torch.device("cuda:0"):
         return cls()
 
 
@@ -195,7 +195,7 @@ def _on_cuda(cls):
 def test_cross_recording_dependency_sees_initialised_memory():
     torch.manual_seed(4)
     m1 = deferred_init(lambda: _on_cuda(lambda: nn.Linear(64, 64)))
-    scale = torch.arange(64, dtype=torch.float32, device="cuda")  # a real, non-scalar operand: generic op
+    scale = torch.arange(64, dtype=torch.float32, device="cuda:0")  # a real, non-scalar operand: generic op
 
     class Derived(nn.Module):
         def __init__(self):

@@ -29,7 +29,8 @@ TransformationHelper.h:84-99, digits = 8: |z| <= 3.33, std 0.7 % low), which is 
 that kernel, not the distribution `normal_` names.  The cast variant needs no such step: its
 reference IS an fp32 sample rounded by `.to(bfloat16)`.
 
-Deterministic tensors (norm weights, rotary inv_freq) stay T0: bit-exact.
+Deterministic tensors stay T0: norm weights bit-exact; the rotary `inv_freq` buffers (float
+arithmetic through `pow`, replayed by ATen's CUDA kernels) to 4 ulp of the reference's CPU result.
 """
 import math
 import os
@@ -126,9 +127,17 @@ def test_llama3_8b_sample_against_reference(key, reference):
     for k, t in mine.items():
         r = ref[k]
         total += t.numel() * t.element_size()
-        if t.dim() < 2:  # T0: norm weights (ones) and rotary inv_freq are deterministic programs
+        if t.dim() < 2:  # deterministic programs: norm weights (ones) and the rotary inv_freq buffers
             # (the bf16 model's reference runs in fp32: a constant program commutes with the cast)
-            assert not isinstance(r, dict) and torch.equal(t.detach().cpu(), r.to(t.dtype)), k
+            assert not isinstance(r, dict), k
+            x, rr = t.detach().cpu(), r.to(t.dtype)
+            if "inv_freq" in k:
+                # arange -> div -> pow -> reciprocal, replayed by ATen on the GPU: CUDA's powf and the
+                # CPU's vectorised pow are both faithful to ~1 ulp but not to each other's last bit
+                # (T0 is stated for zeros/ones/index ops; this is float arithmetic: 4 ulp)
+                torch.testing.assert_close(x, rr, rtol=4 * 2.0 ** -23, atol=0.0)
+            else:
+                assert torch.equal(x, rr), k
             continue
         r_dtype = r["dtype"] if isinstance(r, dict) else str(r.dtype)
         assert t.is_cuda and str(t.dtype) == r_dtype, (k, t.dtype, r_dtype)

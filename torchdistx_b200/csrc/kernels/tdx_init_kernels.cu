@@ -51,6 +51,11 @@ constexpr int kThreads = 256;
 constexpr int kVecsPerThread = TDX_VECS;
 constexpr int kTileVecs = kThreads * kVecsPerThread;  // 1024 x 16 B = 16 KiB per tile
 constexpr int kTilesPerChunk = 64 / TDX_VECS;          // 256 KiB per work grab
+#ifndef TDX_STATIC_TILES
+#define TDX_STATIC_TILES 8
+#endif
+// launches of up to this many tiles per resident CTA are scheduled statically (GroupArgs::static_grabs)
+constexpr unsigned long long kStaticTilesPerCta = TDX_STATIC_TILES;
 
 // ---------------------------------------------------------------------------------------------
 // small device helpers
@@ -241,10 +246,17 @@ __device__ __forceinline__ PhiloxCtx load_philox(const TdxInitDesc& d) {
   c.cw = static_cast<uint32_t>(d.philox_offset >> 32) | 0x80000000u;
   return c;
 }
+// Counter layout (normative, include/tdx_init.h): (off_lo, blk_hi, off_hi | flags, blk_lo).  The word
+// that differs from thread to thread (blk_lo) sits in position 3, which a Philox round only XORs and
+// moves: both products of round 1, one of round 2 and one of round 3 then depend on per-tile
+// uniform values only and are hoisted out of the vector loop -- 16 IMAD.WIDE + 18 LOP3 per block
+// instead of 20 + 20 (IMAD.WIDE is quarter rate on sm_100: the instruction that bounds these
+// kernels).  Every bit of blk_lo still passes through nine multiplying rounds (Philox4x32-7 is the
+// published Crush-resistant minimum).
 template <int R>
 __device__ __forceinline__ uint4 philox_block(const PhiloxCtx& c, uint64_t blk, uint32_t wflag = 0) {
   return philox4x32<R>(
-      make_uint4(static_cast<uint32_t>(blk), static_cast<uint32_t>(blk >> 32), c.cz, c.cw | wflag),
+      make_uint4(c.cz, static_cast<uint32_t>(blk >> 32), c.cw | wflag, static_cast<uint32_t>(blk)),
       c.k0, c.k1);
 }
 
@@ -546,6 +558,10 @@ struct GroupArgs {
   uint32_t tiles_per_chunk;    // 256-thread kernels: tiles per work grab (host-chosen per launch)
   uint32_t n_chunks;           // table kernel: host-built work list (see build_plan)
   const uint4* chunks;         // {descriptor, tiles, first tile in descriptor (lo, hi)}
+  // 256-thread kernels, launches of at most a few tiles per resident CTA: grid = number of grabs,
+  // CTA b takes grab b -- no work counter, no exit protocol (a 1 MB tensor is then one kernel
+  // launch's latency plus its stores, like a stock elementwise kernel)
+  uint32_t static_grabs;
   uint32_t rk[20];
 };
 
@@ -567,32 +583,41 @@ __device__ __forceinline__ void leave_grid(const GroupArgs& g) {
 // 16 KiB tile for small ones (a 1 MB tensor is 64 single-tile grabs on 64 SMs, not 4 grabs of 16
 // tiles on 4).
 template <class F>
+__device__ __forceinline__ void run_tiles(const GroupArgs& g, unsigned long long t, unsigned long long last, F&& f) {
+  uint32_t lo = 0, hi = g.n_desc;  // find d with prefix[d] <= t < prefix[d+1]
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(g.tile_prefix + mid) <= t) lo = mid; else hi = mid;
+  }
+  uint32_t d = lo;
+  while (t < last) {
+    unsigned long long dend = __ldg(g.tile_prefix + d + 1);
+    while (dend <= t) dend = __ldg(g.tile_prefix + (++d) + 1);  // skip empty descriptors
+    const unsigned long long stop = min(dend, last);
+    f(d, t - __ldg(g.tile_prefix + d), stop - t);
+    t = stop;
+  }
+}
+
+template <class F>
 __device__ __forceinline__ void for_each_tile_run(const GroupArgs& g, F&& f) {
   const unsigned int tpc = g.tiles_per_chunk;
+  if (g.static_grabs) {  // (uniform across the grid: a kernel parameter)
+    const unsigned long long t = static_cast<unsigned long long>(blockIdx.x) * tpc;
+    if (t < g.total_tiles) run_tiles(g, t, min(t + tpc, g.total_tiles), f);
+    return;
+  }
   __shared__ unsigned int s_chunk;
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) s_chunk = atomicAdd(g.counter, 1u);
     __syncthreads();
-    unsigned long long t = static_cast<unsigned long long>(s_chunk) * tpc;
+    const unsigned long long t = static_cast<unsigned long long>(s_chunk) * tpc;
     if (t >= g.total_tiles) {
       leave_grid(g);
       return;
     }
-    const unsigned long long last = min(t + tpc, g.total_tiles);
-    uint32_t lo = 0, hi = g.n_desc;  // find d with prefix[d] <= t < prefix[d+1]
-    while (hi - lo > 1) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (__ldg(g.tile_prefix + mid) <= t) lo = mid; else hi = mid;
-    }
-    uint32_t d = lo;
-    while (t < last) {
-      unsigned long long dend = __ldg(g.tile_prefix + d + 1);
-      while (dend <= t) dend = __ldg(g.tile_prefix + (++d) + 1);  // skip empty descriptors
-      const unsigned long long stop = min(dend, last);
-      f(d, t - __ldg(g.tile_prefix + d), stop - t);
-      t = stop;
-    }
+    run_tiles(g, t, min(t + tpc, g.total_tiles), f);
   }
 }
 
@@ -957,6 +982,36 @@ __device__ __noinline__ void lut_ragged_tile(const TdxInitDesc* dp, unsigned lon
   }
 }
 
+// Constant-fill descriptors ride along in the table kernel's work list (the host folds a module's
+// few small fills -- norm weights, biases -- into it instead of paying a kernel launch for them).
+__device__ __noinline__ void lut_fill_tiles(const TdxInitDesc* dp, unsigned long long tile0,
+                                            unsigned long long ntiles) {
+  const TdxInitDesc& d = *dp;
+  const uint4 pat = make_uint4(static_cast<uint32_t>(d.fill_bits[0]), static_cast<uint32_t>(d.fill_bits[0] >> 32),
+                               static_cast<uint32_t>(d.fill_bits[1]), static_cast<uint32_t>(d.fill_bits[1] >> 32));
+  const int isz = d.dtype == TDX_F32 || d.dtype == TDX_RAW32 ? 4 : d.dtype == TDX_RAW64 ? 8 : d.dtype == TDX_RAW8 ? 1 : 2;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(d.dst);
+  const uintptr_t end = a + d.elem_count * isz;
+  const uintptr_t a0 = a & ~static_cast<uintptr_t>(15);
+  const uint64_t nvec = (end - a0 + 15) / 16;
+  for (unsigned long long tile = tile0; tile < tile0 + ntiles; ++tile) {
+    for (int i = 0; i < kLutVecsPerThread; ++i) {
+      const uint64_t j = tile * kLutTileVecs + static_cast<uint64_t>(i) * kLutThreads + threadIdx.x;
+      if (j >= nvec) break;
+      const uintptr_t p = a0 + j * 16;
+      if (p >= a && p + 16 <= end) {
+        store_vec(reinterpret_cast<void*>(p), pat);
+      } else {  // head / tail line: byte-granular, the pattern phase follows the address
+        const unsigned char* pb = reinterpret_cast<const unsigned char*>(&pat);
+        for (int b = 0; b < 16; ++b) {
+          const uintptr_t q = p + b;
+          if (q >= a && q < end) *reinterpret_cast<unsigned char*>(q) = pb[(q - a) % isz];
+        }
+      }
+    }
+  }
+}
+
 // Exponent-all-ones test of either half of a packed pair (inf or NaN).
 template <class Out>
 __device__ __forceinline__ bool any_nonfinite2(uint32_t v) {
@@ -985,6 +1040,10 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_lut16_kernel(const GroupAr
   uint32_t have_di = 0xffffffffu;  // descriptor the table in shared memory was built for
   for_each_listed_chunk(g, slots, [&](uint32_t di, unsigned long long tile0, unsigned long long ntiles) {
     const TdxInitDesc& d = g.descs[di];
+    if (d.src == TDX_SRC_CONST) {  // a fill folded into this launch (build_plan): the table stays as it is
+      lut_fill_tiles(&d, tile0, ntiles);
+      return;
+    }
     typename Gen::Params P = Gen::setup(d);
     // Loop-invariant scalars that come out of a global load: a warp reduction's result lives in a
     // uniform register by construction, so the FFMAs / LOP3s that use them read two vector
@@ -1020,7 +1079,7 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_lut16_kernel(const GroupAr
 #pragma unroll
           for (int i = i0; i < i0 + GROUP; ++i) {
             const int LUT_ELEMS = (i & 1) ? LUT_B : LUT_A;
-            const uint4 c = make_uint4(lo0 + static_cast<uint32_t>(i) * kLutThreads, blk_hi, P.ph.cz, P.ph.cw);
+            const uint4 c = make_uint4(P.ph.cz, blk_hi, P.ph.cw, lo0 + static_cast<uint32_t>(i) * kLutThreads);
             const uint4 w = PKEYS ? philox4x32_rk<R>(c, g.rk) : philox4x32<R>(c, P.ph.k0, P.ph.k1);
             const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
             uint32_t r[4];
@@ -1196,6 +1255,14 @@ uint64_t lut_min_elems() {
   return v;
 }
 
+bool fold_fills() {
+  static const bool v = [] {
+    const char* e = getenv("TDX_FOLD_FILLS");
+    return !(e && e[0] == '0');
+  }();
+  return v;
+}
+
 uint64_t lut_min_launch_elems() {
   static const uint64_t v = [] {
     const char* e = getenv("TDX_LUT_MIN_LAUNCH_ELEMS");
@@ -1363,6 +1430,28 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
         }
     }
   }
+  // A module's constant fills (norm weights, biases: KBs) ride in the largest table launch's work
+  // list instead of costing a launch of their own -- unless they are a real share of the bytes.
+  if (per_family[0] > 0 && fold_fills()) {
+    int host = -1;
+    uint64_t host_bytes = 0, fill_bytes = 0;
+    uint64_t bytes_of[kNumFamilies] = {};
+    for (int i = 0; i < n; ++i) bytes_of[fam[i]] += descs[i].elem_count * itemsize_of(descs[i].dtype);
+    fill_bytes = bytes_of[0];
+    for (int f = 1; f < kNumFamilies; ++f)
+      if (kFamilies[f].lut && per_family[f] > 0 && bytes_of[f] > host_bytes) {
+        host = f;
+        host_bytes = bytes_of[f];
+      }
+    if (host >= 0 && fill_bytes * 16 <= host_bytes) {
+      for (int i = 0; i < n; ++i)
+        if (fam[i] == 0) {
+          fam[i] = host;
+          per_family[0]--;
+          per_family[host]++;
+        }
+    }
+  }
   memset(&hdr, 0, sizeof(hdr));
   hdr.magic = kPlanMagic;
   if (img.size() < plan_bytes(n)) img.resize(plan_bytes(n));
@@ -1396,14 +1485,20 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
     if (kFamilies[f].lut)
       std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
         const TdxInitDesc &x = descs[a], &y = descs[b];
+        if (x.src != y.src) return x.src < y.src;  // (folded fills first: TDX_SRC_CONST == 0)
+        if (x.src == TDX_SRC_CONST) return false;
         if (x.p0 != y.p0) return x.p0 < y.p0;
         if (x.p1 != y.p1) return x.p1 < y.p1;
         if (x.n_epi != y.n_epi) return x.n_epi < y.n_epi;
         return x.n_epi != 0 && memcmp(x.epi, y.epi, sizeof(TdxEpiStep) * x.n_epi) < 0;
       });
+    bool have_seed = false;
     for (int i : order) {
-      if (k == 0) G.seed = descs[i].philox_seed;
-      else if (descs[i].philox_seed != G.seed) G.seed_shared = 0;
+      if (descs[i].src != TDX_SRC_CONST) {
+        if (!have_seed) G.seed = descs[i].philox_seed;
+        else if (descs[i].philox_seed != G.seed) G.seed_shared = 0;
+        have_seed = true;
+      }
       prefix[k] = acc;
       out[k] = descs[i];
       acc += tiles_of(descs[i], kFamilies[f].tile_vecs);
@@ -1520,9 +1615,16 @@ int launch_groups(const PlanHeader& hdr, void* workspace, cudaStream_t stream) {
         static_cast<unsigned long long>(info->sm_count) * info->blocks_per_sm[G.family];
     // 256-thread kernels: full-size grabs only when every resident CTA still gets a few of them
     int tpc = kFamilies[G.family].tiles_per_chunk;
+    a.static_grabs = 0;
     if (!kFamilies[G.family].lut) {
-      const unsigned long long want = G.total_tiles / (resident * 2ull);
-      tpc = static_cast<int>(std::min<unsigned long long>(std::max<unsigned long long>(want, 1ull), tpc));
+      if (G.total_tiles <= resident * kStaticTilesPerCta) {
+        // small launch: one grab of consecutive tiles per CTA, assigned by block index
+        tpc = static_cast<int>((G.total_tiles + resident - 1) / resident);
+        a.static_grabs = 1;
+      } else {
+        const unsigned long long want = G.total_tiles / (resident * 2ull);
+        tpc = static_cast<int>(std::min<unsigned long long>(std::max<unsigned long long>(want, 1ull), tpc));
+      }
     }
     a.tiles_per_chunk = static_cast<uint32_t>(tpc);
     a.n_chunks = G.n_chunks;

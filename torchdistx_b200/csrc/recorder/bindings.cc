@@ -281,6 +281,21 @@ void py_materialize_module(const py::object& module, bool buffers_only, const py
     py::gil_scoped_release nogil;
     session_ptr.reset();
   }
+  {
+    // the recordings outlive this call by a moment: their teardown runs on the helper thread
+    std::vector<std::shared_ptr<tdx::Tape>> tapes;
+    for (const PendingSlot& p : pending) {
+      if (!tdx::can_materialize(p.fake)) continue;
+      const auto& rec = tdx::fake_impl(p.fake)->record();
+      if (rec->tape && (tapes.empty() || tapes.back() != rec->tape) &&
+          std::find(tapes.begin(), tapes.end(), rec->tape) == tapes.end())
+        tapes.push_back(rec->tape);
+    }
+    pending.clear();
+    wrapped.clear();
+    py::gil_scoped_release nogil;
+    tdx::release_in_background(std::move(tapes));
+  }
   if (trace)
     fprintf(stderr, "[tdx] materialize_module: session %.0f us, walked %.0f, wrapped %.0f, joined %.0f, assigned %.0f, "
             "done %.0f (%zu tensors)\n", t_created, t_walked, t_wrapped, t_joined, t_assigned, since(), pending.size());

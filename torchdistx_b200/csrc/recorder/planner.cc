@@ -719,13 +719,24 @@ struct Batch {
     }();
     return v;
   }
+  // Estimate of when the GPU runs out of submitted work (host clock, us): a submission is only
+  // worth its fixed costs (plan upload, launches, a table build and a ramp/tail per launch: ~35 us
+  // for Llama-3-8B's 1 GB first submission) if the GPU would otherwise go idle soon.
+  double gpu_busy_until_us = 0;
   void note(int64_t bytes) {
     pending_bytes += bytes;
     if (flush_threshold > 0 && pending_bytes >= flush_threshold) {
+      if (gpu_busy_until_us - now_us_() > kBacklogGateUs) {
+        // plenty of work queued: let this submission grow instead (fewer, larger launches)
+        flush_threshold = std::min<int64_t>(flush_threshold * 2, int64_t{64} << 30);
+        return;
+      }
       flush();
-      flush_threshold = std::min<int64_t>(flush_threshold * 4, int64_t{16} << 30);
+      flush_threshold = std::min<int64_t>(flush_threshold * 4, int64_t{64} << 30);
     }
   }
+  static constexpr double kBacklogGateUs = 150;
+  static double now_us_();
   void assign_memory();
   void flush();
 };
@@ -733,6 +744,7 @@ struct Batch {
 double now_us() {
   return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
+double Batch::now_us_() { return now_us(); }
 
 // An output tensor without memory yet (see Batch::Pending).  Built like at::detail::empty_generic
 // does, minus the allocation.
@@ -815,6 +827,12 @@ void Batch::flush() {
   g_stats.last_submit_us = now_us() - g_call_begin_us;
   g_last_descs.insert(g_last_descs.end(), descs.begin(), descs.end());
   descs.clear();
+  {
+    // (4.5 bytes/ns: what the slowest of the bulk kernels sustains; an under-estimate only makes
+    // the next submission come a little early)
+    const double t_now = now_us();
+    gpu_busy_until_us = std::max(gpu_busy_until_us, t_now) + static_cast<double>(pending_bytes) / 4.5e3 + 20.0;
+  }
   pending_bytes = 0;
   epoch = g_epoch.fetch_add(1);
   g_stats.launch_us += now_us() - t0;
@@ -1624,6 +1642,13 @@ bool PipelinedMaterialize::ready(size_t ticket) {
 
 at::Tensor PipelinedMaterialize::result(size_t ticket) {
   State::Item& it = *st_->items[ticket];
+  // The helper finishes a tensor every microsecond or two: spin for a while before paying a futex
+  // sleep + wake-up per tensor (and making the helper pay the notify).
+  for (int spin = 0; spin < 4096 && it.done.load(std::memory_order_acquire) == 0; ++spin) {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+  }
   if (it.done.load(std::memory_order_acquire) == 0) {
     std::unique_lock<std::mutex> lock(st_->m);
     st_->caller_waiting.store(true, std::memory_order_release);
@@ -1652,6 +1677,12 @@ void PipelinedMaterialize::join() {
   }
   g_pending_traverse_us = 0;
   if (st_->error) std::rethrow_exception(st_->error);
+}
+
+void release_in_background(std::vector<std::shared_ptr<Tape>> tapes) {
+  if (tapes.empty() || !host_threads_enabled()) return;  // (inline mode: they die with the caller's copies)
+  auto box = std::make_shared<std::vector<std::shared_ptr<Tape>>>(std::move(tapes));
+  HelperThread::get().post([box] { box->clear(); });
 }
 
 void add_wrap_time(double us) { g_stats.wrap_us += us; }
