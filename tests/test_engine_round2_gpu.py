@@ -53,8 +53,13 @@ def test_templates_serve_every_fused_tensor_and_change_nothing():
 
 # ---- slab-backed outputs -------------------------------------------------------------------------
 def test_outputs_share_a_slab_but_own_their_storages():
+    from torchdistx_b200 import _C
+
+    x = torch.randn(3, 64, device="cuda")
+    (x @ torch.randn(64, 64, device="cuda")).sum().item()  # cuBLAS takes its workspace from the allocator once
     m = deferred_init(lambda: cases.build("mlp_stack", "fp32", "cuda"))
     torch.manual_seed(0)
+    torch.cuda.synchronize()
     before = torch.cuda.memory_allocated()
     materialize_module(m)
     ts = list(named(m).values())
@@ -67,7 +72,7 @@ def test_outputs_share_a_slab_but_own_their_storages():
     spans = sorted((t.data_ptr(), t.data_ptr() + t.numel() * t.element_size()) for t in ts)
     assert all(spans[i][1] <= spans[i + 1][0] for i in range(len(spans) - 1))
     # usable like any tensor: autograd, in-place, save/load, storage resize
-    y = m(torch.randn(3, 64, device="cuda"))
+    y = m(x)
     y.sum().backward()
     assert all(p.grad is not None for p in m.parameters())
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
@@ -84,8 +89,9 @@ def test_outputs_share_a_slab_but_own_their_storages():
     assert torch.equal(w.detach(), keep)
     # memory goes back when the last tensor of the slab dies
     del m, ts, y, sd, back, w, keep
+    _C._drain()  # the recording (which also names the tensors) is let go of on the helper thread
     torch.cuda.synchronize()
-    assert torch.cuda.memory_allocated() <= before + (1 << 20)
+    assert torch.cuda.memory_allocated() <= before + (1 << 16)
 
 
 def test_per_tensor_allocation_switch(tmp_path):
@@ -94,6 +100,7 @@ def test_per_tensor_allocation_switch(tmp_path):
             "from torchdistx_b200.deferred_init import deferred_init, materialize_module\n"
             "m = deferred_init(lambda: cases.build('mlp_stack', 'fp32', 'cuda'))\n"
             "torch.manual_seed(0); materialize_module(m)\n"
+            "from torchdistx_b200 import _C; _C._drain()\n"
             "w = m[0].weight; before = torch.cuda.memory_allocated()\n"
             "m[0]._parameters['weight'] = None; del w\n"
             "assert torch.cuda.memory_allocated() < before, 'freeing one tensor must release its memory'\n"
@@ -253,3 +260,68 @@ def test_plan_build_leaves_the_generators_alone():
     s_cpu, s_cuda = torch.get_rng_state(), torch.cuda.get_rng_state()
     InitPlan.from_module(m)
     assert torch.equal(torch.get_rng_state(), s_cpu) and torch.equal(torch.cuda.get_rng_state(), s_cuda)
+
+
+# ---- FSDP1 flat-parameter layout ---------------------------------------------------------
+@pytest.mark.parametrize("world,align", [(1, 0), (2, 0), (3, 8), (8, 8)])
+def test_flat_shard_equals_chunks_of_the_flattened_module(world, align):
+    from torchdistx_b200.deferred_init import materialize_flat_shard
+
+    def build():
+        return deferred_init(lambda: cases.build("padded_embeddings", "bf16", "cuda:0"))
+
+    torch.manual_seed(31)
+    full = build()
+    full_params = [materialize_tensor(p) for p in full.parameters()]  # (the order FSDP flattens in: parameters())
+    flat_parts, offsets, total = [], [], 0
+    for p in full_params:
+        if align > 1 and total % align:
+            pad = align - total % align
+            flat_parts.append(torch.zeros(pad, dtype=p.dtype, device=p.device))
+            total += pad
+        offsets.append(total)
+        flat_parts.append(p.detach().flatten())
+        total += p.numel()
+    flat = torch.cat(flat_parts)
+    chunk = -(-total // world)
+    padded = torch.cat([flat, torch.zeros(chunk * world - total, dtype=flat.dtype, device=flat.device)])
+    off_end = torch.cuda.default_generators[0].get_offset()
+    for rank in range(world):
+        torch.manual_seed(31)
+        m = build()
+        shard, offs = materialize_flat_shard(list(m.parameters()), rank, world, align_numel=align)
+        assert offs == offsets + [total]
+        assert shard.shape == (chunk,) and torch.equal(bits(shard), bits(padded[rank * chunk:(rank + 1) * chunk])), rank
+        assert torch.cuda.default_generators[0].get_offset() == off_end  # every rank consumed the same offsets
+        assert all(is_deferred(p) for p in m.parameters())
+    # into a caller-owned buffer (FSDP's flat_param._local_shard)
+    torch.manual_seed(31)
+    m = build()
+    buf = torch.full((chunk + 5,), 7.0, dtype=torch.bfloat16, device="cuda:0")
+    shard, _ = materialize_flat_shard(list(m.parameters()), world - 1, world, align_numel=align, out=buf)
+    assert shard.data_ptr() == buf.data_ptr()
+    assert torch.equal(bits(buf[:chunk]), bits(padded[(world - 1) * chunk:])) and bool((buf[chunk:] == 7.0).all())
+
+
+def test_flat_shard_with_an_unfusable_parameter_falls_back_to_replay_and_copy():
+    from torchdistx_b200.deferred_init import materialize_flat_shard
+
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = nn.Parameter(torch.empty(33, 7).normal_())
+            self.b = nn.Parameter(torch.sin(torch.arange(40, dtype=torch.float32)))  # generic program
+            self.c = nn.Parameter(torch.full((5,), 2.0))
+
+    def build():
+        return deferred_init(lambda: _on_cuda(M))
+
+    torch.manual_seed(1)
+    full = build()
+    flat = torch.cat([materialize_tensor(p).detach().flatten() for p in full.parameters()])
+    chunk = -(-flat.numel() // 2)
+    padded = torch.cat([flat, flat.new_zeros(2 * chunk - flat.numel())])
+    for rank in range(2):
+        torch.manual_seed(1)
+        shard, _ = materialize_flat_shard(list(build().parameters()), rank, 2)
+        assert torch.equal(shard, padded[rank * chunk:(rank + 1) * chunk])

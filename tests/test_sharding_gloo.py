@@ -20,6 +20,12 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def sd_shapes(key, case):
+    from oracle import cases
+
+    return dict(cases.build(case, "fp32").named_parameters())[key].shape
+
+
 def _worker(rank, world, port, outdir):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -39,6 +45,24 @@ def _worker(rank, world, port, outdir):
     sd = {k: v.detach().clone() for k, v in list(m.named_parameters()) + list(m.named_buffers())}
     sd["__is_param__"] = sorted(k for k, _ in m.named_parameters())
     torch.save(sd, os.path.join(outdir, f"rank{rank}.pt"))
+
+    # the same through a DeviceMesh (FSDP2 / DTensor Shard(0) layout), wrapped as DTensors: the mesh's
+    # group carries the seed agreement, full_tensor() gathers what the ranks built
+    from torch.distributed.device_mesh import init_device_mesh
+    from torch.distributed.tensor import DTensor
+
+    mesh = init_device_mesh("cpu", (world,))
+    torch.manual_seed(200 + rank)  # disagree again: materialize_module(device_mesh=...) syncs by itself
+    m2 = deferred_init(lambda: cases.build("mlp_stack", "fp32"))
+    materialize_module(m2, device_mesh=mesh, as_dtensor=True)
+    assert parallel.check_agreement("cpu")
+    assert parallel.sync_rng("cpu") == parallel.rng_state("cpu")  # derived locally: no second broadcast needed
+    gathered = {}
+    for k, p in m2.named_parameters():
+        assert isinstance(p, torch.nn.Parameter) and isinstance(p.data, DTensor) and p.shape == sd_shapes(k, "mlp_stack"), k
+        gathered[k] = p.full_tensor().detach().clone()
+    if rank == 0:
+        torch.save(gathered, os.path.join(outdir, "mesh_gathered.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -68,3 +92,11 @@ def test_two_gloo_ranks_build_complementary_shards(world, tmp_path):
         else:
             for r in range(world):
                 assert torch.equal(shards[r][k], t), (k, r)
+
+    # DeviceMesh run: rank 0's seed (200) wins; the gathered DTensors are the unsharded module
+    torch.manual_seed(200)
+    full2 = deferred_init(lambda: cases.build("mlp_stack", "fp32"))
+    materialize_module(full2)
+    gathered = torch.load(tmp_path / "mesh_gathered.pt")
+    for k, t in full2.named_parameters():
+        assert torch.equal(gathered[k], t.detach()), k

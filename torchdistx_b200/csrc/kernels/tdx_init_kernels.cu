@@ -563,7 +563,18 @@ struct GroupArgs {
   // launch's latency plus its stores, like a stock elementwise kernel)
   uint32_t static_grabs;
   uint32_t rk[20];
+  // Single-descriptor launches (a lone tensor: materialize_tensor, the kernel sweep) carry their
+  // descriptor in the kernel parameters: no dependent global loads stand between the launch and
+  // the first store.
+  uint32_t inline_desc;  // `one` is the group's (only) descriptor
+  TdxInitDesc one;
 };
+
+// the descriptor `di` of a group (kernels take GroupArgs as a __grid_constant__ parameter, so the
+// address of the inline copy is a constant-bank address)
+__device__ __forceinline__ const TdxInitDesc* desc_of(const GroupArgs& g, uint32_t di) {
+  return g.inline_desc ? &g.one : g.descs + di;
+}
 
 // Every CTA calls this once, after its last (failed) grab: the last one to arrive puts the two
 // counters back to zero, so a plan can be launched again without a memset in between.
@@ -584,6 +595,10 @@ __device__ __forceinline__ void leave_grid(const GroupArgs& g) {
 // tiles on 4).
 template <class F>
 __device__ __forceinline__ void run_tiles(const GroupArgs& g, unsigned long long t, unsigned long long last, F&& f) {
+  if (g.n_desc == 1) {  // one descriptor owns every tile
+    f(0u, t, last - t);
+    return;
+  }
   uint32_t lo = 0, hi = g.n_desc;  // find d with prefix[d] <= t < prefix[d+1]
   while (hi - lo > 1) {
     const uint32_t mid = (lo + hi) >> 1;
@@ -651,14 +666,14 @@ __device__ __forceinline__ void for_each_listed_chunk(const GroupArgs& g, unsign
 // VECS = 16-byte vectors per thread and tile.  Measured (r1 sweep, 4 GiB): the fp32 generators gain
 // 3-5 % from 16 independent vectors in flight, the 16-bit ones (more registers per vector) lose.
 template <class Gen, int VECS = kVecsPerThread>
-__global__ void __launch_bounds__(kThreads) tdx_rng_kernel(const GroupArgs g) {
+__global__ void __launch_bounds__(kThreads) tdx_rng_kernel(const __grid_constant__ GroupArgs g) {
   using Out = typename Gen::OutT;
   using T = OutTraits<Out>;
   constexpr int EPV = Gen::kEpv;
   constexpr int kVecsPerThread = VECS;
   constexpr int kTileVecs = kThreads * VECS;
   for_each_tile_run(g, [&](uint32_t di, unsigned long long tile0, unsigned long long ntiles) {
-    const TdxInitDesc& d = g.descs[di];
+    const TdxInitDesc& d = *desc_of(g, di);
     const typename Gen::Params P = Gen::setup(d);
     const uint64_t begin = d.elem_begin, count = d.elem_count;
     const uint64_t gv0 = begin / EPV;
@@ -719,9 +734,9 @@ __global__ void __launch_bounds__(kThreads) tdx_rng_kernel(const GroupArgs g) {
 }
 
 // constant fill: 16-byte pattern, frame = absolute 16-byte lines of the destination
-__global__ void __launch_bounds__(kThreads) tdx_fill_kernel(const GroupArgs g) {
+__global__ void __launch_bounds__(kThreads) tdx_fill_kernel(const __grid_constant__ GroupArgs g) {
   for_each_tile_run(g, [&](uint32_t di, unsigned long long tile0, unsigned long long ntiles) {
-    const TdxInitDesc& d = g.descs[di];
+    const TdxInitDesc& d = *desc_of(g, di);
     const uint4 pat = make_uint4(static_cast<uint32_t>(d.fill_bits[0]),
                                  static_cast<uint32_t>(d.fill_bits[0] >> 32),
                                  static_cast<uint32_t>(d.fill_bits[1]),
@@ -1321,6 +1336,7 @@ struct PlanHeader {
   unsigned int counters[32];
   unsigned int done[32];
   PlanGroup groups[kNumFamilies];
+  TdxInitDesc one;  // the plan's descriptor if it has exactly one (GroupArgs::one)
 };
 constexpr uint32_t kPlanMagic = 0x58445431u;  // "TDX1"
 static_assert(kNumFamilies <= 32, "counter slots");
@@ -1501,6 +1517,7 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
       }
       prefix[k] = acc;
       out[k] = descs[i];
+      if (n == 1) hdr.one = descs[i];
       acc += tiles_of(descs[i], kFamilies[f].tile_vecs);
       ++k;
     }
@@ -1601,6 +1618,8 @@ int launch_groups(const PlanHeader& hdr, void* workspace, cudaStream_t stream) {
     a.counter = &dev_hdr->counters[gi];  // zero: uploaded so, and put back by the kernel (leave_grid)
     a.done = &dev_hdr->done[gi];
     a.n_desc = G.n_desc;
+    a.inline_desc = (hdr.n_groups == 1 && G.n_desc == 1) ? 1u : 0u;  // (hdr.one is set for one-descriptor plans)
+    a.one = hdr.one;
     a.seed_shared = G.seed_shared;
     {
       uint32_t k0 = static_cast<uint32_t>(G.seed), k1 = static_cast<uint32_t>(G.seed >> 32);

@@ -282,23 +282,68 @@ void py_materialize_module(const py::object& module, bool buffers_only, const py
     session_ptr.reset();
   }
   {
-    // the recordings outlive this call by a moment: their teardown runs on the helper thread
-    std::vector<std::shared_ptr<tdx::Tape>> tapes;
-    for (const PendingSlot& p : pending) {
-      if (!tdx::can_materialize(p.fake)) continue;
-      const auto& rec = tdx::fake_impl(p.fake)->record();
-      if (rec->tape && (tapes.empty() || tapes.back() != rec->tape) &&
-          std::find(tapes.begin(), tapes.end(), rec->tape) == tapes.end())
-        tapes.push_back(rec->tape);
+    // What the call replaced -- ~300 fake Parameter objects, their TensorImpls and meta twins, and
+    // the recording they kept alive (~3000 call frames for Llama-3-8B) -- is torn down on the helper
+    // thread after the call has returned (it takes the GIL for the Python objects when the caller
+    // next lets go of it, e.g. while waiting for the GPU): ~0.3 ms that are nobody's critical path.
+    struct Grave {
+      std::vector<py::object> objs;
+      std::vector<at::Tensor> fakes;
+      std::vector<std::shared_ptr<tdx::Tape>> tapes;
+    };
+    auto grave = std::make_shared<Grave>();
+    grave->objs.reserve(pending.size());
+    grave->fakes.reserve(pending.size());
+    for (PendingSlot& p : pending) {
+      if (tdx::can_materialize(p.fake)) {
+        const auto& rec = tdx::fake_impl(p.fake)->record();
+        if (rec->tape && (grave->tapes.empty() || grave->tapes.back() != rec->tape) &&
+            std::find(grave->tapes.begin(), grave->tapes.end(), rec->tape) == grave->tapes.end())
+          grave->tapes.push_back(rec->tape);
+      }
+      grave->objs.push_back(std::move(p.var));
+      grave->fakes.push_back(std::move(p.fake));
     }
     pending.clear();
     wrapped.clear();
-    py::gil_scoped_release nogil;
-    tdx::release_in_background(std::move(tapes));
+    const bool posted = tdx::post_background([grave] {
+      {
+        py::gil_scoped_acquire gil;
+        grave->fakes.clear();
+        grave->objs.clear();
+      }
+      grave->tapes.clear();
+    });
+    if (!posted) {  // (TDX_HOST_THREADS=0: everything dies here, with the caller)
+      grave->fakes.clear();
+      grave->objs.clear();
+      grave->tapes.clear();
+    }
   }
   if (trace)
     fprintf(stderr, "[tdx] materialize_module: session %.0f us, walked %.0f, wrapped %.0f, joined %.0f, assigned %.0f, "
             "done %.0f (%zu tensors)\n", t_created, t_walked, t_wrapped, t_joined, t_assigned, since(), pending.size());
+}
+
+py::tuple py_materialize_flat_shard(const py::list& vars, int64_t rank, int64_t world, int64_t align_numel,
+                                    const py::object& device, const py::object& out) {
+  std::vector<at::Tensor> fakes;
+  fakes.reserve(vars.size());
+  for (const py::handle& h : vars) {
+    if (!THPVariable_Check(h.ptr()))
+      throw py::type_error(std::string("expected a list of tensors, but got `") + Py_TYPE(h.ptr())->tp_name + "`.");
+    fakes.push_back(THPVariable_Unpack(h.ptr()));
+  }
+  const tdx::MaterializeOptions opts = make_options(device, py::none(), true);
+  std::optional<at::Tensor> out_t;
+  if (!out.is_none()) out_t = py::cast<at::Tensor>(out);
+  std::vector<int64_t> offsets;
+  at::Tensor shard;
+  {
+    py::gil_scoped_release nogil;
+    shard = tdx::materialize_flat_shard(fakes, opts, rank, world, align_numel, out_t, &offsets);
+  }
+  return py::make_tuple(shard, offsets);
 }
 
 py::dict py_last_stats() {
@@ -347,6 +392,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("materialize_module", &py_materialize_module, py::arg("module"), py::arg("buffers_only") = false,
         py::arg("check_fn") = py::none(), py::arg("device") = py::none(), py::arg("shard") = py::none(),
         py::arg("fused") = true);
+  m.def("materialize_flat_shard", &py_materialize_flat_shard, py::arg("tensors"), py::arg("rank"), py::arg("world"),
+        py::arg("align_numel") = 0, py::arg("device") = py::none(), py::arg("out") = py::none());
   m.def("plan_info", [](const at::Tensor& t) {
     const tdx::PlanInfo i = tdx::plan_info(t);
     py::dict d;
@@ -387,6 +434,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     }
     d["segments"] = segs;
     return d;
+  });
+  m.def("_drain", [] {
+    py::gil_scoped_release nogil;  // the helper may need the GIL to let go of Python objects
+    tdx::drain_background();
   });
   m.def("storage_history", &tdx::storage_history);
   m.def("last_stats", &py_last_stats);

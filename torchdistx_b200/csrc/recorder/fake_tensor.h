@@ -17,9 +17,20 @@
 #include <c10/core/Storage.h>
 #include <c10/core/TensorImpl.h>
 
+#include <cstdio>
 #include <memory>
+#include <string>
 
 namespace tdx {
+
+// A double as an ostream would print it ("%g").  Error messages are built from this: the
+// extension's own instantiation of std::ostream::operator<<(double) is not usable (it is emitted
+// into this hidden-visibility library without its locale facets and crashes).
+inline std::string fmt_double(double v) {
+  char buf[32];
+  std::snprintf(buf, sizeof(buf), "%g", v);
+  return buf;
+}
 
 struct TensorRecord;  // deferred-init recording state of one fake tensor (tape.h)
 

@@ -145,6 +145,30 @@ bool scalar_bits(const c10::Scalar& v, ScalarType dtype, unsigned char* out, siz
   }
 }
 
+// The value `v` holds once it has been stored in a tensor of `dtype` (what `full(v, dtype=...)` /
+// `fill_` keep of it: ATen converts with Scalar::to<scalar_t>()), as a Scalar again.  Lets a dtype
+// cast of a constant be folded on the host, exactly: full(v, A).to(B) == B(A(v)).  false: a dtype
+// or a value (out-of-range float -> integer) this does not model.
+bool stored_value(const c10::Scalar& v, ScalarType dtype, c10::Scalar& out) {
+  try {
+    switch (dtype) {
+      case ScalarType::Float: out = static_cast<double>(v.to<float>()); return true;
+      case ScalarType::Double: out = v.to<double>(); return true;
+      case ScalarType::BFloat16: out = static_cast<double>(static_cast<float>(v.to<c10::BFloat16>())); return true;
+      case ScalarType::Half: out = static_cast<double>(static_cast<float>(v.to<c10::Half>())); return true;
+      case ScalarType::Long: out = v.to<int64_t>(); return true;
+      case ScalarType::Int: out = static_cast<int64_t>(v.to<int32_t>()); return true;
+      case ScalarType::Short: out = static_cast<int64_t>(v.to<int16_t>()); return true;
+      case ScalarType::Char: out = static_cast<int64_t>(v.to<int8_t>()); return true;
+      case ScalarType::Byte: out = static_cast<int64_t>(v.to<uint8_t>()); return true;
+      case ScalarType::Bool: out = v.to<bool>(); return true;
+      default: return false;
+    }
+  } catch (...) {
+    return false;
+  }
+}
+
 // While a tape is analysed at the end of its recording (analyze_tape) the target device is not
 // known yet, and a constant chain must be folded with the target device's arithmetic: such
 // storages are evaluated when they are materialised instead.  The same holds for programs that
@@ -415,12 +439,12 @@ void transition(Tape& tape, uint32_t op_idx, uint32_t S, State& st) {
       Sym sy;
       sy.src = uni ? Sym::Uniform : Sym::Normal;
       if (uni) {
-        TORCH_CHECK(*a <= *c, "uniform_ expects to return a [from, to) range, but found from=", *a,
-                    " > to=", *c);
+        TORCH_CHECK(*a <= *c, "uniform_ expects to return a [from, to) range, but found from=", fmt_double(*a),
+                    " > to=", fmt_double(*c));
         sy.p0 = round_to_dtype(*a, out.dtype);
         sy.p1 = round_to_dtype(*c, out.dtype);
       } else {
-        TORCH_CHECK(*c >= 0.0, "normal expects std >= 0.0, but found std ", *c);
+        TORCH_CHECK(*c >= 0.0, "normal expects std >= 0.0, but found std ", fmt_double(*c));
         sy.p0 = *a;
         sy.p1 = *c;
       }
@@ -528,6 +552,16 @@ void transition(Tape& tape, uint32_t op_idx, uint32_t S, State& st) {
         continue;
       }
       if (sy.src == Sym::Const) {
+        if (op.kind == OpKind::CastOut && sy.has_scalar && !sy.cval.defined()) {
+          // a dtype cast of a plain constant (`ones(n).to(bf16)`, every norm weight of a model
+          // converted with Module.to): exact on the host, no 1-element tensor, no device round trip
+          c10::Scalar kept, probe;
+          if (stored_value(sy.cscalar, st.dtype, kept) && stored_value(kept, out.dtype, probe)) {
+            sy.cscalar = kept;
+            new_dtype = out.dtype;
+            continue;
+          }
+        }
         ScalarType dt = st.dtype;
         if (!fold_const(op, sy, dt, /*inplace=*/false) || dt != out.dtype) { st = make_opaque(); return; }
         new_dtype = out.dtype;
@@ -726,11 +760,9 @@ struct Batch {
   void note(int64_t bytes) {
     pending_bytes += bytes;
     if (flush_threshold > 0 && pending_bytes >= flush_threshold) {
-      if (gpu_busy_until_us - now_us_() > kBacklogGateUs) {
-        // plenty of work queued: let this submission grow instead (fewer, larger launches)
-        flush_threshold = std::min<int64_t>(flush_threshold * 2, int64_t{64} << 30);
-        return;
-      }
+      // plenty of work queued: let this submission grow until the GPU is about to run dry
+      // (fewer, larger launches); the next tensor asks again
+      if (gpu_busy_until_us - now_us_() > kBacklogGateUs) return;
       flush();
       flush_threshold = std::min<int64_t>(flush_threshold * 4, int64_t{64} << 30);
     }
@@ -1085,6 +1117,17 @@ struct Engine {
       const uint32_t v = tape.ops[oi].inputs[k].value;
       if (v == kNoValue) continue;
       if (tape.values[v].real.defined()) continue;
+      // A dependency whose whole program folds is built by the kernels (unsharded: the op reads all
+      // of it), not replayed op by op: faster, and its values do not depend on whether it or its
+      // reader was asked for first.  (A storage the reader saw in an intermediate state is opaque
+      // to the planner -- eval_storage's reader rule -- and is replayed up to `oi` as before.)
+      if (!tape.storages[tape.values[v].storage].fused_done) {
+        const std::optional<ShardSpec> saved = opts.shard;
+        opts.shard = std::nullopt;
+        const bool fused = try_fused(tape, v);
+        opts.shard = saved;
+        if (fused) continue;
+      }
       collect_storage(tape, tape.values[v].storage, oi, mark, visited_upto);
     }
   }
@@ -1251,6 +1294,178 @@ struct Engine {
     bytes_out = bytes;
     base_out = std::move(base);
     return true;
+  }
+
+  // ---- FSDP1 layout ----------------------------------------------------------------------------
+  // The parameters of one FlatParameter, flattened and concatenated in order (each start optionally
+  // aligned to `align` elements), chunked `world` ways by torch.chunk's rule, the last chunk
+  // right-padded with zeros ($TORCH/distributed/fsdp/_flat_param.py:1089-1140 `_get_shard`,
+  // :560-640 alignment padding): rank r's chunk is written straight into one 1-D tensor.  Neither a
+  // parameter nor the flat parameter ever exists unsharded.  Every parameter's RNG passes are
+  // assigned whether or not its elements fall into this rank's chunk, so all ranks agree.
+  at::Tensor flat_shard(const std::vector<at::Tensor>& fakes, int64_t rank, int64_t world, int64_t align,
+                        const std::optional<at::Tensor>& out_opt, std::vector<int64_t>* offsets_out) {
+    TORCH_CHECK_VALUE(world >= 1 && rank >= 0 && rank < world, "flat shard: 0 <= rank < world_size required");
+    struct Item {
+      std::shared_ptr<Tape> tape;
+      uint32_t value = kNoValue;
+      int64_t offset = 0, numel = 0;
+    };
+    std::vector<Item> items;
+    items.reserve(fakes.size());
+    ScalarType dtype = ScalarType::Undefined;
+    std::optional<c10::Device> dev;
+    int64_t total = 0;
+    for (const at::Tensor& f : fakes) {
+      TORCH_CHECK_VALUE(can_materialize(f), "flat shard: every parameter must be a deferred (fake) tensor");
+      const auto rec = fake_impl(f)->record();
+      const ValueInfo& vi = rec->tape->values[rec->value];
+      if (dtype == ScalarType::Undefined) dtype = vi.dtype;
+      TORCH_CHECK_VALUE(vi.dtype == dtype, "flat shard: parameters of one flat parameter share one dtype");
+      const c10::Device d = target_device(vi.device);
+      TORCH_CHECK_VALUE(d.is_cuda(), "flat shard: the target device must be a CUDA device");
+      if (!dev) dev = d;
+      TORCH_CHECK_VALUE(*dev == d, "flat shard: parameters live on different devices");
+      if (align > 1 && total % align) total += align - total % align;
+      Item it;
+      it.tape = rec->tape;
+      it.value = rec->value;
+      it.offset = total;
+      it.numel = vi.numel;
+      total += vi.numel;
+      if (offsets_out) offsets_out->push_back(it.offset);
+      items.push_back(std::move(it));
+    }
+    TORCH_CHECK_VALUE(dev.has_value(), "flat shard: no parameters");
+    const size_t isz = c10::elementSize(dtype);
+    const int64_t chunk = (total + world - 1) / world;
+    const int64_t lo = std::min(total, rank * chunk), hi = std::min(total, lo + chunk);
+    if (offsets_out) offsets_out->push_back(total);
+
+    if (batch.device != *dev) {
+      batch.flush();
+      batch.device = *dev;
+    }
+    at::Tensor out;
+    Batch::Pending pend;
+    char* abs_base = nullptr;
+    if (out_opt && out_opt->defined()) {
+      out = *out_opt;
+      TORCH_CHECK_VALUE(out.is_cuda() && out.device() == *dev && out.scalar_type() == dtype && out.dim() == 1 &&
+                            out.is_contiguous() && out.numel() >= chunk,
+                        "flat shard: `out` must be a contiguous 1-D CUDA tensor of the parameters' dtype with at "
+                        "least ceil(total / world) elements");
+      abs_base = static_cast<char*>(out.data_ptr());
+    } else {
+      pend.nbytes = static_cast<size_t>(chunk) * isz;
+      const int64_t sizes[1] = {chunk};
+      out = make_output(sizes, dtype, *dev, pend.nbytes, pend.storage);
+    }
+    pend.first_desc = static_cast<uint32_t>(batch.descs.size());
+    auto place = [&](int64_t flat_index) {  // dst of a flat element of this rank's chunk
+      return reinterpret_cast<void*>(abs_base + static_cast<uintptr_t>(flat_index - lo) * isz);
+    };
+    auto zero_fill = [&](int64_t b, int64_t e) {
+      if (b >= e) return;
+      TdxInitDesc d;
+      std::memset(&d, 0, sizeof(d));
+      d.src = TDX_SRC_CONST;
+      d.dtype = isz == 1 ? TDX_RAW8 : isz == 2 ? TDX_RAW16 : isz == 4 ? TDX_RAW32 : TDX_RAW64;
+      d.dst = place(b);
+      d.elem_count = static_cast<uint64_t>(e - b);
+      batch.descs.push_back(d);
+    };
+    struct Deferred {  // parameters the kernels cannot express: replayed whole, then copied (after the flush)
+      at::Tensor full;
+      int64_t src_begin, dst_begin, count;
+    };
+    std::vector<Deferred> deferred;
+    int64_t bytes = 0, covered = lo;  // [lo, covered) has been written or queued
+    for (const Item& it : items) {
+      Tape& tape = *it.tape;
+      const ValueInfo& vi = tape.values[it.value];
+      const uint32_t S = vi.storage;
+      StorageInfo& si = tape.storages[S];
+      const int64_t b = std::max(it.offset, lo), e = std::min(it.offset + it.numel, hi);
+      // alignment gap in front of this parameter
+      if (it.offset > covered && covered < hi) zero_fill(covered, std::min(it.offset, hi));
+      covered = std::max(covered, std::min(it.offset + it.numel, hi));
+      StorageTemplate tmp;
+      const StorageTemplate* t = nullptr;
+      bool fusible = opts.fused && !si.replayed && !si.fused_done && !vi.real.defined() && vi.covers_storage;
+      if (fusible) {
+        if (si.tmpl && si.tmpl->fast) {
+          t = si.tmpl.get();
+          g_stats.template_hits++;
+        } else if (!(si.tmpl && si.tmpl->st.opaque)) {
+          if (si.tmpl) {
+            tmp.st = si.tmpl->st;
+          } else {
+            struct FoldOn {
+              c10::Device prev = g_fold_device;
+              explicit FoldOn(c10::Device d) { g_fold_device = d; }
+              ~FoldOn() { g_fold_device = prev; }
+            } fold_on(*dev);
+            c10::DeviceGuard fold_guard(*dev);
+            tmp.st = eval_storage(tape, S, static_cast<uint32_t>(tape.ops.size()));
+          }
+          if (build_fast(tape, si, tmp, /*may_sync=*/true)) t = &tmp;
+        }
+        fusible = t != nullptr && t->st.dtype == dtype;
+      }
+      if (!fusible) {
+        // generic replay of the whole parameter on the GPU, then its slice is copied into the chunk
+        at::Tensor full = materialize_value(it.tape, it.value);
+        if (b < e) deferred.push_back(Deferred{full, b - it.offset, b, e - b});
+        continue;
+      }
+      for (const RngPass& r : t->st.rng_chain) {  // every rank assigns every pass, owner or not
+        RngSlot& slot = tape.rng[r.slot];
+        if (!slot.assigned) assign_rng(tape, slot, r.numel, *dev, gens);
+      }
+      if (b >= e) continue;
+      const int64_t pb = b - it.offset, pe = e - it.offset;  // the parameter's own elements this rank holds
+      for (const FastSeg& sg : t->segs) {
+        const int64_t slo = std::max(sg.begin, pb), shi = std::min(sg.end, pe);
+        if (slo >= shi) continue;
+        batch.descs.push_back(sg.proto);
+        TdxInitDesc& d = batch.descs.back();
+        d.dst = place(it.offset + slo);
+        d.elem_count = static_cast<uint64_t>(shi - slo);
+        if (sg.rng_slot != kNoValue) {
+          d.elem_begin = static_cast<uint64_t>(slo - sg.origin);
+          const RngSlot& r = tape.rng[sg.rng_slot];
+          d.philox_seed = r.seed;
+          d.philox_offset = r.offset;
+          if (sg.wide && wide_observable(tape, *sg.sym)) d.algo = TDX_ALGO_WIDE32;
+        }
+        bytes += (shi - slo) * static_cast<int64_t>(isz);
+      }
+    }
+    // the right zero-pad of the last rank(s): [hi, lo + chunk)
+    if (covered < lo + chunk) {
+      const int64_t b = std::max(covered, lo);
+      TdxInitDesc d;
+      std::memset(&d, 0, sizeof(d));
+      d.src = TDX_SRC_CONST;
+      d.dtype = isz == 1 ? TDX_RAW8 : isz == 2 ? TDX_RAW16 : isz == 4 ? TDX_RAW32 : TDX_RAW64;
+      d.dst = place(b);
+      d.elem_count = static_cast<uint64_t>(lo + chunk - b);
+      if (d.elem_count) batch.descs.push_back(d);
+    }
+    if (!abs_base) {
+      pend.n_desc = static_cast<uint32_t>(batch.descs.size()) - pend.first_desc;
+      batch.pending.push_back(std::move(pend));
+    }
+    g_stats.bytes_written += bytes;
+    g_stats.fused_tensors += static_cast<int64_t>(items.size() - deferred.size());
+    batch.flush();
+    if (!deferred.empty()) {
+      NoInterception guard;
+      for (const Deferred& d : deferred)
+        out.narrow(0, d.dst_begin - lo, d.count).copy_(d.full.reshape({-1}).narrow(0, d.src_begin, d.count));
+    }
+    return out;
   }
 
   // Fused path for the storage of value `v`.  Returns false if the program is not fusible.
@@ -1453,6 +1668,64 @@ bool host_threads_enabled() {
 
 }  // namespace
 
+// The recording of a model is cold in the caches when it is materialised, and planning one tensor is
+// a chain of dependent loads (tensor -> its record -> value -> storage -> analysis block -> RNG
+// slots): ~100 ns each, more than the arithmetic.  The helper walks that chain a few queued tensors
+// ahead, one link per tensor per step, with prefetches -- by the time a tensor is planned its lines
+// have arrived.
+class ChainPrefetcher {
+ public:
+  static constexpr int kDepth = 6;
+  void advance(const at::Tensor& fake, int stage) {
+    if (!is_fake(fake)) return;
+    const FakeTensorImpl* impl = fake_impl(fake);
+    switch (stage) {
+      case 0:
+        __builtin_prefetch(impl);
+        __builtin_prefetch(reinterpret_cast<const char*>(impl) + sizeof(c10::TensorImpl));  // (record_ lives past the base)
+        return;
+      case 1: {
+        const TensorRecord* r = impl->record().get();
+        if (r) __builtin_prefetch(r);
+        return;
+      }
+      default: break;
+    }
+    const TensorRecord* r = impl->record().get();
+    if (!r || !r->tape || r->value == kNoValue) return;
+    const Tape& tape = *r->tape;
+    if (r->value >= tape.values.size()) return;
+    const ValueInfo* vi = &tape.values[r->value];
+    if (stage == 2) {
+      __builtin_prefetch(vi);
+      __builtin_prefetch(reinterpret_cast<const char*>(vi) + 64);
+      __builtin_prefetch(reinterpret_cast<const char*>(vi) + 128);
+      return;
+    }
+    const StorageInfo* si = &tape.storages[vi->storage];
+    if (stage == 3) {
+      __builtin_prefetch(si);
+      __builtin_prefetch(reinterpret_cast<const char*>(si) + 64);
+      return;
+    }
+    const StorageTemplate* t = si->tmpl.get();
+    if (!t) return;
+    if (stage == 4) {
+      for (int k = 0; k < 6; ++k) __builtin_prefetch(reinterpret_cast<const char*>(t) + 64 * k);
+      return;
+    }
+    if (stage == 5) {
+      if (!t->st.rng_chain.empty()) {
+        __builtin_prefetch(t->st.rng_chain.data());
+        // (the slot index is in the chain entry; the first entry's slot is the earliest of the tensor)
+      }
+      if (!t->segs.empty() && t->segs[0].rng_slot != kNoValue && t->segs[0].rng_slot < tape.rng.size())
+        __builtin_prefetch(&tape.rng[t->segs[0].rng_slot]);
+      if (t->segs.size() > 0) __builtin_prefetch(reinterpret_cast<const char*>(&t->segs[0]) + 128);
+    }
+  }
+};
+
 struct PipelinedMaterialize::State {
   struct Item {
     at::Tensor fake;
@@ -1530,7 +1803,13 @@ struct PipelinedMaterialize::State {
           first = next;
           next = items.size();
         }
-        for (size_t i = 0; i < batch.size(); ++i) process(s, *batch[i], first + i);
+        ChainPrefetcher pf;
+        for (size_t i = 0; i < batch.size(); ++i) {
+          // tensor i + d is at link (kDepth - d) of its chain
+          for (int d = 1; d <= ChainPrefetcher::kDepth; ++d)
+            if (i + d < batch.size()) pf.advance(batch[i + d]->fake, ChainPrefetcher::kDepth - d);
+          process(s, *batch[i], first + i);
+        }
         if (fin && batch.empty()) break;  // finish() was requested and nothing arrived after it
       }
       if (!failed()) {
@@ -1685,11 +1964,55 @@ void release_in_background(std::vector<std::shared_ptr<Tape>> tapes) {
   HelperThread::get().post([box] { box->clear(); });
 }
 
+bool post_background(std::function<void()> fn) {
+  if (!host_threads_enabled()) return false;
+  HelperThread::get().post(std::move(fn));
+  return true;
+}
+
+void drain_background() {
+  if (!host_threads_enabled()) return;
+  struct Gate {
+    std::mutex m;
+    std::condition_variable cv;
+    bool done = false;
+  };
+  auto gate = std::make_shared<Gate>();
+  HelperThread::get().post([gate] {
+    std::lock_guard<std::mutex> lock(gate->m);
+    gate->done = true;
+    gate->cv.notify_all();
+  });
+  std::unique_lock<std::mutex> lock(gate->m);
+  gate->cv.wait(lock, [&] { return gate->done; });
+}
+
 void add_wrap_time(double us) { g_stats.wrap_us += us; }
 // (materialize_many resets the counters: the traversal that precedes it is reported through a
 // pending value that the next reset picks up)
 void add_traverse_time(double us) { g_pending_traverse_us += us; }
 void add_assign_time(double us) { g_stats.assign_us += us; }
+
+at::Tensor materialize_flat_shard(const std::vector<at::Tensor>& fakes, const MaterializeOptions& opts, int64_t rank,
+                                  int64_t world, int64_t align_numel, const std::optional<at::Tensor>& out,
+                                  std::vector<int64_t>* offsets) {
+  g_stats = MaterializeStats{};
+  g_last_descs.clear();
+  g_call_begin_us = now_us();
+  Batch batch;
+  Engine eng{opts, batch};
+  at::Tensor result;
+  try {
+    result = eng.flat_shard(fakes, rank, world, align_numel, out, offsets);
+  } catch (...) {
+    try { batch.flush(); } catch (...) {}
+    try { eng.gens.write_back(); } catch (...) {}
+    throw;
+  }
+  eng.gens.write_back();
+  g_stats.tensors = static_cast<int64_t>(fakes.size());
+  return result;
+}
 
 at::Tensor materialize_one(const at::Tensor& fake, const MaterializeOptions& opts) {
   if (!can_materialize(fake)) return fake;

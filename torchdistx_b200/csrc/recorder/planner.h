@@ -19,6 +19,7 @@
 #include <ATen/Tensor.h>
 
 #include <cstdint>
+#include <functional>
 #include <memory>
 #include <optional>
 #include <string>
@@ -71,6 +72,16 @@ at::Tensor materialize_one(const at::Tensor& fake, const MaterializeOptions& opt
 std::vector<at::Tensor> materialize_many(const std::vector<at::Tensor>& fakes,
                                          const MaterializeOptions& opts,
                                          const std::vector<uint8_t>* shard_mask = nullptr);
+
+// FSDP1's layout: this rank's chunk of the FlatParameter the given parameters form --
+// flattened, concatenated in order (each start aligned to `align_numel` elements if > 1), chunked
+// `world` ways like torch.chunk, right-padded with zeros ($TORCH/distributed/fsdp/_flat_param.py
+// `_get_shard`) -- written directly into one 1-D tensor (`out`, if given: e.g. the handle's
+// `_local_shard`).  Nothing unsharded is ever allocated.  `offsets` (optional) receives every
+// parameter's start in the flat parameter, then the total.  opts.shard is ignored.
+at::Tensor materialize_flat_shard(const std::vector<at::Tensor>& fakes, const MaterializeOptions& opts, int64_t rank,
+                                  int64_t world, int64_t align_numel, const std::optional<at::Tensor>& out,
+                                  std::vector<int64_t>* offsets = nullptr);
 
 // The same, one tensor at a time: `materialize_module` walks the module tree and feeds tensors as it
 // finds them, so the first kernels are on the GPU while the walk is still going on (the walk of a
@@ -126,6 +137,12 @@ class PipelinedMaterialize {
 // thread, which lets go of them after the call has returned.
 struct Tape;
 void release_in_background(std::vector<std::shared_ptr<Tape>> tapes);
+// Runs `fn` on the helper thread after everything queued so far; false (and `fn` not run) when host
+// threads are disabled.
+bool post_background(std::function<void()> fn);
+// Returns once the helper thread has finished everything queued so far (recordings handed to
+// release_in_background included).  Call without the GIL.
+void drain_background();
 
 MaterializeStats last_stats();
 void add_wrap_time(double us);

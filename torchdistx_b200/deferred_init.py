@@ -18,20 +18,27 @@ target device and dim-0 sharding:
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, Optional, Tuple, TypeVar, Union
+from typing import Callable, Dict, List, Optional, Sequence, Tuple, TypeVar, Union
 
 import torch
 from torch import Tensor
 from torch.nn import Module
 
+import atexit
+
 from . import _C
 from . import fake  # noqa: F401  (installs the fake-aware Tensor.__repr__)
+
+# materialize_module leaves the teardown of a finished recording to the engine's helper thread;
+# it must be done with Python objects before the interpreter goes away
+atexit.register(_C._drain)
 
 __all__ = [
     "deferred_init",
     "is_deferred",
     "materialize_tensor",
     "materialize_module",
+    "materialize_flat_shard",
     "last_materialize_stats",
     "last_descriptors",
     "plan_report",
@@ -88,6 +95,8 @@ def materialize_module(
     *,
     device: DeviceLike = None,
     shard: Shard = None,
+    device_mesh=None,
+    as_dtensor: bool = False,
 ) -> None:
     """Materialises ``module`` and its descendants in place.
 
@@ -100,10 +109,73 @@ def materialize_module(
         shard: ``(rank, world_size)``: build only this rank's ``torch.chunk(..., dim=0)`` slice of
             every parameter (buffers and 0-dim tensors are replicated).  All ranks must hold the
             same generator state; see :func:`torchdistx_b200.parallel.sync_rng`.
+        device_mesh: a 1-D ``torch.distributed.device_mesh.DeviceMesh``: shorthand for
+            ``shard=(mesh.get_local_rank(), mesh.size())`` on this rank's device of the mesh, with the
+            generator state agreed over the mesh's process group first (the path's one collective,
+            16 bytes).  The layout is FSDP2's / DTensor's ``Shard(0)``
+            ($TORCH/distributed/fsdp/_fully_shard/_fsdp_param.py:381-402).
+        as_dtensor: with ``device_mesh``: wrap every dim-0-sharded parameter as a
+            ``DTensor(mesh, [Shard(0)])`` over its local chunk (no copy, no communication).
     """
+    if device_mesh is not None:
+        from . import parallel
+
+        if device_mesh.ndim != 1:
+            raise ValueError("materialize_module: `device_mesh` must be 1-D (pass the mesh dimension to shard over)")
+        if shard is not None:
+            raise ValueError("materialize_module: pass either `shard` or `device_mesh`")
+        shard = (device_mesh.get_local_rank(), device_mesh.size())
+        if device is None and device_mesh.device_type == "cuda":
+            device = torch.device("cuda", torch.cuda.current_device())
+        parallel.sync_rng(device if device is not None else torch.device(device_mesh.device_type),
+                          group=device_mesh.get_group())
+    elif as_dtensor:
+        raise ValueError("materialize_module: `as_dtensor` needs a `device_mesh`")
+    shapes = None
+    if as_dtensor:
+        shapes = {id(mod): {k: (tuple(p.shape), tuple(p.stride())) for k, p in mod._parameters.items()
+                            if p is not None and _C.can_materialize(p)} for mod in module.modules()}
     # (a ValueError raised while a tensor is materialised comes back as the reference words it,
     # deferred_init.py:110-113: "'<key>' has already been materialized."; others pass unchanged)
     _C.materialize_module(module, buffers_only, check_fn, _device(device), shard)
+    if as_dtensor and not buffers_only:
+        from torch.distributed.tensor import DTensor, Shard
+
+        for mod in module.modules():
+            for k, (shape, stride) in shapes.get(id(mod), {}).items():
+                p = mod._parameters[k]
+                if len(shape) == 0 or isinstance(p, DTensor) or _C.can_materialize(p):
+                    continue  # 0-dim parameters are replicated; skipped modules (check_fn) are still fake
+                dt = DTensor.from_local(p.detach(), device_mesh, [Shard(0)], run_check=False, shape=torch.Size(shape),
+                                        stride=stride)
+                mod._parameters[k] = torch.nn.Parameter(dt, requires_grad=p.requires_grad)
+
+
+def materialize_flat_shard(
+    params: Sequence[Tensor],
+    rank: int,
+    world_size: int,
+    *,
+    device: DeviceLike = None,
+    align_numel: int = 0,
+    out: Optional[Tensor] = None,
+) -> Tuple[Tensor, List[int]]:
+    """FSDP1's layout: this rank's chunk of the ``FlatParameter`` the deferred ``params`` form.
+
+    The parameters are (virtually) flattened and concatenated in order -- each start aligned to
+    ``align_numel`` elements when > 1, as ``FlatParamHandle`` does under ``use_orig_params`` -- the
+    flat vector is chunked ``world_size`` ways like ``torch.chunk`` and the last chunk right-padded
+    with zeros ($TORCH/distributed/fsdp/_flat_param.py ``_get_shard``).  Rank ``rank``'s chunk is
+    written by the kernels straight into one 1-D tensor (``out`` if given, e.g. the handle's
+    ``flat_param._local_shard``); neither the parameters nor the flat parameter exist unsharded at
+    any time.  Returns ``(local_shard, offsets)``: ``offsets[i]`` is the start of ``params[i]`` in
+    the flat parameter, ``offsets[-1]`` its unpadded total.
+
+    The parameters stay deferred; all ranks must hold the same generator state
+    (:func:`torchdistx_b200.parallel.sync_rng`) and pass the same list.
+    """
+    shard, offsets = _C.materialize_flat_shard(list(params), rank, world_size, align_numel, _device(device), out)
+    return shard, list(offsets)
 
 
 def plan_report(module: Module) -> Dict[str, Dict[str, object]]:
