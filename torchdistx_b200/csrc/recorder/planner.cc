@@ -27,6 +27,7 @@
 #include <ATen/ThreadLocalState.h>
 #include <ATen/detail/CUDAHooksInterface.h>
 #include <c10/cuda/CUDAFunctions.h>
+#include <cuda_runtime_api.h>
 
 #include "fake_tensor.h"
 #include "stack_walk.h"
@@ -42,6 +43,34 @@ using torch::jit::Stack;
 namespace {
 
 thread_local MaterializeStats g_stats;
+
+// TDX_PROFILE=1: where the per-tensor host time of a materialize call goes (TSC ticks per phase,
+// printed on stderr when the session finishes).  Diagnostics only.
+struct Prof {
+  static bool on() {
+    static const bool v = getenv("TDX_PROFILE") != nullptr;
+    return v;
+  }
+  static uint64_t tick() {
+#if defined(__x86_64__)
+    return __builtin_ia32_rdtsc();
+#else
+    return 0;
+#endif
+  }
+  uint64_t acc[12] = {};
+  const char* names[12] = {"add:record", "add:materialize_value", "add:finish", "emit:geometry+output", "emit:rng",
+                           "emit:descs", "fused:note", "real_of", "process:total", "emit:total", "", ""};
+};
+thread_local Prof g_prof;
+struct ProfScope {
+  int k;
+  uint64_t t0;
+  explicit ProfScope(int k_) : k(k_), t0(Prof::on() ? Prof::tick() : 0) {}
+  ~ProfScope() {
+    if (Prof::on()) g_prof.acc[k] += Prof::tick() - t0;
+  }
+};
 thread_local double g_pending_traverse_us = 0;  // see add_traverse_time
 // Where constant chains are folded.  ATen's CPU and CUDA kernels differ in the last bit for 16-bit
 // dtypes (the CPU kernels round a Python scalar to the tensor dtype first, the CUDA kernels keep it
@@ -829,6 +858,19 @@ void Batch::assign_memory() {
   g_stats.alloc_us += now_us() - t0;
 }
 
+// TDX_TRACE=1: every submission's host time, bytes and GPU start / end (CUDA events, read back when
+// the session finishes).
+struct SubmissionTrace {
+  double host_us = 0, bytes = 0;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+thread_local std::vector<SubmissionTrace> g_sub_trace;
+thread_local cudaEvent_t g_trace_origin = nullptr;
+bool trace_on() {
+  static const bool v = getenv("TDX_TRACE") != nullptr;
+  return v;
+}
+
 void Batch::flush() {
   NoInterception guard;
   c10::DeviceGuard dg(device.is_cuda() ? device : c10::Device(c10::kCPU));
@@ -849,8 +891,24 @@ void Batch::flush() {
   at::Tensor ws = at::detail::empty_cuda({static_cast<int64_t>(std::max<size_t>(ws_bytes, 16))}, at::kByte,
                                          device, std::nullopt);
   auto stream = c10::cuda::getCurrentCUDAStream(device.index());
+  SubmissionTrace tr;
+  if (trace_on()) {
+    if (!g_trace_origin) {
+      cudaEventCreate(&g_trace_origin);
+      cudaEventRecord(g_trace_origin, stream.stream());
+    }
+    cudaEventCreate(&tr.e0);
+    cudaEventCreate(&tr.e1);
+    cudaEventRecord(tr.e0, stream.stream());
+  }
   rc = tdx_init_submit(ws.data_ptr(), ws_bytes, stream.stream());
   TORCH_CHECK(rc == 0, "libtdx_init: launch failed (", rc, "): ", tdx_last_error());
+  if (trace_on()) {
+    cudaEventRecord(tr.e1, stream.stream());
+    tr.host_us = now_us() - g_call_begin_us;
+    tr.bytes = static_cast<double>(pending_bytes);
+    g_sub_trace.push_back(tr);
+  }
   g_stats.kernel_launches += tdx_last_launch_count();
   g_stats.descriptors += n;
   g_stats.submissions++;
@@ -860,10 +918,10 @@ void Batch::flush() {
   g_last_descs.insert(g_last_descs.end(), descs.begin(), descs.end());
   descs.clear();
   {
-    // (4.5 bytes/ns: what the slowest of the bulk kernels sustains; an under-estimate only makes
-    // the next submission come a little early)
+    // (4.5 TB/s = 4.5e6 bytes/us: what the slowest of the bulk kernels sustains; an under-estimate
+    // only makes the next submission come a little early)
     const double t_now = now_us();
-    gpu_busy_until_us = std::max(gpu_busy_until_us, t_now) + static_cast<double>(pending_bytes) / 4.5e3 + 20.0;
+    gpu_busy_until_us = std::max(gpu_busy_until_us, t_now) + static_cast<double>(pending_bytes) / 4.5e6 + 20.0;
   }
   pending_bytes = 0;
   epoch = g_epoch.fetch_add(1);
@@ -1240,9 +1298,11 @@ struct Engine {
 
   bool emit_from(Tape& tape, const StorageTemplate& t, const ValueInfo& vi, const std::optional<ShardSpec>& shard,
                  c10::Device dev, at::Tensor& base_out, int64_t& bytes_out) {
+    ProfScope p_total(9);
     const State& st = t.st;
     const size_t isz = t.isz;
     // geometry of what this rank writes
+    const uint64_t pt0 = Prof::on() ? Prof::tick() : 0;
     ShardGeom g;
     if (vi.covers_storage && vi.dtype == st.dtype) {
       g = shard_of(vi, shard);
@@ -1258,6 +1318,7 @@ struct Engine {
     Batch::Pending pend;
     pend.nbytes = static_cast<size_t>(g.count) * isz;
     at::Tensor base = make_output(g.sizes, st.dtype, dev, pend.nbytes, pend.storage);
+    const uint64_t pt1 = Prof::on() ? Prof::tick() : 0;
 
     // every RNG pass on the chain consumes its slice of the stream, live or dead
     for (const RngPass& r : st.rng_chain) {
@@ -1268,6 +1329,12 @@ struct Engine {
       for (const FastSeg& sg : t.segs) live |= sg.rng_slot == r.slot;
       if (!live) g_stats.elided_rng_ops++;
     }
+    const uint64_t pt2 = Prof::on() ? Prof::tick() : 0;
+    if (Prof::on()) {
+      g_prof.acc[3] += pt1 - pt0;
+      g_prof.acc[4] += pt2 - pt1;
+    }
+    ProfScope p_descs(5);
 
     pend.first_desc = static_cast<uint32_t>(batch.descs.size());
     int64_t bytes = 0;
@@ -1487,9 +1554,55 @@ struct Engine {
     // (the storage's writer ops are not marked done one by one: `fused_done` stops every walk over
     // them -- collect_storage, eval_storage's callers -- and costs no cache line per op)
     g_stats.fused_tensors++;
-    batch.note(bytes);  // may submit what has accumulated so far
+    {
+      ProfScope p(6);
+      batch.note(bytes);  // may submit what has accumulated so far
+    }
     return true;
   }
+
+  // Does anything that determines storage S (as of op `upto`) draw random numbers?  A pure walk
+  // over the recording (no side effects): programs without RNG can be replayed at any point of the
+  // call without changing what anybody gets -- they neither read nor advance a generator.
+  static bool is_random_op(const TapeOp& op) {
+    switch (op.kind) {
+      case OpKind::Randn: case OpKind::Rand: case OpKind::UniformInplace: case OpKind::NormalInplace: return true;
+      default: break;
+    }
+    if (!op.handle) return false;
+    const auto& schema = op.handle->schema();
+    for (const auto& a : schema.arguments())
+      if (a.name() == "generator") return true;
+    const std::string& n = schema.name();
+    return n.find("dropout") != std::string::npos || n.find("rrelu") != std::string::npos ||
+           n.find("rand") != std::string::npos || n.find("bernoulli") != std::string::npos ||
+           n.find("multinomial") != std::string::npos || n.find("poisson") != std::string::npos;
+  }
+  bool deterministic_slice(Tape& tape, uint32_t S, uint32_t upto, std::vector<uint32_t>& seen_upto) {
+    if (seen_upto[S] >= upto) return true;
+    seen_upto[S] = upto;
+    const StorageInfo& si = tape.storages[S];
+    if (si.fused_done) return true;
+    for (uint32_t oi : si.touching_ops) {
+      if (oi >= upto) break;
+      const TapeOp& op = tape.ops[oi];
+      if (op.done) continue;
+      bool writes = false;
+      for (uint32_t v : op.outputs) writes |= v != kNoValue && tape.values[v].storage == S;
+      if (!writes) continue;
+      if (is_random_op(op)) return false;
+      for (const InputRef& in : op.inputs) {
+        if (in.foreign) return false;  // (another recording: keep it simple)
+        if (in.value == kNoValue || tape.values[in.value].real.defined()) continue;
+        if (!deterministic_slice(tape, tape.values[in.value].storage, oi, seen_upto)) return false;
+      }
+    }
+    return true;
+  }
+  // Set by the session: unfusable programs without RNG are not replayed where the walk meets them but
+  // after the call's last fused submission -- their dozen ATen dispatches (Llama's rotary inv_freq:
+  // ~0.25 ms of host time) then run while the GPU already works on the whole model.
+  bool defer_generic = false;
 
   // This rank's dim-0 chunk of a fully materialised tensor (generic replay always builds the whole
   // tensor: its ops are recorded on whole tensors).
@@ -1511,7 +1624,14 @@ struct Engine {
       return (sharding(vi) && !si.base_is_shard) ? chunk_of(vi, t) : t;
     }
     if (vi.real.defined()) return sharding(vi) ? chunk_of(vi, vi.real) : vi.real;
-    if (try_fused(tape, v)) return real_of(tape, v);
+    if (try_fused(tape, v)) {
+      ProfScope p(7);
+      return real_of(tape, v);
+    }
+    if (defer_generic) {
+      std::vector<uint32_t> seen(tape.storages.size(), 0);
+      if (deterministic_slice(tape, vi.storage, static_cast<uint32_t>(tape.ops.size()), seen)) return at::Tensor();
+    }
 
     // generic replay, in recorded order, of everything that determines this storage.  Pending fused
     // descriptors stay in the batch (replay() submits them first if one of its inputs is among them):
@@ -1546,8 +1666,20 @@ struct MaterializeSession::Impl {
   double t_begin;
   double add_us = 0;
   bool finished = false;
+  struct Deferred {
+    at::Tensor fake;
+    bool apply_shard;
+    size_t ticket;
+  };
+  std::vector<Deferred> deferred;
+  std::function<void(size_t, at::Tensor)> sink;
   explicit Impl(const MaterializeOptions& o) : opts(o), eng{o, batch}, t_begin(now_us()) {}
 };
+
+void MaterializeSession::defer_generic_programs(std::function<void(size_t, at::Tensor)> sink) {
+  impl_->sink = std::move(sink);
+  impl_->eng.defer_generic = static_cast<bool>(impl_->sink);
+}
 
 MaterializeSession::MaterializeSession(const MaterializeOptions& opts) {
   g_stats = MaterializeStats{};
@@ -1567,21 +1699,81 @@ MaterializeSession::~MaterializeSession() {
   }
 }
 
-at::Tensor MaterializeSession::add(const at::Tensor& t, bool apply_shard) {
+at::Tensor MaterializeSession::add(const at::Tensor& t, bool apply_shard, size_t ticket) {
   g_stats.tensors++;
   if (!can_materialize(t)) return t;
   const double t0 = now_us();
   impl_->eng.opts.shard = apply_shard ? impl_->opts.shard : std::nullopt;
-  const auto rec = fake_impl(t)->record();  // copy: keeps the tape alive while we work
-  at::Tensor out = finish_tensor(t, impl_->eng.materialize_value(rec->tape, rec->value));
+  std::shared_ptr<TensorRecord> rec;
+  {
+    ProfScope p(0);
+    rec = fake_impl(t)->record();  // copy: keeps the tape alive while we work
+  }
+  at::Tensor value;
+  {
+    ProfScope p(1);
+    value = impl_->eng.materialize_value(rec->tape, rec->value);
+  }
+  if (!value.defined()) {  // an unfusable program without RNG: replayed after the last submission (finish)
+    impl_->deferred.push_back(Impl::Deferred{t, apply_shard, ticket});
+    impl_->add_us += now_us() - t0;
+    return at::Tensor();
+  }
+  at::Tensor out;
+  {
+    ProfScope p(2);
+    out = finish_tensor(t, std::move(value));
+  }
   impl_->add_us += now_us() - t0;
   return out;
 }
 
 void MaterializeSession::finish() {
+  struct TraceDump {
+    ~TraceDump() {
+      if (!trace_on() || g_sub_trace.empty()) return;
+      cudaEventSynchronize(g_sub_trace.back().e1);
+      fprintf(stderr, "[tdx] submissions (host us since call | MB | GPU start..end us since the first submission's enqueue):");
+      for (SubmissionTrace& t : g_sub_trace) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, g_trace_origin, t.e0);
+        cudaEventElapsedTime(&b, g_trace_origin, t.e1);
+        fprintf(stderr, "  [%.0f | %.0f | %.0f..%.0f]", t.host_us, t.bytes / 1e6, a * 1e3, b * 1e3);
+        cudaEventDestroy(t.e0);
+        cudaEventDestroy(t.e1);
+      }
+      fprintf(stderr, "\n");
+      g_sub_trace.clear();
+      cudaEventDestroy(g_trace_origin);
+      g_trace_origin = nullptr;
+    }
+  } trace_dump;
+  if (Prof::on()) {
+    const uint64_t c0 = Prof::tick();
+    const double u0 = now_us();
+    while (now_us() - u0 < 200.0) {}
+    const double ticks_per_us = static_cast<double>(Prof::tick() - c0) / (now_us() - u0);
+    fprintf(stderr, "[tdx-prof] %lld tensors:", static_cast<long long>(g_stats.tensors));
+    for (int k = 0; k < 10; ++k) fprintf(stderr, " %s=%.0fus", g_prof.names[k], g_prof.acc[k] / ticks_per_us);
+    fprintf(stderr, "\n");
+    g_prof = Prof{};
+  }
   const double t0 = now_us();
   impl_->batch.flush();
   impl_->eng.gens.write_back();
+  // the deferred programs: the kernels of every fused tensor are on the stream by now
+  impl_->eng.defer_generic = false;
+  for (Impl::Deferred& d : impl_->deferred) {
+    impl_->eng.opts.shard = d.apply_shard ? impl_->opts.shard : std::nullopt;
+    const auto rec = fake_impl(d.fake)->record();
+    at::Tensor out = finish_tensor(d.fake, impl_->eng.materialize_value(rec->tape, rec->value));
+    impl_->sink(d.ticket, std::move(out));
+  }
+  if (!impl_->deferred.empty()) {
+    impl_->deferred.clear();
+    impl_->batch.flush();  // (dependencies of the deferred programs that took the fused path)
+    impl_->eng.gens.write_back();
+  }
   impl_->finished = true;
   impl_->add_us += now_us() - t0;
   g_stats.plan_us = impl_->add_us - g_stats.launch_us;
@@ -1593,10 +1785,12 @@ std::vector<at::Tensor> materialize_many(const std::vector<at::Tensor>& fakes,
                                          const MaterializeOptions& opts,
                                          const std::vector<uint8_t>* shard_mask) {
   MaterializeSession session(opts);
-  std::vector<at::Tensor> out;
-  out.reserve(fakes.size());
-  for (size_t i = 0; i < fakes.size(); ++i)
-    out.push_back(session.add(fakes[i], !(shard_mask && !(*shard_mask)[i])));
+  std::vector<at::Tensor> out(fakes.size());
+  session.defer_generic_programs([&out](size_t i, at::Tensor t) { out[i] = std::move(t); });
+  for (size_t i = 0; i < fakes.size(); ++i) {
+    at::Tensor t = session.add(fakes[i], !(shard_mask && !(*shard_mask)[i]), i);
+    if (t.defined()) out[i] = std::move(t);
+  }
   session.finish();
   return out;
 }
@@ -1756,20 +1950,30 @@ struct PipelinedMaterialize::State {
     if (!error) {
       error = std::current_exception();
       error_ticket = ticket;
+      has_error.store(true, std::memory_order_release);
     }
   }
-  bool failed() {
-    std::lock_guard<std::mutex> lock(m);
-    return static_cast<bool>(error);
-  }
+  std::atomic<bool> has_error{false};
+  bool failed() { return has_error.load(std::memory_order_acquire); }  // (asked once per tensor: no lock)
   void process(MaterializeSession& s, Item& it, size_t ticket) {
+    ProfScope p_total(8);
     if (!failed()) {
       try {
-        it.out = s.add(it.fake, it.apply_shard);
+        it.out = s.add(it.fake, it.apply_shard, ticket);
+        if (!it.out.defined()) return;  // deferred to the end of the session: deliver() completes it
       } catch (...) {
         record_error(ticket);
       }
     }
+    it.done.store(1, std::memory_order_release);
+    if (caller_waiting.load(std::memory_order_acquire)) {
+      std::lock_guard<std::mutex> lock(m);
+      cv_done.notify_all();
+    }
+  }
+  void deliver(size_t ticket, at::Tensor t) {  // a deferred result (MaterializeSession::finish)
+    Item& it = *items[ticket];
+    it.out = std::move(t);
     it.done.store(1, std::memory_order_release);
     if (caller_waiting.load(std::memory_order_acquire)) {
       std::lock_guard<std::mutex> lock(m);
@@ -1786,6 +1990,7 @@ struct PipelinedMaterialize::State {
       if (caller_device >= 0) c10::cuda::set_device(caller_device);
       for (const auto& st : streams) c10::cuda::setCurrentCUDAStream(st);
       MaterializeSession s(opts);
+      s.defer_generic_programs([this](size_t ticket, at::Tensor t) { deliver(ticket, std::move(t)); });
       size_t next = 0, first = 0;
       std::vector<Item*> batch;
       for (;;) {
@@ -1856,6 +2061,8 @@ PipelinedMaterialize::PipelinedMaterialize(const MaterializeOptions& opts) : st_
     HelperThread::get().post([st] { st->run_on_helper(); });
   } else {
     st_->session = std::make_unique<MaterializeSession>(opts);
+    State* raw = st_.get();
+    st_->session->defer_generic_programs([raw](size_t ticket, at::Tensor t) { raw->deliver(ticket, std::move(t)); });
   }
 }
 
@@ -1869,7 +2076,10 @@ PipelinedMaterialize::~PipelinedMaterialize() {
   std::unique_lock<std::mutex> lock(st_->m);
   if (!st_->finish_requested) {
     st_->finish_requested = true;
-    if (!st_->error) st_->error = std::make_exception_ptr(std::runtime_error("materialize_module was abandoned"));
+    if (!st_->error) {
+      st_->error = std::make_exception_ptr(std::runtime_error("materialize_module was abandoned"));
+      st_->has_error.store(true, std::memory_order_release);
+    }
     st_->cv_work.notify_one();
   }
   st_->cv_done.wait(lock, [&] { return st_->finished; });

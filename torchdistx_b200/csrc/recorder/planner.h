@@ -94,7 +94,13 @@ class MaterializeSession {
   ~MaterializeSession();
   MaterializeSession(const MaterializeSession&) = delete;
   MaterializeSession& operator=(const MaterializeSession&) = delete;
-  at::Tensor add(const at::Tensor& fake, bool apply_shard = true);
+  // Returns the tensor -- or an undefined tensor if its program was deferred (see below); the
+  // result then arrives through the sink, tagged with `ticket`, during finish().
+  at::Tensor add(const at::Tensor& fake, bool apply_shard = true, size_t ticket = 0);
+  // Programs the kernels cannot express and that draw no random numbers (rotary inv_freq, position
+  // ids, masks) are replayed through ATen after the call's last fused submission instead of where the
+  // walk meets them: their dispatches then overlap the GPU's work on the whole model.
+  void defer_generic_programs(std::function<void(size_t ticket, at::Tensor result)> sink);
   void finish();
 
  private:
