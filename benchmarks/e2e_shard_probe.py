@@ -28,9 +28,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--worlds", default="1,2,4,8")
     ap.add_argument("--gc", type=int, default=1, help="0: collect before and disable the Python GC inside every timed call (like timeit)")
+    ap.add_argument("--prewarm-ms", type=float, default=0.0,
+                    help="keep the GPU busy for this long right before every timed call (diagnostic: how much of the "
+                         "end-to-end time is the GPU leaving its idle clocks)")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
+    spin = torch.empty(1 << 24, device=dev)
     for world in [int(w) for w in a.worlds.split(",")]:
         fakes = [deferred_init(bench.build_model, a.model) for _ in range(a.steps + 2)]
         shard = None if world == 1 else (0, world)
@@ -41,6 +45,11 @@ def main():
             if not a.gc:
                 gc.collect()
                 gc.disable()
+            if a.prewarm_ms > 0:
+                t_end = time.perf_counter() + a.prewarm_ms / 1e3
+                while time.perf_counter() < t_end:
+                    spin.normal_()
+                torch.cuda.synchronize()
             t0 = time.perf_counter()
             e0.record()
             materialize_module(m, device=dev, shard=shard)

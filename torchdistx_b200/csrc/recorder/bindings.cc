@@ -56,6 +56,24 @@ tdx::MaterializeOptions make_options(const py::object& device, const py::object&
   return o;
 }
 
+// `out` as a Python object of `like`'s class (no identity bookkeeping: see wrap_like).
+py::object wrap_only(const py::handle& like, const at::Tensor& out) {
+  PyTypeObject* type = Py_TYPE(like.ptr());
+  if (reinterpret_cast<PyObject*>(type) == reinterpret_cast<PyObject*>(THPVariableClass)) return py::cast(out);
+  if (reinterpret_cast<PyObject*>(type) == ParameterClass && out.use_count() > 0 &&
+      out.unsafeGetTensorImpl()->pyobj_slot()->load_pyobj() == nullptr && !out.grad_fn()) {
+    // A fresh leaf that Python has never seen: it can be born a Parameter (what
+    // Tensor._make_subclass does, minus the detach() and the trip through the argument parser --
+    // a microsecond per tensor, hundreds of tensors per call).
+    py::object r = py::reinterpret_steal<py::object>(THPVariable_Wrap(out, type));
+    if (!r) throw py::error_already_set();
+    return r;
+  }
+  static py::object make_subclass = py::module_::import("torch").attr("Tensor").attr("_make_subclass");
+  return make_subclass(py::reinterpret_borrow<py::object>(reinterpret_cast<PyObject*>(type)), py::cast(out),
+                       out.requires_grad());
+}
+
 // Gives `out` the Python class of `like` and remembers the result for identity.
 py::object wrap_like(const py::handle& like, const at::Tensor& fake, const at::Tensor& out) {
   at::Tensor cached = tdx::cached_python_tensor(fake);
@@ -165,6 +183,10 @@ struct PendingSlot {
   py::object var;  // the fake tensor object (its Python class is what the result must have)
   at::Tensor fake;
   size_t ticket;  // of the planner's result; kNoTicket: the tensor was handed out before
+  // The output the walking thread built itself (PipelinedMaterialize::add), already wearing its Python
+  // class; confirmed against the planner's result after the join.
+  at::Tensor speculative;
+  py::object speculative_wrapped;
 };
 constexpr size_t kNoTicket = static_cast<size_t>(-1);
 
@@ -196,10 +218,13 @@ void walk_and_feed(const py::handle& module, bool buffers_only, const py::object
       const at::Tensor& t = THPVariable_Unpack(item.second.ptr());
       if (!tdx::can_materialize(t)) continue;  // real tensors stay where they are
       PendingSlot p{d, py::reinterpret_borrow<py::object>(item.first),
-                    py::reinterpret_borrow<py::object>(item.second), t, kNoTicket};
+                    py::reinterpret_borrow<py::object>(item.second), t, kNoTicket, {}, {}};
       // tensors that were already handed out keep their identity and are not touched again
       // (parameters are chunked, buffers replicated -- no isinstance(): which dict it came from says it)
-      if (!tdx::cached_python_tensor(t).defined()) p.ticket = session.add(t, /*apply_shard=*/!sharded || is_parameter);
+      if (!tdx::cached_python_tensor(t).defined()) {
+        p.ticket = session.add(t, /*apply_shard=*/!sharded || is_parameter, &p.speculative);
+        if (p.speculative.defined()) p.speculative_wrapped = wrap_only(p.var, p.speculative);
+      }
       pending.push_back(std::move(p));
     }
   }
@@ -235,6 +260,7 @@ void py_materialize_module(const py::object& module, bool buffers_only, const py
         wrapped[i] = py::cast(tdx::cached_python_tensor(p.fake));
         continue;
       }
+      if (p.speculative.defined()) continue;  // wrapped during the walk; confirmed after the join
       at::Tensor out;
       if (session.ready(p.ticket)) {
         out = session.result(p.ticket);
@@ -252,6 +278,19 @@ void py_materialize_module(const py::object& module, bool buffers_only, const py
       session.join();
     }
     t_joined = since();
+    // the speculative wraps: almost always the planner returned the very tensor the walk had built
+    for (size_t i = 0; i < pending.size(); ++i) {
+      PendingSlot& p = pending[i];
+      if (!p.speculative.defined()) continue;
+      at::Tensor out = session.result(p.ticket);
+      if (out.unsafeGetTensorImpl() == p.speculative.unsafeGetTensorImpl() && !tdx::cached_python_tensor(p.fake).defined()) {
+        tdx::cache_python_tensor(p.fake, py::cast<at::Tensor>(p.speculative_wrapped));
+        wrapped[i] = std::move(p.speculative_wrapped);
+      } else {
+        p.speculative_wrapped = py::object();
+        wrapped[i] = wrap_like(p.var, p.fake, out);
+      }
+    }
     const auto t0 = std::chrono::steady_clock::now();
     // (assignment through the dict, like Module.__setattr__ does for an existing entry)
     for (size_t i = 0; i < pending.size(); ++i) pending[i].dict[pending[i].key] = wrapped[i];
@@ -368,6 +407,7 @@ py::dict py_last_stats() {
   d["first_submit_us"] = s.first_submit_us;
   d["last_submit_us"] = s.last_submit_us;
   d["template_hits"] = s.template_hits;
+  d["prebuilt_outputs"] = s.prebuilt_outputs;
   return d;
 }
 

@@ -1270,12 +1270,12 @@ struct Engine {
   // write; `vi` is the value whose geometry the tensor takes (the parameter itself, normally).
   // Returns false if the program is not fusible.  `bytes_out`: algorithmic bytes of the descriptors.
   bool emit_fused(Tape& tape, uint32_t S, const ValueInfo& vi, const std::optional<ShardSpec>& shard,
-                  at::Tensor& base_out, int64_t& bytes_out) {
+                  at::Tensor& base_out, int64_t& bytes_out, Prebuilt* pre = nullptr) {
     const StorageInfo& si = tape.storages[S];
     const c10::Device dev = target_device(vi.device);
     if (si.tmpl && si.tmpl->fast) {  // analysed when the recording ended: nothing to evaluate
       g_stats.template_hits++;
-      return emit_from(tape, *si.tmpl, vi, shard, dev, base_out, bytes_out);
+      return emit_from(tape, *si.tmpl, vi, shard, dev, base_out, bytes_out, pre);
     }
     if (si.tmpl && si.tmpl->st.opaque) return false;
     StorageTemplate tmp;
@@ -1297,7 +1297,7 @@ struct Engine {
   }
 
   bool emit_from(Tape& tape, const StorageTemplate& t, const ValueInfo& vi, const std::optional<ShardSpec>& shard,
-                 c10::Device dev, at::Tensor& base_out, int64_t& bytes_out) {
+                 c10::Device dev, at::Tensor& base_out, int64_t& bytes_out, Prebuilt* pre = nullptr) {
     ProfScope p_total(9);
     const State& st = t.st;
     const size_t isz = t.isz;
@@ -1317,7 +1317,15 @@ struct Engine {
     }
     Batch::Pending pend;
     pend.nbytes = static_cast<size_t>(g.count) * isz;
-    at::Tensor base = make_output(g.sizes, st.dtype, dev, pend.nbytes, pend.storage);
+    at::Tensor base;
+    if (pre && pre->out.defined() && pre->nbytes == pend.nbytes && pre->out.scalar_type() == st.dtype &&
+        pre->out.device() == dev && pre->out.sizes() == c10::IntArrayRef(g.sizes)) {
+      base = std::move(pre->out);  // the calling thread built the (memory-less) output while it walked the module
+      pend.storage = std::move(pre->storage);
+      g_stats.prebuilt_outputs++;
+    } else {
+      base = make_output(g.sizes, st.dtype, dev, pend.nbytes, pend.storage);
+    }
     const uint64_t pt1 = Prof::on() ? Prof::tick() : 0;
 
     // every RNG pass on the chain consumes its slice of the stream, live or dead
@@ -1536,7 +1544,7 @@ struct Engine {
   }
 
   // Fused path for the storage of value `v`.  Returns false if the program is not fusible.
-  bool try_fused(Tape& tape, uint32_t v) {
+  bool try_fused(Tape& tape, uint32_t v, Prebuilt* pre = nullptr) {
     ValueInfo& vi = tape.values[v];
     const uint32_t S = vi.storage;
     StorageInfo& si = tape.storages[S];
@@ -1546,7 +1554,7 @@ struct Engine {
     if (sharded && !vi.covers_storage) return false;
     at::Tensor base;
     int64_t bytes = 0;
-    if (!emit_fused(tape, S, vi, sharded ? opts.shard : std::nullopt, base, bytes)) return false;
+    if (!emit_fused(tape, S, vi, sharded ? opts.shard : std::nullopt, base, bytes, pre)) return false;
     si.base = std::move(base);
     si.base_is_shard = sharded;
     si.fused_done = true;
@@ -1614,7 +1622,7 @@ struct Engine {
     return full.narrow(0, start, g.sizes[0]).clone();
   }
 
-  at::Tensor materialize_value(const std::shared_ptr<Tape>& tape_ptr, uint32_t v) {
+  at::Tensor materialize_value(const std::shared_ptr<Tape>& tape_ptr, uint32_t v, Prebuilt* pre = nullptr) {
     Tape& tape = *tape_ptr;
     ValueInfo& vi = tape.values[v];
     StorageInfo& si = tape.storages[vi.storage];
@@ -1624,7 +1632,7 @@ struct Engine {
       return (sharding(vi) && !si.base_is_shard) ? chunk_of(vi, t) : t;
     }
     if (vi.real.defined()) return sharding(vi) ? chunk_of(vi, vi.real) : vi.real;
-    if (try_fused(tape, v)) {
+    if (try_fused(tape, v, pre)) {
       ProfScope p(7);
       return real_of(tape, v);
     }
@@ -1658,6 +1666,36 @@ at::Tensor finish_tensor(const at::Tensor& fake, at::Tensor out) {
 }
 
 }  // namespace
+
+// Runs on the thread that walks the module (while the helper plans earlier tensors): builds the
+// memory-less output tensor of `fake` -- TensorImpl, StorageImpl, autograd meta: half of what a
+// tensor costs the helper -- if the analysis left on the recording says its storage will take the
+// fused path.  The helper checks the geometry again and falls back to its own if anything differs.
+bool prebuild_output(const at::Tensor& fake, const MaterializeOptions& opts, bool apply_shard, Prebuilt& pre) {
+  if (!opts.fused || !can_materialize(fake)) return false;
+  const TensorRecord* rec = fake_impl(fake)->record().get();
+  if (!rec || !rec->tape || rec->value == kNoValue) return false;
+  const Tape& tape = *rec->tape;
+  const ValueInfo& vi = tape.values[rec->value];
+  const StorageInfo& si = tape.storages[vi.storage];
+  const StorageTemplate* t = si.tmpl.get();
+  if (!t || !t->fast || si.fused_done || si.replayed || vi.real.defined()) return false;
+  c10::Device dev = opts.device ? *opts.device : vi.device;
+  if (!dev.is_cuda()) return false;
+  if (!dev.has_index()) dev = c10::Device(c10::kCUDA, c10::cuda::current_device());
+  const bool sharded = apply_shard && opts.shard && opts.shard->world > 1 && !vi.sizes.empty();
+  if (sharded && !vi.covers_storage) return false;
+  ShardGeom g;
+  if (vi.covers_storage && vi.dtype == t->st.dtype) {
+    g = shard_of(vi, sharded ? opts.shard : std::nullopt);
+  } else {
+    g.count = t->numel;
+    g.sizes.assign(1, t->numel);
+  }
+  pre.nbytes = static_cast<size_t>(g.count) * t->isz;
+  pre.out = make_output(g.sizes, t->st.dtype, dev, pre.nbytes, pre.storage);
+  return true;
+}
 
 struct MaterializeSession::Impl {
   MaterializeOptions opts;
@@ -1699,20 +1737,20 @@ MaterializeSession::~MaterializeSession() {
   }
 }
 
-at::Tensor MaterializeSession::add(const at::Tensor& t, bool apply_shard, size_t ticket) {
+at::Tensor MaterializeSession::add(const at::Tensor& t, bool apply_shard, size_t ticket, Prebuilt* pre) {
   g_stats.tensors++;
   if (!can_materialize(t)) return t;
   const double t0 = now_us();
   impl_->eng.opts.shard = apply_shard ? impl_->opts.shard : std::nullopt;
-  std::shared_ptr<TensorRecord> rec;
+  const TensorRecord* rec;
   {
     ProfScope p(0);
-    rec = fake_impl(t)->record();  // copy: keeps the tape alive while we work
+    rec = fake_impl(t)->record().get();  // (`t` keeps its record, and the record the tape, alive while we work)
   }
   at::Tensor value;
   {
     ProfScope p(1);
-    value = impl_->eng.materialize_value(rec->tape, rec->value);
+    value = impl_->eng.materialize_value(rec->tape, rec->value, pre);
   }
   if (!value.defined()) {  // an unfusable program without RNG: replayed after the last submission (finish)
     impl_->deferred.push_back(Impl::Deferred{t, apply_shard, ticket});
@@ -1925,6 +1963,7 @@ struct PipelinedMaterialize::State {
     at::Tensor fake;
     bool apply_shard = true;
     at::Tensor out;
+    Prebuilt pre;  // built by the calling thread (PipelinedMaterialize::add), consumed by the helper
     std::atomic<uint8_t> done{0};
   };
   MaterializeOptions opts;
@@ -1959,7 +1998,7 @@ struct PipelinedMaterialize::State {
     ProfScope p_total(8);
     if (!failed()) {
       try {
-        it.out = s.add(it.fake, it.apply_shard, ticket);
+        it.out = s.add(it.fake, it.apply_shard, ticket, it.pre.out.defined() ? &it.pre : nullptr);
         if (!it.out.defined()) return;  // deferred to the end of the session: deliver() completes it
       } catch (...) {
         record_error(ticket);
@@ -2085,10 +2124,15 @@ PipelinedMaterialize::~PipelinedMaterialize() {
   st_->cv_done.wait(lock, [&] { return st_->finished; });
 }
 
-size_t PipelinedMaterialize::add(const at::Tensor& fake, bool apply_shard) {
+size_t PipelinedMaterialize::add(const at::Tensor& fake, bool apply_shard, at::Tensor* speculative) {
   auto item = std::make_unique<State::Item>();
   item->fake = fake;
   item->apply_shard = apply_shard;
+  if (st_->threaded && speculative && prebuild_output(fake, st_->opts, apply_shard, item->pre)) {
+    // what the helper will (almost certainly) return for this tensor: the caller may give it its
+    // Python identity right away and confirm with result() at the end
+    *speculative = finish_tensor(fake, item->pre.out);
+  }
   State::Item* raw = item.get();
   size_t ticket;
   bool wake;

@@ -17,6 +17,7 @@
 #pragma once
 
 #include <ATen/Tensor.h>
+#include <c10/core/StorageImpl.h>
 
 #include <cstdint>
 #include <functional>
@@ -61,6 +62,7 @@ struct MaterializeStats {
   double first_submit_us = 0;    // host time from the start of the call to the first submission
   double last_submit_us = 0;     // ... and to the last one
   int64_t template_hits = 0;     // storages whose analysis was done when the recording ended
+  int64_t prebuilt_outputs = 0;  // outputs the calling thread had built before the helper planned them
 };
 
 // Materialises `fake` (a no-op returning `fake` itself for real tensors).
@@ -88,6 +90,14 @@ at::Tensor materialize_flat_shard(const std::vector<at::Tensor>& fakes, const Ma
 // Llama-3-8B costs as much host time as planning a third of it).  add() order defines RNG
 // consumption; finish() submits what is left and writes the generators back (the destructor does
 // the latter on error paths too).
+// An output tensor built ahead of its planning (PipelinedMaterialize::add): no memory yet -- the
+// submission that carries its descriptors assigns it.
+struct Prebuilt {
+  at::Tensor out;
+  c10::intrusive_ptr<c10::StorageImpl> storage;
+  size_t nbytes = 0;
+};
+
 class MaterializeSession {
  public:
   explicit MaterializeSession(const MaterializeOptions& opts);
@@ -96,7 +106,7 @@ class MaterializeSession {
   MaterializeSession& operator=(const MaterializeSession&) = delete;
   // Returns the tensor -- or an undefined tensor if its program was deferred (see below); the
   // result then arrives through the sink, tagged with `ticket`, during finish().
-  at::Tensor add(const at::Tensor& fake, bool apply_shard = true, size_t ticket = 0);
+  at::Tensor add(const at::Tensor& fake, bool apply_shard = true, size_t ticket = 0, Prebuilt* pre = nullptr);
   // Programs the kernels cannot express and that draw no random numbers (rotary inv_freq, position
   // ids, masks) are replayed through ATen after the call's last fused submission instead of where the
   // walk meets them: their dispatches then overlap the GPU's work on the whole model.
@@ -123,7 +133,11 @@ class PipelinedMaterialize {
   ~PipelinedMaterialize();
   PipelinedMaterialize(const PipelinedMaterialize&) = delete;
   PipelinedMaterialize& operator=(const PipelinedMaterialize&) = delete;
-  size_t add(const at::Tensor& fake, bool apply_shard = true);
+  // `speculative` (optional): receives, if the recording's analysis says the tensor takes the fused
+  // path, the very tensor object result(ticket) is going to return -- built on the calling thread,
+  // before the helper has planned it.  The caller may wrap it at once but must compare with
+  // result(ticket) in the end (the helper falls back to a tensor of its own when anything differs).
+  size_t add(const at::Tensor& fake, bool apply_shard = true, at::Tensor* speculative = nullptr);
   void finish();
   at::Tensor result(size_t ticket);
   bool ready(size_t ticket);  // result(ticket) would not block
