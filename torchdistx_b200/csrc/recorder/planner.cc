@@ -827,22 +827,44 @@ void Batch::assign_memory() {
   c10::Allocator* alloc = c10::cuda::CUDACachingAllocator::get();
   constexpr size_t kAlign = 256;  // vector stores need 16; 256 keeps every tensor on its own L2 lines
   if (slab_enabled() && pending.size() > 1) {
-    size_t total = 0;
-    for (const Pending& p : pending) total += (p.nbytes + kAlign - 1) & ~(kAlign - 1);
-    if (total) {
-      auto slab = std::make_shared<Slab>();
-      slab->block = alloc->allocate(total);
-      char* base = static_cast<char*>(slab->block.get());
-      size_t off = 0;
-      for (Pending& p : pending) {
-        if (p.nbytes == 0) continue;
-        char* ptr = base + off;
-        off += (p.nbytes + kAlign - 1) & ~(kAlign - 1);
-        p.storage->set_data_ptr_noswap(
-            c10::DataPtr(ptr, new std::shared_ptr<Slab>(slab), &slab_ref_delete, device));
-        for (uint32_t k = p.first_desc; k < p.first_desc + p.n_desc; ++k)
-          descs[k].dst = ptr + reinterpret_cast<uintptr_t>(descs[k].dst);
+    // Slabs hold at most kSlabBytes (a tensor larger than that gets one of its own) and their sizes
+    // are rounded to 1/32 of a power of two (<= 3 % over): where a call cuts its submissions depends on
+    // timing, and slabs of arbitrary sizes would miss the caching allocator's free lists from one
+    // call to the next (a miss is a cudaMalloc -- milliseconds, and a device synchronisation).
+    constexpr size_t kSlabBytes = size_t{1} << 30;
+    auto rounded = [](size_t n) {
+      if (n <= (size_t{2} << 20)) return (n + 511) & ~size_t{511};
+      size_t p2 = size_t{1} << 21;
+      while (p2 < n) p2 <<= 1;
+      const size_t step = p2 >> 5;
+      return (n + step - 1) / step * step;
+    };
+    size_t i = 0;
+    while (i < pending.size()) {
+      size_t j = i, total = 0;
+      while (j < pending.size()) {
+        const size_t sz = (pending[j].nbytes + kAlign - 1) & ~(kAlign - 1);
+        if (j > i && total + sz > kSlabBytes) break;
+        total += sz;
+        ++j;
       }
+      if (total) {
+        auto slab = std::make_shared<Slab>();
+        slab->block = alloc->allocate(rounded(total));
+        char* base = static_cast<char*>(slab->block.get());
+        size_t off = 0;
+        for (size_t k = i; k < j; ++k) {
+          Pending& p = pending[k];
+          if (p.nbytes == 0) continue;
+          char* ptr = base + off;
+          off += (p.nbytes + kAlign - 1) & ~(kAlign - 1);
+          p.storage->set_data_ptr_noswap(
+              c10::DataPtr(ptr, new std::shared_ptr<Slab>(slab), &slab_ref_delete, device));
+          for (uint32_t q = p.first_desc; q < p.first_desc + p.n_desc; ++q)
+            descs[q].dst = ptr + reinterpret_cast<uintptr_t>(descs[q].dst);
+        }
+      }
+      i = j;
     }
   } else {
     for (Pending& p : pending) {
