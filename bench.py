@@ -248,6 +248,8 @@ def measure_model(cx, model: str, steps: int, warmup: int, first_call: bool = Fa
 
     dev, world, rank, local, lib, stream = cx.dev, cx.world, cx.rank, cx.local, cx.lib, cx.stream
     shard = (rank, world) if world > 1 else None
+    if getattr(cx, "as_rank_of", 0) > 1:  # diagnostic: one process builds rank 0's share of a W-way sharded model
+        shard = (0, cx.as_rank_of)
     dtype = MODELS[model][2]
     res = {"model": model, "dtype": dtype}
 
@@ -511,6 +513,7 @@ def run_ours(a):
         dist.init_process_group("nccl", device_id=dev)
     assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
     cx.lib = C.load()
+    cx.as_rank_of = a.as_rank_of
     cx.stream = torch.cuda.current_stream().cuda_stream
     dtype = MODELS[a.model][2]
 
@@ -638,6 +641,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the side measurements (the other BASELINE configs, the kernel sweep, baseline B)")
+    ap.add_argument("--as-rank-of", type=int, default=0,
+                    help="diagnostic (N = 1 only): build rank 0's dim-0 shard of a model sharded W ways -- the kernels "
+                         "and host path of one rank of an N = W job without W GPUs; the line's params/s are then 1/W of a job's")
     ap.add_argument("--roofline-only", action="store_true",
                     help="for ncu: one materialize (1 launch per family), then 3+steps launches of the "
                          "dominant kernel's plan only; prints nothing")

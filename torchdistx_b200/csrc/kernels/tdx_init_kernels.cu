@@ -933,6 +933,10 @@ struct TabNormal {
   using Gen = GenNormalICDF16<Out, R, EPI>;
   using Params = typename Gen::Params;
   static constexpr bool kHasTail = true;
+  // The grid x = k/32768 - 1 is symmetric about k = 32768 and, with mean == +0 and no epilogue, so is
+  // the value (fma(q, -x, +0) == -fma(q, x, +0), rounding included): the upper half of the table is
+  // the lower half with the sign bit flipped -- half the evaluations per table build.
+  __device__ static __forceinline__ bool mirrored(const Params& p) { return !EPI && __float_as_uint(p.mean) == 0u; }
   __device__ static __forceinline__ float value(const Params& p, float magic) {
     float t;
     const float v = Gen::element(p, magic, t);  // k == 0: +-inf or NaN (lg2(0) = -inf)
@@ -953,6 +957,7 @@ struct TabUniform {
   using Gen = GenUniform16<Out, R, EPI>;
   using Params = typename Gen::Params;
   static constexpr bool kHasTail = false;
+  __device__ static __forceinline__ bool mirrored(const Params&) { return false; }
   __device__ static __forceinline__ float value(const Params& p, float magic) {
     const float x = fminf(fmaf(magic - 8388608.0f, p.scale, p.from), p.to_prev);  // == Gen::gen, element by element
     return EPI ? apply_epi<Out>(p.epi, x) : x;
@@ -1068,9 +1073,18 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_lut16_kernel(const GroupAr
     P.ph.cw = __reduce_or_sync(0xffffffffu, P.ph.cw);
     if (have_di == 0xffffffffu || (di != have_di && !same_table(d, g.descs[have_di]))) {
       __syncthreads();  // everyone is done reading the old table
-      for (uint32_t k = threadIdx.x; k < 65536u; k += kLutThreads) {
-        const Out o = static_cast<Out>(Tab::value(P, __uint_as_float(0x4b000000u | k)));
-        lut[k] = (Tab::kHasTail && k == 0) ? kLutSentinel : *reinterpret_cast<const unsigned short*>(&o);
+      if (Tab::mirrored(P)) {
+        for (uint32_t k = threadIdx.x; k <= 32768u; k += kLutThreads) {
+          const Out o = static_cast<Out>(Tab::value(P, __uint_as_float(0x4b000000u | k)));
+          const unsigned short bits = *reinterpret_cast<const unsigned short*>(&o);
+          lut[k] = (Tab::kHasTail && k == 0) ? kLutSentinel : bits;
+          if (k != 0u && k != 32768u) lut[65536u - k] = bits ^ 0x8000u;
+        }
+      } else {
+        for (uint32_t k = threadIdx.x; k < 65536u; k += kLutThreads) {
+          const Out o = static_cast<Out>(Tab::value(P, __uint_as_float(0x4b000000u | k)));
+          lut[k] = (Tab::kHasTail && k == 0) ? kLutSentinel : *reinterpret_cast<const unsigned short*>(&o);
+        }
       }
       __syncthreads();
     }

@@ -782,22 +782,17 @@ struct Batch {
     }();
     return v;
   }
-  // Estimate of when the GPU runs out of submitted work (host clock, us): a submission is only
-  // worth its fixed costs (plan upload, launches, a table build and a ramp/tail per launch: ~35 us
-  // for Llama-3-8B's 1 GB first submission) if the GPU would otherwise go idle soon.
-  double gpu_busy_until_us = 0;
+  // (Submission points depend on bytes only, never on timing: a call then cuts the same slabs every
+  // time, which is what lets the caching allocator serve them from its free lists.  A gate on the
+  // estimated GPU backlog -- submit only when the GPU is about to run dry -- saved one launch per
+  // call at N = 1 and cost a cudaMalloc, i.e. a device synchronisation, whenever the cut moved.)
   void note(int64_t bytes) {
     pending_bytes += bytes;
     if (flush_threshold > 0 && pending_bytes >= flush_threshold) {
-      // plenty of work queued: let this submission grow until the GPU is about to run dry
-      // (fewer, larger launches); the next tensor asks again
-      if (gpu_busy_until_us - now_us_() > kBacklogGateUs) return;
       flush();
       flush_threshold = std::min<int64_t>(flush_threshold * 4, int64_t{64} << 30);
     }
   }
-  static constexpr double kBacklogGateUs = 150;
-  static double now_us_();
   void assign_memory();
   void flush();
 };
@@ -805,7 +800,6 @@ struct Batch {
 double now_us() {
   return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
-double Batch::now_us_() { return now_us(); }
 
 // An output tensor without memory yet (see Batch::Pending).  Built like at::detail::empty_generic
 // does, minus the allocation.
@@ -939,12 +933,6 @@ void Batch::flush() {
   g_stats.last_submit_us = now_us() - g_call_begin_us;
   g_last_descs.insert(g_last_descs.end(), descs.begin(), descs.end());
   descs.clear();
-  {
-    // (4.5 TB/s = 4.5e6 bytes/us: what the slowest of the bulk kernels sustains; an under-estimate
-    // only makes the next submission come a little early)
-    const double t_now = now_us();
-    gpu_busy_until_us = std::max(gpu_busy_until_us, t_now) + static_cast<double>(pending_bytes) / 4.5e6 + 20.0;
-  }
   pending_bytes = 0;
   epoch = g_epoch.fetch_add(1);
   g_stats.launch_us += now_us() - t0;
