@@ -346,10 +346,16 @@ void py_materialize_module(const py::object& module, bool buffers_only, const py
     pending.clear();
     wrapped.clear();
     const bool posted = tdx::post_background([grave] {
-      {
+      // a few objects per turn with the GIL: the caller gets it back within microseconds when it
+      // returns from a blocking call (stream.synchronize()) in the middle of this
+      size_t i = 0;
+      const size_t n = grave->objs.size();
+      while (i < n) {
         py::gil_scoped_acquire gil;
-        grave->fakes.clear();
-        grave->objs.clear();
+        for (size_t k = 0; k < 8 && i < n; ++k, ++i) {
+          grave->fakes[i] = at::Tensor();
+          grave->objs[i] = py::object();
+        }
       }
       grave->tapes.clear();
     });
@@ -408,6 +414,7 @@ py::dict py_last_stats() {
   d["last_submit_us"] = s.last_submit_us;
   d["template_hits"] = s.template_hits;
   d["prebuilt_outputs"] = s.prebuilt_outputs;
+  d["deferred_us"] = s.deferred_us;
   return d;
 }
 

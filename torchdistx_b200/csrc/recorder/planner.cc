@@ -882,8 +882,8 @@ struct SubmissionTrace {
 };
 thread_local std::vector<SubmissionTrace> g_sub_trace;
 thread_local cudaEvent_t g_trace_origin = nullptr;
-bool trace_on() {
-  static const bool v = getenv("TDX_TRACE") != nullptr;
+bool trace_on() {  // TDX_TRACE=2: + the GPU timeline of the submissions (synchronises at the end of the call)
+  static const bool v = getenv("TDX_TRACE") != nullptr && getenv("TDX_TRACE")[0] == '2';
   return v;
 }
 
@@ -1810,6 +1810,7 @@ void MaterializeSession::finish() {
   impl_->batch.flush();
   impl_->eng.gens.write_back();
   // the deferred programs: the kernels of every fused tensor are on the stream by now
+  const double t_deferred = now_us();
   impl_->eng.defer_generic = false;
   for (Impl::Deferred& d : impl_->deferred) {
     impl_->eng.opts.shard = d.apply_shard ? impl_->opts.shard : std::nullopt;
@@ -1822,6 +1823,7 @@ void MaterializeSession::finish() {
     impl_->batch.flush();  // (dependencies of the deferred programs that took the fused path)
     impl_->eng.gens.write_back();
   }
+  g_stats.deferred_us = now_us() - t_deferred;
   impl_->finished = true;
   impl_->add_us += now_us() - t0;
   g_stats.plan_us = impl_->add_us - g_stats.launch_us;
@@ -1851,15 +1853,20 @@ namespace {
 // One helper thread per process, started on first use (and again in a forked child).
 class HelperThread {
  public:
-  static HelperThread& get() {
+  // the planner of materialize_module calls
+  static HelperThread& get() { return instance(0); }
+  // Cleans up after them (recordings, replaced fake tensors).  A thread of its own: a call that
+  // follows another one closely must not find the planner busy with the previous call's teardown.
+  static HelperThread& reaper() { return instance(1); }
+  static HelperThread& instance(int which) {
     static std::mutex m;
-    static std::unique_ptr<HelperThread> inst;
+    static std::unique_ptr<HelperThread> inst[2];
     std::lock_guard<std::mutex> lock(m);
-    if (!inst || inst->pid_ != getpid()) {
-      if (inst && inst->pid_ != getpid()) inst.release();  // forked child: the parent's thread is not ours to join
-      inst.reset(new HelperThread());
+    if (!inst[which] || inst[which]->pid_ != getpid()) {
+      if (inst[which] && inst[which]->pid_ != getpid()) inst[which].release();  // forked child: the parent's thread is not ours to join
+      inst[which].reset(new HelperThread());
     }
-    return *inst;
+    return *inst[which];
   }
   void post(std::function<void()> fn) {
     {
@@ -2225,12 +2232,12 @@ void PipelinedMaterialize::join() {
 void release_in_background(std::vector<std::shared_ptr<Tape>> tapes) {
   if (tapes.empty() || !host_threads_enabled()) return;  // (inline mode: they die with the caller's copies)
   auto box = std::make_shared<std::vector<std::shared_ptr<Tape>>>(std::move(tapes));
-  HelperThread::get().post([box] { box->clear(); });
+  HelperThread::reaper().post([box] { box->clear(); });
 }
 
 bool post_background(std::function<void()> fn) {
   if (!host_threads_enabled()) return false;
-  HelperThread::get().post(std::move(fn));
+  HelperThread::reaper().post(std::move(fn));
   return true;
 }
 
@@ -2239,16 +2246,18 @@ void drain_background() {
   struct Gate {
     std::mutex m;
     std::condition_variable cv;
-    bool done = false;
+    int pending = 2;
   };
   auto gate = std::make_shared<Gate>();
-  HelperThread::get().post([gate] {
+  auto arrive = [gate] {
     std::lock_guard<std::mutex> lock(gate->m);
-    gate->done = true;
+    --gate->pending;
     gate->cv.notify_all();
-  });
+  };
+  HelperThread::get().post(arrive);
+  HelperThread::reaper().post(arrive);
   std::unique_lock<std::mutex> lock(gate->m);
-  gate->cv.wait(lock, [&] { return gate->done; });
+  gate->cv.wait(lock, [&] { return gate->pending == 0; });
 }
 
 void add_wrap_time(double us) { g_stats.wrap_us += us; }
