@@ -321,49 +321,23 @@ void py_materialize_module(const py::object& module, bool buffers_only, const py
     session_ptr.reset();
   }
   {
-    // What the call replaced -- ~300 fake Parameter objects, their TensorImpls and meta twins, and
-    // the recording they kept alive (~3000 call frames for Llama-3-8B) -- is torn down on the helper
-    // thread after the call has returned (it takes the GIL for the Python objects when the caller
-    // next lets go of it, e.g. while waiting for the GPU): ~0.3 ms that are nobody's critical path.
-    struct Grave {
-      std::vector<py::object> objs;
-      std::vector<at::Tensor> fakes;
-      std::vector<std::shared_ptr<tdx::Tape>> tapes;
-    };
-    auto grave = std::make_shared<Grave>();
-    grave->objs.reserve(pending.size());
-    grave->fakes.reserve(pending.size());
+    // What the call replaced: ~300 fake Parameter objects (their TensorImpls, meta twins, records) die
+    // here, with the GIL, on the calling thread -- a background thread that needs the GIL for them
+    // starves the caller the moment it returns to Python (measured: milliseconds).  The recording
+    // they kept alive (~3000 recorded call frames for Llama-3-8B, ~0.5 ms of destructors, no Python
+    // objects of its own) is handed to the reaper thread.
+    std::vector<std::shared_ptr<tdx::Tape>> tapes;
     for (PendingSlot& p : pending) {
-      if (tdx::can_materialize(p.fake)) {
-        const auto& rec = tdx::fake_impl(p.fake)->record();
-        if (rec->tape && (grave->tapes.empty() || grave->tapes.back() != rec->tape) &&
-            std::find(grave->tapes.begin(), grave->tapes.end(), rec->tape) == grave->tapes.end())
-          grave->tapes.push_back(rec->tape);
-      }
-      grave->objs.push_back(std::move(p.var));
-      grave->fakes.push_back(std::move(p.fake));
+      if (!tdx::can_materialize(p.fake)) continue;
+      const auto& rec = tdx::fake_impl(p.fake)->record();
+      if (rec->tape && (tapes.empty() || tapes.back() != rec->tape) &&
+          std::find(tapes.begin(), tapes.end(), rec->tape) == tapes.end())
+        tapes.push_back(rec->tape);
     }
     pending.clear();
     wrapped.clear();
-    const bool posted = tdx::post_background([grave] {
-      // a few objects per turn with the GIL: the caller gets it back within microseconds when it
-      // returns from a blocking call (stream.synchronize()) in the middle of this
-      size_t i = 0;
-      const size_t n = grave->objs.size();
-      while (i < n) {
-        py::gil_scoped_acquire gil;
-        for (size_t k = 0; k < 8 && i < n; ++k, ++i) {
-          grave->fakes[i] = at::Tensor();
-          grave->objs[i] = py::object();
-        }
-      }
-      grave->tapes.clear();
-    });
-    if (!posted) {  // (TDX_HOST_THREADS=0: everything dies here, with the caller)
-      grave->fakes.clear();
-      grave->objs.clear();
-      grave->tapes.clear();
-    }
+    py::gil_scoped_release nogil;
+    tdx::release_in_background(std::move(tapes));
   }
   if (trace)
     fprintf(stderr, "[tdx] materialize_module: session %.0f us, walked %.0f, wrapped %.0f, joined %.0f, assigned %.0f, "
