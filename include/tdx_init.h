@@ -53,13 +53,14 @@ extern "C" {
 #define TDX_C_API
 #endif
 
-#define TDX_ABI_VERSION 1
+#define TDX_ABI_VERSION 2 /* 2: TdxPlan is 4 KiB; TDX_SRC_IOTA, TDX_I64, TDX_EPI_RPOW/RECIP; counter layout of the stream */
 
 /* element type of the destination */
 enum {
   TDX_F32 = 0,
   TDX_BF16 = 1,
   TDX_F16 = 2,
+  TDX_I64 = 3, /* only valid with TDX_SRC_IOTA (arange buffers: position ids) */
   /* raw widths: only valid with TDX_SRC_CONST (bit-pattern fill) */
   TDX_RAW8 = 8,
   TDX_RAW16 = 9,
@@ -72,6 +73,12 @@ enum {
   TDX_SRC_CONST = 0,   /* fill_/zero_/zeros/ones/full, constant-folded chains */
   TDX_SRC_UNIFORM = 1, /* uniform_(from,to), rand, kaiming_uniform_, xavier_uniform_ */
   TDX_SRC_NORMAL = 2,  /* normal_(mean,std), randn, kaiming_normal_, xavier_normal_ */
+  /* element g = p0 + g * p1 (both integers, exactly representable in the destination), then the
+   * epilogue: `arange` buffers and the index programs built on them -- rotary inv_freq is
+   * arange -> float -> / dim -> base ** x -> reciprocal -> * scale.  dtype TDX_F32 (epilogue
+   * allowed) or TDX_I64 (none).  The reference replays these op by op through ATen
+   * (deferred_init.cc:256-272); here they are one descriptor in the module's launch. */
+  TDX_SRC_IOTA = 3,
 };
 
 /* sampling algorithm.  0 = the shipped default for (src, dtype). */
@@ -96,6 +103,10 @@ enum {
   TDX_EPI_ADD = 2,    /* x = x + a            (add_, add.Tensor/Scalar with alpha folded) */
   TDX_EPI_ERFINV = 3, /* x = erfinv(x)        (trunc_normal_)            */
   TDX_EPI_CLAMP = 4,  /* x = min(max(x,a),b)  (clamp_)                   */
+  TDX_EPI_RPOW = 5,   /* x = powf(a, x)       (pow.Scalar: scalar ** tensor) */
+  TDX_EPI_RECIP = 6,  /* x = 1 / x            (reciprocal; `1.0 / t`)    */
+  /* (`t / c` with a scalar c is TDX_EPI_MUL by the fp32 reciprocal of c: what ATen's CUDA kernel
+   * computes, $TORCH/.../cuda/BinaryDivTrueKernel.cu) */
 };
 /* OR-able into TdxEpiStep.op: do not round to the destination dtype after this step (the step
  * was recorded on an fp32 intermediate that is cast to the destination dtype later). */
@@ -164,7 +175,7 @@ TDX_C_API int tdx_init_submit(void* workspace, size_t workspace_bytes, void* str
  * memset between launches; one plan must not run on two streams at once).
  */
 typedef struct TdxPlan {
-  uint64_t opaque[256]; /* host-side copy of the plan header; owned by the caller */
+  uint64_t opaque[512]; /* host-side copy of the plan header; owned by the caller */
 } TdxPlan;
 TDX_C_API int tdx_plan_upload(const TdxInitDesc* descs, int n, void* workspace,
                               size_t workspace_bytes, void* stream, TdxPlan* plan);

@@ -30,7 +30,7 @@ def test_abi_exports_every_declared_symbol():
     lib = C.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.tdx_abi_version() == 1
+    assert lib.tdx_abi_version() == 2
     assert ctypes.sizeof(C.TdxInitDesc) == 128 and ctypes.sizeof(C.TdxPlan) == 2048
     assert lib.tdx_init_workspace_bytes(100) >= 100 * 128
     assert lib.tdx_elems_per_block(C.TDX_BF16, C.TDX_SRC_NORMAL, 0) == 8

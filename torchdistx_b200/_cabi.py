@@ -19,14 +19,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TDX_INIT_LIB") or os.path.join(_HERE, "libtdx_init.so")
 
 # enums of tdx_init.h
-TDX_F32, TDX_BF16, TDX_F16 = 0, 1, 2
+TDX_F32, TDX_BF16, TDX_F16, TDX_I64 = 0, 1, 2, 3
 TDX_RAW8, TDX_RAW16, TDX_RAW32, TDX_RAW64 = 8, 9, 10, 11
-TDX_SRC_CONST, TDX_SRC_UNIFORM, TDX_SRC_NORMAL = 0, 1, 2
+TDX_SRC_CONST, TDX_SRC_UNIFORM, TDX_SRC_NORMAL, TDX_SRC_IOTA = 0, 1, 2, 3
 TDX_ALGO_DEFAULT, TDX_ALGO_ICDF16, TDX_ALGO_BM32, TDX_ALGO_BM16 = 0, 1, 2, 3
 TDX_ALGO_WIDE32 = 2
 TDX_ALGO_R7 = 0x10
 TDX_ALGO_NOLUT = 0x20
-TDX_EPI_MUL, TDX_EPI_ADD, TDX_EPI_ERFINV, TDX_EPI_CLAMP = 1, 2, 3, 4
+TDX_EPI_MUL, TDX_EPI_ADD, TDX_EPI_ERFINV, TDX_EPI_CLAMP, TDX_EPI_RPOW, TDX_EPI_RECIP = 1, 2, 3, 4, 5, 6
 TDX_MAX_EPI = 4
 TDX_EPI_NOROUND = 0x100
 TDX_FLAG_SRC_NOROUND = 0x1
@@ -70,7 +70,7 @@ class TdxInitDesc(ctypes.Structure):
 
 
 class TdxPlan(ctypes.Structure):
-    _fields_ = [("opaque", ctypes.c_uint64 * 256)]
+    _fields_ = [("opaque", ctypes.c_uint64 * 512)]
 
 
 assert ctypes.sizeof(TdxInitDesc) == 128, ctypes.sizeof(TdxInitDesc)

@@ -222,6 +222,8 @@ __device__ __forceinline__ float apply_epi(const EpiParams& e, float v) {
         case TDX_EPI_ADD: v = v + e.a[i]; break;
         case TDX_EPI_ERFINV: v = erfinvf(v); break;
         case TDX_EPI_CLAMP: v = fminf(fmaxf(v, e.a[i]), e.b[i]); break;
+        case TDX_EPI_RPOW: v = powf(e.a[i], v); break;
+        case TDX_EPI_RECIP: v = 1.0f / v; break;
         default: break;
       }
       if (!(e.op[i] & TDX_EPI_NOROUND)) v = T::round_through(v);
@@ -770,6 +772,37 @@ __global__ void __launch_bounds__(kThreads) tdx_fill_kernel(const __grid_constan
 }
 
 
+// index programs: element g = start + g * step (integers), then the epilogue (fp32 only).  Tiny
+// buffers (rotary inv_freq: 64 elements, position ids: a few K): nothing to optimise but the launch
+// they no longer need -- they ride in the module's plan like any other descriptor.
+__global__ void __launch_bounds__(kThreads) tdx_iota_kernel(const __grid_constant__ GroupArgs g) {
+  for_each_tile_run(g, [&](uint32_t di, unsigned long long tile0, unsigned long long ntiles) {
+    const TdxInitDesc& d = *desc_of(g, di);
+    const long long start = static_cast<long long>(d.p0), step = static_cast<long long>(d.p1);
+    const EpiParams epi = load_epi(d);
+    const bool as_i64 = d.dtype == TDX_I64;
+    const uint64_t per_vec = as_i64 ? 2 : 4;
+    // (frame: element i of the descriptor is global element elem_begin + i; one "vector" = 16 bytes)
+    for (unsigned long long tile = tile0; tile < tile0 + ntiles; ++tile) {
+      for (int i = 0; i < kVecsPerThread; ++i) {
+        const uint64_t vec = tile * kTileVecs + static_cast<uint64_t>(i) * kThreads + threadIdx.x;
+        for (uint64_t e = 0; e < per_vec; ++e) {
+          const uint64_t j = vec * per_vec + e;
+          if (j >= d.elem_count) break;
+          const long long val = start + static_cast<long long>(d.elem_begin + j) * step;
+          if (as_i64) {
+            static_cast<long long*>(d.dst)[j] = val;
+          } else {
+            float v = static_cast<float>(val);
+            if (epi.n) v = apply_epi<float>(epi, v);
+            static_cast<float*>(d.dst)[j] = v;
+          }
+        }
+      }
+    }
+  });
+}
+
 // ---------------------------------------------------------------------------------------------
 // 16-bit outputs through a shared-memory table
 // ---------------------------------------------------------------------------------------------
@@ -1194,6 +1227,7 @@ using f16 = __half;
 
 static const Family kFamilies[] = {
     {TDX_SRC_CONST, -1, 0, 0, 0, tdx_fill_kernel, "fill"},
+    {TDX_SRC_IOTA, -1, 0, 0, 0, tdx_iota_kernel, "iota"},
     // shipped defaults
     TDX_FAM_V16(TDX_SRC_UNIFORM, TDX_F32, 0, 10, 0, GenUniform32<float, 10, false>),
     TDX_FAM(TDX_SRC_UNIFORM, TDX_F32, 0, 10, 1, GenUniform32<float, 10, true>),
@@ -1256,7 +1290,7 @@ int itemsize_of(int dtype) {
     case TDX_F32: case TDX_RAW32: return 4;
     case TDX_BF16: case TDX_F16: case TDX_RAW16: return 2;
     case TDX_RAW8: return 1;
-    case TDX_RAW64: return 8;
+    case TDX_RAW64: case TDX_I64: return 8;
     default: return 0;
   }
 }
@@ -1302,6 +1336,7 @@ uint64_t lut_min_launch_elems() {
 
 int family_of(const TdxInitDesc& d) {
   if (d.src == TDX_SRC_CONST) return 0;
+  if (d.src == TDX_SRC_IOTA) return 1;
   const int algo = resolve_algo(d);
   const int rounds = (d.algo & TDX_ALGO_R7) ? 7 : 10;
   const int epi = d.n_epi ? 1 : 0;
@@ -1309,7 +1344,7 @@ int family_of(const TdxInitDesc& d) {
                         (d.src == TDX_SRC_UNIFORM && algo == 0 && d.dtype != TDX_F32);
   const bool want_lut = lut_kind && rounds == 10 && !(d.algo & TDX_ALGO_NOLUT) &&
                         lut_min_elems() != 0 && d.elem_count >= lut_min_elems();
-  for (int f = 1; f < kNumFamilies; ++f) {
+  for (int f = 2; f < kNumFamilies; ++f) {
     const Family& F = kFamilies[f];
     if (F.src == d.src && F.dtype == d.dtype && F.algo == algo && F.rounds == rounds &&
         F.epi == epi && F.lut == want_lut)
@@ -1325,6 +1360,9 @@ uint64_t tiles_of(const TdxInitDesc& d, int tile_vecs) {
     const uint64_t a = reinterpret_cast<uintptr_t>(d.dst);
     const uint64_t end = a + d.elem_count * itemsize_of(d.dtype);
     nvec = (end - (a & ~15ull) + 15) / 16;
+  } else if (d.src == TDX_SRC_IOTA) {  // vectors are counted from the descriptor's first element
+    const uint64_t epv = 16 / itemsize_of(d.dtype);
+    nvec = (d.elem_count + epv - 1) / epv;
   } else {
     const uint64_t epv = 16 / itemsize_of(d.dtype);
     nvec = (d.elem_begin + d.elem_count - 1) / epv - d.elem_begin / epv + 1;
@@ -1425,6 +1463,9 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
     if (isz == 0) return fail(TDX_E_BADARG, "unknown dtype");
     if (d.src != TDX_SRC_CONST && d.dtype >= TDX_RAW8)
       return fail(TDX_E_BADARG, "raw dtypes are only valid with TDX_SRC_CONST");
+    if ((d.dtype == TDX_I64 && d.src != TDX_SRC_IOTA) ||
+        (d.src == TDX_SRC_IOTA && !(d.dtype == TDX_F32 || (d.dtype == TDX_I64 && d.n_epi == 0))))
+      return fail(TDX_E_BADARG, "TDX_SRC_IOTA writes TDX_F32 (epilogue allowed) or TDX_I64 (none); TDX_I64 is IOTA-only");
     if (d.n_epi > TDX_MAX_EPI) return fail(TDX_E_BADARG, "n_epi > TDX_MAX_EPI");
     if (d.elem_count && d.dst == nullptr) return fail(TDX_E_BADARG, "dst == NULL");
     if (reinterpret_cast<uintptr_t>(d.dst) % isz) return fail(TDX_E_BADARG, "dst not element-aligned");
