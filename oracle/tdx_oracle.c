@@ -149,6 +149,8 @@ static float apply_epi(const TdxInitDesc* d, float v) {
       case TDX_EPI_ADD: v = v + d->epi[i].a; break;
       case TDX_EPI_ERFINV: v = (float)(ndtri(((double)v + 1.0) * 0.5) * 0.70710678118654752440); break;
       case TDX_EPI_CLAMP: v = fminf(fmaxf(v, d->epi[i].a), d->epi[i].b); break;
+      case TDX_EPI_RPOW: v = powf(d->epi[i].a, v); break; /* libm vs CUDA powf: both ~1 ulp, not each other's bits */
+      case TDX_EPI_RECIP: v = 1.0f / v; break;
       default: break;
     }
     if (!(op & TDX_EPI_NOROUND)) v = round_through(v, d->dtype);
@@ -244,6 +246,16 @@ int tdx_oracle_generate(const TdxInitDesc* d, void* out) {
     unsigned char pat[16];
     memcpy(pat, d->fill_bits, 16);
     for (uint64_t i = 0; i < d->elem_count; ++i) memcpy((unsigned char*)out + i * isz, pat, isz);
+    return 0;
+  }
+  if (d->src == TDX_SRC_IOTA) { /* element g = p0 + g * p1 (integers), then the fp32 epilogue */
+    const int64_t start = (int64_t)d->p0, step = (int64_t)d->p1;
+    if (!(d->dtype == TDX_F32 || (d->dtype == TDX_I64 && d->n_epi == 0))) return -1;
+    for (uint64_t i = 0; i < d->elem_count; ++i) {
+      const int64_t val = start + (int64_t)(d->elem_begin + i) * step;
+      if (d->dtype == TDX_I64) ((int64_t*)out)[i] = val;
+      else ((float*)out)[i] = d->n_epi ? apply_epi(d, (float)val) : (float)val;
+    }
     return 0;
   }
   if (d->dtype != TDX_F32 && d->dtype != TDX_BF16 && d->dtype != TDX_F16) return -1;

@@ -47,7 +47,7 @@ def generate(desc) -> np.ndarray:
     `desc` is a torchdistx_b200._cabi.TdxInitDesc (only its bytes are read)."""
     from torchdistx_b200 import _cabi as C
 
-    isz = {C.TDX_F32: 4, C.TDX_RAW32: 4, C.TDX_RAW64: 8, C.TDX_RAW8: 1}.get(desc.dtype, 2)
+    isz = {C.TDX_F32: 4, C.TDX_RAW32: 4, C.TDX_RAW64: 8, C.TDX_I64: 8, C.TDX_RAW8: 1}.get(desc.dtype, 2)
     np_dtype = {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[isz]
     out = np.empty(int(desc.elem_count), dtype=np_dtype)
     rc = lib().tdx_oracle_generate(ctypes.byref(desc), out.ctypes.data_as(ctypes.c_void_p))

@@ -41,7 +41,7 @@ def test_templates_serve_every_fused_tensor_and_change_nothing():
     if os.environ.get("TDX_HOST_THREADS", "1") != "0":
         # the walking thread built the outputs ahead of the planner, which adopted every one of them
         assert st["prebuilt_outputs"] == st["fused_tensors"], st
-    assert st["generic_ops"] > 0  # rotary inv_freq: replayed after the last fused submission
+    assert st["generic_ops"] == 0  # rotary inv_freq is an index program (TDX_SRC_IOTA + 4 epilogue steps) now
     # the same module through the uncached route (materialize_tensor on a recording whose templates
     # do not cover constant folding: `init_zoo.const`) and through generic replay: same bits
     torch.manual_seed(3)
@@ -334,3 +334,70 @@ def test_flat_shard_with_an_unfusable_parameter_falls_back_to_replay_and_copy():
         torch.manual_seed(1)
         shard, _ = materialize_flat_shard(list(build().parameters()), rank, 2)
         assert torch.equal(shard, padded[rank * chunk:(rank + 1) * chunk])
+
+
+# ---- index programs: arange and what models build on it --------------------------------
+def test_rotary_inv_freq_is_one_descriptor_and_equals_the_aten_replay():
+    from torchdistx_b200 import _C
+
+    def build():
+        return deferred_init(lambda: cases.build("tiny_llama", "bf16", "cuda:0"))
+
+    m = build()
+    materialize_module(m)
+    st = last_materialize_stats()
+    assert st["generic_ops"] == 0 and st["fused_tensors"] == st["tensors"], st
+    g = build()
+    _C.materialize_module(g, False, None, None, None, False)  # fused=False: every op replayed by ATen on the GPU
+    assert last_materialize_stats()["fused_tensors"] == 0
+    for name in ("model.rotary_emb.inv_freq", "model.rotary_emb.original_inv_freq"):
+        a, b = named(m)[name], named(g)[name]
+        assert a.dtype == b.dtype == torch.float32 and a.shape == b.shape
+        # same arithmetic as ATen's CUDA kernels (x * (1/dim), powf, 1/x): bit for bit
+        assert torch.equal(a, b), (name, (a - b).abs().max().item())
+
+
+def test_iota_descriptors_through_the_c_abi():
+    import numpy as np
+
+    from oracle import tdx_oracle as O
+    from torchdistx_b200 import _cabi as C
+
+    lib = C.load()
+    n = 5000
+    ws = torch.empty(lib.tdx_init_workspace_bytes(4), dtype=torch.uint8, device="cuda")
+    ids = torch.empty(n, dtype=torch.int64, device="cuda")
+    half = torch.empty(n - 7, dtype=torch.int64, device="cuda")
+    freq = torch.empty(n, dtype=torch.float32, device="cuda")
+    epi = [(C.TDX_EPI_MUL, 1.0 / 128), (C.TDX_EPI_RPOW, 500000.0), (C.TDX_EPI_RECIP, 0.0), (C.TDX_EPI_MUL, 1.0)]
+    descs = [C.make_desc(ids.data_ptr(), dtype=C.TDX_I64, src=C.TDX_SRC_IOTA, elem_count=n, p0=3, p1=-2),
+             C.make_desc(half.data_ptr(), dtype=C.TDX_I64, src=C.TDX_SRC_IOTA, elem_begin=7, elem_count=n - 7, p0=3, p1=-2),
+             C.make_desc(freq.data_ptr(), dtype=C.TDX_F32, src=C.TDX_SRC_IOTA, elem_count=n, p0=0, p1=2, epi=epi)]
+    C.launch(descs, ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(ids.cpu(), 3 - 2 * torch.arange(n)) and torch.equal(half, ids[7:])
+    assert np.array_equal(O.generate(descs[0]).view(np.int64), ids.cpu().numpy())
+    # against ATen's CUDA kernels: the same program, op by op
+    x = torch.arange(0, 2 * n, 2, dtype=torch.int64, device="cuda").to(torch.float32) / 128
+    ref = (1.0 / (500000.0 ** x)) * 1.0
+    assert torch.equal(freq, ref), (freq - ref).abs().max().item()
+    # against the CPU restatement: libm's powf and CUDA's agree to a couple of ulp, not bit for bit
+    exp = torch.from_numpy(O.generate(descs[2]).view(np.float32).copy())
+    torch.testing.assert_close(freq.cpu(), exp, rtol=4 * 2.0 ** -23, atol=1e-45)
+
+
+def test_position_ids_and_arange_buffers_fold():
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.register_buffer("position_ids", torch.arange(512).expand((1, -1)))
+            self.register_buffer("steps", torch.arange(2, 40, 3))
+            self.register_buffer("half_steps", torch.arange(10, dtype=torch.float32) / 4)
+
+    m = deferred_init(lambda: _on_cuda(M))
+    materialize_module(m)
+    st = last_materialize_stats()
+    assert st["generic_ops"] == 0 and st["fused_tensors"] == 3, st
+    assert torch.equal(m.position_ids.cpu(), torch.arange(512).expand((1, -1)))
+    assert torch.equal(m.steps.cpu(), torch.arange(2, 40, 3)) and m.steps.dtype == torch.int64
+    assert torch.equal(m.half_steps.cpu(), torch.arange(10, dtype=torch.float32) / 4)

@@ -31,7 +31,7 @@ def test_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert lib.tdx_abi_version() == 2
-    assert ctypes.sizeof(C.TdxInitDesc) == 128 and ctypes.sizeof(C.TdxPlan) == 2048
+    assert ctypes.sizeof(C.TdxInitDesc) == 128 and ctypes.sizeof(C.TdxPlan) == 4096
     assert lib.tdx_init_workspace_bytes(100) >= 100 * 128
     assert lib.tdx_elems_per_block(C.TDX_BF16, C.TDX_SRC_NORMAL, 0) == 8
     assert lib.tdx_elems_per_block(C.TDX_F32, C.TDX_SRC_UNIFORM, 0) == 4
@@ -160,3 +160,18 @@ def test_prepare_lays_out_extreme_plans_within_the_workspace_bound():
     arr = (C.TdxInitDesc * 1)(llama[0])
     assert lib.tdx_init_prepare(arr, 1, ctypes.byref(need)) == 0 and need.value > 0
     assert lib.tdx_init_submit(None, 0, None) != 0
+
+
+def test_oracle_iota_matches_torch_on_the_cpu():
+    """TDX_SRC_IOTA in the CPU restatement: arange exactly, the rotary inv_freq program to fp32 rounding."""
+    import numpy as np
+    import torch
+
+    n = 64
+    d = C.make_desc(0, dtype=C.TDX_I64, src=C.TDX_SRC_IOTA, elem_begin=5, elem_count=n, p0=-4, p1=3)
+    assert np.array_equal(O.generate(d).view(np.int64), (-4 + 3 * (5 + np.arange(n))))
+    epi = [(C.TDX_EPI_MUL, 1.0 / 128), (C.TDX_EPI_RPOW, 500000.0), (C.TDX_EPI_RECIP, 0.0), (C.TDX_EPI_MUL, 1.0)]
+    d = C.make_desc(0, dtype=C.TDX_F32, src=C.TDX_SRC_IOTA, elem_count=n, p0=0, p1=2, epi=epi)
+    got = torch.from_numpy(O.generate(d).view(np.float32).copy())
+    ref = 1.0 / (500000.0 ** (torch.arange(0, 2 * n, 2, dtype=torch.int64).float() / 128))
+    torch.testing.assert_close(got, ref, rtol=4 * 2.0 ** -23, atol=0.0)

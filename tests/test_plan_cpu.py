@@ -15,8 +15,9 @@ def test_plan_of_tiny_llama_round_trips_through_json(tmp_path):
     w = by_name["model.layers.0.mlp.up_proj.weight"]
     assert (w.source, w.dtype, w.p0, w.p1, w.rng_numels) == ("normal", "BFloat16", 0.0, 0.02, [128 * 64] * 2)
     assert by_name["model.norm.weight"].source == "const"
-    inv = by_name["model.rotary_emb.inv_freq"]  # arange -> pow -> reciprocal: stored by value
-    assert inv.source == "value" and inv.kind == "buffer"
+    inv = by_name["model.rotary_emb.inv_freq"]  # arange -> float -> / dim -> base ** x -> 1 / x -> * 1.0: an index program
+    assert inv.source == "iota" and inv.kind == "buffer" and (inv.p0, inv.p1) == (0.0, 2.0)
+    assert [e[0] for e in inv.epilogue] == [1, 5, 6, 1] and inv.epilogue[1][1] == 10000.0
     assert plan.num_params == sum(p.numel() for p in m.parameters())
     path = tmp_path / "plan.json"
     plan.save(str(path))

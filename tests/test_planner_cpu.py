@@ -31,8 +31,8 @@ def test_init_idioms_fold_as_documented():
     s = r["scaled"]  # randn * 0.02 + 1.0
     assert s["source"] == "normal" and s["n_epilogue"] == 2
     assert r["int_fill"]["source"] == "const" and r["int_fill"]["dtype"] == "Long"
-    for name in ("mask", "steps"):  # tril / arange: replayed by ATen on the target device
-        assert r[name]["source"] == "opaque" and not r[name]["fusible"]
+    assert r["mask"]["source"] == "opaque" and not r["mask"]["fusible"]  # tril(...).bool(): replayed by ATen on the target device
+    assert r["steps"]["source"] == "iota" and r["steps"]["fusible"] and (r["steps"]["p0"], r["steps"]["p1"]) == (0.0, 1.0)
     assert r["bn.num_batches_tracked"]["source"] == "real"  # torch.tensor(0) is never intercepted
 
 
@@ -71,22 +71,35 @@ def test_more_hf_families_and_torch_modules():
 
 
 def test_mid_history_reader_forces_generic_replay():
-    def build():
+    def build(reader):
         w = torch.empty(8, 8).uniform_()
-        snapshot = w * 2.0  # reads the uniform state ...
+        snapshot = reader(w)  # reads the uniform state ...
         w.normal_()  # ... which is then overwritten
         m = nn.Module()
         m.w, m.s = nn.Parameter(w), nn.Parameter(snapshot)
         return m
 
-    m = deferred_init(build)
-    r = plan_report(m)
-    assert r["w"]["source"] == "opaque"  # the reader must run at its own point in history
     from torchdistx_b200.deferred_init import materialize_module
+
+    # a reader the planner cannot express must run at its own point in history: w is replayed
+    m = deferred_init(build, torch.sin)
+    r = plan_report(m)
+    assert r["w"]["source"] == "opaque" and r["s"]["source"] == "opaque"
     torch.manual_seed(0)
     materialize_module(m)
     torch.manual_seed(0)
-    e = build()
+    e = build(torch.sin)
+    assert torch.equal(m.w, e.w) and torch.equal(m.s, e.s)
+
+    # a reader whose result folds symbolically (uniform * 2: the state of w AS OF the reader) pins nothing
+    m = deferred_init(build, lambda w: w * 2.0)
+    r = plan_report(m)
+    assert (r["w"]["source"], r["w"]["rng_ops"]) == ("normal", 2)
+    assert (r["s"]["source"], r["s"]["n_epilogue"], r["s"]["rng_ops"]) == ("uniform", 1, 1)
+    torch.manual_seed(0)
+    materialize_module(m)  # (CPU tensors: ATen replay either way, bit-exact with eager)
+    torch.manual_seed(0)
+    e = build(lambda w: w * 2.0)
     assert torch.equal(m.w, e.w) and torch.equal(m.s, e.s)
 
 

@@ -94,11 +94,13 @@ struct NoInterception {
 // whole is one segment; `weight.normal_(); weight[padding_idx].zero_()` (nn.Embedding, BERT, Gemma,
 // OPT, Phi-3) is three; an in-place op through a contiguous view splits the segments it crosses.
 struct Sym {
-  enum Src { Uninit, Const, Uniform, Normal } src = Uninit;
+  // Iota: element i = p0 + (i - origin) * p1 (integers): `arange`, and -- with epilogue steps -- the
+  // index programs built on it (rotary inv_freq: arange -> float -> / dim -> base ** x -> 1/x -> * s)
+  enum Src { Uninit, Const, Uniform, Normal, Iota } src = Uninit;
   at::Tensor cval;                           // Const: a 1-element tensor of the state's dtype (built lazily)
   c10::Scalar cscalar;                       // Const: the value, while no folding has needed a tensor
   bool has_scalar = false;
-  double p0 = 0, p1 = 1;                     // Uniform: from,to   Normal: mean,std
+  double p0 = 0, p1 = 1;                     // Uniform: from,to   Normal: mean,std   Iota: start,step
   uint32_t rng_op = kNoValue;                // the live RNG op
   c10::SmallVector<TdxEpiStep, TDX_MAX_EPI> epi;
   // The RNG source ran on an fp32 tensor that was later cast to a 16-bit dtype: keep the fp32
@@ -439,6 +441,30 @@ void transition(Tape& tape, uint32_t op_idx, uint32_t S, State& st) {
       st.rng_chain.push_back(RngPass{op_idx, out.numel, rng_slot_of(tape, op_idx)});
       return;
     }
+    case OpKind::Arange: {
+      // arange([start,] end[, step]) with integer start / step: exact in int64, and in fp32 as long as
+      // every value stays below 2^24 (then no question of how the kernel rounds start + i * step)
+      if (!out.covers_storage || !(out.dtype == ScalarType::Long || out.dtype == ScalarType::Float)) {
+        st = make_opaque();
+        return;
+      }
+      const size_t ps = find_arg(op, "start"), pt = find_arg(op, "step");
+      const auto start = ps == static_cast<size_t>(-1) ? std::optional<double>(0.0) : scalar_arg(op, ps);
+      const auto step = pt == static_cast<size_t>(-1) ? std::optional<double>(1.0) : scalar_arg(op, pt);
+      const double kExact = out.dtype == ScalarType::Float ? 16777216.0 : 9007199254740992.0;
+      if (!start || !step || *start != std::floor(*start) || *step != std::floor(*step) ||
+          std::fabs(*start) + std::fabs(*step) * static_cast<double>(out.numel) >= kExact) {
+        st = make_opaque();
+        return;
+      }
+      Sym sy;
+      sy.src = Sym::Iota;
+      sy.p0 = *start;
+      sy.p1 = *step;
+      st.rng_chain.clear();
+      fresh(std::move(sy));
+      return;
+    }
     case OpKind::Alias:
     case OpKind::View:
     case OpKind::HookVariableData:
@@ -446,6 +472,39 @@ void transition(Tape& tape, uint32_t op_idx, uint32_t S, State& st) {
       return;  // same elements under another tensor object
     default:
       break;
+  }
+
+  // ---- dst.copy_(src): the range `out` names becomes src's elements ------------------------------
+  if (op.kind == OpKind::CopyInplace) {
+    int64_t b = 0, e = 0;
+    if (st.opaque || out.dtype != st.dtype || !range_of(out, b, e) || st.segs.empty() || b < 0 ||
+        e > st.segs.back().end || op.inputs.size() < 2 || op.inputs[1].value == kNoValue) {
+      st = make_opaque();
+      return;
+    }
+    const ValueInfo& in = tape.values[op.inputs[1].value];
+    int64_t sb = 0, se = 0;
+    if (in.numel != out.numel || in.dtype != out.dtype || in.storage == S || !range_of(in, sb, se) ||
+        in.sizes != out.sizes) {  // (no broadcasting, no dtype conversion)
+      st = make_opaque();
+      return;
+    }
+    State src = eval_storage(tape, in.storage, op_idx);
+    if (src.opaque || src.dtype != in.dtype || src.segs.empty() || sb < 0 || se > src.segs.back().end) {
+      st = make_opaque();
+      return;
+    }
+    for (Seg& g : src.segs) {
+      const int64_t gb = std::max(g.begin, sb), ge = std::min(g.end, se);
+      if (gb >= ge) continue;
+      overwrite(st, b + (gb - sb), b + (ge - sb), g.st, g.origin - sb + b);
+    }
+    for (const RngPass& r : src.rng_chain) {  // the source's passes must have their streams when dst is built
+      bool have = false;
+      for (const RngPass& q : st.rng_chain) have |= q.op == r.op;
+      if (!have) st.rng_chain.push_back(r);
+    }
+    return;
   }
 
   // ---- in-place writers through `out` (the whole tensor or a contiguous view of part of it) ----
@@ -519,6 +578,7 @@ void transition(Tape& tape, uint32_t op_idx, uint32_t S, State& st) {
         if (!fold_const(op, sy, dt, /*inplace=*/true) || dt != st.dtype) { st = make_opaque(); return; }
         continue;
       }
+      if (sy.src == Sym::Iota && st.dtype != ScalarType::Float) { st = make_opaque(); return; }
       bool ok = true;
       if (op.kind == OpKind::MulInplace) {
         const auto c = scalar_arg(op, 1);
@@ -542,7 +602,8 @@ void transition(Tape& tape, uint32_t op_idx, uint32_t S, State& st) {
 
   // ---- out-of-place unary ops: a new storage whose state derives from the argument's -------------
   if (op.kind == OpKind::MulOut || op.kind == OpKind::AddOut || op.kind == OpKind::CloneOut ||
-      op.kind == OpKind::CastOut) {
+      op.kind == OpKind::CastOut || op.kind == OpKind::DivOut || op.kind == OpKind::PowScalarOut ||
+      op.kind == OpKind::ReciprocalOut) {
     if (op.inputs.empty() || op.inputs[0].value == kNoValue || !out.covers_storage) { st = make_opaque(); return; }
     const ValueInfo& in = tape.values[op.inputs[0].value];
     int64_t b = 0, e = 0;
@@ -594,6 +655,61 @@ void transition(Tape& tape, uint32_t op_idx, uint32_t S, State& st) {
         ScalarType dt = st.dtype;
         if (!fold_const(op, sy, dt, /*inplace=*/false) || dt != out.dtype) { st = make_opaque(); return; }
         new_dtype = out.dtype;
+        continue;
+      }
+      if (sy.src == Sym::Iota) {
+        // index programs: everything after the arange runs in fp32 (the kernel's epilogue)
+        if (op.kind == OpKind::CastOut) {
+          if (out.dtype == st.dtype) continue;
+          if (!(st.dtype == ScalarType::Long && out.dtype == ScalarType::Float && sy.epi.empty()) ||
+              std::fabs(sy.p0) + std::fabs(sy.p1) * static_cast<double>(out.numel) >= 16777216.0) {
+            st = make_opaque();
+            return;
+          }
+          new_dtype = out.dtype;  // int64 -> fp32 of values below 2^24: exact
+          continue;
+        }
+        if (out.dtype != ScalarType::Float ||
+            !(st.dtype == ScalarType::Float || (st.dtype == ScalarType::Long && op.kind == OpKind::DivOut && sy.epi.empty())) ||
+            std::fabs(sy.p0) + std::fabs(sy.p1) * static_cast<double>(out.numel) >= 16777216.0) {
+          st = make_opaque();
+          return;
+        }
+        new_dtype = out.dtype;  // (an int64 arange divided by a number is promoted to fp32 first, like ATen does)
+      }
+      if (op.kind == OpKind::DivOut || op.kind == OpKind::PowScalarOut || op.kind == OpKind::ReciprocalOut) {
+        // fp32 only, with the arithmetic of ATen's CUDA kernels: `t / c` multiplies by the fp32
+        // reciprocal of c (BinaryDivTrueKernel.cu), `c ** t` is powf(c, t) (PowKernel.cu), reciprocal
+        // is 1.0f / t
+        if (out.dtype != ScalarType::Float || (sy.src != Sym::Iota && st.dtype != ScalarType::Float)) {
+          st = make_opaque();
+          return;
+        }
+        bool ok = false;
+        if (op.kind == OpKind::DivOut) {
+          const auto c = scalar_arg(op, 1);
+          const size_t pm = find_arg(op, "rounding_mode");
+          ok = c && pm == static_cast<size_t>(-1) &&
+               push_epi(sy, TDX_EPI_MUL, static_cast<double>(1.0f / static_cast<float>(*c)));
+        } else if (op.kind == OpKind::PowScalarOut) {
+          const auto base = scalar_arg(op, 0);
+          ok = base && *base != 1.0 && push_epi(sy, TDX_EPI_RPOW, *base);
+        } else {
+          ok = push_epi(sy, TDX_EPI_RECIP, 0);
+        }
+        if (!ok) { st = make_opaque(); return; }
+        continue;
+      }
+      if (sy.src == Sym::Iota && (op.kind == OpKind::MulOut || op.kind == OpKind::AddOut)) {
+        bool ok;
+        if (op.kind == OpKind::MulOut) {
+          const auto c = scalar_arg(op, 1);
+          ok = c && push_epi(sy, TDX_EPI_MUL, *c);
+        } else {
+          const auto c = scalar_arg(op, 1), alpha = scalar_arg(op, 2);
+          ok = c && alpha && push_epi(sy, TDX_EPI_ADD, *c * *alpha);
+        }
+        if (!ok) { st = make_opaque(); return; }
         continue;
       }
       // RNG source followed by an elementwise op
@@ -667,6 +783,26 @@ bool is_pure_alias(OpKind k) {
   return k == OpKind::Alias || k == OpKind::View || k == OpKind::HookVariableData || k == OpKind::HookSetData;
 }
 
+// A reader of an intermediate state does not pin its argument to generic replay if nobody will ever
+// have to RUN it: every tensor it produced has a final state the planner can derive symbolically
+// (e.g. `original = buf.clone()` followed by `buf.copy_(...)`, `original.copy_(...)`: HF's rotary
+// embeddings).  Deriving such a state evaluates the argument as of the reader, never its final state.
+thread_local int g_reader_depth = 0;
+bool reader_resolves_symbolically(Tape& tape, const TapeOp& op) {
+  if (g_reader_depth >= 4) return false;
+  struct Depth {
+    Depth() { ++g_reader_depth; }
+    ~Depth() { --g_reader_depth; }
+  } depth;
+  for (uint32_t v : op.outputs) {
+    if (v == kNoValue) continue;
+    const ValueInfo& ov = tape.values[v];
+    if (ov.real.defined() || tape.storages[ov.storage].replayed) return false;
+    if (eval_storage(tape, ov.storage, static_cast<uint32_t>(tape.ops.size())).opaque) return false;
+  }
+  return true;
+}
+
 // State of storage S after every recorded op with index < upto.
 State eval_storage(Tape& tape, uint32_t S, uint32_t upto) {
   const StorageInfo& si = tape.storages[S];
@@ -690,7 +826,8 @@ State eval_storage(Tape& tape, uint32_t S, uint32_t upto) {
       // A reader that saw an intermediate state which a later op overwrote must run at its own
       // point in history: only generic replay can do that.  (`p.data = t` names p's old storage
       // as an argument but never reads it.)
-      if (op.kind != OpKind::HookSetData && !op.done && last_writer != kNoValue && oi < last_writer)
+      if (op.kind != OpKind::HookSetData && !op.done && last_writer != kNoValue && oi < last_writer &&
+          !reader_resolves_symbolically(tape, op))
         return make_opaque();
       continue;
     }
@@ -711,7 +848,8 @@ State eval_storage(Tape& tape, uint32_t S, uint32_t upto) {
 // cold in the caches by the time a model is materialised: every line touched is ~100 ns).
 struct FastSeg {
   int64_t begin = 0, end = 0, origin = 0;
-  uint32_t rng_slot = kNoValue;  // kNoValue: a constant segment
+  uint32_t rng_slot = kNoValue;  // kNoValue: no RNG pass (a constant or an index program)
+  bool indexed = false;          // the descriptor's elem_begin matters (RNG and iota sources)
   bool wide = false;
   const Sym* sym = nullptr;      // (into StorageTemplate::st) for the rare questions: wide_observable
   TdxInitDesc proto;             // everything but dst / elem_begin / elem_count / seed / offset
@@ -1083,8 +1221,18 @@ bool build_fast(const Tape& tape, const StorageInfo& si, StorageTemplate& t, boo
       }
       for (size_t i = 0; i < 16; i += isz) std::memcpy(pat + i, one, isz);
       std::memcpy(d.fill_bits, pat, 16);
+    } else if (sy.src == Sym::Iota) {
+      if (!(st.dtype == ScalarType::Float || (st.dtype == ScalarType::Long && sy.epi.empty()))) return false;
+      d.src = TDX_SRC_IOTA;
+      d.dtype = st.dtype == ScalarType::Float ? TDX_F32 : TDX_I64;
+      d.p0 = sy.p0;
+      d.p1 = sy.p1;
+      d.n_epi = static_cast<uint8_t>(sy.epi.size());
+      for (size_t i = 0; i < sy.epi.size(); ++i) d.epi[i] = sy.epi[i];
+      f.indexed = true;
     } else {
       if (tdx_dtype_of(st.dtype) < 0) return false;
+      f.indexed = true;
       d.src = sy.src == Sym::Uniform ? TDX_SRC_UNIFORM : TDX_SRC_NORMAL;
       d.dtype = static_cast<uint8_t>(tdx_dtype_of(st.dtype));
       d.p0 = sy.p0;
@@ -1364,8 +1512,8 @@ struct Engine {
       // byte offset inside the output until the submission gives the output its address
       d.dst = reinterpret_cast<void*>(static_cast<uintptr_t>(lo - g.begin) * isz);
       d.elem_count = static_cast<uint64_t>(hi - lo);
+      if (sg.indexed) d.elem_begin = static_cast<uint64_t>(lo - sg.origin);  // index in the tensor the source op ran on
       if (sg.rng_slot != kNoValue) {
-        d.elem_begin = static_cast<uint64_t>(lo - sg.origin);  // index in the tensor the RNG op ran on
         const RngSlot& r = tape.rng[sg.rng_slot];
         d.philox_seed = r.seed;
         d.philox_offset = r.offset;
@@ -1517,8 +1665,8 @@ struct Engine {
         TdxInitDesc& d = batch.descs.back();
         d.dst = place(it.offset + slo);
         d.elem_count = static_cast<uint64_t>(shi - slo);
+        if (sg.indexed) d.elem_begin = static_cast<uint64_t>(slo - sg.origin);
         if (sg.rng_slot != kNoValue) {
-          d.elem_begin = static_cast<uint64_t>(slo - sg.origin);
           const RngSlot& r = tape.rng[sg.rng_slot];
           d.philox_seed = r.seed;
           d.philox_offset = r.offset;
@@ -2322,7 +2470,7 @@ PlanInfo plan_info(const at::Tensor& fake) {
   State fresh;
   if (!si.tmpl) fresh = eval_storage(tape, vi.storage, static_cast<uint32_t>(tape.ops.size()));
   const State& st = si.tmpl ? si.tmpl->st : fresh;
-  static const char* names[] = {"uninit", "const", "uniform", "normal"};
+  static const char* names[] = {"uninit", "const", "uniform", "normal", "iota"};
   if (st.opaque || st.segs.empty()) {
     info.source = "opaque";
     // best effort: the first op on the storage the planner does not model

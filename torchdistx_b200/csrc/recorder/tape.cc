@@ -55,6 +55,11 @@ OpKind kind_from_name(const std::string& name, const std::string& overload) {
   if (n == "mul" && (overload == "Tensor" || overload == "Scalar")) return OpKind::MulOut;
   if (n == "add" && (overload == "Tensor" || overload == "Scalar")) return OpKind::AddOut;
   if (n == "clone") return OpKind::CloneOut;
+  if (n == "arange") return OpKind::Arange;
+  if (n == "div" && (overload == "Tensor" || overload == "Scalar")) return OpKind::DivOut;
+  if (n == "pow" && overload == "Scalar") return OpKind::PowScalarOut;
+  if (n == "reciprocal") return OpKind::ReciprocalOut;
+  if (n == "copy_") return OpKind::CopyInplace;
   if (n == "_to_copy" || (n == "to" && (overload == "dtype" || overload == "dtype_layout")))
     return OpKind::CastOut;
   return OpKind::Generic;

@@ -41,7 +41,7 @@ constexpr uint32_t kNoValue = 0xffffffffu;
 enum class OpKind : uint8_t {
   Generic = 0,
   // factories (new storage)
-  Empty, Zeros, Ones, Full, Randn, Rand,
+  Empty, Zeros, Ones, Full, Randn, Rand, Arange,
   // full aliases of the input (same storage, same elements)
   Alias,  // detach, alias, view-like ops are classified Alias only when they cover the storage
   // a view of PART of the input's storage (select / narrow / slice / a[i]): same memory, nothing
@@ -51,7 +51,9 @@ enum class OpKind : uint8_t {
   UniformInplace, NormalInplace, FillInplace, ZeroInplace,
   MulInplace, AddInplace, ErfinvInplace, ClampInplace,
   // out-of-place unary elementwise (new storage, same geometry)
-  MulOut, AddOut, CastOut, CloneOut,
+  MulOut, AddOut, CastOut, CloneOut, DivOut, PowScalarOut, ReciprocalOut,
+  // dst.copy_(src): dst's elements become src's
+  CopyInplace,
   // autograd hook pseudo-ops
   HookVariableData, HookSetData,
 };

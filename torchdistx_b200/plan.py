@@ -115,7 +115,7 @@ class InitPlan:
                         continue
                     seen[id(t)] = name
                     info = dict(_C.plan_info(t))
-                    if info["source"] in ("const", "uniform", "normal", "uninit") and info["fusible"]:
+                    if info["source"] in ("const", "uniform", "normal", "uninit", "iota") and info["fusible"]:
                         segs = [dict(begin=g["begin"], end=g["end"], origin=g["origin"], source=g["source"],
                                      p0=g["p0"], p1=g["p1"], epilogue=[tuple(e) for e in g["epilogue"]],
                                      const_bytes=base64.b64encode(g["const_bytes"]).decode(),
@@ -267,6 +267,11 @@ class InitPlan:
                         descs.append(_cabi.make_desc(
                             dst, dtype=_RAW[isz], src=_cabi.TDX_SRC_CONST, elem_count=hi - lo,
                             fill_bits=int.from_bytes(base64.b64decode(g["const_bytes"]), "little"), fill_itemsize=isz))
+                    elif g["source"] == "iota":  # arange and the index programs built on it (rotary inv_freq)
+                        descs.append(_cabi.make_desc(
+                            dst, dtype=_cabi.TDX_F32 if dtype == torch.float32 else _cabi.TDX_I64,
+                            src=_cabi.TDX_SRC_IOTA, elem_begin=lo - g["origin"], elem_count=hi - lo,
+                            p0=g["p0"], p1=g["p1"], epi=g["epilogue"]))
                     else:
                         descs.append(_cabi.make_desc(
                             dst, dtype=_TDX_DTYPE[dtype],
