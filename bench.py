@@ -607,7 +607,7 @@ def run_ours(a):
                    "params": n_params, "tensors": main["tensors"], "descriptors_per_rank": main["descs"],
                    "fused_tensors": st["fused_tensors"], "generic_ops": st["generic_ops"],
                    "elided_rng_ops": st["elided_rng_ops"], "record_s_per_model": main["record_s_per_model"],
-                   "host_us": {k: round(st[k]) for k in ("traverse_us", "plan_us", "eval_us", "alloc_us", "launch_us", "wrap_us", "assign_us", "first_submit_us", "last_submit_us", "deferred_us", "submissions", "template_hits")},
+                   "host_us": {k: round(st[k]) for k in ("traverse_us", "plan_us", "eval_us", "alloc_us", "launch_us", "wrap_us", "assign_us", "first_submit_us", "last_submit_us", "deferred_us", "helper_start_us", "helper_done_us", "submissions", "template_hits")},
                    "e2e_host_split_ms": main["host_split"],
                    "l2": "outputs per step (GBs) exceed the 126 MB L2; no flush needed",
                    "collective": "one 16-byte broadcast of (seed, offset) before the first step; later steps derive their offsets locally (parallel.sync_rng), agreement asserted after the timed region",

@@ -389,6 +389,8 @@ py::dict py_last_stats() {
   d["template_hits"] = s.template_hits;
   d["prebuilt_outputs"] = s.prebuilt_outputs;
   d["deferred_us"] = s.deferred_us;
+  d["helper_start_us"] = s.helper_start_us;
+  d["helper_done_us"] = s.helper_done_us;
   return d;
 }
 

@@ -238,7 +238,10 @@ std::optional<double> scalar_arg(const TapeOp& op, size_t pos) {
     if (slot >= op.inputs.size()) return std::nullopt;
     const at::Tensor& t = op.inputs[slot].real;
     if (!t.defined() || t.numel() != 1 || !t.is_cpu() || t.is_complex()) return std::nullopt;
-    if (g_analysis_only) {  // its value is read when the storage is materialised, not now
+    // A Python number the argument parser wrapped into a 0-dim tensor is nobody else's to mutate:
+    // its value can be read when the tape is analysed.  Any other real tensor is read when the
+    // storage is materialised (it may change until then: the version check must see that).
+    if (g_analysis_only && !t.unsafeGetTensorImpl()->is_wrapped_number()) {
       g_analysis_deferred = true;
       return std::nullopt;
     }
@@ -1594,7 +1597,6 @@ struct Engine {
       const int64_t sizes[1] = {chunk};
       out = make_output(sizes, dtype, *dev, pend.nbytes, pend.storage);
     }
-    pend.first_desc = static_cast<uint32_t>(batch.descs.size());
     auto place = [&](int64_t flat_index) {  // dst of a flat element of this rank's chunk
       return reinterpret_cast<void*>(abs_base + static_cast<uintptr_t>(flat_index - lo) * isz);
     };
@@ -1613,17 +1615,18 @@ struct Engine {
       int64_t src_begin, dst_begin, count;
     };
     std::vector<Deferred> deferred;
-    int64_t bytes = 0, covered = lo;  // [lo, covered) has been written or queued
-    for (const Item& it : items) {
+    // Pass 1, in order (it is the order RNG offsets are handed out in): decide per parameter, assign
+    // the RNG passes of the fusible ones, replay the others now -- a replay may submit the batch, so
+    // none of this chunk's descriptors may be in it yet.
+    std::vector<std::unique_ptr<StorageTemplate>> owned;
+    std::vector<const StorageTemplate*> plan(items.size(), nullptr);
+    for (size_t k = 0; k < items.size(); ++k) {
+      const Item& it = items[k];
       Tape& tape = *it.tape;
       const ValueInfo& vi = tape.values[it.value];
       const uint32_t S = vi.storage;
       StorageInfo& si = tape.storages[S];
       const int64_t b = std::max(it.offset, lo), e = std::min(it.offset + it.numel, hi);
-      // alignment gap in front of this parameter
-      if (it.offset > covered && covered < hi) zero_fill(covered, std::min(it.offset, hi));
-      covered = std::max(covered, std::min(it.offset + it.numel, hi));
-      StorageTemplate tmp;
       const StorageTemplate* t = nullptr;
       bool fusible = opts.fused && !si.replayed && !si.fused_done && !vi.real.defined() && vi.covers_storage;
       if (fusible) {
@@ -1631,8 +1634,9 @@ struct Engine {
           t = si.tmpl.get();
           g_stats.template_hits++;
         } else if (!(si.tmpl && si.tmpl->st.opaque)) {
+          auto tmp = std::make_unique<StorageTemplate>();
           if (si.tmpl) {
-            tmp.st = si.tmpl->st;
+            tmp->st = si.tmpl->st;
           } else {
             struct FoldOn {
               c10::Device prev = g_fold_device;
@@ -1640,23 +1644,43 @@ struct Engine {
               ~FoldOn() { g_fold_device = prev; }
             } fold_on(*dev);
             c10::DeviceGuard fold_guard(*dev);
-            tmp.st = eval_storage(tape, S, static_cast<uint32_t>(tape.ops.size()));
+            tmp->st = eval_storage(tape, S, static_cast<uint32_t>(tape.ops.size()));
           }
-          if (build_fast(tape, si, tmp, /*may_sync=*/true)) t = &tmp;
+          if (build_fast(tape, si, *tmp, /*may_sync=*/true)) {
+            t = tmp.get();
+            owned.push_back(std::move(tmp));
+          }
         }
         fusible = t != nullptr && t->st.dtype == dtype;
       }
       if (!fusible) {
-        // generic replay of the whole parameter on the GPU, then its slice is copied into the chunk
+        // generic replay of the whole parameter on the GPU; its slice is copied into the chunk below
         at::Tensor full = materialize_value(it.tape, it.value);
         if (b < e) deferred.push_back(Deferred{full, b - it.offset, b, e - b});
         continue;
       }
+      plan[k] = t;
       for (const RngPass& r : t->st.rng_chain) {  // every rank assigns every pass, owner or not
         RngSlot& slot = tape.rng[r.slot];
         if (!slot.assigned) assign_rng(tape, slot, r.numel, *dev, gens);
       }
-      if (b >= e) continue;
+    }
+    if (batch.device != *dev) {
+      batch.flush();
+      batch.device = *dev;
+    }
+    pend.first_desc = static_cast<uint32_t>(batch.descs.size());
+    // Pass 2: this chunk's descriptors (nothing else touches the batch from here to the flush)
+    int64_t bytes = 0, covered = lo;  // [lo, covered) has been written or queued
+    for (size_t k = 0; k < items.size(); ++k) {
+      const Item& it = items[k];
+      Tape& tape = *it.tape;
+      const int64_t b = std::max(it.offset, lo), e = std::min(it.offset + it.numel, hi);
+      // alignment gap in front of this parameter
+      if (it.offset > covered && covered < hi) zero_fill(covered, std::min(it.offset, hi));
+      covered = std::max(covered, std::min(it.offset + it.numel, hi));
+      const StorageTemplate* t = plan[k];
+      if (!t || b >= e) continue;
       const int64_t pb = b - it.offset, pe = e - it.offset;  // the parameter's own elements this rank holds
       for (const FastSeg& sg : t->segs) {
         const int64_t slo = std::max(sg.begin, pb), shi = std::min(sg.end, pe);
@@ -2133,6 +2157,7 @@ struct PipelinedMaterialize::State {
   };
   MaterializeOptions opts;
   bool threaded = false;
+  double t_api_begin = now_us();               // (diagnostics: when the helper got going / was done, on the call's clock)
   at::ThreadLocalState tls;                    // the caller's, applied around the whole session
   std::vector<c10::cuda::CUDAStream> streams;  // the caller's current streams (its device, the target device)
   c10::DeviceIndex caller_device = -1;         // the caller's current CUDA device
@@ -2193,6 +2218,7 @@ struct PipelinedMaterialize::State {
       // rank of a multi-GPU job).  Device and streams stay until the next call sets its own.
       if (caller_device >= 0) c10::cuda::set_device(caller_device);
       for (const auto& st : streams) c10::cuda::setCurrentCUDAStream(st);
+      const double helper_start = now_us() - t_api_begin;
       MaterializeSession s(opts);
       s.defer_generic_programs([this](size_t ticket, at::Tensor t) { deliver(ticket, std::move(t)); });
       size_t next = 0, first = 0;
@@ -2228,6 +2254,8 @@ struct PipelinedMaterialize::State {
           record_error();
         }
       }
+      g_stats.helper_start_us = helper_start;
+      g_stats.helper_done_us = now_us() - t_api_begin;
       stats = g_stats;  // the helper thread's counters of this session
       descs = g_last_descs;
     } catch (...) {  // (session construction / thread-local state)

@@ -62,6 +62,7 @@ struct MaterializeStats {
   double first_submit_us = 0;    // host time from the start of the call to the first submission
   double last_submit_us = 0;     // ... and to the last one
   int64_t template_hits = 0;     // storages whose analysis was done when the recording ended
+  double helper_start_us = 0, helper_done_us = 0;  // when the planner thread started / finished, since the call began
   double deferred_us = 0;        // host time replaying the RNG-free unfusable programs after the last submission
   int64_t prebuilt_outputs = 0;  // outputs the calling thread had built before the helper planned them
 };
