@@ -2167,6 +2167,11 @@ struct PipelinedMaterialize::State {
   std::vector<std::unique_ptr<Item>> items;  // pushed by the caller, consumed in order by the helper
   bool finish_requested = false;
   bool helper_waiting = false;
+  // Mirrors of items.size() / finish_requested the helper polls without the mutex: it plans faster
+  // than the caller walks, and a helper that went to sleep after every tensor cost the CALLER a futex
+  // wake-up per tensor (the walk of Llama-3-8B went from 0.2 to 0.6 ms when the planner got fast).
+  std::atomic<size_t> n_items{0};
+  std::atomic<bool> finish_flag{false};
   std::atomic<bool> caller_waiting{false};
   bool finished = false;
   std::exception_ptr error;
@@ -2225,6 +2230,13 @@ struct PipelinedMaterialize::State {
       std::vector<Item*> batch;
       for (;;) {
         bool fin;
+        // a call lasts a millisecond: poll for that long before sleeping
+        for (int spin = 0; spin < 200000 && next == n_items.load(std::memory_order_acquire) &&
+                           !finish_flag.load(std::memory_order_acquire); ++spin) {
+#if defined(__x86_64__) || defined(__i386__)
+          __builtin_ia32_pause();
+#endif
+        }
         {
           std::unique_lock<std::mutex> lock(m);
           while (next == items.size() && !finish_requested) {
@@ -2308,6 +2320,7 @@ PipelinedMaterialize::~PipelinedMaterialize() {
   std::unique_lock<std::mutex> lock(st_->m);
   if (!st_->finish_requested) {
     st_->finish_requested = true;
+    st_->finish_flag.store(true, std::memory_order_release);
     if (!st_->error) {
       st_->error = std::make_exception_ptr(std::runtime_error("materialize_module was abandoned"));
       st_->has_error.store(true, std::memory_order_release);
@@ -2333,6 +2346,7 @@ size_t PipelinedMaterialize::add(const at::Tensor& fake, bool apply_shard, at::T
     std::lock_guard<std::mutex> lock(st_->m);
     ticket = st_->items.size();
     st_->items.push_back(std::move(item));
+    st_->n_items.store(st_->items.size(), std::memory_order_release);
     wake = st_->helper_waiting;
   }
   if (!st_->threaded) {
@@ -2359,6 +2373,7 @@ void PipelinedMaterialize::finish() {
   }
   std::lock_guard<std::mutex> lock(st_->m);
   st_->finish_requested = true;
+  st_->finish_flag.store(true, std::memory_order_release);
   st_->cv_work.notify_one();
 }
 
