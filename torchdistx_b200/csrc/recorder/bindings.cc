@@ -334,10 +334,18 @@ void py_materialize_module(const py::object& module, bool buffers_only, const py
           std::find(tapes.begin(), tapes.end(), rec->tape) == tapes.end())
         tapes.push_back(rec->tape);
     }
+    const double t_a = since();
     pending.clear();
+    const double t_b = since();
     wrapped.clear();
-    py::gil_scoped_release nogil;
-    tdx::release_in_background(std::move(tapes));
+    const double t_c = since();
+    {
+      py::gil_scoped_release nogil;
+      tdx::release_in_background(std::move(tapes));
+    }
+    if (trace)
+      fprintf(stderr, "[tdx]   teardown: tapes listed %.0f us, fakes destroyed %.0f, wrapped list %.0f, posted %.0f\n", t_a, t_b,
+              t_c, since());
   }
   if (trace)
     fprintf(stderr, "[tdx] materialize_module: session %.0f us, walked %.0f, wrapped %.0f, joined %.0f, assigned %.0f, "

@@ -148,11 +148,16 @@ uint32_t rng_slot_of(Tape& tape, uint32_t op_idx) {
   return op.rng_slot;
 }
 
+// (inline storage: a recording holds one State per storage, and every heap block of a recording is
+// one somebody has to free when it dies)
+using SegList = c10::SmallVector<Seg, 1>;
+using RngChain = c10::SmallVector<RngPass, 2>;
+
 struct State {
   bool opaque = true;
   ScalarType dtype = ScalarType::Undefined;  // dtype of the tensor currently holding the state
-  std::vector<Seg> segs;                     // sorted, disjoint, covering [0, numel)
-  std::vector<RngPass> rng_chain;            // every RNG pass met, live or dead, chronological
+  SegList segs;        // sorted, disjoint, covering [0, numel)
+  RngChain rng_chain;  // every RNG pass met, live or dead, chronological
 };
 
 State make_opaque() { return State{}; }
@@ -337,7 +342,7 @@ bool range_of(const ValueInfo& v, int64_t& begin, int64_t& end) {
 }
 
 // Cuts the segments at `at` so that none straddles it.
-void split_at(std::vector<Seg>& segs, int64_t at) {
+void split_at(SegList& segs, int64_t at) {
   for (size_t i = 0; i < segs.size(); ++i) {
     if (segs[i].begin < at && at < segs[i].end) {
       Seg right = segs[i];
@@ -354,7 +359,7 @@ void overwrite(State& s, int64_t b, int64_t e, Sym st, int64_t origin) {
   if (b >= e) return;
   split_at(s.segs, b);
   split_at(s.segs, e);
-  std::vector<Seg> out;
+  SegList out;
   out.reserve(s.segs.size() + 1);
   bool placed = false;
   for (Seg& g : s.segs) {
@@ -395,7 +400,7 @@ void transition(Tape& tape, uint32_t op_idx, uint32_t S, State& st) {
     return true;
   };
   auto fresh = [&](Sym sy) {  // a factory: one segment over the whole (new) storage
-    std::vector<RngPass> chain = std::move(st.rng_chain);
+    RngChain chain = std::move(st.rng_chain);
     st = State{};
     st.opaque = false;
     st.dtype = out.dtype;
@@ -1422,8 +1427,7 @@ struct Engine {
     });
     op.results = std::move(stack);
     op.done = true;
-    op.tls.reset();
-    op.args.clear();
+    op.tls.reset();  // (args stay: a later analysis of the tape still reads their scalars)
     g_stats.generic_ops++;
   }
 

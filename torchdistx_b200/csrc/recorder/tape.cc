@@ -244,7 +244,8 @@ void append(std::optional<OperatorHandle> handle, OpKind kind, Stack frame, size
     op->inputs.push_back(std::move(in));
     t = at::Tensor();  // the frame never keeps tensors alive; InputRef does
   });
-  op->args = std::move(frame);
+  op->args.reserve(frame.size());
+  for (IValue& v : frame) op->args.push_back(std::move(v));
 
   for_each_tensor_mut(outputs, nret, [&](at::Tensor& t) {
     if (!is_fake(t)) {
