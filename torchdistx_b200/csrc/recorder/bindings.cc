@@ -338,11 +338,12 @@ void py_materialize_module(const py::object& module, bool buffers_only, const py
     pending.clear();
     const double t_b = since();
     wrapped.clear();
+    // (a recording nobody else refers to any more: its tensors are released here, under the GIL --
+    // see drop_tensor_refs -- and only memory is left for the reaper)
+    for (const auto& t : tapes)
+      if (t.use_count() == 1) tdx::drop_tensor_refs(*t);
     const double t_c = since();
-    {
-      py::gil_scoped_release nogil;
-      tdx::release_in_background(std::move(tapes));
-    }
+    tdx::release_in_background(std::move(tapes));
     if (trace)
       fprintf(stderr, "[tdx]   teardown: tapes listed %.0f us, fakes destroyed %.0f, wrapped list %.0f, posted %.0f\n", t_a, t_b,
               t_c, since());

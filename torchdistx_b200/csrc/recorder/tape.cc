@@ -467,6 +467,21 @@ void leave_deferred_init() noexcept {
   }
 }
 
+void drop_tensor_refs(Tape& tape) noexcept {
+  for (ValueInfo& v : tape.values) {
+    v.real.reset();
+    v.py_wrapped.reset();
+  }
+  for (StorageInfo& s : tape.storages) {
+    s.base.reset();
+    s.full_base.reset();
+  }
+  for (TapeOp& op : tape.ops) {
+    for (InputRef& in : op.inputs) in.real.reset();
+    if (!op.results.empty()) op.results.clear();
+  }
+}
+
 bool can_materialize(const at::Tensor& t) noexcept {
   return is_fake(t) && fake_impl(t)->record() != nullptr;
 }

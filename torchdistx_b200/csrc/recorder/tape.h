@@ -178,4 +178,11 @@ OpKind classify(const c10::OperatorHandle& op);
 // and reports its error, when it is materialised).
 void analyze_tape(Tape& tape) noexcept;
 
+// Lets go of every tensor a tape that is about to die still refers to (materialised outputs, replay
+// results, real arguments).  For the thread that holds the GIL: since torch 2.10 dropping the last
+// C++ reference to a tensor that has a Python wrapper (refcount 2 -> 1) hands ownership back to the
+// wrapper with a Py_DECREF -- which takes the GIL.  A background thread tearing down a recording of
+// 300 materialised parameters would fight the caller for it 300 times.
+void drop_tensor_refs(Tape& tape) noexcept;
+
 }  // namespace tdx
