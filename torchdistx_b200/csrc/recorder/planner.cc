@@ -932,14 +932,63 @@ struct Batch {
   // time, which is what lets the caching allocator serve them from its free lists.  A gate on the
   // estimated GPU backlog -- submit only when the GPU is about to run dry -- saved one launch per
   // call at N = 1 and cost a cudaMalloc, i.e. a device synchronisation, whenever the cut moved.)
+  // When the call materialises a whole recording the total is known in advance (Tape::fused_bytes,
+  // divided by the world size of a sharded call), and so is how fast the host plans relative to the
+  // GPU: planning costs ~1.5 us per tensor whatever its size, the kernels write ~4.8 GB/ms.  After
+  // the first (256 MiB) submission the rest is cut into at most three more whose sizes grow by the
+  // ratio q of the two rates, clamped to [1, 4]: with big tensors (one GPU, q = 4) the GPU is the
+  // bottleneck and every chunk hides the planning of the next, larger one -- three launches for
+  // 16 GB; when a rank owns an eighth of the model the host is as slow as the GPU (q = 1), the call
+  // ends one chunk's GPU time after the last tensor has been planned, and equal chunks make that
+  // the smallest.  A function of byte counts only, like the fallback rule (x4 per submission) that
+  // applies when there is no estimate or the call outgrows it.
+  int64_t expected_total = 0, expected_tensors = 0, submitted_bytes = 0;
+  c10::SmallVector<int64_t, 4> schedule;  // thresholds of the submissions after the first
+  size_t schedule_pos = 0;
+  int64_t last_threshold = 0;
+  void expect(int64_t total_bytes, int64_t tensors) {
+    if (expected_total == 0 && submitted_bytes == 0) {
+      expected_total = total_bytes;
+      expected_tensors = tensors;
+    }
+  }
+  int64_t next_threshold() {
+    constexpr int64_t kNever = int64_t{1} << 62;
+    const int64_t fallback = std::min<int64_t>(last_threshold * 4, int64_t{64} << 30);
+    if (expected_total <= 0) return fallback;
+    if (submitted_bytes >= expected_total) {  // more than the recording promised (several recordings in one call)
+      expected_total = 0;
+      return fallback;
+    }
+    if (schedule.empty()) {
+      const double rest = static_cast<double>(expected_total - submitted_bytes);
+      const double per_tensor = static_cast<double>(expected_total) / static_cast<double>(std::max<int64_t>(expected_tensors, 1));
+      const double q = std::min(4.0, std::max(1.0, per_tensor / 7.2e6));
+      int m = 1;
+      double sum = q, term = q;
+      while (m < 3 && static_cast<double>(submitted_bytes) * sum < rest) {
+        ++m;
+        term *= q;
+        sum += term;
+      }
+      term = q;
+      for (int i = 0; i + 1 < m; ++i) {  // the last chunk is whatever is left when the call ends
+        schedule.push_back(std::max<int64_t>(static_cast<int64_t>(rest * term / sum), int64_t{64} << 20));
+        term *= q;
+      }
+      schedule.push_back(kNever);
+    }
+    const int64_t t = schedule[std::min(schedule_pos, schedule.size() - 1)];
+    ++schedule_pos;
+    return t;
+  }
   void note(int64_t bytes) {
     pending_bytes += bytes;
     if (flush_threshold > 0 && pending_bytes >= flush_threshold) {
+      submitted_bytes += pending_bytes;
+      if (flush_threshold < (int64_t{1} << 60)) last_threshold = flush_threshold;
       flush();
-      // 256 MiB, 512 MiB, 1 GiB, then x4: a rank that owns 2 GB of the model (Llama-3-8B over 8 GPUs,
-      // where the host plans about as fast as the GPU writes) ends on a small submission instead
-      // of a 0.75 GB one; a rank that owns 16 GB still gets by with five
-      flush_threshold = std::min<int64_t>(flush_threshold * (flush_threshold < (int64_t{1} << 30) ? 2 : 4), int64_t{64} << 30);
+      flush_threshold = next_threshold();
     }
   }
   void assign_memory();
@@ -1753,6 +1802,9 @@ struct Engine {
     g_stats.fused_tensors++;
     {
       ProfScope p(6);
+      if (batch.expected_total == 0 && tape.fused_bytes)
+        batch.expect(static_cast<int64_t>(tape.fused_bytes / static_cast<uint64_t>(opts.shard ? std::max<int64_t>(opts.shard->world, 1) : 1)),
+                     tape.fused_storages);
       batch.note(bytes);  // may submit what has accumulated so far
     }
     return true;
@@ -2627,6 +2679,10 @@ void analyze_tape(Tape& tape) noexcept {
       auto t = std::make_shared<StorageTemplate>();
       t->st = std::move(st);
       build_fast(tape, si, *t, /*may_sync=*/false);
+      if (t->fast && si.live > 0) {
+        tape.fused_bytes += static_cast<uint64_t>(t->numel) * t->isz;
+        tape.fused_storages++;
+      }
       si.tmpl = std::move(t);
     } catch (...) {
       // (e.g. uniform_ with from > to: the error is raised when the tensor is materialised)

@@ -140,6 +140,11 @@ struct Tape : std::enable_shared_from_this<Tape> {
   std::vector<StorageInfo> storages;
   std::unordered_map<const c10::StorageImpl*, uint32_t> storage_ids;
   uint32_t storage_id(const c10::Storage& s);
+  // From the analysis at the end of the recording: bytes / number of the storages that the fused
+  // path can build and that a fake tensor still names -- an estimate of what materialising the whole
+  // recording will write (the planner sizes its submissions with it).
+  uint64_t fused_bytes = 0;
+  uint32_t fused_storages = 0;
 };
 
 // Recording state attached to a fake tensor (FakeTensorImpl::record()).
