@@ -152,7 +152,7 @@ def test_prepare_lays_out_extreme_plans_within_the_workspace_bound():
                                      offset=64 * len(llama), p0=0.0, p1=0.02))
     llama += [C.make_desc(base, dtype=C.TDX_BF16, src=C.TDX_SRC_NORMAL, elem_count=128256 * 4096, seed=3, offset=1 << 30,
                           p0=0.0, p1=0.02)] * 2
-    assert 100 << 10 < prepare(llama) < 400 << 10
+    assert 40 << 10 < prepare(llama) < 400 << 10  # (291 descriptors x 128 B + a work list of ~1000 grabs)
     # nothing to do
     assert prepare([C.make_desc(base, dtype=C.TDX_F32, src=C.TDX_SRC_NORMAL, elem_count=0, seed=1, offset=0)]) >= 0
     # submit without a device must fail cleanly, not crash (there is no GPU in the CPU test run)

@@ -560,6 +560,10 @@ struct GroupArgs {
   uint32_t tiles_per_chunk;    // 256-thread kernels: tiles per work grab (host-chosen per launch)
   uint32_t n_chunks;           // table kernel: host-built work list (see build_plan)
   const uint4* chunks;         // {descriptor, tiles, first tile in descriptor (lo, hi)}
+  // table kernel: the first n_static entries of the list are pre-assigned -- CTA b owns entries
+  // [seg_off[b], seg_off[b + 1]) -- and the rest is handed out by the counter (for_each_listed_chunk)
+  uint32_t n_static;
+  const uint32_t* seg_off;     // [gridDim.x + 1]
   // 256-thread kernels, launches of at most a few tiles per resident CTA: grid = number of grabs,
   // CTA b takes grab b -- no work counter, no exit protocol (a 1 MB tensor is then one kernel
   // launch's latency plus its stores, like a stock elementwise kernel)
@@ -639,29 +643,159 @@ __device__ __forceinline__ void for_each_tile_run(const GroupArgs& g, F&& f) {
 }
 
 // Scheduler of the table kernel: a host-built work list instead of (chunk index -> binary search).
-// Measured on the table kernel (4 GiB, one descriptor): every grab costs ~2 us -- 32 warps drain
-// into the barrier, then the descriptor is found and set up again: 0.631 / 0.667 / 0.686 / 0.697 of
-// the HBM roof with 0.5 / 1 / 2 / 4 MiB grabs -- and a binary search over a module's few hundred
-// descriptors adds ~8 dependent L2 round trips to each.  So the host cuts every descriptor into
-// grabs of its own (guided sizes: up to 4 MiB while there is plenty of work left, down to one
-// 256 KiB tile at the end, for balance), and a grab is one 16-byte load.  Thread 0 fetches the
-// NEXT list index at the start of the current grab (the atomic's round trip hides behind the
-// grab's work); the single barrier at the end of the grab publishes it.
+// Measured on the table kernel (4 GiB, one descriptor, round 1): every grab cost ~2 us -- 32 warps
+// drain into the barrier, then three dependent trips through a memory system that is saturated with
+// stores (work counter, list entry, descriptor: ~0.7 us each) before the first new store:
+// 0.631 / 0.667 / 0.686 / 0.697 of the HBM roof with 0.5 / 1 / 2 / 4 MiB grabs.  So
+//  * the host cuts every descriptor into grabs of its own (guided sizes: up to 4 MiB while there is
+//    plenty of work left, down to one 256 KiB tile at the end, for balance);
+//  * all but the last ~1/8 of the work is PRE-ASSIGNED: the host deals the large grabs out to the
+//    CTAs (least loaded first) and CTA b walks its own segment of the list -- no counter, and the
+//    index of the next grab is known when the current one starts.  Only the tail is handed out
+//    dynamically, which is what keeps the CTAs finishing together;
+//  * the NEXT grab is brought into shared memory while the current one is being written: thread 0
+//    starts an asynchronous copy (cp.async: no destination register, nothing to stall on) of the
+//    16-byte list entry when a grab starts and, one tile later, prefetches the 128-byte descriptor
+//    it names into the SM's L1.  After the barrier at the end of the grab everything the next one
+//    needs is a shared-memory read or an L1 hit away.  All of thread 0's scheduling state lives in shared memory: the hot
+//    loop has no register to spare (64 per thread at 1024 threads).
+#ifdef TDX_LUT_TIMELINE
+// Measurement build only (benchmarks/lut_timeline.py): per-CTA timestamps of the table kernel.
+// 16 slots per CTA: 0 enter, 1 first grab known, 2 first table built, 3 last grab done, 4 grabs,
+// 5 ns thread 0 spent in barriers at grab ends, 6 ns from a grab's barrier to its first tile,
+// 7 exit, 8 tiles, 9 table builds, 10 ns in table builds, 11 ns in prefetch_start/finish.
+__device__ unsigned long long* g_lut_timeline = nullptr;
+__device__ __forceinline__ unsigned long long tl_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TL_SET(i, v) do { if (threadIdx.x == 0 && g_lut_timeline) g_lut_timeline[blockIdx.x * 16 + (i)] = (v); } while (0)
+#define TL_ADD(i, v) do { if (threadIdx.x == 0 && g_lut_timeline) g_lut_timeline[blockIdx.x * 16 + (i)] += (v); } while (0)
+#else
+#define TL_SET(i, v) do { } while (0)
+#define TL_ADD(i, v) do { } while (0)
+#endif
+struct LutSched {
+  unsigned int next[2];  // list index of the grab in each slot (>= n_chunks: no more work)
+  unsigned int pos, end; // CTA's segment of the pre-assigned part: next entry, one past the last
+  volatile unsigned int stage;  // of the prefetch of the next grab: 2 = entry under way, 3 = descriptor under way / nothing to do
+  unsigned int pad_[3];
+  uint4 item[2];         // {descriptor, tiles, first tile in descriptor (lo, hi)}
+  TdxInitDesc tab;       // the descriptor the table in shared memory was built for
+};
+static_assert(sizeof(TdxInitDesc) == 128, "a descriptor is one 128-byte line");
+static_assert(sizeof(LutSched) % 16 == 0 && offsetof(LutSched, item) % 16 == 0, "LutSched follows the table in dynamic shared memory");
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Thread 0's side job during a grab (every function is called by thread 0 only).
+__device__ __forceinline__ void lut_prefetch_start(const GroupArgs& g, LutSched* s, unsigned int slot) {
+  unsigned int c = s->pos;
+  if (c < s->end) {
+    s->pos = c + 1u;
+  } else {
+    // dynamic tail: this thread waits for the counter here (~1 us, once per tail grab)
+    c = g.n_static + atomicAdd(g.counter, 1u);
+  }
+  s->next[slot] = c;
+  if (c < g.n_chunks) {
+    cp_async16(&s->item[slot], g.chunks + c);
+    cp_async_commit();
+    s->stage = 2u;
+  } else {
+    s->stage = 3u;
+  }
+}
+__device__ __forceinline__ void lut_prefetch_desc(const GroupArgs& g, LutSched* s, unsigned int slot) {
+  cp_async_wait_all();
+  const uint32_t di = *reinterpret_cast<volatile uint32_t*>(&s->item[slot]);
+  // (into this SM's L1, where the loads after the barrier find it; the descriptor table is 128-byte
+  // aligned, so a descriptor is one line.  A copy into shared memory was tried: with the descriptor
+  // behind a shared-memory reference ptxas no longer keeps the generator's constants in uniform
+  // registers across the hot loop and reloads them from local memory for every group of vectors.)
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(g.descs + di));
+  s->stage = 3u;
+}
+// hook of the tile loop (after the grab's first tile)
+__device__ __forceinline__ void lut_prefetch_hook(const GroupArgs& g, LutSched* s, unsigned int slot) {
+  if (s->stage == 2u) lut_prefetch_desc(g, s, slot);
+}
+__device__ __forceinline__ void lut_prefetch_finish(const GroupArgs& g, LutSched* s, unsigned int slot) {
+  if (s->stage == 2u) lut_prefetch_desc(g, s, slot);  // (the grab was too short, or too odd, to overlap it)
+  cp_async_wait_all();
+}
+
+// f(desc_index, descriptor, first tile, tiles, slot of the next grab)
 template <class F>
-__device__ __forceinline__ void for_each_listed_chunk(const GroupArgs& g, unsigned int* s_next, F&& f) {
-  if (threadIdx.x == 0) s_next[0] = atomicAdd(g.counter, 1u);
+__device__ __forceinline__ void for_each_listed_chunk(const GroupArgs& g, LutSched* s, F&& f) {
+#ifdef TDX_LUT_TIMELINE
+  if (threadIdx.x == 0 && g_lut_timeline)
+    for (int i = 0; i < 16; ++i) g_lut_timeline[blockIdx.x * 16 + i] = 0;
+  TL_SET(0, tl_now());
+  unsigned long long tl_bar = 0;
+#endif
+  if (threadIdx.x == 0) {
+    unsigned int lo = 0u, hi = 0u;
+    if (g.n_static) {
+      lo = __ldg(g.seg_off + blockIdx.x);
+      hi = __ldg(g.seg_off + blockIdx.x + 1u);
+    }
+    s->pos = lo;
+    s->end = hi;
+    unsigned int c;
+    if (lo < hi) {
+      c = lo;
+      s->pos = lo + 1u;
+    } else {
+      c = g.n_static + atomicAdd(g.counter, 1u);
+    }
+    s->next[0] = c;
+    if (c < g.n_chunks) s->item[0] = __ldg(g.chunks + c);
+  }
   __syncthreads();
+  TL_SET(1, tl_now());
   for (unsigned int it = 0;; ++it) {
-    const unsigned int c = s_next[it & 1u];
-    if (c >= g.n_chunks) {
+    const unsigned int slot = it & 1u;
+    if (s->next[slot] >= g.n_chunks) {
+#ifdef TDX_LUT_TIMELINE
+      TL_SET(3, tl_bar);
+      TL_SET(4, it);
+#endif
       leave_grid(g);
+      TL_SET(7, tl_now());
       return;
     }
-    if (threadIdx.x == 0) s_next[(it + 1u) & 1u] = atomicAdd(g.counter, 1u);
-    const uint4 e = __ldg(g.chunks + c);
-    f(e.x, static_cast<unsigned long long>(e.z) | (static_cast<unsigned long long>(e.w) << 32),
-      static_cast<unsigned long long>(e.y));
+    const uint4 e = s->item[slot];
+#ifdef TDX_LUT_TIMELINE
+    const unsigned long long tl_a = tl_now();
+#endif
+    if (threadIdx.x == 0) lut_prefetch_start(g, s, slot ^ 1u);
+#ifdef TDX_LUT_TIMELINE
+    const unsigned long long tl_b = tl_now();
+    TL_ADD(11, tl_b - tl_a);
+    TL_ADD(8, e.y);
+#endif
+    f(e.x, g.descs[e.x], static_cast<unsigned long long>(e.z) | (static_cast<unsigned long long>(e.w) << 32),
+      static_cast<unsigned long long>(e.y), slot ^ 1u);
+#ifdef TDX_LUT_TIMELINE
+    const unsigned long long tl_c = tl_now();
+#endif
+    if (threadIdx.x == 0) lut_prefetch_finish(g, s, slot ^ 1u);
+#ifdef TDX_LUT_TIMELINE
+    const unsigned long long tl_d = tl_now();
+    TL_ADD(11, tl_d - tl_c);
+#endif
     __syncthreads();
+#ifdef TDX_LUT_TIMELINE
+    tl_bar = tl_now();
+    TL_ADD(5, tl_bar - tl_d);
+#endif
   }
 }
 
@@ -1065,6 +1199,33 @@ __device__ __noinline__ void lut_fill_tiles(const TdxInitDesc* dp, unsigned long
   }
 }
 
+// ... and so do index programs (rotary inv_freq, position ids: a few hundred bytes).
+__device__ __noinline__ void lut_iota_tiles(const TdxInitDesc* dp, unsigned long long tile0, unsigned long long ntiles) {
+  const TdxInitDesc& d = *dp;
+  const long long start = static_cast<long long>(d.p0), step = static_cast<long long>(d.p1);
+  const EpiParams epi = load_epi(d);
+  const bool as_i64 = d.dtype == TDX_I64;
+  const uint64_t per_vec = as_i64 ? 2 : 4;
+  for (unsigned long long tile = tile0; tile < tile0 + ntiles; ++tile) {
+    for (int i = 0; i < kLutVecsPerThread; ++i) {
+      const uint64_t vec = tile * kLutTileVecs + static_cast<uint64_t>(i) * kLutThreads + threadIdx.x;
+      if (vec * per_vec >= d.elem_count) break;
+      for (uint64_t e = 0; e < per_vec; ++e) {
+        const uint64_t j = vec * per_vec + e;
+        if (j >= d.elem_count) break;
+        const long long val = start + static_cast<long long>(d.elem_begin + j) * step;
+        if (as_i64) {
+          static_cast<long long*>(d.dst)[j] = val;
+        } else {
+          float v = static_cast<float>(val);
+          if (epi.n) v = apply_epi<float>(epi, v);
+          static_cast<float*>(d.dst)[j] = v;
+        }
+      }
+    }
+  }
+}
+
 // Exponent-all-ones test of either half of a packed pair (inf or NaN).
 template <class Out>
 __device__ __forceinline__ bool any_nonfinite2(uint32_t v) {
@@ -1088,13 +1249,18 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_lut16_kernel(const GroupAr
   // scheduler's two slots follow the table), so the byte address of entry k is 2*k plus a constant
   // that fits the LDS immediate, and the IDP that forms 2*k reads one vector register.
   extern __shared__ __align__(16) unsigned short lut[];
-  unsigned int* const slots = reinterpret_cast<unsigned int*>(lut + 65536);
+  LutSched* const sched = reinterpret_cast<LutSched*>(lut + 65536);
   const bool base_ok = static_cast<uint32_t>(__cvta_generic_to_shared(lut)) == kDynSmemBase;
-  uint32_t have_di = 0xffffffffu;  // descriptor the table in shared memory was built for
-  for_each_listed_chunk(g, slots, [&](uint32_t di, unsigned long long tile0, unsigned long long ntiles) {
-    const TdxInitDesc& d = g.descs[di];
+  uint32_t have_di = 0xffffffffu;  // descriptor the table in shared memory was built for (its copy: sched->tab)
+  const bool t0 = threadIdx.x == 0;
+  for_each_listed_chunk(g, sched, [&](uint32_t di, const TdxInitDesc& d, unsigned long long tile0,
+                                      unsigned long long ntiles, unsigned int next_slot) {
     if (d.src == TDX_SRC_CONST) {  // a fill folded into this launch (build_plan): the table stays as it is
       lut_fill_tiles(&d, tile0, ntiles);
+      return;
+    }
+    if (d.src == TDX_SRC_IOTA) {
+      lut_iota_tiles(&d, tile0, ntiles);
       return;
     }
     typename Gen::Params P = Gen::setup(d);
@@ -1104,8 +1270,13 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_lut16_kernel(const GroupAr
     Tab::uniformize(P);
     P.ph.cz = __reduce_or_sync(0xffffffffu, P.ph.cz);
     P.ph.cw = __reduce_or_sync(0xffffffffu, P.ph.cw);
-    if (have_di == 0xffffffffu || (di != have_di && !same_table(d, g.descs[have_di]))) {
-      __syncthreads();  // everyone is done reading the old table
+#ifdef TDX_LUT_TIMELINE
+    const unsigned long long tl_t0 = tl_now();
+#endif
+    if (have_di == 0xffffffffu || (di != have_di && !same_table(d, sched->tab))) {
+      __syncthreads();  // everyone is done reading the old table (and comparing with its descriptor)
+      if (threadIdx.x < 8)
+        reinterpret_cast<uint4*>(&sched->tab)[threadIdx.x] = reinterpret_cast<const uint4*>(&d)[threadIdx.x];
       if (Tab::mirrored(P)) {
         for (uint32_t k = threadIdx.x; k <= 32768u; k += kLutThreads) {
           const Out o = static_cast<Out>(Tab::value(P, __uint_as_float(0x4b000000u | k)));
@@ -1120,6 +1291,11 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_lut16_kernel(const GroupAr
         }
       }
       __syncthreads();
+#ifdef TDX_LUT_TIMELINE
+      TL_ADD(9, 1);
+      TL_ADD(10, tl_now() - tl_t0);
+      if (have_di == 0xffffffffu) TL_SET(2, tl_now());
+#endif
     }
     have_di = di;
     const uint64_t begin = d.elem_begin;
@@ -1127,6 +1303,7 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_lut16_kernel(const GroupAr
     char* const dst = static_cast<char*>(d.dst);
     const bool aligned = (begin % 8 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
     const uint64_t nfull = aligned ? d.elem_count / 8 : 0;
+    TL_ADD(6, tl_now() - tl_t0);
     for (unsigned long long tile = tile0; tile < tile0 + ntiles; ++tile) {
       const uint64_t tbase = tile * kLutTileVecs;  // first vector of the tile (descriptor-relative)
       const uint64_t gfirst = gv0 + tbase;         // its global block index
@@ -1181,6 +1358,8 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_lut16_kernel(const GroupAr
       } else {
         lut_ragged_tile<Gen>(&d, tile);
       }
+      // (thread 0, after the grab's first tile: the next list entry has arrived -- start on its descriptor)
+      if (t0 && tile == tile0) lut_prefetch_hook(g, sched, next_slot);
     }
   });
 }
@@ -1219,7 +1398,7 @@ struct Family {
 #define TDX_FAM_LUT(src, dt, algo, epi, name, out, la, lb, ...)                                          \
   { src, dt, algo, 10, epi,                                                                           \
     static_cast<KernelFn>(tdx_lut16_kernel<__VA_ARGS__, out, 10, TDX_LUT_PKEYS != 0, la, lb>), name,   \
-    kLutThreads, kLutTileVecs, static_cast<int>(kLutBytes) + 128, true, kLutTilesPerChunk,              \
+    kLutThreads, kLutTileVecs, static_cast<int>(kLutBytes + sizeof(LutSched)), true, kLutTilesPerChunk, \
     static_cast<KernelFn>(tdx_lut16_kernel<__VA_ARGS__, out, 10, false, la, lb>) }
 
 using bf16 = __nv_bfloat16;
@@ -1381,6 +1560,9 @@ struct PlanGroup {
   uint32_t seed_shared;
   uint32_t n_chunks;             // table kernel only: entries of the work list
   unsigned long long chunk_off;  // and its byte offset
+  uint32_t n_static;             // leading entries that are pre-assigned to CTAs (GroupArgs::n_static)
+  uint32_t list_ctas;            // ... to this many
+  unsigned long long seg_off_off;  // byte offset of the [list_ctas + 1] segment table
 };
 struct PlanHeader {
   uint32_t magic;
@@ -1397,6 +1579,15 @@ static_assert(kNumFamilies <= 32, "counter slots");
 // launch so that this holds), a guided tail, and one partial grab per descriptor.
 constexpr size_t kMaxListChunks = 8192;
 constexpr size_t kMaxListTail = 4096;
+constexpr size_t kMaxListCtas = 1024;  // segment table of the pre-assigned part (one entry per CTA + 1)
+// TDX_LUT_STATIC=0: every grab of the table kernel comes from the work counter (round 1's scheduler)
+bool lut_static_enabled() {
+  static const bool v = [] {
+    const char* e = getenv("TDX_LUT_STATIC");
+    return !(e && e[0] == '0');
+  }();
+  return v;
+}
 size_t lut_family_count() {
   static const size_t v = [] {
     size_t c = 0;
@@ -1411,7 +1602,8 @@ size_t plan_bytes(int n) {
   return sizeof(PlanHeader) + (static_cast<size_t>(n) + kNumFamilies) * sizeof(unsigned long long) +
          static_cast<size_t>(n) * sizeof(TdxInitDesc) +
          (lut_family_count() * (kMaxListChunks + kMaxListTail) + static_cast<size_t>(n)) * sizeof(uint4) +
-         16 * static_cast<size_t>(kNumFamilies) + 64;
+         lut_family_count() * kMaxListCtas * sizeof(uint32_t) +
+         (16 + 128) * static_cast<size_t>(kNumFamilies) + 64;
 }
 
 struct DeviceInfo {
@@ -1503,12 +1695,18 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
   }
   // A module's constant fills (norm weights, biases: KBs) ride in the largest table launch's work
   // list instead of costing a launch of their own -- unless they are a real share of the bytes.
-  if (per_family[0] > 0 && fold_fills()) {
+  static_assert(TDX_SRC_CONST == 0, "family 0 = fills");
+  const int iota_family = [] {
+    for (int f = 0; f < kNumFamilies; ++f)
+      if (kFamilies[f].src == TDX_SRC_IOTA) return f;
+    return -1;
+  }();
+  if ((per_family[0] > 0 || (iota_family >= 0 && per_family[iota_family] > 0)) && fold_fills()) {
     int host = -1;
     uint64_t host_bytes = 0, fill_bytes = 0;
     uint64_t bytes_of[kNumFamilies] = {};
     for (int i = 0; i < n; ++i) bytes_of[fam[i]] += descs[i].elem_count * itemsize_of(descs[i].dtype);
-    fill_bytes = bytes_of[0];
+    fill_bytes = bytes_of[0] + (iota_family >= 0 ? bytes_of[iota_family] : 0);
     for (int f = 1; f < kNumFamilies; ++f)
       if (kFamilies[f].lut && per_family[f] > 0 && bytes_of[f] > host_bytes) {
         host = f;
@@ -1516,9 +1714,9 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
       }
     if (host >= 0 && fill_bytes * 16 <= host_bytes) {
       for (int i = 0; i < n; ++i)
-        if (fam[i] == 0) {
+        if (fam[i] == 0 || fam[i] == iota_family) {
+          per_family[fam[i]]--;
           fam[i] = host;
-          per_family[0]--;
           per_family[host]++;
         }
     }
@@ -1529,6 +1727,7 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
   int sm_count = 148;
   if (DeviceInfo* info = device_info()) sm_count = info->sm_count;
   std::vector<int> order;
+  thread_local std::vector<uint32_t> seg_fill;
   order.reserve(static_cast<size_t>(n));
   size_t off = (sizeof(PlanHeader) + 15) & ~static_cast<size_t>(15);
   for (int f = 0; f < kNumFamilies; ++f) {
@@ -1539,7 +1738,7 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
     G.prefix_off = off;
     auto* prefix = reinterpret_cast<unsigned long long*>(img.data() + off);
     off += (static_cast<size_t>(G.n_desc) + 1) * sizeof(unsigned long long);
-    off = (off + 15) & ~static_cast<size_t>(15);
+    off = (off + 127) & ~static_cast<size_t>(127);  // (a descriptor = one cache line: lut_prefetch_desc)
     G.desc_off = off;
     auto* out = reinterpret_cast<TdxInitDesc*>(img.data() + off);
     off += static_cast<size_t>(G.n_desc) * sizeof(TdxInitDesc);
@@ -1556,8 +1755,9 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
     if (kFamilies[f].lut)
       std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
         const TdxInitDesc &x = descs[a], &y = descs[b];
-        if (x.src != y.src) return x.src < y.src;  // (folded fills first: TDX_SRC_CONST == 0)
-        if (x.src == TDX_SRC_CONST) return false;
+        const bool xr = x.src != TDX_SRC_CONST && x.src != TDX_SRC_IOTA, yr = y.src != TDX_SRC_CONST && y.src != TDX_SRC_IOTA;
+        if (xr != yr) return yr;  // (folded fills and index programs first)
+        if (!xr) return false;
         if (x.p0 != y.p0) return x.p0 < y.p0;
         if (x.p1 != y.p1) return x.p1 < y.p1;
         if (x.n_epi != y.n_epi) return x.n_epi < y.n_epi;
@@ -1565,7 +1765,7 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
       });
     bool have_seed = false;
     for (int i : order) {
-      if (descs[i].src != TDX_SRC_CONST) {
+      if (descs[i].src != TDX_SRC_CONST && descs[i].src != TDX_SRC_IOTA) {
         if (!have_seed) G.seed = descs[i].philox_seed;
         else if (descs[i].philox_seed != G.seed) G.seed_shared = 0;
         have_seed = true;
@@ -1579,32 +1779,65 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
     prefix[k] = acc;
     G.total_tiles = acc;
     if (kFamilies[f].lut) {
-      // guided work list: grab = remaining / (2 * CTAs), between 1 tile and the cap
+      // Work list of the table kernel (for_each_listed_chunk).  Head: all but the last eighth of the
+      // tiles (and never less than four, nor more than eight, tiles per CTA of tail) is cut into one
+      // contiguous, equal share per CTA -- a share is a few grabs, broken only where a descriptor
+      // ends -- and CTA b owns entries [seg[b], seg[b + 1]).  Tail: guided sizes handed out by the
+      // work counter (grab = remaining / (2 * CTAs), between one tile and the cap), which is what
+      // lets the CTAs finish together whatever their speeds were.  Fewer grabs matter: a grab ends
+      // in a barrier that re-aligns the 32 warps of a CTA, and the lock-step phase that follows
+      // costs ~2-3 us of throughput (benchmarks/lut_timeline.py, profiles/r2_lut_timeline.jsonl).
       off = (off + 15) & ~static_cast<size_t>(15);
       G.chunk_off = off;
       auto* list = reinterpret_cast<uint4*>(img.data() + off);
       const unsigned long long ctas = static_cast<unsigned long long>(std::max(sm_count, 1));
       const unsigned long long cap =
           std::max<unsigned long long>(kLutMaxTilesPerChunk, (acc + kMaxListChunks - 1) / kMaxListChunks);
-      // below this many remaining tiles the sizes shrink; the tail is at most kMaxListTail entries
+      unsigned long long static_tiles = 0;
+      if (lut_static_enabled() && ctas < kMaxListCtas && acc >= ctas * 16ull)
+        static_tiles = acc - std::min(std::max(acc / 8ull, ctas * 4ull), ctas * 8ull);
+      seg_fill.assign(static_cast<size_t>(ctas) + 1, 0u);  // seg_fill[b] = first entry of CTA b
       unsigned long long remaining = acc;
-      uint32_t nc = 0;
+      uint32_t nc = 0, cta = 0;
+      unsigned long long room = static_tiles / ctas + (0 < static_tiles % ctas ? 1 : 0);  // CTA 0's share
       for (uint32_t di = 0; di < G.n_desc; ++di) {
         unsigned long long t = 0;
         const unsigned long long nt = prefix[di + 1] - prefix[di];
         while (t < nt) {
-          unsigned long long sz = std::min(std::max(remaining / (2 * ctas), 1ull), cap);
-          sz = std::min(sz, nt - t);
+          unsigned long long sz;
+          if (cta < ctas && static_tiles) {  // pre-assigned part
+            sz = std::min<unsigned long long>(std::min(nt - t, room), 0xffffffffull);
+          } else {
+            sz = std::min(std::min(std::max(remaining / (2 * ctas), 1ull), cap), nt - t);
+          }
           if (off + (static_cast<size_t>(nc) + 1) * sizeof(uint4) > img.size())
             return fail(TDX_E_WORKSPACE, "internal: work list exceeds its bound");
           list[nc++] = make_uint4(di, static_cast<uint32_t>(sz), static_cast<uint32_t>(t),
                                   static_cast<uint32_t>(t >> 32));
           t += sz;
           remaining -= sz;
+          if (cta < ctas && static_tiles) {
+            room -= sz;
+            if (room == 0) {
+              ++cta;
+              seg_fill[cta] = nc;
+              room = static_tiles / ctas + (cta < static_tiles % ctas ? 1 : 0);
+            }
+          }
         }
       }
       G.n_chunks = nc;
       off += static_cast<size_t>(nc) * sizeof(uint4);
+      G.n_static = 0;
+      G.list_ctas = static_cast<uint32_t>(ctas);
+      G.seg_off_off = off;
+      if (static_tiles && cta == ctas) {
+        if (off + (static_cast<size_t>(ctas) + 1) * sizeof(uint32_t) > img.size())
+          return fail(TDX_E_WORKSPACE, "internal: segment table exceeds its bound");
+        memcpy(img.data() + off, seg_fill.data(), (static_cast<size_t>(ctas) + 1) * sizeof(uint32_t));
+        G.n_static = seg_fill[ctas];
+        off += (static_cast<size_t>(ctas) + 1) * sizeof(uint32_t);
+      }
     }
   }
   memcpy(img.data(), &hdr, sizeof(hdr));
@@ -1703,9 +1936,12 @@ int launch_groups(const PlanHeader& hdr, void* workspace, cudaStream_t stream) {
     a.tiles_per_chunk = static_cast<uint32_t>(tpc);
     a.n_chunks = G.n_chunks;
     a.chunks = reinterpret_cast<const uint4*>(base + G.chunk_off);
+    a.n_static = G.n_static;
+    a.seg_off = reinterpret_cast<const uint32_t*>(base + G.seg_off_off);
     const unsigned long long chunks =
         kFamilies[G.family].lut ? G.n_chunks : (G.total_tiles + tpc - 1) / tpc;
     const unsigned int grid = static_cast<unsigned int>(std::min(chunks, resident));
+    if (G.n_static && grid != G.list_ctas) return fail(TDX_E_BADARG, "internal: work list was cut for another grid");
     const Family& F = kFamilies[G.family];
     const KernelFn fn = (F.fn_any_seed && !G.seed_shared) ? F.fn_any_seed : F.fn;
     fn<<<grid, F.threads, F.dyn_smem, stream>>>(a);
@@ -1817,6 +2053,11 @@ TDX_C_API int tdx_elems_per_block(int dtype, int src, int algo) {
   return 8;
 }
 
+#ifdef TDX_LUT_TIMELINE
+TDX_C_API int tdx_debug_lut_timeline(unsigned long long* dev_buf) {
+  return cudaMemcpyToSymbol(tdx::g_lut_timeline, &dev_buf, sizeof(dev_buf)) == cudaSuccess ? 0 : -1;
+}
+#endif
 TDX_C_API int tdx_abi_version(void) { return TDX_ABI_VERSION; }
 TDX_C_API const char* tdx_last_error(void) { return tdx::g_err; }
 
