@@ -702,6 +702,9 @@ __device__ __forceinline__ void lut_prefetch_start(const GroupArgs& g, LutSched*
   } else {
     // dynamic tail: this thread waits for the counter here (~1 us, once per tail grab)
     c = g.n_static + atomicAdd(g.counter, 1u);
+#ifdef TDX_LUT_TIMELINE
+    if (g_lut_timeline && g_lut_timeline[blockIdx.x * 16 + 12] == 0) g_lut_timeline[blockIdx.x * 16 + 12] = tl_now();
+#endif
   }
   s->next[slot] = c;
   if (c < g.n_chunks) {
@@ -1580,6 +1583,10 @@ static_assert(kNumFamilies <= 32, "counter slots");
 constexpr size_t kMaxListChunks = 8192;
 constexpr size_t kMaxListTail = 4096;
 constexpr size_t kMaxListCtas = 1024;  // segment table of the pre-assigned part (one entry per CTA + 1)
+unsigned long long env_ull(const char* name, unsigned long long dflt) {
+  const char* e = getenv(name);
+  return e && *e ? strtoull(e, nullptr, 10) : dflt;
+}
 // TDX_LUT_STATIC=0: every grab of the table kernel comes from the work counter (round 1's scheduler)
 bool lut_static_enabled() {
   static const bool v = [] {
@@ -1779,8 +1786,9 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
     prefix[k] = acc;
     G.total_tiles = acc;
     if (kFamilies[f].lut) {
-      // Work list of the table kernel (for_each_listed_chunk).  Head: all but the last eighth of the
-      // tiles (and never less than four, nor more than eight, tiles per CTA of tail) is cut into one
+      // Work list of the table kernel (for_each_listed_chunk).  Head: everything but four tiles per
+      // CTA of tail (measured, profiles/r2_lut_tail_sweep.txt: two leave the CTAs 27 us apart at the
+      // end of a 16 GB launch, eight cost more grabs than they buy balance) is cut into one
       // contiguous, equal share per CTA -- a share is a few grabs, broken only where a descriptor
       // ends -- and CTA b owns entries [seg[b], seg[b + 1]).  Tail: guided sizes handed out by the
       // work counter (grab = remaining / (2 * CTAs), between one tile and the cap), which is what
@@ -1794,8 +1802,10 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
       const unsigned long long cap =
           std::max<unsigned long long>(kLutMaxTilesPerChunk, (acc + kMaxListChunks - 1) / kMaxListChunks);
       unsigned long long static_tiles = 0;
+      static const unsigned long long tail_min = env_ull("TDX_LUT_TAIL_MIN", 4), tail_max = env_ull("TDX_LUT_TAIL_MAX", 4),
+                                      tail_div = std::max(env_ull("TDX_LUT_TAIL_DIV", 2), 1ull);
       if (lut_static_enabled() && ctas < kMaxListCtas && acc >= ctas * 16ull)
-        static_tiles = acc - std::min(std::max(acc / 8ull, ctas * 4ull), ctas * 8ull);
+        static_tiles = acc - std::min(std::max(acc / 8ull, ctas * tail_min), ctas * tail_max);
       seg_fill.assign(static_cast<size_t>(ctas) + 1, 0u);  // seg_fill[b] = first entry of CTA b
       unsigned long long remaining = acc;
       uint32_t nc = 0, cta = 0;
@@ -1808,7 +1818,7 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
           if (cta < ctas && static_tiles) {  // pre-assigned part
             sz = std::min<unsigned long long>(std::min(nt - t, room), 0xffffffffull);
           } else {
-            sz = std::min(std::min(std::max(remaining / (2 * ctas), 1ull), cap), nt - t);
+            sz = std::min(std::min(std::max(remaining / ((static_tiles ? tail_div : 2ull) * ctas), 1ull), cap), nt - t);
           }
           if (off + (static_cast<size_t>(nc) + 1) * sizeof(uint4) > img.size())
             return fail(TDX_E_WORKSPACE, "internal: work list exceeds its bound");
