@@ -319,6 +319,60 @@ def test_table_driven_normal_is_bit_identical_to_the_direct_kernel(dtype):
     assert torch.equal(torch.cat([a, b]).view(torch.int16), full.view(torch.int16))
 
 
+def test_table_kernel_preassigned_shares_and_folded_programs_match_the_direct_kernels():
+    """A launch of >= 16 tiles (4 MiB) per SM takes the two-phase work list: every CTA walks its own
+    pre-assigned share (broken where descriptors end), the tail comes from the work counter, and the
+    module's constant fills and index programs ride in the same list.  Same bits as the direct
+    kernels (TDX_ALGO_NOLUT: RNG, fill and iota kernels of their own), descriptor by descriptor --
+    unaligned sizes, two parameter sets (table rebuilds inside a share), a shard that starts inside a
+    vector."""
+    dtype = C.TDX_BF16
+    sizes = [(1 << 27) + 9, (1 << 26) + (1 << 25) + 12345, (1 << 27) + 7, (1 << 21) + 3, 3 << 24]
+    assert sum(sizes) * 2 >= 148 * 16 * (256 << 10) * 1.2  # the pre-assigned path, with room to spare
+    epi = [(C.TDX_EPI_MUL, 1.0 / 128), (C.TDX_EPI_RPOW, 500000.0), (C.TDX_EPI_RECIP, 0.0), (C.TDX_EPI_MUL, 1.0)]
+    outs, counts = {}, {}
+    for flag in (0, C.TDX_ALGO_NOLUT):
+        bufs, descs = [], []
+        for i, n in enumerate(sizes):
+            t = torch.zeros(n, dtype=torch.bfloat16, device="cuda")
+            bufs.append(t)
+            descs.append(C.make_desc(t.data_ptr(), dtype=dtype, src=C.TDX_SRC_NORMAL, elem_count=n, elem_begin=5 if i == 4 else 0,
+                                     seed=91, offset=4096 * i, p0=0.0, p1=0.02 if i % 2 else 0.03,
+                                     algo=C.TDX_ALGO_ICDF16 | flag))
+        ones = torch.zeros(4099, dtype=torch.bfloat16, device="cuda")
+        freq = torch.zeros(64, dtype=torch.float32, device="cuda")
+        ids = torch.zeros(1000, dtype=torch.int64, device="cuda")
+        bufs += [ones, freq, ids]
+        descs += [C.make_desc(ones.data_ptr(), dtype=dtype, src=C.TDX_SRC_CONST, elem_count=ones.numel(), fill_bits=0x3F80, fill_itemsize=2),
+                  C.make_desc(freq.data_ptr(), dtype=C.TDX_F32, src=C.TDX_SRC_IOTA, elem_count=64, p0=0, p1=2, epi=epi),
+                  C.make_desc(ids.data_ptr(), dtype=C.TDX_I64, src=C.TDX_SRC_IOTA, elem_count=1000, p0=3, p1=-2)]
+        counts[flag] = run_descs(descs, bufs)
+        outs[flag] = bufs
+    assert counts[0] == 1 and counts[C.TDX_ALGO_NOLUT] == 3  # one table launch carries everything
+    for a, b in zip(outs[0], outs[C.TDX_ALGO_NOLUT]):
+        assert torch.equal(a.view(torch.uint8), b.view(torch.uint8))
+    assert torch.equal(outs[0][5], torch.ones(4099, dtype=torch.bfloat16, device="cuda"))
+    assert torch.equal(outs[0][7], 3 - 2 * torch.arange(1000, device="cuda"))
+    # launching the same plan twice gives the same bits (the work counter is put back; shares are static)
+    again = [torch.zeros_like(t) for t in outs[0][:5]]
+    descs2 = [C.make_desc(t.data_ptr(), dtype=dtype, src=C.TDX_SRC_NORMAL, elem_count=n, elem_begin=5 if i == 4 else 0, seed=91,
+                          offset=4096 * i, p0=0.0, p1=0.02 if i % 2 else 0.03, algo=C.TDX_ALGO_ICDF16)
+              for i, (t, n) in enumerate(zip(again, sizes))]
+    lib = C.load()
+    ws = torch.empty(lib.tdx_init_workspace_bytes(len(descs2)), dtype=torch.uint8, device="cuda")
+    plan = C.TdxPlan()
+    stream = torch.cuda.current_stream().cuda_stream
+    arr = (C.TdxInitDesc * len(descs2))(*descs2)
+    C.check(lib.tdx_plan_upload(arr, len(descs2), ws.data_ptr(), ws.numel(), stream, ctypes.byref(plan)))
+    for _ in range(2):
+        for t in again:
+            t.zero_()
+        C.check(lib.tdx_plan_launch(ctypes.byref(plan), ws.data_ptr(), stream))
+        torch.cuda.synchronize()
+        for a, b in zip(again, outs[0][:5]):
+            assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+
+
 @pytest.mark.parametrize("dtype,src", [(C.TDX_BF16, C.TDX_SRC_NORMAL), (C.TDX_F32, C.TDX_SRC_UNIFORM)])
 def test_beyond_2_to_32_elements(dtype, src):
     """BASELINE config #5 reaches 16 GB tensors: global element indices above 2^32 must index the
