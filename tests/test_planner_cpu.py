@@ -183,3 +183,31 @@ def test_materialize_module_rewords_only_per_tensor_value_errors():
         materialize_module(m, shard=(3, 2))
     materialize_module(m)
     assert not plan_report(m)["weight"]["deferred"]
+
+
+def test_submission_sizes_follow_the_recordings_total():
+    """How a materialize_module call cuts its submissions (Batch::note): a first 256 MiB one, then at
+    most three more whose sizes grow by the ratio of the host's planning rate to the GPU's writing
+    rate -- x4 when one GPU owns the whole model (big tensors: the GPU is the bottleneck), equal
+    chunks when a rank owns an eighth (the call ends one chunk's GPU time after the last tensor is
+    planned).  A function of byte counts only."""
+    import torch  # noqa: F401  (loads the libraries _C links against)
+
+    from torchdistx_b200 import _C
+
+    total, n = 16_060_000_000, 293  # Llama-3-8B bf16
+    one = _C._submission_sizes(total, n)
+    assert len(one) <= 4 and abs(sum(one) - total) < n
+    assert one[0] < 300e6 and one[-1] > 0.6 * total and all(b > 2 * a for a, b in zip(one, one[1:]))
+    eighth = _C._submission_sizes(total // 8, n)
+    assert len(eighth) == 4 and eighth[0] < 300e6
+    assert max(eighth[1:]) < 1.1 * min(eighth[1:]) and eighth[-1] < 0.3 * (total // 8)
+    quarter = _C._submission_sizes(total // 4, n)
+    assert len(quarter) == 4 and all(1.5 * a < b < 2.5 * a for a, b in zip(quarter[1:], quarter[2:]))
+    # no estimate (several recordings in one call): x4 per submission, whatever the sizes
+    blind = _C._submission_sizes(total, n, with_estimate=False)
+    assert blind[0] < 300e6 and 3.5 < blind[1] / blind[0] < 4.5 and 3.5 < blind[2] / blind[1] < 4.5
+    # deterministic
+    assert _C._submission_sizes(total // 8, n) == eighth
+    # a call below the first threshold is one submission
+    assert _C._submission_sizes(50_000_000, 100) == [50_000_000]

@@ -471,6 +471,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     py::gil_scoped_release nogil;  // the helper may need the GIL to let go of Python objects
     tdx::drain_background();
   });
+  m.def("_submission_sizes", &tdx::submission_sizes, py::arg("total_bytes"), py::arg("tensors"), py::arg("with_estimate") = true);
   m.def("storage_history", &tdx::storage_history);
   m.def("last_stats", &py_last_stats);
   m.def("last_descriptors", [] { return py::bytes(tdx::last_descriptors()); });

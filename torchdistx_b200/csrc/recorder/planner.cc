@@ -2532,6 +2532,28 @@ void drain_background() {
   gate->cv.wait(lock, [&] { return gate->pending == 0; });
 }
 
+std::vector<int64_t> submission_sizes(int64_t total_bytes, int64_t tensors, bool with_estimate) {
+  // (a copy of the bookkeeping in Batch::note with the flush itself left out)
+  Batch b;
+  std::vector<int64_t> out;
+  if (tensors <= 0 || total_bytes <= 0) return out;
+  if (with_estimate) b.expect(total_bytes, tensors);
+  const int64_t each = total_bytes / tensors;
+  int64_t pending = 0;
+  for (int64_t i = 0; i < tensors; ++i) {
+    pending += each;
+    if (b.flush_threshold > 0 && pending >= b.flush_threshold) {
+      b.submitted_bytes += pending;
+      if (b.flush_threshold < (int64_t{1} << 60)) b.last_threshold = b.flush_threshold;
+      out.push_back(pending);
+      pending = 0;
+      b.flush_threshold = b.next_threshold();
+    }
+  }
+  if (pending) out.push_back(pending);
+  return out;
+}
+
 void add_wrap_time(double us) { g_stats.wrap_us += us; }
 // (materialize_many resets the counters: the traversal that precedes it is reported through a
 // pending value that the next reset picks up)

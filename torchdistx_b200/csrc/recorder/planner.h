@@ -166,6 +166,11 @@ bool post_background(std::function<void()> fn);
 // release_in_background included).  Call without the GIL.
 void drain_background();
 
+// The sizes (bytes) a materialize_module call cuts its submissions at, for a call that will write
+// `total_bytes` in `tensors` tensors of `tensor_bytes` each (the rule of Batch::note; for tests and
+// documentation -- nothing is allocated or launched).
+std::vector<int64_t> submission_sizes(int64_t total_bytes, int64_t tensors, bool with_estimate);
+
 MaterializeStats last_stats();
 void add_wrap_time(double us);
 void add_traverse_time(double us);
