@@ -69,8 +69,9 @@ def main():
         "enter_us": stat(t[:, 0] - t0), "first_grab_known_us": stat(t[:, 1] - t[:, 0]),
         "first_table_done_us": stat(t[:, 2] - t[:, 0]), "last_grab_done_us": stat(t[:, 3] - t0),
         "exit_us": stat(t[:, 7] - t0), "grabs": stat(t[:, 4] * 1e3), "tiles": stat(t[:, 8] * 1e3),
-        "barrier_wait_thread0_us": stat(t[:, 5]), "grab_setup_us": stat(t[:, 6]),
-        "table_builds": stat(t[:, 9] * 1e3), "table_build_us": stat(t[:, 10]), "prefetch_us": stat(t[:, 11]),
+        "barrier_wait_thread0_us": stat(t[:, 5]), "grab_setup_us": stat(t[:, 6]),  # (barriers: end of the share + one per tail grab)
+        "table_builds": stat(t[:, 9] * 1e3), "table_build_us": stat(t[:, 10]),
+        "share_done_us": stat(t[t[:, 13] > 0][:, 13] - t0) if bool((t[:, 13] > 0).any()) else None,
         "busy_us": stat(t[:, 3] - t[:, 0]),
         # when a CTA asked the work counter for the first time (one grab before its pre-assigned share ends)
         "first_dynamic_request_us": stat(t[t[:, 12] > 0][:, 12] - t0) if bool((t[:, 12] > 0).any()) else None,

@@ -650,11 +650,11 @@ __device__ __forceinline__ void for_each_tile_run(const GroupArgs& g, F&& f) {
 //  * the host cuts every descriptor into grabs of its own (guided sizes: up to 4 MiB while there is
 //    plenty of work left, down to one 256 KiB tile at the end, for balance);
 //  * all but the last ~1/8 of the work is PRE-ASSIGNED: the host deals the large grabs out to the
-//    CTAs (least loaded first) and CTA b walks its own segment of the list -- no counter, and the
-//    index of the next grab is known when the current one starts.  Only the tail is handed out
-//    dynamically, which is what keeps the CTAs finishing together;
-//  * the NEXT grab is brought into shared memory while the current one is being written: thread 0
-//    starts an asynchronous copy (cp.async: no destination register, nothing to stall on) of the
+//    CTAs (one contiguous, equal share each) and CTA b walks its own segment of the list -- no
+//    counter, no barrier (see for_each_listed_chunk).  Only the tail is handed out dynamically,
+//    which is what keeps the CTAs finishing together;
+//  * in the tail the NEXT grab is brought into shared memory while the current one is being
+//    written: thread 0 starts an asynchronous copy (cp.async: no destination register, nothing to stall on) of the
 //    16-byte list entry when a grab starts and, one tile later, prefetches the 128-byte descriptor
 //    it names into the SM's L1.  After the barrier at the end of the grab everything the next one
 //    needs is a shared-memory read or an L1 hit away.  All of thread 0's scheduling state lives in shared memory: the hot
@@ -662,8 +662,9 @@ __device__ __forceinline__ void for_each_tile_run(const GroupArgs& g, F&& f) {
 #ifdef TDX_LUT_TIMELINE
 // Measurement build only (benchmarks/lut_timeline.py): per-CTA timestamps of the table kernel.
 // 16 slots per CTA: 0 enter, 1 first grab known, 2 first table built, 3 last grab done, 4 grabs,
-// 5 ns thread 0 spent in barriers at grab ends, 6 ns from a grab's barrier to its first tile,
-// 7 exit, 8 tiles, 9 table builds, 10 ns in table builds, 11 ns in prefetch_start/finish.
+// 5 ns thread 0 spent in barriers at grab ends, 6 ns from a grab's start to its first tile,
+// 7 exit, 8 tiles, 9 table builds, 10 ns in table builds, 12 first request to the work counter,
+// 13 end of the pre-assigned share.
 __device__ unsigned long long* g_lut_timeline = nullptr;
 __device__ __forceinline__ unsigned long long tl_now() {
   unsigned long long t;
@@ -694,18 +695,13 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// Thread 0's side job during a grab (every function is called by thread 0 only).
+// Thread 0's side job during a grab of the dynamic tail (every function is called by thread 0 only).
 __device__ __forceinline__ void lut_prefetch_start(const GroupArgs& g, LutSched* s, unsigned int slot) {
-  unsigned int c = s->pos;
-  if (c < s->end) {
-    s->pos = c + 1u;
-  } else {
-    // dynamic tail: this thread waits for the counter here (~1 us, once per tail grab)
-    c = g.n_static + atomicAdd(g.counter, 1u);
+  // (this thread waits for the counter here, ~1 us, once per tail grab)
+  const unsigned int c = g.n_static + atomicAdd(g.counter, 1u);
 #ifdef TDX_LUT_TIMELINE
-    if (g_lut_timeline && g_lut_timeline[blockIdx.x * 16 + 12] == 0) g_lut_timeline[blockIdx.x * 16 + 12] = tl_now();
+  if (g_lut_timeline && g_lut_timeline[blockIdx.x * 16 + 12] == 0) g_lut_timeline[blockIdx.x * 16 + 12] = tl_now();
 #endif
-  }
   s->next[slot] = c;
   if (c < g.n_chunks) {
     cp_async16(&s->item[slot], g.chunks + c);
@@ -734,14 +730,21 @@ __device__ __forceinline__ void lut_prefetch_finish(const GroupArgs& g, LutSched
   cp_async_wait_all();
 }
 
-// f(desc_index, descriptor, first tile, tiles, slot of the next grab)
+// f(desc_index, descriptor, first tile, tiles, slot of the next dynamic grab)
+//
+// Two phases.  While a CTA walks its pre-assigned share there is NO barrier and no shared scheduler
+// state: every thread reads the list entries itself (a uniform load, L1-resident after the first
+// warp; thread 0 prefetches the next entry's descriptor), so the 32 warps of the CTA drift apart --
+// which is how they run best -- and a descriptor boundary inside the share costs a few hundred
+// nanoseconds instead of ~3 us.  (A table rebuild inside f still synchronises: every warp reaches
+// it at the same list entry.)  At the end of the share the CTA re-aligns once and takes the tail
+// from the work counter, one barrier per grab.
 template <class F>
 __device__ __forceinline__ void for_each_listed_chunk(const GroupArgs& g, LutSched* s, F&& f) {
 #ifdef TDX_LUT_TIMELINE
   if (threadIdx.x == 0 && g_lut_timeline)
     for (int i = 0; i < 16; ++i) g_lut_timeline[blockIdx.x * 16 + i] = 0;
   TL_SET(0, tl_now());
-  unsigned long long tl_bar = 0;
 #endif
   if (threadIdx.x == 0) {
     unsigned int lo = 0u, hi = 0u;
@@ -751,54 +754,60 @@ __device__ __forceinline__ void for_each_listed_chunk(const GroupArgs& g, LutSch
     }
     s->pos = lo;
     s->end = hi;
-    unsigned int c;
-    if (lo < hi) {
-      c = lo;
-      s->pos = lo + 1u;
-    } else {
-      c = g.n_static + atomicAdd(g.counter, 1u);
+    s->stage = 3u;
+    if (lo >= hi) {  // nothing pre-assigned (a small launch): the first grab comes from the counter
+      lut_prefetch_start(g, s, 0u);
+      lut_prefetch_finish(g, s, 0u);
     }
-    s->next[0] = c;
-    if (c < g.n_chunks) s->item[0] = __ldg(g.chunks + c);
   }
   __syncthreads();
   TL_SET(1, tl_now());
-  for (unsigned int it = 0;; ++it) {
-    const unsigned int slot = it & 1u;
-    if (s->next[slot] >= g.n_chunks) {
-#ifdef TDX_LUT_TIMELINE
-      TL_SET(3, tl_bar);
-      TL_SET(4, it);
-#endif
-      leave_grid(g);
-      TL_SET(7, tl_now());
-      return;
+  unsigned int pos = s->pos;
+  const unsigned int hi = s->end;
+  bool walking = pos < hi;
+  unsigned int it = 0;
+  for (;;) {
+    uint4 e;
+    unsigned int next_slot = 0u;
+    if (walking) {
+      e = __ldg(g.chunks + pos);
+      ++pos;
+      if (threadIdx.x == 0) {
+        if (pos < hi) {
+          const uint32_t ndi = __ldg(reinterpret_cast<const uint32_t*>(g.chunks + pos));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(g.descs + ndi));
+        } else {
+          lut_prefetch_start(g, s, 0u);  // last grab of the share: ask the counter for the first tail grab meanwhile
+        }
+      }
+    } else {
+      const unsigned int slot = it & 1u;
+      if (s->next[slot] >= g.n_chunks) {
+        TL_SET(3, tl_now());
+        leave_grid(g);
+        TL_SET(7, tl_now());
+        return;
+      }
+      e = s->item[slot];
+      next_slot = slot ^ 1u;
+      if (threadIdx.x == 0) lut_prefetch_start(g, s, next_slot);
+      ++it;
     }
-    const uint4 e = s->item[slot];
-#ifdef TDX_LUT_TIMELINE
-    const unsigned long long tl_a = tl_now();
-#endif
-    if (threadIdx.x == 0) lut_prefetch_start(g, s, slot ^ 1u);
-#ifdef TDX_LUT_TIMELINE
-    const unsigned long long tl_b = tl_now();
-    TL_ADD(11, tl_b - tl_a);
+    TL_ADD(4, 1);
     TL_ADD(8, e.y);
-#endif
     f(e.x, g.descs[e.x], static_cast<unsigned long long>(e.z) | (static_cast<unsigned long long>(e.w) << 32),
-      static_cast<unsigned long long>(e.y), slot ^ 1u);
-#ifdef TDX_LUT_TIMELINE
-    const unsigned long long tl_c = tl_now();
-#endif
-    if (threadIdx.x == 0) lut_prefetch_finish(g, s, slot ^ 1u);
+      static_cast<unsigned long long>(e.y), next_slot);
+    if (walking) {
+      if (pos < hi) continue;
+      walking = false;  // end of the share: re-align and publish the first tail grab (slot 0)
+      TL_SET(13, tl_now());
+    }
+    if (threadIdx.x == 0) lut_prefetch_finish(g, s, next_slot);
 #ifdef TDX_LUT_TIMELINE
     const unsigned long long tl_d = tl_now();
-    TL_ADD(11, tl_d - tl_c);
 #endif
     __syncthreads();
-#ifdef TDX_LUT_TIMELINE
-    tl_bar = tl_now();
-    TL_ADD(5, tl_bar - tl_d);
-#endif
+    TL_ADD(5, tl_now() - tl_d);
   }
 }
 
