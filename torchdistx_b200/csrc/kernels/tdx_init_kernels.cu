@@ -270,6 +270,18 @@ __device__ __forceinline__ float halfword_as_magic(const uint4& w, int e) {
   return __uint_as_float(bits);
 }
 
+// half-word `e` of a Philox block as the float k (one I2F.U16 with a half-word operand select: no
+// byte-permute constant to keep in a register, which the table kernel -- 64 registers per thread --
+// re-materialised for every vector)
+__device__ __forceinline__ float halfword_as_float(const uint4& w, int e) {
+  const uint32_t word = (e >> 1) == 0 ? w.x : (e >> 1) == 1 ? w.y : (e >> 1) == 2 ? w.z : w.w;
+  unsigned short lo, hi;
+  asm("mov.b32 {%0, %1}, %2;" : "=h"(lo), "=h"(hi) : "r"(word));
+  float f;
+  asm("cvt.rn.f32.u16 %0, %1;" : "=f"(f) : "h"((e & 1) ? hi : lo));
+  return f;
+}
+
 // ---- uniform, 16 random bits per element (bf16 / fp16 outputs) -----------------------------
 template <class Out, int R, bool EPI>
 struct GenUniform16 {
@@ -468,7 +480,14 @@ struct GenNormalICDF16 {
   }
   // one element: `magic` = 2^23 + k as a float; returns the value, `t` = 1 - x^2 (0 iff k == 0)
   __device__ static __forceinline__ float element_l(const Params& p, float magic, float& t, float& l) {
-    const float x = fmaf(magic, 3.0517578125e-05f, -257.0f);  // k/32768 - 1
+    return element_x(p, fmaf(magic, 3.0517578125e-05f, -257.0f), t, l);  // k/32768 - 1 (exact)
+  }
+  // ... from k itself as a float: the same x, exactly (both forms are exact)
+  __device__ static __forceinline__ float element_kf(const Params& p, float kf) {
+    float t, l;
+    return element_x(p, fmaf(kf, 3.0517578125e-05f, -1.0f), t, l);
+  }
+  __device__ static __forceinline__ float element_x(const Params& p, float x, float& t, float& l) {
     t = fmaf(-x, x, 1.0f);
     l = mufu_lg2(t);
     float q = fmaf(p.c5, l, p.c4);
@@ -650,9 +669,9 @@ __device__ __forceinline__ void for_each_tile_run(const GroupArgs& g, F&& f) {
 //  * the host cuts every descriptor into grabs of its own (guided sizes: up to 4 MiB while there is
 //    plenty of work left, down to one 256 KiB tile at the end, for balance);
 //  * all but the last ~1/8 of the work is PRE-ASSIGNED: the host deals the large grabs out to the
-//    CTAs (one contiguous, equal share each) and CTA b walks its own segment of the list -- no
-//    counter, no barrier (see for_each_listed_chunk).  Only the tail is handed out dynamically,
-//    which is what keeps the CTAs finishing together;
+//    CTAs (one contiguous, equal share each) and CTA b walks its own segment of the list through a
+//    shared-memory window -- no counter, no barrier (see for_each_listed_chunk).  Only the tail is
+//    handed out dynamically, which is what keeps the CTAs finishing together;
 //  * in the tail the NEXT grab is brought into shared memory while the current one is being
 //    written: thread 0 starts an asynchronous copy (cp.async: no destination register, nothing to stall on) of the
 //    16-byte list entry when a grab starts and, one tile later, prefetches the 128-byte descriptor
@@ -677,11 +696,14 @@ __device__ __forceinline__ unsigned long long tl_now() {
 #define TL_SET(i, v) do { } while (0)
 #define TL_ADD(i, v) do { } while (0)
 #endif
+constexpr unsigned int kLutWindow = 16;
 struct LutSched {
   unsigned int next[2];  // list index of the grab in each slot (>= n_chunks: no more work)
   unsigned int pos, end; // CTA's segment of the pre-assigned part: next entry, one past the last
   volatile unsigned int stage;  // of the prefetch of the next grab: 2 = entry under way, 3 = descriptor under way / nothing to do
-  unsigned int pad_[3];
+  unsigned int pf_slot;  // slot the prefetch under way fills (thread 0's own note)
+  unsigned int pad_[2];
+  uint4 win[kLutWindow]; // window of the CTA's pre-assigned share of the list
   uint4 item[2];         // {descriptor, tiles, first tile in descriptor (lo, hi)}
   TdxInitDesc tab;       // the descriptor the table in shared memory was built for
 };
@@ -703,6 +725,7 @@ __device__ __forceinline__ void lut_prefetch_start(const GroupArgs& g, LutSched*
   if (g_lut_timeline && g_lut_timeline[blockIdx.x * 16 + 12] == 0) g_lut_timeline[blockIdx.x * 16 + 12] = tl_now();
 #endif
   s->next[slot] = c;
+  s->pf_slot = slot;
   if (c < g.n_chunks) {
     cp_async16(&s->item[slot], g.chunks + c);
     cp_async_commit();
@@ -722,23 +745,33 @@ __device__ __forceinline__ void lut_prefetch_desc(const GroupArgs& g, LutSched* 
   s->stage = 3u;
 }
 // hook of the tile loop (after the grab's first tile)
-__device__ __forceinline__ void lut_prefetch_hook(const GroupArgs& g, LutSched* s, unsigned int slot) {
-  if (s->stage == 2u) lut_prefetch_desc(g, s, slot);
+__device__ __forceinline__ void lut_prefetch_hook(const GroupArgs& g, LutSched* s) {
+  if (s->stage == 2u) lut_prefetch_desc(g, s, s->pf_slot);
 }
-__device__ __forceinline__ void lut_prefetch_finish(const GroupArgs& g, LutSched* s, unsigned int slot) {
-  if (s->stage == 2u) lut_prefetch_desc(g, s, slot);  // (the grab was too short, or too odd, to overlap it)
+__device__ __forceinline__ void lut_prefetch_finish(const GroupArgs& g, LutSched* s) {
+  if (s->stage == 2u) lut_prefetch_desc(g, s, s->pf_slot);  // (the grab was too short, or too odd, to overlap it)
   cp_async_wait_all();
 }
 
-// f(desc_index, descriptor, first tile, tiles, slot of the next dynamic grab)
+// f(desc_index, descriptor, first tile, tiles)
 //
-// Two phases.  While a CTA walks its pre-assigned share there is NO barrier and no shared scheduler
-// state: every thread reads the list entries itself (a uniform load, L1-resident after the first
-// warp; thread 0 prefetches the next entry's descriptor), so the 32 warps of the CTA drift apart --
-// which is how they run best -- and a descriptor boundary inside the share costs a few hundred
-// nanoseconds instead of ~3 us.  (A table rebuild inside f still synchronises: every warp reaches
-// it at the same list entry.)  At the end of the share the CTA re-aligns once and takes the tail
-// from the work counter, one barrier per grab.
+// Rounds.  A round is a window of (up to kLutWindow entries of) the CTA's pre-assigned share, copied
+// into shared memory, or one grab of the dynamic tail.  Inside a round there is NO barrier and no
+// shared scheduler state being written: the 32 warps of the CTA drift apart -- which is how they run
+// best -- and a descriptor boundary inside the share costs a few hundred nanoseconds instead of ~3 us
+// (a table rebuild inside f still synchronises: every warp reaches it at the same list entry).
+// Rounds end in one barrier; the tail takes its grabs from the work counter, one round each.
+//
+// The SHAPE of this function is load-bearing.  ptxas keeps the generator's constants (warp-reduction
+// results) in uniform registers across the hot loop inside f only if it can prove the warps converged
+// there, and it proves that from control flow whose conditions are shared-memory loads at
+// thread-independent addresses, kernel parameters and counters derived from them -- an outer loop
+// that ends in a barrier, an inner counted loop around the single call of f.  Forms that read the list
+// entries straight from global memory, keep a per-warp position, or `continue` past the barrier
+// (all tried) make it guard every REDUX with BRA.DIV and keep the constants in local memory, reloaded
+// for every group of vectors: 0.65 instead of 0.75 of the roof on Llama-3-8B (check:
+// `ptxas -v` must report < 100 bytes of spill loads for tdx_lut16_kernel<TabNormal...>, and the SASS
+// must contain no BRA.DIV).
 template <class F>
 __device__ __forceinline__ void for_each_listed_chunk(const GroupArgs& g, LutSched* s, F&& f) {
 #ifdef TDX_LUT_TIMELINE
@@ -757,29 +790,28 @@ __device__ __forceinline__ void for_each_listed_chunk(const GroupArgs& g, LutSch
     s->stage = 3u;
     if (lo >= hi) {  // nothing pre-assigned (a small launch): the first grab comes from the counter
       lut_prefetch_start(g, s, 0u);
-      lut_prefetch_finish(g, s, 0u);
+      lut_prefetch_finish(g, s);
     }
   }
   __syncthreads();
   TL_SET(1, tl_now());
-  unsigned int pos = s->pos;
+  // Everything the loop's control flow depends on is read from shared memory at thread-independent
+  // addresses (or counted from such values): that is what lets ptxas prove the warps converged and
+  // keep the generator's constants in uniform registers across the hot loop inside f.  (List
+  // entries read straight from global memory, or per-warp positions, are "divergent" to it: the
+  // constants then live in local memory and are reloaded for every group of vectors -- 0.65 instead
+  // of 0.75 of the roof.)  So a CTA copies its share of the list into a shared-memory window first.
   const unsigned int hi = s->end;
-  bool walking = pos < hi;
-  unsigned int it = 0;
+  unsigned int base = s->pos;  // next list entry of the pre-assigned share
+  unsigned int it = 0u;        // tail grabs taken
   for (;;) {
-    uint4 e;
-    unsigned int next_slot = 0u;
-    if (walking) {
-      e = __ldg(g.chunks + pos);
-      ++pos;
-      if (threadIdx.x == 0) {
-        if (pos < hi) {
-          const uint32_t ndi = __ldg(reinterpret_cast<const uint32_t*>(g.chunks + pos));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(g.descs + ndi));
-        } else {
-          lut_prefetch_start(g, s, 0u);  // last grab of the share: ask the counter for the first tail grab meanwhile
-        }
-      }
+    // One round = the entries in s->win[0, n): a window of the CTA's share, or one grab of the tail.
+    unsigned int n;
+    if (base < hi) {
+      n = min(hi - base, kLutWindow);
+      if (threadIdx.x < n) s->win[threadIdx.x] = __ldg(g.chunks + base + threadIdx.x);
+      base += n;
+      __syncthreads();
     } else {
       const unsigned int slot = it & 1u;
       if (s->next[slot] >= g.n_chunks) {
@@ -788,21 +820,35 @@ __device__ __forceinline__ void for_each_listed_chunk(const GroupArgs& g, LutSch
         TL_SET(7, tl_now());
         return;
       }
-      e = s->item[slot];
-      next_slot = slot ^ 1u;
-      if (threadIdx.x == 0) lut_prefetch_start(g, s, next_slot);
+      if (threadIdx.x == 0) {
+        s->win[0] = s->item[slot];
+        lut_prefetch_start(g, s, slot ^ 1u);
+      }
+      n = 1u;
       ++it;
+      __syncthreads();
     }
-    TL_ADD(4, 1);
-    TL_ADD(8, e.y);
-    f(e.x, g.descs[e.x], static_cast<unsigned long long>(e.z) | (static_cast<unsigned long long>(e.w) << 32),
-      static_cast<unsigned long long>(e.y), next_slot);
-    if (walking) {
-      if (pos < hi) continue;
-      walking = false;  // end of the share: re-align and publish the first tail grab (slot 0)
-      TL_SET(13, tl_now());
+    // Inside a round there is no barrier: the 32 warps of the CTA drift apart -- which is how they
+    // run best -- and a descriptor boundary costs a few hundred nanoseconds instead of ~3 us.  (A
+    // table rebuild inside f still synchronises: every warp reaches it at the same list entry.)
+    for (unsigned int j = 0; j < n; ++j) {
+      const uint4 e = s->win[j];
+      if (threadIdx.x == 0) {
+        if (j + 1u < n) {
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(g.descs + s->win[j + 1u].x));
+        } else if (s->stage == 3u && base >= hi && it == 0u) {
+          lut_prefetch_start(g, s, 0u);  // last grab of the share: ask the counter for the first tail grab meanwhile
+        }
+      }
+      TL_ADD(4, 1);
+      TL_ADD(8, e.y);
+      f(e.x, g.descs[e.x], static_cast<unsigned long long>(e.z) | (static_cast<unsigned long long>(e.w) << 32),
+        static_cast<unsigned long long>(e.y));
     }
-    if (threadIdx.x == 0) lut_prefetch_finish(g, s, next_slot);
+    TL_SET(13, tl_now());
+    // end of the round: re-align (thread 0 first completes the prefetch of the next tail grab, if
+    // one is under way) before the window is overwritten
+    if (threadIdx.x == 0) lut_prefetch_finish(g, s);
 #ifdef TDX_LUT_TIMELINE
     const unsigned long long tl_d = tl_now();
 #endif
@@ -1121,6 +1167,11 @@ struct TabNormal {
     const float v = Gen::element(p, magic, t);  // k == 0: +-inf or NaN (lg2(0) = -inf)
     return EPI ? apply_epi<Out>(p.epi, v) : v;
   }
+  // the same value from k as a float (hot loop: halfword_as_float)
+  __device__ static __forceinline__ float value_kf(const Params& p, float kf) {
+    const float v = Gen::element_kf(p, kf);
+    return EPI ? apply_epi<Out>(p.epi, v) : v;
+  }
   __device__ static __forceinline__ void uniformize(Params& p) {
     p.mean = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(p.mean)));
     p.c0 = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(p.c0)));
@@ -1139,6 +1190,10 @@ struct TabUniform {
   __device__ static __forceinline__ bool mirrored(const Params&) { return false; }
   __device__ static __forceinline__ float value(const Params& p, float magic) {
     const float x = fminf(fmaf(magic - 8388608.0f, p.scale, p.from), p.to_prev);  // == Gen::gen, element by element
+    return EPI ? apply_epi<Out>(p.epi, x) : x;
+  }
+  __device__ static __forceinline__ float value_kf(const Params& p, float kf) {
+    const float x = fminf(fmaf(kf, p.scale, p.from), p.to_prev);  // magic - 2^23 == k exactly
     return EPI ? apply_epi<Out>(p.epi, x) : x;
   }
   __device__ static __forceinline__ void uniformize(Params& p) {
@@ -1266,7 +1321,7 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_lut16_kernel(const GroupAr
   uint32_t have_di = 0xffffffffu;  // descriptor the table in shared memory was built for (its copy: sched->tab)
   const bool t0 = threadIdx.x == 0;
   for_each_listed_chunk(g, sched, [&](uint32_t di, const TdxInitDesc& d, unsigned long long tile0,
-                                      unsigned long long ntiles, unsigned int next_slot) {
+                                      unsigned long long ntiles) {
     if (d.src == TDX_SRC_CONST) {  // a fill folded into this launch (build_plan): the table stays as it is
       lut_fill_tiles(&d, tile0, ntiles);
       return;
@@ -1340,10 +1395,10 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_lut16_kernel(const GroupAr
               if (lo_lut && hi_lut) {
                 r[q] = pack_u16(lds_u16_tab(lut_off_lo(ws[q])), lds_u16_tab(lut_off_hi(ws[q])));
               } else if (!lo_lut && !hi_lut) {
-                r[q] = T::pack2(Tab::value(P, halfword_as_magic(w, 2 * q)),
-                                Tab::value(P, halfword_as_magic(w, 2 * q + 1)));
+                r[q] = T::pack2(Tab::value_kf(P, halfword_as_float(w, 2 * q)),
+                                Tab::value_kf(P, halfword_as_float(w, 2 * q + 1)));
               } else {  // low half from the table, high half computed
-                const uint32_t hi16 = T::pack2(0.0f, Tab::value(P, halfword_as_magic(w, 2 * q + 1)));
+                const uint32_t hi16 = T::pack2(0.0f, Tab::value_kf(P, halfword_as_float(w, 2 * q + 1)));
                 r[q] = (hi16 & 0xffff0000u) | lds_u16_tab(lut_off_lo(ws[q]));
               }
             }
@@ -1371,7 +1426,7 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_lut16_kernel(const GroupAr
         lut_ragged_tile<Gen>(&d, tile);
       }
       // (thread 0, after the grab's first tile: the next list entry has arrived -- start on its descriptor)
-      if (t0 && tile == tile0) lut_prefetch_hook(g, sched, next_slot);
+      if (t0 && tile == tile0) lut_prefetch_hook(g, sched);
     }
   });
 }
