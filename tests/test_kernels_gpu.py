@@ -373,6 +373,32 @@ def test_table_kernel_preassigned_shares_and_folded_programs_match_the_direct_ke
             assert torch.equal(a.view(torch.int16), b.view(torch.int16))
 
 
+def test_table_kernel_share_longer_than_its_shared_memory_window():
+    """A CTA copies its pre-assigned share of the work list into shared memory 16 entries at a time
+    (kLutWindow).  3,600 table-eligible descriptors of ~0.5 MiB (two tiles and a ragged end each, so
+    ~3 list entries per descriptor, ~70 per CTA) make every CTA refill its window several times;
+    three parameter sets make tables change inside windows.  Same bits as the direct kernel."""
+    dtype, n_desc = C.TDX_BF16, 3600
+    sizes = [(1 << 18) + 8 * (i % 7) + (i % 3) for i in range(n_desc)]
+    offs = np.concatenate([[0], np.cumsum([(n + 7) // 8 * 8 for n in sizes])])  # 16-byte aligned starts
+    outs = {}
+    for flag in (0, C.TDX_ALGO_NOLUT):
+        buf = torch.full((int(offs[-1]),), -1, dtype=torch.int16, device="cuda").view(torch.bfloat16)  # NaN pattern
+        descs = [C.make_desc(buf.data_ptr() + 2 * int(offs[i]), dtype=dtype, src=C.TDX_SRC_NORMAL, elem_count=n, seed=123,
+                             offset=64 * i, p0=0.0, p1=(0.02, 0.03, 0.5)[(i // 40) % 3], algo=C.TDX_ALGO_ICDF16 | flag)
+                 for i, n in enumerate(sizes)]
+        assert run_descs(descs, [buf]) == 1
+        outs[flag] = buf
+    assert torch.equal(outs[0].view(torch.int16), outs[C.TDX_ALGO_NOLUT].view(torch.int16))
+    # every element of every descriptor was written (finite), the padding between descriptors was not
+    inside = torch.ones(int(offs[-1]), dtype=torch.bool, device="cuda")
+    for i, n in enumerate(sizes):
+        inside[int(offs[i]) + n:int(offs[i + 1])] = False
+    bits = outs[0].view(torch.int16)
+    assert bool((bits[inside] != -1).all()) and bool((bits[~inside] == -1).all())
+    assert bool(torch.isfinite(outs[0][inside].float()).all())
+
+
 @pytest.mark.parametrize("dtype,src", [(C.TDX_BF16, C.TDX_SRC_NORMAL), (C.TDX_F32, C.TDX_SRC_UNIFORM)])
 def test_beyond_2_to_32_elements(dtype, src):
     """BASELINE config #5 reaches 16 GB tensors: global element indices above 2^32 must index the
