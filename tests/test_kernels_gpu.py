@@ -373,11 +373,11 @@ def test_table_kernel_preassigned_shares_and_folded_programs_match_the_direct_ke
             assert torch.equal(a.view(torch.int16), b.view(torch.int16))
 
 
-def test_table_kernel_share_longer_than_its_shared_memory_window():
-    """A CTA copies its pre-assigned share of the work list into shared memory 16 entries at a time
-    (kLutWindow).  3,600 table-eligible descriptors of ~0.5 MiB (two tiles and a ragged end each, so
-    ~3 list entries per descriptor, ~70 per CTA) make every CTA refill its window several times;
-    three parameter sets make tables change inside windows.  Same bits as the direct kernel."""
+def test_table_kernel_with_thousands_of_small_descriptors_in_one_launch():
+    """3,600 table-eligible descriptors of ~0.5 MiB (two tiles and a ragged end each, so ~3 work-list
+    entries per descriptor and ~70 per CTA: every pre-assigned share crosses dozens of descriptor
+    boundaries); three parameter sets make tables change inside a share.  Same bits as the direct
+    kernel, nothing written outside the descriptors."""
     dtype, n_desc = C.TDX_BF16, 3600
     sizes = [(1 << 18) + 8 * (i % 7) + (i % 3) for i in range(n_desc)]
     offs = np.concatenate([[0], np.cumsum([(n + 7) // 8 * 8 for n in sizes])])  # 16-byte aligned starts

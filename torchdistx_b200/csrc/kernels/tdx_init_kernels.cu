@@ -669,11 +669,11 @@ __device__ __forceinline__ void for_each_tile_run(const GroupArgs& g, F&& f) {
 //  * the host cuts every descriptor into grabs of its own (guided sizes: up to 4 MiB while there is
 //    plenty of work left, down to one 256 KiB tile at the end, for balance);
 //  * all but the last ~1/8 of the work is PRE-ASSIGNED: the host deals the large grabs out to the
-//    CTAs (one contiguous, equal share each) and CTA b walks its own segment of the list through a
-//    shared-memory window -- no counter, no barrier (see for_each_listed_chunk).  Only the tail is
-//    handed out dynamically, which is what keeps the CTAs finishing together;
-//  * in the tail the NEXT grab is brought into shared memory while the current one is being
-//    written: thread 0 starts an asynchronous copy (cp.async: no destination register, nothing to stall on) of the
+//    CTAs (least loaded first) and CTA b walks its own segment of the list -- no counter, and the
+//    index of the next grab is known when the current one starts.  Only the tail is handed out
+//    dynamically, which is what keeps the CTAs finishing together;
+//  * the NEXT grab is brought into shared memory while the current one is being written: thread 0
+//    starts an asynchronous copy (cp.async: no destination register, nothing to stall on) of the
 //    16-byte list entry when a grab starts and, one tile later, prefetches the 128-byte descriptor
 //    it names into the SM's L1.  After the barrier at the end of the grab everything the next one
 //    needs is a shared-memory read or an L1 hit away.  All of thread 0's scheduling state lives in shared memory: the hot
@@ -681,9 +681,8 @@ __device__ __forceinline__ void for_each_tile_run(const GroupArgs& g, F&& f) {
 #ifdef TDX_LUT_TIMELINE
 // Measurement build only (benchmarks/lut_timeline.py): per-CTA timestamps of the table kernel.
 // 16 slots per CTA: 0 enter, 1 first grab known, 2 first table built, 3 last grab done, 4 grabs,
-// 5 ns thread 0 spent in barriers at grab ends, 6 ns from a grab's start to its first tile,
-// 7 exit, 8 tiles, 9 table builds, 10 ns in table builds, 12 first request to the work counter,
-// 13 end of the pre-assigned share.
+// 5 ns thread 0 spent in barriers at grab ends, 6 ns from a grab's barrier to its first tile,
+// 7 exit, 8 tiles, 9 table builds, 10 ns in table builds, 11 ns in prefetch_start/finish.
 __device__ unsigned long long* g_lut_timeline = nullptr;
 __device__ __forceinline__ unsigned long long tl_now() {
   unsigned long long t;
@@ -696,14 +695,11 @@ __device__ __forceinline__ unsigned long long tl_now() {
 #define TL_SET(i, v) do { } while (0)
 #define TL_ADD(i, v) do { } while (0)
 #endif
-constexpr unsigned int kLutWindow = 16;
 struct LutSched {
   unsigned int next[2];  // list index of the grab in each slot (>= n_chunks: no more work)
   unsigned int pos, end; // CTA's segment of the pre-assigned part: next entry, one past the last
   volatile unsigned int stage;  // of the prefetch of the next grab: 2 = entry under way, 3 = descriptor under way / nothing to do
-  unsigned int pf_slot;  // slot the prefetch under way fills (thread 0's own note)
-  unsigned int pad_[2];
-  uint4 win[kLutWindow]; // window of the CTA's pre-assigned share of the list
+  unsigned int pad_[3];
   uint4 item[2];         // {descriptor, tiles, first tile in descriptor (lo, hi)}
   TdxInitDesc tab;       // the descriptor the table in shared memory was built for
 };
@@ -717,15 +713,19 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// Thread 0's side job during a grab of the dynamic tail (every function is called by thread 0 only).
+// Thread 0's side job during a grab (every function is called by thread 0 only).
 __device__ __forceinline__ void lut_prefetch_start(const GroupArgs& g, LutSched* s, unsigned int slot) {
-  // (this thread waits for the counter here, ~1 us, once per tail grab)
-  const unsigned int c = g.n_static + atomicAdd(g.counter, 1u);
+  unsigned int c = s->pos;
+  if (c < s->end) {
+    s->pos = c + 1u;
+  } else {
+    // dynamic tail: this thread waits for the counter here (~1 us, once per tail grab)
+    c = g.n_static + atomicAdd(g.counter, 1u);
 #ifdef TDX_LUT_TIMELINE
-  if (g_lut_timeline && g_lut_timeline[blockIdx.x * 16 + 12] == 0) g_lut_timeline[blockIdx.x * 16 + 12] = tl_now();
+    if (g_lut_timeline && g_lut_timeline[blockIdx.x * 16 + 12] == 0) g_lut_timeline[blockIdx.x * 16 + 12] = tl_now();
 #endif
+  }
   s->next[slot] = c;
-  s->pf_slot = slot;
   if (c < g.n_chunks) {
     cp_async16(&s->item[slot], g.chunks + c);
     cp_async_commit();
@@ -745,39 +745,34 @@ __device__ __forceinline__ void lut_prefetch_desc(const GroupArgs& g, LutSched* 
   s->stage = 3u;
 }
 // hook of the tile loop (after the grab's first tile)
-__device__ __forceinline__ void lut_prefetch_hook(const GroupArgs& g, LutSched* s) {
-  if (s->stage == 2u) lut_prefetch_desc(g, s, s->pf_slot);
+__device__ __forceinline__ void lut_prefetch_hook(const GroupArgs& g, LutSched* s, unsigned int slot) {
+  if (s->stage == 2u) lut_prefetch_desc(g, s, slot);
 }
-__device__ __forceinline__ void lut_prefetch_finish(const GroupArgs& g, LutSched* s) {
-  if (s->stage == 2u) lut_prefetch_desc(g, s, s->pf_slot);  // (the grab was too short, or too odd, to overlap it)
+__device__ __forceinline__ void lut_prefetch_finish(const GroupArgs& g, LutSched* s, unsigned int slot) {
+  if (s->stage == 2u) lut_prefetch_desc(g, s, slot);  // (the grab was too short, or too odd, to overlap it)
   cp_async_wait_all();
 }
 
-// f(desc_index, descriptor, first tile, tiles)
+// f(desc_index, descriptor, first tile, tiles, slot of the next grab)
 //
-// Rounds.  A round is a window of (up to kLutWindow entries of) the CTA's pre-assigned share, copied
-// into shared memory, or one grab of the dynamic tail.  Inside a round there is NO barrier and no
-// shared scheduler state being written: the 32 warps of the CTA drift apart -- which is how they run
-// best -- and a descriptor boundary inside the share costs a few hundred nanoseconds instead of ~3 us
-// (a table rebuild inside f still synchronises: every warp reaches it at the same list entry).
-// Rounds end in one barrier; the tail takes its grabs from the work counter, one round each.
-//
-// The SHAPE of this function is load-bearing.  ptxas keeps the generator's constants (warp-reduction
+// The SHAPE of this loop is load-bearing.  ptxas keeps the generator's constants (warp-reduction
 // results) in uniform registers across the hot loop inside f only if it can prove the warps converged
 // there, and it proves that from control flow whose conditions are shared-memory loads at
-// thread-independent addresses, kernel parameters and counters derived from them -- an outer loop
-// that ends in a barrier, an inner counted loop around the single call of f.  Forms that read the list
-// entries straight from global memory, keep a per-warp position, or `continue` past the barrier
-// (all tried) make it guard every REDUX with BRA.DIV and keep the constants in local memory, reloaded
-// for every group of vectors: 0.65 instead of 0.75 of the roof on Llama-3-8B (check:
-// `ptxas -v` must report < 100 bytes of spill loads for tdx_lut16_kernel<TabNormal...>, and the SASS
-// must contain no BRA.DIV).
+// thread-independent addresses, kernel parameters and counters derived from them.  A barrier-free
+// walk of the pre-assigned share (list entries read by every thread from global memory, or per-warp
+// positions, or `continue` past the barrier -- all tried) made it guard every REDUX with BRA.DIV and
+// keep the constants in local memory, reloaded for every group of vectors: 0.65 instead of 0.75 of
+// the roof on Llama-3-8B, every test green.  A convergence-friendly barrier-free form (the share
+// copied to a shared-memory window, inner counted loop) compiles well but measured 0.4-0.8 % SLOWER
+// than this one barrier per grab (profiles/r2_codegen_regression.md): with the next grab prefetched,
+// the barrier costs less than warps that drift apart.  tests/test_lut_codegen.py guards the codegen.
 template <class F>
 __device__ __forceinline__ void for_each_listed_chunk(const GroupArgs& g, LutSched* s, F&& f) {
 #ifdef TDX_LUT_TIMELINE
   if (threadIdx.x == 0 && g_lut_timeline)
     for (int i = 0; i < 16; ++i) g_lut_timeline[blockIdx.x * 16 + i] = 0;
   TL_SET(0, tl_now());
+  unsigned long long tl_bar = 0;
 #endif
   if (threadIdx.x == 0) {
     unsigned int lo = 0u, hi = 0u;
@@ -787,73 +782,54 @@ __device__ __forceinline__ void for_each_listed_chunk(const GroupArgs& g, LutSch
     }
     s->pos = lo;
     s->end = hi;
-    s->stage = 3u;
-    if (lo >= hi) {  // nothing pre-assigned (a small launch): the first grab comes from the counter
-      lut_prefetch_start(g, s, 0u);
-      lut_prefetch_finish(g, s);
+    unsigned int c;
+    if (lo < hi) {
+      c = lo;
+      s->pos = lo + 1u;
+    } else {
+      c = g.n_static + atomicAdd(g.counter, 1u);
     }
+    s->next[0] = c;
+    if (c < g.n_chunks) s->item[0] = __ldg(g.chunks + c);
   }
   __syncthreads();
   TL_SET(1, tl_now());
-  // Everything the loop's control flow depends on is read from shared memory at thread-independent
-  // addresses (or counted from such values): that is what lets ptxas prove the warps converged and
-  // keep the generator's constants in uniform registers across the hot loop inside f.  (List
-  // entries read straight from global memory, or per-warp positions, are "divergent" to it: the
-  // constants then live in local memory and are reloaded for every group of vectors -- 0.65 instead
-  // of 0.75 of the roof.)  So a CTA copies its share of the list into a shared-memory window first.
-  const unsigned int hi = s->end;
-  unsigned int base = s->pos;  // next list entry of the pre-assigned share
-  unsigned int it = 0u;        // tail grabs taken
-  for (;;) {
-    // One round = the entries in s->win[0, n): a window of the CTA's share, or one grab of the tail.
-    unsigned int n;
-    if (base < hi) {
-      n = min(hi - base, kLutWindow);
-      if (threadIdx.x < n) s->win[threadIdx.x] = __ldg(g.chunks + base + threadIdx.x);
-      base += n;
-      __syncthreads();
-    } else {
-      const unsigned int slot = it & 1u;
-      if (s->next[slot] >= g.n_chunks) {
-        TL_SET(3, tl_now());
-        leave_grid(g);
-        TL_SET(7, tl_now());
-        return;
-      }
-      if (threadIdx.x == 0) {
-        s->win[0] = s->item[slot];
-        lut_prefetch_start(g, s, slot ^ 1u);
-      }
-      n = 1u;
-      ++it;
-      __syncthreads();
+  for (unsigned int it = 0;; ++it) {
+    const unsigned int slot = it & 1u;
+    if (s->next[slot] >= g.n_chunks) {
+#ifdef TDX_LUT_TIMELINE
+      TL_SET(3, tl_bar);
+      TL_SET(4, it);
+#endif
+      leave_grid(g);
+      TL_SET(7, tl_now());
+      return;
     }
-    // Inside a round there is no barrier: the 32 warps of the CTA drift apart -- which is how they
-    // run best -- and a descriptor boundary costs a few hundred nanoseconds instead of ~3 us.  (A
-    // table rebuild inside f still synchronises: every warp reaches it at the same list entry.)
-    for (unsigned int j = 0; j < n; ++j) {
-      const uint4 e = s->win[j];
-      if (threadIdx.x == 0) {
-        if (j + 1u < n) {
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(g.descs + s->win[j + 1u].x));
-        } else if (s->stage == 3u && base >= hi && it == 0u) {
-          lut_prefetch_start(g, s, 0u);  // last grab of the share: ask the counter for the first tail grab meanwhile
-        }
-      }
-      TL_ADD(4, 1);
-      TL_ADD(8, e.y);
-      f(e.x, g.descs[e.x], static_cast<unsigned long long>(e.z) | (static_cast<unsigned long long>(e.w) << 32),
-        static_cast<unsigned long long>(e.y));
-    }
-    TL_SET(13, tl_now());
-    // end of the round: re-align (thread 0 first completes the prefetch of the next tail grab, if
-    // one is under way) before the window is overwritten
-    if (threadIdx.x == 0) lut_prefetch_finish(g, s);
+    const uint4 e = s->item[slot];
+#ifdef TDX_LUT_TIMELINE
+    const unsigned long long tl_a = tl_now();
+#endif
+    if (threadIdx.x == 0) lut_prefetch_start(g, s, slot ^ 1u);
+#ifdef TDX_LUT_TIMELINE
+    const unsigned long long tl_b = tl_now();
+    TL_ADD(11, tl_b - tl_a);
+    TL_ADD(8, e.y);
+#endif
+    f(e.x, g.descs[e.x], static_cast<unsigned long long>(e.z) | (static_cast<unsigned long long>(e.w) << 32),
+      static_cast<unsigned long long>(e.y), slot ^ 1u);
+#ifdef TDX_LUT_TIMELINE
+    const unsigned long long tl_c = tl_now();
+#endif
+    if (threadIdx.x == 0) lut_prefetch_finish(g, s, slot ^ 1u);
 #ifdef TDX_LUT_TIMELINE
     const unsigned long long tl_d = tl_now();
+    TL_ADD(11, tl_d - tl_c);
 #endif
     __syncthreads();
-    TL_ADD(5, tl_now() - tl_d);
+#ifdef TDX_LUT_TIMELINE
+    tl_bar = tl_now();
+    TL_ADD(5, tl_bar - tl_d);
+#endif
   }
 }
 
@@ -1321,7 +1297,7 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_lut16_kernel(const GroupAr
   uint32_t have_di = 0xffffffffu;  // descriptor the table in shared memory was built for (its copy: sched->tab)
   const bool t0 = threadIdx.x == 0;
   for_each_listed_chunk(g, sched, [&](uint32_t di, const TdxInitDesc& d, unsigned long long tile0,
-                                      unsigned long long ntiles) {
+                                      unsigned long long ntiles, unsigned int next_slot) {
     if (d.src == TDX_SRC_CONST) {  // a fill folded into this launch (build_plan): the table stays as it is
       lut_fill_tiles(&d, tile0, ntiles);
       return;
@@ -1426,7 +1402,7 @@ __global__ void __launch_bounds__(kLutThreads, 1) tdx_lut16_kernel(const GroupAr
         lut_ragged_tile<Gen>(&d, tile);
       }
       // (thread 0, after the grab's first tile: the next list entry has arrived -- start on its descriptor)
-      if (t0 && tile == tile0) lut_prefetch_hook(g, sched);
+      if (t0 && tile == tile0) lut_prefetch_hook(g, sched, next_slot);
     }
   });
 }
