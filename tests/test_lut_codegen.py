@@ -42,8 +42,11 @@ def test_table_kernel_keeps_its_constants_in_uniform_registers():
         assert stores and last, f"{name}: hot loop not found"
         hot = lines[stores[0]:last[0] + 1]
         ldl = sum("LDL" in l for l in hot)
-        # (the rare k == 0 path, one call site per group of four vectors, may reload a few values)
-        assert ldl <= 8, f"{name}: {ldl} local-memory reloads between the vector stores of a tile"
+        # (the rare k == 0 path, one call site per group of four vectors, may reload a few values; the
+        # twin for launches whose descriptors do not share one seed -- PKEYS = false -- keeps the Philox
+        # keys in vector registers and has less room)
+        pkeys = "Li10ELb1ELi7" in name
+        assert ldl <= (8 if pkeys else 16), f"{name}: {ldl} local-memory reloads between the vector stores of a tile"
         # the polynomial's coefficients are uniform-register operands of the FFMAs
         ffma = [l for l in hot if "FFMA" in l]
         assert sum("UR" in l for l in ffma) >= len(ffma) // 2, f"{name}: FFMA constants are not in uniform registers"
