@@ -75,8 +75,9 @@ enum {
   TDX_SRC_NORMAL = 2,  /* normal_(mean,std), randn, kaiming_normal_, xavier_normal_ */
   /* element g = p0 + g * p1 (both integers, exactly representable in the destination), then the
    * epilogue: `arange` buffers and the index programs built on them -- rotary inv_freq is
-   * arange -> float -> / dim -> base ** x -> reciprocal -> * scale.  dtype TDX_F32 (epilogue
-   * allowed) or TDX_I64 (none).  The reference replays these op by op through ATen
+   * arange -> float -> / dim -> base ** x -> reciprocal -> * scale.  dtype TDX_F32, or TDX_BF16 /
+   * TDX_F16 (the fp32 value rounded once, to nearest even, at the store: `inv_freq.to(bf16)`)
+   * -- epilogue allowed -- or TDX_I64 (none).  The reference replays these op by op through ATen
    * (deferred_init.cc:256-272); here they are one descriptor in the module's launch. */
   TDX_SRC_IOTA = 3,
 };

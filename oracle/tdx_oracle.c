@@ -250,11 +250,20 @@ int tdx_oracle_generate(const TdxInitDesc* d, void* out) {
   }
   if (d->src == TDX_SRC_IOTA) { /* element g = p0 + g * p1 (integers), then the fp32 epilogue */
     const int64_t start = (int64_t)d->p0, step = (int64_t)d->p1;
-    if (!(d->dtype == TDX_F32 || (d->dtype == TDX_I64 && d->n_epi == 0))) return -1;
+    if (!(d->dtype == TDX_F32 || d->dtype == TDX_BF16 || d->dtype == TDX_F16 || (d->dtype == TDX_I64 && d->n_epi == 0)))
+      return -1;
     for (uint64_t i = 0; i < d->elem_count; ++i) {
       const int64_t val = start + (int64_t)(d->elem_begin + i) * step;
-      if (d->dtype == TDX_I64) ((int64_t*)out)[i] = val;
-      else ((float*)out)[i] = d->n_epi ? apply_epi(d, (float)val) : (float)val;
+      if (d->dtype == TDX_I64) { ((int64_t*)out)[i] = val; continue; }
+      float v = (float)val;
+      if (d->n_epi) { /* index programs run in fp32 whatever the output type (kernel: apply_epi<float>) */
+        TdxInitDesc f = *d;
+        f.dtype = TDX_F32;
+        v = apply_epi(&f, v);
+      }
+      if (d->dtype == TDX_F32) ((float*)out)[i] = v;
+      else if (d->dtype == TDX_BF16) ((uint16_t*)out)[i] = f32_to_bf16(v); /* one rounding, at the store */
+      else ((uint16_t*)out)[i] = f32_to_f16(v);
     }
     return 0;
   }

@@ -357,6 +357,26 @@ def test_rotary_inv_freq_is_one_descriptor_and_equals_the_aten_replay():
         assert torch.equal(a, b), (name, (a - b).abs().max().item())
 
 
+def test_rotary_buffers_of_a_model_converted_to_bf16_fuse_and_equal_the_aten_replay():
+    """BASELINE cfg 3's `.to(torch.bfloat16)` variant: Module.to converts the rotary buffers as well.
+    One 16-bit iota descriptor each; bit for bit what ATen's CUDA kernels give op by op."""
+    from torchdistx_b200 import _C
+
+    def build():
+        return deferred_init(lambda: cases.build("tiny_llama", "fp32", "cuda:0").to(torch.bfloat16))
+
+    m = build()
+    materialize_module(m)
+    st = last_materialize_stats()
+    assert st["generic_ops"] == 0 and st["fused_tensors"] == st["tensors"], st
+    g = build()
+    _C.materialize_module(g, False, None, None, None, False)  # fused=False: every op replayed by ATen on the GPU
+    for name in ("model.rotary_emb.inv_freq", "model.rotary_emb.original_inv_freq"):
+        a, b = named(m)[name], named(g)[name]
+        assert a.dtype == b.dtype == torch.bfloat16 and a.shape == b.shape
+        assert torch.equal(a, b), (name, (a.float() - b.float()).abs().max().item())
+
+
 def test_iota_descriptors_through_the_c_abi():
     import numpy as np
 
@@ -384,6 +404,22 @@ def test_iota_descriptors_through_the_c_abi():
     # against the CPU restatement: libm's powf and CUDA's agree to a couple of ulp, not bit for bit
     exp = torch.from_numpy(O.generate(descs[2]).view(np.float32).copy())
     torch.testing.assert_close(freq.cpu(), exp, rtol=4 * 2.0 ** -23, atol=1e-45)
+    # 16-bit outputs: the fp32 program rounded once at the store == `freq.to(dtype)`, in the iota kernel
+    # and in the table kernel's work list alike
+    for dt, tdt in ((C.TDX_BF16, torch.bfloat16), (C.TDX_F16, torch.float16)):
+        out = torch.empty(n - 3, dtype=tdt, device="cuda")
+        d16 = C.make_desc(out.data_ptr(), dtype=dt, src=C.TDX_SRC_IOTA, elem_begin=3, elem_count=n - 3, p0=0, p1=2, epi=epi)
+        C.launch([d16], ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert torch.equal(out, freq[3:].to(tdt))
+    big = torch.empty(1 << 26, dtype=torch.bfloat16, device="cuda")
+    out = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+    ws2 = torch.empty(lib.tdx_init_workspace_bytes(2), dtype=torch.uint8, device="cuda")
+    launches = C.launch([C.make_desc(big.data_ptr(), dtype=C.TDX_BF16, src=C.TDX_SRC_NORMAL, elem_count=big.numel(), seed=1, p1=0.02),
+                         C.make_desc(out.data_ptr(), dtype=C.TDX_BF16, src=C.TDX_SRC_IOTA, elem_count=n, p0=0, p1=2, epi=epi)],
+                        ws2.data_ptr(), ws2.numel(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert launches == 1 and torch.equal(out, freq.to(torch.bfloat16))
 
 
 def test_position_ids_and_arange_buffers_fold():

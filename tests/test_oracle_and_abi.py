@@ -175,3 +175,8 @@ def test_oracle_iota_matches_torch_on_the_cpu():
     got = torch.from_numpy(O.generate(d).view(np.float32).copy())
     ref = 1.0 / (500000.0 ** (torch.arange(0, 2 * n, 2, dtype=torch.int64).float() / 128))
     torch.testing.assert_close(got, ref, rtol=4 * 2.0 ** -23, atol=0.0)
+    # 16-bit outputs (`inv_freq.to(torch.bfloat16)`): the SAME fp32 program, rounded once at the store
+    for dt, tdt in ((C.TDX_BF16, torch.bfloat16), (C.TDX_F16, torch.float16)):
+        d16 = C.make_desc(0, dtype=dt, src=C.TDX_SRC_IOTA, elem_count=n, p0=0, p1=2, epi=epi)
+        got16 = torch.from_numpy(O.generate(d16).view(np.int16).copy())
+        assert torch.equal(got16, got.to(tdt).view(torch.int16))

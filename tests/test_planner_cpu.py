@@ -36,6 +36,17 @@ def test_init_idioms_fold_as_documented():
     assert r["bn.num_batches_tracked"]["source"] == "real"  # torch.tensor(0) is never intercepted
 
 
+def test_rotary_buffers_of_a_converted_model_stay_index_programs():
+    """`LlamaForCausalLM(...).to(torch.bfloat16)` converts the fp32 rotary buffers too: arange -> ... ->
+    reciprocal -> to(bf16) is still one iota descriptor (fp32 program, one rounding at the store)."""
+    import torch
+
+    r = report(lambda: cases.build("tiny_llama", "fp32").to(torch.bfloat16))
+    for name in ("model.rotary_emb.inv_freq", "model.rotary_emb.original_inv_freq"):
+        assert (r[name]["source"], r[name]["dtype"], r[name]["fusible"]) == ("iota", "BFloat16", True), r[name]
+    assert fusible_fraction(r) == 1.0
+
+
 def test_llama_linear_chain_has_one_dead_uniform():
     r = report(lambda: cases.build("tiny_llama", "bf16"))
     w = r["model.layers.0.mlp.up_proj.weight"]

@@ -940,7 +940,23 @@ __global__ void __launch_bounds__(kThreads) tdx_fill_kernel(const __grid_constan
 }
 
 
-// index programs: element g = start + g * step (integers), then the epilogue (fp32 only).  Tiny
+// One element of an index program: the integer, then (floating outputs) the epilogue in fp32, then
+// -- TDX_BF16 / TDX_F16: `inv_freq.to(torch.bfloat16)`, what Module.to(dtype) does to a rotary
+// buffer -- one rounding to nearest even at the store.
+__device__ __forceinline__ uint64_t iota_itemsize(int dtype) { return dtype == TDX_I64 ? 8 : dtype == TDX_F32 ? 4 : 2; }
+__device__ __forceinline__ void iota_store(const TdxInitDesc& d, const EpiParams& epi, uint64_t j, long long val) {
+  if (d.dtype == TDX_I64) {
+    static_cast<long long*>(d.dst)[j] = val;
+    return;
+  }
+  float v = static_cast<float>(val);
+  if (epi.n) v = apply_epi<float>(epi, v);
+  if (d.dtype == TDX_F32) static_cast<float*>(d.dst)[j] = v;
+  else if (d.dtype == TDX_BF16) static_cast<__nv_bfloat16*>(d.dst)[j] = __float2bfloat16_rn(v);
+  else static_cast<__half*>(d.dst)[j] = __float2half_rn(v);
+}
+
+// index programs: element g = start + g * step (integers), then the epilogue (in fp32).  Tiny
 // buffers (rotary inv_freq: 64 elements, position ids: a few K): nothing to optimise but the launch
 // they no longer need -- they ride in the module's plan like any other descriptor.
 __global__ void __launch_bounds__(kThreads) tdx_iota_kernel(const __grid_constant__ GroupArgs g) {
@@ -948,8 +964,7 @@ __global__ void __launch_bounds__(kThreads) tdx_iota_kernel(const __grid_constan
     const TdxInitDesc& d = *desc_of(g, di);
     const long long start = static_cast<long long>(d.p0), step = static_cast<long long>(d.p1);
     const EpiParams epi = load_epi(d);
-    const bool as_i64 = d.dtype == TDX_I64;
-    const uint64_t per_vec = as_i64 ? 2 : 4;
+    const uint64_t per_vec = 16 / iota_itemsize(d.dtype);
     // (frame: element i of the descriptor is global element elem_begin + i; one "vector" = 16 bytes)
     for (unsigned long long tile = tile0; tile < tile0 + ntiles; ++tile) {
       for (int i = 0; i < kVecsPerThread; ++i) {
@@ -957,14 +972,7 @@ __global__ void __launch_bounds__(kThreads) tdx_iota_kernel(const __grid_constan
         for (uint64_t e = 0; e < per_vec; ++e) {
           const uint64_t j = vec * per_vec + e;
           if (j >= d.elem_count) break;
-          const long long val = start + static_cast<long long>(d.elem_begin + j) * step;
-          if (as_i64) {
-            static_cast<long long*>(d.dst)[j] = val;
-          } else {
-            float v = static_cast<float>(val);
-            if (epi.n) v = apply_epi<float>(epi, v);
-            static_cast<float*>(d.dst)[j] = v;
-          }
+          iota_store(d, epi, j, start + static_cast<long long>(d.elem_begin + j) * step);
         }
       }
     }
@@ -1247,8 +1255,7 @@ __device__ __noinline__ void lut_iota_tiles(const TdxInitDesc* dp, unsigned long
   const TdxInitDesc& d = *dp;
   const long long start = static_cast<long long>(d.p0), step = static_cast<long long>(d.p1);
   const EpiParams epi = load_epi(d);
-  const bool as_i64 = d.dtype == TDX_I64;
-  const uint64_t per_vec = as_i64 ? 2 : 4;
+  const uint64_t per_vec = 16 / iota_itemsize(d.dtype);
   for (unsigned long long tile = tile0; tile < tile0 + ntiles; ++tile) {
     for (int i = 0; i < kLutVecsPerThread; ++i) {
       const uint64_t vec = tile * kLutTileVecs + static_cast<uint64_t>(i) * kLutThreads + threadIdx.x;
@@ -1256,14 +1263,7 @@ __device__ __noinline__ void lut_iota_tiles(const TdxInitDesc* dp, unsigned long
       for (uint64_t e = 0; e < per_vec; ++e) {
         const uint64_t j = vec * per_vec + e;
         if (j >= d.elem_count) break;
-        const long long val = start + static_cast<long long>(d.elem_begin + j) * step;
-        if (as_i64) {
-          static_cast<long long*>(d.dst)[j] = val;
-        } else {
-          float v = static_cast<float>(val);
-          if (epi.n) v = apply_epi<float>(epi, v);
-          static_cast<float*>(d.dst)[j] = v;
-        }
+        iota_store(d, epi, j, start + static_cast<long long>(d.elem_begin + j) * step);
       }
     }
   }
@@ -1703,8 +1703,8 @@ int build_plan(const TdxInitDesc* descs, int n, std::vector<unsigned char>& img,
     if (d.src != TDX_SRC_CONST && d.dtype >= TDX_RAW8)
       return fail(TDX_E_BADARG, "raw dtypes are only valid with TDX_SRC_CONST");
     if ((d.dtype == TDX_I64 && d.src != TDX_SRC_IOTA) ||
-        (d.src == TDX_SRC_IOTA && !(d.dtype == TDX_F32 || (d.dtype == TDX_I64 && d.n_epi == 0))))
-      return fail(TDX_E_BADARG, "TDX_SRC_IOTA writes TDX_F32 (epilogue allowed) or TDX_I64 (none); TDX_I64 is IOTA-only");
+        (d.src == TDX_SRC_IOTA && !(d.dtype == TDX_F32 || d.dtype == TDX_BF16 || d.dtype == TDX_F16 || (d.dtype == TDX_I64 && d.n_epi == 0))))
+      return fail(TDX_E_BADARG, "TDX_SRC_IOTA writes TDX_F32 / TDX_BF16 / TDX_F16 (epilogue allowed) or TDX_I64 (none); TDX_I64 is IOTA-only");
     if (d.n_epi > TDX_MAX_EPI) return fail(TDX_E_BADARG, "n_epi > TDX_MAX_EPI");
     if (d.elem_count && d.dst == nullptr) return fail(TDX_E_BADARG, "dst == NULL");
     if (reinterpret_cast<uintptr_t>(d.dst) % isz) return fail(TDX_E_BADARG, "dst not element-aligned");

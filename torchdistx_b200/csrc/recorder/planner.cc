@@ -669,6 +669,13 @@ void transition(Tape& tape, uint32_t op_idx, uint32_t S, State& st) {
         // index programs: everything after the arange runs in fp32 (the kernel's epilogue)
         if (op.kind == OpKind::CastOut) {
           if (out.dtype == st.dtype) continue;
+          if (st.dtype == ScalarType::Float && (out.dtype == ScalarType::BFloat16 || out.dtype == ScalarType::Half)) {
+            // `inv_freq.to(torch.bfloat16)` (Module.to(dtype) converts floating buffers too): the fp32
+            // program, rounded once at the store.  Terminal: nothing folds onto a 16-bit index program
+            // (every later elementwise transition asks for fp32).
+            new_dtype = out.dtype;
+            continue;
+          }
           if (!(st.dtype == ScalarType::Long && out.dtype == ScalarType::Float && sy.epi.empty()) ||
               std::fabs(sy.p0) + std::fabs(sy.p1) * static_cast<double>(out.numel) >= 16777216.0) {
             st = make_opaque();
@@ -1282,9 +1289,9 @@ bool build_fast(const Tape& tape, const StorageInfo& si, StorageTemplate& t, boo
       for (size_t i = 0; i < 16; i += isz) std::memcpy(pat + i, one, isz);
       std::memcpy(d.fill_bits, pat, 16);
     } else if (sy.src == Sym::Iota) {
-      if (!(st.dtype == ScalarType::Float || (st.dtype == ScalarType::Long && sy.epi.empty()))) return false;
+      if (!(tdx_dtype_of(st.dtype) >= 0 || (st.dtype == ScalarType::Long && sy.epi.empty()))) return false;
       d.src = TDX_SRC_IOTA;
-      d.dtype = st.dtype == ScalarType::Float ? TDX_F32 : TDX_I64;
+      d.dtype = st.dtype == ScalarType::Long ? TDX_I64 : static_cast<uint8_t>(tdx_dtype_of(st.dtype));
       d.p0 = sy.p0;
       d.p1 = sy.p1;
       d.n_epi = static_cast<uint8_t>(sy.epi.size());

@@ -269,7 +269,7 @@ class InitPlan:
                             fill_bits=int.from_bytes(base64.b64decode(g["const_bytes"]), "little"), fill_itemsize=isz))
                     elif g["source"] == "iota":  # arange and the index programs built on it (rotary inv_freq)
                         descs.append(_cabi.make_desc(
-                            dst, dtype=_cabi.TDX_F32 if dtype == torch.float32 else _cabi.TDX_I64,
+                            dst, dtype=_cabi.TDX_I64 if dtype == torch.int64 else _TDX_DTYPE[dtype],
                             src=_cabi.TDX_SRC_IOTA, elem_begin=lo - g["origin"], elem_count=hi - lo,
                             p0=g["p0"], p1=g["p1"], epi=g["epilogue"]))
                     else:
