@@ -115,7 +115,7 @@ def test_per_tensor_allocation_switch(tmp_path):
             "assert torch.cuda.memory_allocated() < before, 'freeing one tensor must release its memory'\n"
             "print('ok')\n" % ROOT)
     env = dict(os.environ, TDX_SLAB="0")
-    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=ROOT)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=ROOT, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
 
 
@@ -125,7 +125,7 @@ def padded_reference(tmp_path_factory):
     d = tmp_path_factory.mktemp("padref")
     path = str(d / "p.pt")
     subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_driver.py"), "--case", "padded_embeddings",
-                    "--dtype", "fp32", "--seed", "5", "--out", path], check=True, cwd=ROOT)
+                    "--dtype", "fp32", "--seed", "5", "--out", path], check=True, cwd=ROOT, timeout=300)
     return torch.load(path)
 
 

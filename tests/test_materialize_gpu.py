@@ -43,7 +43,7 @@ def reference(tmp_path_factory):
         d = tmp_path_factory.mktemp(f"ref{seed}")
         subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_driver.py"), "--cases",
                         ",".join(f"{c}:{t}" for c, t in CASES), "--seed", str(seed), "--outdir", str(d)],
-                       check=True, cwd=ROOT)
+                       check=True, cwd=ROOT, timeout=300)
         out[seed] = {(c, t): torch.load(d / f"{c}_{t}.pt") for c, t in CASES}
     return out
 

@@ -33,7 +33,7 @@ def reference_outputs(tmp_path_factory):
     outdir = tmp_path_factory.mktemp("ref")
     subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_driver.py"), "--cases",
                     ",".join(f"{c}:{d}" for c, d in CASES), "--seed", str(SEED), "--outdir", str(outdir)],
-                   check=True, cwd=ROOT)
+                   check=True, cwd=ROOT, timeout=300)
     return outdir
 
 

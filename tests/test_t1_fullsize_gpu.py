@@ -64,7 +64,7 @@ def run_reference(tmp, key):
            "--seed", str(SEED), "--stats", "--out", path]
     if round_to:
         cmd += ["--round-to", round_to]
-    subprocess.run(cmd, check=True, cwd=ROOT)
+    subprocess.run(cmd, check=True, cwd=ROOT, timeout=300)
     return torch.load(path)
 
 
