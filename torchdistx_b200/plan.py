@@ -87,6 +87,74 @@ class PlanEntry:
                      src_noround=self.src_noround, rng_pass=len(self.rng_numels) - 1)]
 
 
+def shard_range(e: "PlanEntry", shard: Optional[Tuple[int, int]]) -> Tuple[int, int, List[int]]:
+    """(first element, element count, sizes) of this rank's part of an entry: parameters are cut on
+    dim 0 like ``torch.chunk`` (ceil(d0 / world) rows per rank, trailing ranks may get none), buffers
+    are replicated -- the layout of ``materialize_module(shard=...)`` and of FSDP2's ``Shard(0)``."""
+    sizes = list(e.sizes)
+    numel = 1
+    for s in sizes:
+        numel *= s
+    if shard is None or shard[1] <= 1 or e.kind != "param" or not sizes:
+        return 0, numel, sizes
+    rank, world = shard
+    d0 = sizes[0]
+    inner = numel // d0 if d0 else 0
+    per = -(-d0 // world)
+    start = min(d0, rank * per)
+    rows = min(per, d0 - start)
+    return start * inner, rows * inner, [rows] + sizes[1:]
+
+
+def assign_pass_offsets(e: "PlanEntry", assigned: Dict[int, int], offset: int) -> Tuple[List[int], int]:
+    """Philox offsets of the entry's RNG passes, and the generator offset after them.  Every pass on
+    the chain takes its slice of the stream once per pass identity: a clone names its source's
+    passes again (same stream, nothing consumed)."""
+    ids = e.rng_ids if e.rng_ids else [None] * len(e.rng_numels)
+    pass_offset = []
+    for pid, n in zip(ids, e.rng_numels):
+        if pid is not None and pid in assigned:
+            pass_offset.append(assigned[pid])
+            continue
+        pass_offset.append(offset)
+        if pid is not None:
+            assigned[pid] = offset
+        offset += offset_increment(n)
+    return pass_offset, offset
+
+
+def entry_descriptors(e: "PlanEntry", base: int, begin: int, count: int, seed: int,
+                      pass_offset: List[int]) -> list:
+    """The C-ABI descriptors that write elements [begin, begin + count) of an entry into a buffer
+    whose first byte is at address `base` (plain data in, ``TdxInitDesc`` out: no device needed)."""
+    dtype = _DTYPES[e.dtype]
+    isz = torch.empty((), dtype=dtype).element_size()
+    descs = []
+    for g in e.segment_list():
+        lo, hi = max(g["begin"], begin), min(g["end"], begin + count)
+        if lo >= hi or g["source"] == "uninit":
+            continue
+        dst = base + (lo - begin) * isz
+        if g["source"] == "const":
+            descs.append(_cabi.make_desc(
+                dst, dtype=_RAW[isz], src=_cabi.TDX_SRC_CONST, elem_count=hi - lo,
+                fill_bits=int.from_bytes(base64.b64decode(g["const_bytes"]), "little"), fill_itemsize=isz))
+        elif g["source"] == "iota":  # arange and the index programs built on it (rotary inv_freq)
+            descs.append(_cabi.make_desc(
+                dst, dtype=_cabi.TDX_I64 if dtype == torch.int64 else _TDX_DTYPE[dtype],
+                src=_cabi.TDX_SRC_IOTA, elem_begin=lo - g["origin"], elem_count=hi - lo,
+                p0=g["p0"], p1=g["p1"], epi=g["epilogue"]))
+        else:
+            descs.append(_cabi.make_desc(
+                dst, dtype=_TDX_DTYPE[dtype],
+                src=_cabi.TDX_SRC_UNIFORM if g["source"] == "uniform" else _cabi.TDX_SRC_NORMAL,
+                elem_begin=lo - g["origin"], elem_count=hi - lo, seed=seed,
+                offset=pass_offset[g["rng_pass"]], p0=g["p0"], p1=g["p1"],
+                epi=g["epilogue"], algo=_cabi.TDX_ALGO_WIDE32 if g["wide"] else 0,
+                flags=_cabi.TDX_FLAG_SRC_NOROUND if g["src_noround"] else 0))
+    return descs
+
+
 class InitPlan:
     def __init__(self, entries: List[PlanEntry]):
         self.entries = entries
@@ -185,6 +253,24 @@ class InitPlan:
                 n += k
         return n
 
+    # ------------------------------------------------------------------------------ descriptors
+    def descriptors(self, seed: int, offset: int, shard: Optional[Tuple[int, int]] = None):
+        """The plan as the C ABI sees it, without a device: ``([(entry, sizes, descs)], offset after)``
+        for the tensors :meth:`materialize` would build from generator state ``(seed, offset)`` on
+        this rank.  ``descs`` address each tensor from byte 0 (``dst`` = byte offset inside it); value
+        and alias entries have none.  A host that is not Python rebuilds exactly this table from the
+        JSON file; tests evaluate it with the stream's CPU restatement."""
+        assigned: Dict[int, int] = {}
+        table = []
+        for e in self.entries:
+            if e.source in ("alias", "value"):
+                table.append((e, list(e.sizes), []))
+                continue
+            begin, count, sizes = shard_range(e, shard)
+            pass_offset, offset = assign_pass_offsets(e, assigned, offset)
+            table.append((e, sizes, entry_descriptors(e, 0, begin, count, seed, pass_offset)))
+        return table, offset
+
     # ------------------------------------------------------------------------------ materialise
     def materialize(self, device="cuda", shard: Optional[Tuple[int, int]] = None,
                     generator: Optional[torch.Generator] = None,
@@ -224,19 +310,7 @@ class InitPlan:
                         t = target
                     out[e.name] = t if target is not None else _wrap(t, e)
                     continue
-                sizes, begin = list(e.sizes), 0
-                numel = 1
-                for s in sizes:
-                    numel *= s
-                count = numel
-                if shard is not None and shard[1] > 1 and e.kind == "param" and sizes:
-                    rank, world = shard
-                    d0 = sizes[0]
-                    inner = numel // d0 if d0 else 0
-                    per = -(-d0 // world)
-                    start = min(d0, rank * per)
-                    rows = min(per, d0 - start)
-                    begin, count, sizes = start * inner, rows * inner, [rows] + sizes[1:]
+                begin, count, sizes = shard_range(e, shard)
                 if target is not None:
                     if not (target.is_cuda and target.is_contiguous() and target.dtype == dtype
                             and target.numel() >= count):
@@ -245,41 +319,8 @@ class InitPlan:
                     t = target
                 else:
                     t = torch.empty(sizes, dtype=dtype, device=device)
-                # every RNG pass on the chain takes its slice of the stream, once per pass identity (a
-                # clone names its source's passes again: same stream, nothing consumed)
-                ids = e.rng_ids if e.rng_ids else [None] * len(e.rng_numels)
-                pass_offset = []
-                for pid, n in zip(ids, e.rng_numels):
-                    if pid is not None and pid in assigned:
-                        pass_offset.append(assigned[pid])
-                        continue
-                    pass_offset.append(offset)
-                    if pid is not None:
-                        assigned[pid] = offset
-                    offset += offset_increment(n)
-                isz = t.element_size()
-                for g in e.segment_list():
-                    lo, hi = max(g["begin"], begin), min(g["end"], begin + count)
-                    if lo >= hi or g["source"] == "uninit":
-                        continue
-                    dst = t.data_ptr() + (lo - begin) * isz
-                    if g["source"] == "const":
-                        descs.append(_cabi.make_desc(
-                            dst, dtype=_RAW[isz], src=_cabi.TDX_SRC_CONST, elem_count=hi - lo,
-                            fill_bits=int.from_bytes(base64.b64decode(g["const_bytes"]), "little"), fill_itemsize=isz))
-                    elif g["source"] == "iota":  # arange and the index programs built on it (rotary inv_freq)
-                        descs.append(_cabi.make_desc(
-                            dst, dtype=_cabi.TDX_I64 if dtype == torch.int64 else _TDX_DTYPE[dtype],
-                            src=_cabi.TDX_SRC_IOTA, elem_begin=lo - g["origin"], elem_count=hi - lo,
-                            p0=g["p0"], p1=g["p1"], epi=g["epilogue"]))
-                    else:
-                        descs.append(_cabi.make_desc(
-                            dst, dtype=_TDX_DTYPE[dtype],
-                            src=_cabi.TDX_SRC_UNIFORM if g["source"] == "uniform" else _cabi.TDX_SRC_NORMAL,
-                            elem_begin=lo - g["origin"], elem_count=hi - lo, seed=seed,
-                            offset=pass_offset[g["rng_pass"]], p0=g["p0"], p1=g["p1"],
-                            epi=g["epilogue"], algo=_cabi.TDX_ALGO_WIDE32 if g["wide"] else 0,
-                            flags=_cabi.TDX_FLAG_SRC_NOROUND if g["src_noround"] else 0))
+                pass_offset, offset = assign_pass_offsets(e, assigned, offset)
+                descs += entry_descriptors(e, t.data_ptr(), begin, count, seed, pass_offset)
                 out[e.name] = t if target is not None else _wrap(t, e)
             if descs:
                 ws_bytes = _cabi.prepare(descs)  # exactly what this table needs (not the ~1.6 MB upper bound)
