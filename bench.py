@@ -154,7 +154,10 @@ def reference_sample(model: str, layers: int, reps: int):
     dtype = MODELS[model][2]
     code = REF_SNIPPET.format(root=ROOT, model=model, layers=layers, reps=reps, dtype=dtype,
                               vocab=SAMPLE_VOCAB.get(model))
-    out = subprocess.run([sys.executable, "-c", code], check=True, capture_output=True, text=True, cwd=ROOT)
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the reference arm gets every host core it can use
+    env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS")}
+    out = subprocess.run([sys.executable, "-c", code], check=True, capture_output=True, text=True, cwd=ROOT,
+                         env=env, timeout=1500)
     return json.loads(out.stdout.strip().splitlines()[-1])
 
 
