@@ -20,7 +20,7 @@ def build(verbose: bool = False) -> str:
     os.makedirs(build_dir, exist_ok=True)
     cpp_extension.load(
         name="_C",
-        sources=[os.path.join(SRC, f) for f in ("fake_tensor.cc", "tape.cc", "planner.cc", "bindings.cc")],
+        sources=[os.path.join(SRC, f) for f in ("fake_tensor.cc", "tape.cc", "planner.cc", "bindings.cc", "public_api.cc")],
         extra_include_paths=[os.path.join(ROOT, "include"), SRC, "/usr/local/cuda/include"],
         extra_cflags=["-O2", "-std=c++17", "-fvisibility=hidden"],
         extra_ldflags=[f"-L{PKG}", "-ltdx_init", '-Wl,-rpath,\'$$ORIGIN\'', f"-Wl,-rpath,{PKG}", "-lc10_cuda", "-Wl,--no-as-needed", "-ltorch_cuda", "-Wl,--as-needed"],
