@@ -222,7 +222,8 @@ def reference_on_gpu(model: str, index: int, reps: int = 3):
     """`oracle/_ref` (the reference's own engine) with the model recorded for cuda: one dispatcher
     call and one stock ATen kernel per recorded op, dead ops included (deferred_init.cc:218-220)."""
     code = GPU_REF_SNIPPET.format(root=ROOT, model=model, index=index, reps=reps)
-    out = subprocess.run([sys.executable, "-c", code], check=True, capture_output=True, text=True, cwd=ROOT)
+    out = subprocess.run([sys.executable, "-c", code], check=True, capture_output=True, text=True, cwd=ROOT,
+                         timeout=600)  # (a side measurement: a stuck child must not take the headline with it)
     return json.loads(out.stdout.strip().splitlines()[-1])
 
 

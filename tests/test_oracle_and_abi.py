@@ -23,6 +23,35 @@ def test_oracle_philox_matches_golden_vectors():
         assert O.philox4x32(v["ctr"], v["key"]) == v["out"], v
 
 
+def test_oracle_stream_matches_golden_vectors():
+    """The normative stream (uniform / normal in fp32, bf16, fp16, the fp32 stream rounded, epilogues,
+    index programs, fills) at three (seed, offset, first element) points each: the restatement may
+    only change together with tests/golden/stream_vectors.json (make_stream_vectors.py)."""
+    doc = json.load(open(os.path.join(ROOT, "tests", "golden", "stream_vectors.json")))
+    assert doc["abi_version"] == C.load().tdx_abi_version() and len(doc["vectors"]) >= 50
+    names = set()
+    for v in doc["vectors"]:
+        kw = dict(v["desc"])
+        kw["epi"] = [tuple(e) for e in kw.get("epi", [])]
+        d = C.make_desc(0, elem_count=v["elem_count"], elem_begin=v["elem_begin"], seed=v["seed"], offset=v["offset"], **kw)
+        assert O.generate(d).tobytes().hex() == v["out_hex"], (v["name"], v["seed"], v["offset"], v["elem_begin"])
+        names.add(v["name"])
+    assert {"uniform_f32", "normal_bf16", "normal_bf16_from_the_fp32_stream", "trunc_normal_bf16", "rotary_inv_freq_f32",
+            "rotary_inv_freq_bf16", "arange_i64", "fill_bool"} <= names
+    # and the vectors mean what their names say (decoded, against the parameters they were made with)
+    by = {(v["name"], v["elem_begin"]): v for v in doc["vectors"]}  # (0: the vector at seed 0, offset 0, first element 0)
+    u = np.frombuffer(bytes.fromhex(by[("uniform_f32", 0)]["out_hex"]), dtype=np.float32)
+    assert u.min() >= np.float32(-0.05) and u.max() < np.float32(0.03)
+    t = np.frombuffer(bytes.fromhex(by[("trunc_normal_f32", 0)]["out_hex"]), dtype=np.float32)
+    assert t.min() >= np.float32(-0.04) and t.max() <= np.float32(0.06)
+    a = np.frombuffer(bytes.fromhex(by[("arange_i64", 0)]["out_hex"]), dtype=np.int64)
+    assert a.tolist() == [5 + 3 * i for i in range(40)]
+    f = np.frombuffer(bytes.fromhex(by[("rotary_inv_freq_f32", 0)]["out_hex"]), dtype=np.float32)
+    exp = 1.0 / (500000.0 ** (np.arange(0, 80, 2, dtype=np.float64) / 128.0))
+    np.testing.assert_allclose(f, exp, rtol=4e-7)
+    assert np.frombuffer(bytes.fromhex(by[("fill_bf16_one", 0)]["out_hex"]), dtype=np.uint16).tolist() == [0x3F80] * 40
+
+
 def test_abi_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "tdx_init.h")).read()
     declared = set(re.findall(r"TDX_C_API\s+[\w\s\*]+?\b(tdx_\w+)\s*\(", header))
