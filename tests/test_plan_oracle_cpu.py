@@ -24,7 +24,7 @@ import torch
 from oracle import cases
 from oracle import tdx_oracle as O
 from torchdistx_b200.deferred_init import deferred_init
-from torchdistx_b200.plan import InitPlan, offset_increment
+from torchdistx_b200.plan import InitPlan, offset_increment, value_tensor
 
 SEED, OFFSET = 1234, 40
 
@@ -59,9 +59,8 @@ def evaluate(plan, shard=None, seed=SEED, offset=OFFSET):
             continue
         dtype = _DTYPES[e.dtype]
         if e.source == "value":
-            import base64
-            raw = torch.frombuffer(bytearray(base64.b64decode(e.value)), dtype=torch.uint8)
-            out[e.name] = raw.view(dtype).reshape(e.sizes)
+            out[e.name] = value_tensor(e, shard)
+            assert list(out[e.name].shape) == sizes
             continue
         numel = int(np.prod(sizes)) if sizes else 1
         isz = torch.empty((), dtype=dtype).element_size()
@@ -247,3 +246,31 @@ def test_seed_and_offset_select_the_stream():
     d, _ = evaluate(plan, offset=OFFSET + 4)
     w = next(e.name for e in plan.entries if e.source in ("uniform", "normal"))
     assert torch.equal(a[w], b[w]) and not torch.equal(a[w], c[w]) and not torch.equal(a[w], d[w])
+
+
+def test_a_parameter_stored_by_value_is_chunked_like_the_others():
+    """A deterministic program the planner cannot fold (`tril`) is embedded in the plan; as a
+    PARAMETER it is still this rank's rows only (what materialize_module(shard=...) does with a
+    replayed parameter), as a buffer it is replicated."""
+    from torch import nn
+
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.p = nn.Parameter(torch.tril(torch.ones(7, 4)) * 0.5)
+            self.register_buffer("b", torch.tril(torch.ones(5, 5)))
+            self.w = nn.Parameter(torch.empty(7, 3).normal_())
+
+    plan = InitPlan.from_module(deferred_init(M))
+    kinds = {e.name: e.source for e in plan.entries}
+    assert kinds["p"] == "value" and kinds["b"] == "value" and kinds["w"] == "normal", kinds
+    full, end = evaluate(plan)
+    assert torch.equal(full["p"], torch.tril(torch.ones(7, 4)) * 0.5)
+    for world in (2, 3, 8):
+        parts = [evaluate(plan, shard=(r, world)) for r in range(world)]
+        assert all(e == end for _, e in parts)
+        for name in ("p", "w"):
+            assert torch.equal(torch.cat([p[name] for p, _ in parts]), full[name]), (name, world)
+            assert [p[name].shape[0] for p, _ in parts] == [c.shape[0] for c in torch.chunk(full[name], world, 0)] + \
+                [0] * (world - len(torch.chunk(full[name], world, 0))), (name, world)
+        assert all(torch.equal(p["b"], full["b"]) for p, _ in parts)

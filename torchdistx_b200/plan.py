@@ -106,6 +106,17 @@ def shard_range(e: "PlanEntry", shard: Optional[Tuple[int, int]]) -> Tuple[int, 
     return start * inner, rows * inner, [rows] + sizes[1:]
 
 
+def value_tensor(e: "PlanEntry", shard: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+    """A by-value entry as a CPU tensor: whole, or this rank's dim-0 chunk of a parameter (what
+    ``materialize_module(shard=...)`` does with a replayed parameter: narrow + clone)."""
+    raw = torch.frombuffer(bytearray(base64.b64decode(e.value)), dtype=torch.uint8)
+    t = raw.view(_DTYPES[e.dtype]).reshape(e.sizes)
+    begin, count, sizes = shard_range(e, shard)
+    if count != t.numel():
+        t = t.reshape(-1)[begin: begin + count].reshape(sizes)
+    return t
+
+
 def assign_pass_offsets(e: "PlanEntry", assigned: Dict[int, int], offset: int) -> Tuple[List[int], int]:
     """Philox offsets of the entry's RNG passes, and the generator offset after them.  Every pass on
     the chain takes its slice of the stream once per pass identity: a clone names its source's
@@ -263,8 +274,8 @@ class InitPlan:
         assigned: Dict[int, int] = {}
         table = []
         for e in self.entries:
-            if e.source in ("alias", "value"):
-                table.append((e, list(e.sizes), []))
+            if e.source in ("alias", "value"):  # (a by-value parameter is chunked like any other: value_tensor)
+                table.append((e, shard_range(e, shard)[2] if e.source == "value" else list(e.sizes), []))
                 continue
             begin, count, sizes = shard_range(e, shard)
             pass_offset, offset = assign_pass_offsets(e, assigned, offset)
@@ -303,8 +314,7 @@ class InitPlan:
                 dtype = _DTYPES[e.dtype]
                 target = None if into is None else into.get(e.name)
                 if e.source == "value":
-                    raw = torch.frombuffer(bytearray(base64.b64decode(e.value)), dtype=torch.uint8)
-                    t = raw.view(dtype).reshape(e.sizes).to(device)
+                    t = value_tensor(e, shard).to(device)
                     if target is not None:
                         target.copy_(t)
                         t = target
