@@ -79,19 +79,25 @@ def evaluate(plan, shard=None, seed=SEED, offset=OFFSET):
     return out, end
 
 
-def check_t1(name, x, ref, sixteen_bit):
+def check_t1(name, x, ref, sixteen_bit, moments=True, scale=1.0, alpha=1e-3):
     from scipy import stats
 
     xd, rd = x.double().flatten(), ref.double().flatten()
     n = xd.numel()
     assert bool(torch.isfinite(xd).all()), name
     r_mean, r_std = rd.mean().item(), rd.std().item()
-    assert abs(xd.mean().item() - r_mean) <= 5 * r_std / math.sqrt(n), (name, xd.mean().item(), r_mean, r_std, n)
-    slack = 2.0 ** -8 if sixteen_bit else 0.0
-    assert abs(xd.std().item() / r_std - 1) <= 5 / math.sqrt(2 * n) + slack, (name, xd.std().item(), r_std, n)
+    if r_std == 0.0:  # (a program that clamps -- almost -- everything to one value)
+        assert (xd == rd[0]).double().mean().item() >= 0.99, name
+        return
+    if n < 64:  # (a few elements: the reference sample's own moments are too noisy to be a yardstick)
+        return
+    if moments:  # (the bounds assume a sample whose variance estimate is not ruled by a few tail events)
+        assert abs(xd.mean().item() - r_mean) <= scale * 5 * r_std / math.sqrt(n), (name, xd.mean().item(), r_mean, r_std, n)
+        slack = 2.0 ** -8 if sixteen_bit else 0.0
+        assert abs(xd.std().item() / r_std - 1) <= scale * 5 / math.sqrt(2 * n) + slack, (name, xd.std().item(), r_std, n)
     if n >= 1024:
         ks = stats.ks_2samp(xd.numpy(), rd.numpy())
-        assert ks.pvalue > 1e-3, (name, ks)
+        assert ks.pvalue > alpha, (name, ks)
 
 
 def eager(case, dtype, post=None):
@@ -106,7 +112,7 @@ def eager(case, dtype, post=None):
     return named(a), named(b)
 
 
-def compare_with_eager(plan, got, own, wide, skip=()):
+def compare_with_eager(plan, got, own, wide, skip=(), clamps_by_ks_only=False, scale=1.0, alpha=1e-3):
     n_rng = n_const = n_iota = 0
     for e in plan.entries:
         if e.source == "alias":  # tied parameters stay one tensor
@@ -142,7 +148,10 @@ def compare_with_eager(plan, got, own, wide, skip=()):
                 # `uniform_ -> erfinv_ -> mul_ -> add_ -> clamp_` rounds to the dtype, near 1.0 in steps
                 # of 2^-8, and the epilogue restates exactly that (TDX_EPI_NOROUND is the opt-out)
                 ref = wflat[lo:hi].to(x.dtype) if sixteen and g["source"] == "normal" else rs
-                check_t1(f"{e.name}[{lo}:{hi}]", xs, ref, sixteen)
+                # (a clamp that keeps a far tail -- randn().clamp_(2, 3) -- leaves a mixture whose moments
+                # are decided by a handful of elements: the distribution test alone judges those)
+                clamped = clamps_by_ks_only and any(step[0] == 4 for step in g["epilogue"])  # TDX_EPI_CLAMP
+                check_t1(f"{e.name}[{lo}:{hi}]", xs, ref, sixteen, moments=not clamped, scale=scale, alpha=alpha)
                 if g["source"] == "uniform" and not g["epilogue"]:  # hard range: uniform in [from, to)
                     lim = lambda v: torch.tensor(v, dtype=x.dtype).item()  # (uniform_ rounds its bounds to the dtype)
                     assert xs.min().item() >= lim(g["p0"]) and xs.max().item() <= lim(g["p1"]), (e.name, g["p0"], g["p1"])

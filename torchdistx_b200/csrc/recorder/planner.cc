@@ -286,6 +286,14 @@ bool fold_const(const TapeOp& op, Sym& st, ScalarType& dtype, bool inplace) {
   ensure_cval(st, dtype);
   st.has_scalar = false;
   if (!op.handle || !st.cval.defined()) return false;
+  if (inplace) {
+    // Segments are split by copying (`w[i].zero_()` makes three of one): their constants are handles
+    // to ONE 1-element tensor until somebody writes.  An in-place op replayed on a shared constant
+    // would reach every segment that holds it (`full(c); w[i].zero_(); w.add_(1)` added 1 twice to
+    // the two outer segments; `w[a:b].mul_(2)` doubled the whole tensor): write to a private copy.
+    NoInterception guard;
+    st.cval = st.cval.clone();
+  }
   Stack stack;
   size_t slot = 0;
   bool ok = true, first_tensor = true;

@@ -267,7 +267,12 @@ void append(std::optional<OperatorHandle> handle, OpKind kind, Stack frame, size
   // argument is a view.  If it re-describes exactly the argument's elements (view / reshape /
   // flatten / unsqueeze of a contiguous tensor) it is a plain alias; otherwise (select / narrow /
   // slice / a[i] / t() ...) it names part of the storage -- nothing is read or written either way.
-  if (kind == OpKind::Generic && op->outputs.size() == 1 && op->outputs[0] != kNoValue &&
+  // The same goes for a conversion that had nothing to convert: `x.to(dtype)` / `x.float()` /
+  // `Module.to(device)` on a tensor that already is what was asked for returns `x` itself (the
+  // CompositeImplicit `aten::to.*` is recorded whole, as the reference does) -- without this, every
+  // tensor of `Model().float()` or `Model().to(device)` looked like a cast onto its own storage and
+  // fell off the fused path.
+  if ((kind == OpKind::Generic || kind == OpKind::CastOut) && op->outputs.size() == 1 && op->outputs[0] != kNoValue &&
       !op->inputs.empty() && op->inputs[0].value != kNoValue) {
     const ValueInfo& out = tape.values[op->outputs[0]];
     const ValueInfo& in = tape.values[op->inputs[0].value];

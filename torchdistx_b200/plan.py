@@ -218,7 +218,15 @@ class InitPlan:
                                 f"(first unfusable op: {info['first_unfusable_op'] or 'n/a'}); a plan cannot embed it")
                         devs = [torch.device(info["device"])] if info["device"].startswith("cuda") and torch.cuda.is_available() else []
                         with torch.random.fork_rng(devices=devs):
+                            before = [torch.get_rng_state()] + [torch.cuda.get_rng_state(d) for d in devs]
                             real = materialize_tensor(t)
+                            after = [torch.get_rng_state()] + [torch.cuda.get_rng_state(d) for d in devs]
+                        # (the names above only see this tensor's own storage: `randn(n).sub_(c) * 2 + 3` draws
+                        # its numbers in a dependency.  A generator that moved says so whatever the program is.)
+                        if any(not torch.equal(a, b) for a, b in zip(before, after)):
+                            raise ValueError(
+                                f"'{name}' has a random initialisation program the planner cannot fold "
+                                f"(first unfusable op: {info['first_unfusable_op'] or 'n/a'}); a plan cannot embed it")
                     else:
                         real = t
                     nbytes = real.numel() * real.element_size()
