@@ -1407,7 +1407,15 @@ struct Engine {
     for (size_t k = 0; k < tape.ops[oi].inputs.size(); ++k) {
       const uint32_t v = tape.ops[oi].inputs[k].value;
       if (v == kNoValue) continue;
-      if (tape.values[v].real.defined()) continue;
+      if (tape.values[v].real.defined()) {
+        // Built already -- by the op that produced it.  In-place writers recorded on its storage after
+        // that op and before this reader may still be waiting: `b = a.clone(); b[2:5].normal_();
+        // c = b * 2` with `a` materialised first replays the clone as part of a's history (it reads
+        // a), and `b * 2` then found b "real" and never ran the normal_.  Collect what is left of
+        // the storage's history up to this op (ops that ran are skipped: TapeOp::done).
+        collect_storage(tape, tape.values[v].storage, oi, mark, visited_upto);
+        continue;
+      }
       // A dependency whose whole program folds is built by the kernels (unsharded: the op reads all
       // of it), not replayed op by op: faster, and its values do not depend on whether it or its
       // reader was asked for first.  (A storage the reader saw in an intermediate state is opaque
