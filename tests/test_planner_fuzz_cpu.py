@@ -227,7 +227,7 @@ def test_the_bugs_the_fuzzer_found_stay_fixed():
 
     # (c) a random draw in a DEPENDENCY of an unfusable program is still a random program: not embedded
     def hidden():
-        return nn.ParameterList([nn.Parameter(torch.randn(8, 8).sub_(0.02) * 2.0 + 3.0)])
+        return nn.ParameterList([nn.Parameter(torch.sin(torch.randn(8, 8)) * 2.0 + 3.0)])  # (sin: not a foldable step)
 
     assert not plan_report(deferred_init(hidden))["0"]["fusible"]
     s0 = torch.get_rng_state()

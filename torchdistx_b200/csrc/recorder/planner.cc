@@ -527,7 +527,8 @@ void transition(Tape& tape, uint32_t op_idx, uint32_t S, State& st) {
   const bool inplace = op.kind == OpKind::UniformInplace || op.kind == OpKind::NormalInplace ||
                        op.kind == OpKind::FillInplace || op.kind == OpKind::ZeroInplace ||
                        op.kind == OpKind::MulInplace || op.kind == OpKind::AddInplace ||
-                       op.kind == OpKind::ErfinvInplace || op.kind == OpKind::ClampInplace;
+                       op.kind == OpKind::ErfinvInplace || op.kind == OpKind::ClampInplace ||
+                       op.kind == OpKind::SubInplace || op.kind == OpKind::NegInplace || op.kind == OpKind::DivInplace;
   if (inplace) {
     int64_t b = 0, e = 0;
     if (st.opaque || out.dtype != st.dtype || !range_of(out, b, e) || st.segs.empty() ||
@@ -602,6 +603,17 @@ void transition(Tape& tape, uint32_t op_idx, uint32_t S, State& st) {
       } else if (op.kind == OpKind::AddInplace) {
         const auto c = scalar_arg(op, 1), alpha = scalar_arg(op, 2);
         ok = c && alpha && push_epi(sy, TDX_EPI_ADD, *c * *alpha);
+      } else if (op.kind == OpKind::SubInplace) {
+        // x - alpha * c is computed by ATen as x + (-alpha) * c (sub is add with the sign of alpha flipped)
+        const auto c = scalar_arg(op, 1), alpha = scalar_arg(op, 2);
+        ok = c && alpha && push_epi(sy, TDX_EPI_ADD, -(*c * *alpha));
+      } else if (op.kind == OpKind::NegInplace) {
+        ok = push_epi(sy, TDX_EPI_MUL, -1.0);
+      } else if (op.kind == OpKind::DivInplace) {
+        // fp32 only, like DivOut below: ATen's CUDA kernel multiplies by the fp32 reciprocal of the divisor
+        const auto c = scalar_arg(op, 1);
+        ok = c && st.dtype == ScalarType::Float && *c != 0.0 &&
+             push_epi(sy, TDX_EPI_MUL, static_cast<double>(1.0f / static_cast<float>(*c)));
       } else if (op.kind == OpKind::ErfinvInplace) {
         ok = push_epi(sy, TDX_EPI_ERFINV, 0);
       } else {  // clamp_(min, max), either may be None
@@ -619,7 +631,7 @@ void transition(Tape& tape, uint32_t op_idx, uint32_t S, State& st) {
   // ---- out-of-place unary ops: a new storage whose state derives from the argument's -------------
   if (op.kind == OpKind::MulOut || op.kind == OpKind::AddOut || op.kind == OpKind::CloneOut ||
       op.kind == OpKind::CastOut || op.kind == OpKind::DivOut || op.kind == OpKind::PowScalarOut ||
-      op.kind == OpKind::ReciprocalOut) {
+      op.kind == OpKind::ReciprocalOut || op.kind == OpKind::SubOut || op.kind == OpKind::NegOut) {
     if (op.inputs.empty() || op.inputs[0].value == kNoValue || !out.covers_storage) { st = make_opaque(); return; }
     const ValueInfo& in = tape.values[op.inputs[0].value];
     int64_t b = 0, e = 0;
@@ -768,9 +780,16 @@ void transition(Tape& tape, uint32_t op_idx, uint32_t S, State& st) {
       if (op.kind == OpKind::MulOut) {
         const auto c = scalar_arg(op, 1);
         ok = c && push_epi(sy, TDX_EPI_MUL, *c);
-      } else {
+      } else if (op.kind == OpKind::NegOut) {
+        ok = push_epi(sy, TDX_EPI_MUL, -1.0);
+      } else if (op.kind == OpKind::SubOut) {
+        const auto c = scalar_arg(op, 1), alpha = scalar_arg(op, 2);
+        ok = c && alpha && push_epi(sy, TDX_EPI_ADD, -(*c * *alpha));
+      } else if (op.kind == OpKind::AddOut) {
         const auto c = scalar_arg(op, 1), alpha = scalar_arg(op, 2);
         ok = c && alpha && push_epi(sy, TDX_EPI_ADD, *c * *alpha);
+      } else {
+        ok = false;  // (every kind admitted above is handled before this point)
       }
       if (!ok) { st = make_opaque(); return; }
     }

@@ -50,6 +50,11 @@ OpKind kind_from_name(const std::string& name, const std::string& overload) {
   if (n == "zero_") return OpKind::ZeroInplace;
   if (n == "mul_") return OpKind::MulInplace;
   if (n == "add_") return OpKind::AddInplace;
+  if (n == "sub_" && (overload == "Tensor" || overload == "Scalar")) return OpKind::SubInplace;
+  if (n == "neg_") return OpKind::NegInplace;
+  if (n == "div_" && (overload == "Tensor" || overload == "Scalar")) return OpKind::DivInplace;  // (no rounding_mode)
+  if (n == "sub" && (overload == "Tensor" || overload == "Scalar")) return OpKind::SubOut;
+  if (n == "neg") return OpKind::NegOut;
   if (n == "erfinv_") return OpKind::ErfinvInplace;
   if (n == "clamp_" && overload.empty()) return OpKind::ClampInplace;
   if (n == "mul" && (overload == "Tensor" || overload == "Scalar")) return OpKind::MulOut;

@@ -56,6 +56,8 @@ enum class OpKind : uint8_t {
   CopyInplace,
   // autograd hook pseudo-ops
   HookVariableData, HookSetData,
+  // more affine maps by a number: x - c, -x, x / c (folded as + (-c), * (-1), * (1 / c))
+  SubInplace, NegInplace, DivInplace, SubOut, NegOut,
 };
 
 struct Tape;
