@@ -199,6 +199,22 @@ def test_nested_deferred_init_and_cross_scope_inputs():
     assert torch.equal(out, w.detach() * 2.0)
 
 
+def test_cross_scope_input_without_random_draws_is_built_on_demand():
+    """A tensor of a LATER deferred_init that reads one of an EARLIER one, materialised first: the
+    earlier tensor is built on the spot as its argument -- also when its program draws no random
+    numbers (such programs are otherwise replayed at the end of a call; as an argument that handed
+    back nothing: "Expected a proper Tensor but got None")."""
+    for src_fn in (lambda: torch.full((4, 3), 2.0), lambda: Parameter(torch.ones(4, 3) * 2.0),
+                   lambda: torch.tril(torch.ones(4, 3)) * 2.0):
+        for reader in (lambda a: a * 2.0 + 1.0, lambda a: a.clone(), lambda a: a.detach().clone().mul_(3.0),
+                       lambda a: torch.zeros(4, 3).copy_(a)):
+            a = deferred_init(src_fn)
+            b = deferred_init(lambda: Parameter(reader(a.detach())))
+            out = materialize_tensor(b)  # (a is still fake here)
+            assert torch.equal(out.detach(), reader(src_fn().detach()))
+            assert torch.equal(materialize_tensor(a).detach(), src_fn().detach())
+
+
 def test_materialize_module_error_leaves_the_module_untouched_and_does_not_hang():
     """materialize_module plans on a helper thread; a failure there must surface as the same
     exception on the calling thread, with no tensor assigned and the next call working."""

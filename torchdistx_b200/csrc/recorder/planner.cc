@@ -1476,6 +1476,16 @@ struct Engine {
         if (isi.fused_done && isi.fused_epoch == batch.epoch) batch.flush();
       } else if (in.foreign) {
         // (recorded by an earlier deferred_init: same rule -- its descriptor may still be in the batch)
+        // It is needed NOW, as an argument: the session's "replay RNG-free programs after the last
+        // submission" rule is for tensors the caller asked for, and would hand back nothing here
+        // (`b = deferred_init(lambda: a * 2 + 1)` with `a = deferred_init(torch.ones, ...)` raised
+        // "Expected a proper Tensor but got None" unless `a` had been materialised first).
+        struct NoDeferral {
+          bool& flag;
+          const bool saved;
+          explicit NoDeferral(bool& f) : flag(f), saved(f) { flag = false; }
+          ~NoDeferral() { flag = saved; }
+        } now(defer_generic);
         t = materialize_value(in.foreign, in.foreign_value);
         const StorageInfo& fsi = in.foreign->storages[in.foreign->values[in.foreign_value].storage];
         if (fsi.fused_done && fsi.fused_epoch == batch.epoch) batch.flush();
