@@ -234,6 +234,56 @@ class LinkedHolder(nn.Module):
 
 
 
+# ---- the Parameter / `.data` / nn.init / Module.to idioms of model code (HF `_init_weights`) ----------
+DATA_STEPS = ["data_normal", "data_uniform", "data_zero_row", "data_fill", "data_assign_affine", "data_assign_clone", "data_copy_const",
+              "nograd_mul", "nograd_row_fill", "data_mul", "data_slice_normal", "requires_grad_false", "data_to16", "data_float",
+              "module_to16", "module_float", "module_to_cpu", "data_clamp", "init_trunc", "init_kaiming", "init_zeros", "init_constant", "init_normal", "init_xavier_u"]
+
+class Cell(nn.Module):
+    def __init__(self, prog, dsteps):
+        super().__init__()
+        self.p = nn.Parameter(run_program(prog))
+        rows, cols = self.p.shape
+        for (k, a, b, c, d) in dsteps:
+            a = min(a, rows - 1); b = max(a + 1, min(b, rows))
+            p = self.p
+            if k == "data_normal": p.data.normal_(d, abs(c))
+            elif k == "data_uniform": p.data.uniform_(-abs(c), abs(c))
+            elif k == "data_zero_row": p.data[a].zero_()
+            elif k == "data_fill": p.data.fill_(c)
+            elif k == "data_assign_affine": p.data = p.data * c + d
+            elif k == "data_assign_clone": p.data = p.data.clone()
+            elif k == "data_copy_const": p.data.copy_(torch.full(tuple(p.shape), c, dtype=p.dtype))
+            elif k == "nograd_mul":
+                with torch.no_grad(): p.mul_(c)
+            elif k == "nograd_row_fill":
+                with torch.no_grad(): p[a:b].fill_(d)
+            elif k == "data_mul": p.data.mul_(c)
+            elif k == "data_slice_normal": p.data[a:b].normal_(0.0, abs(c))
+            elif k == "requires_grad_false": p.requires_grad_(False)
+            elif k == "data_to16": p.data = p.data.to(torch.bfloat16)
+            elif k == "data_float": p.data = p.data.float()
+            elif k == "module_to16": self.to(torch.bfloat16)
+            elif k == "module_float": self.float()
+            elif k == "module_to_cpu": self.to("cpu")
+            elif k == "data_clamp": p.data.clamp_(min(c, d), max(c, d))
+            elif k == "init_trunc": nn.init.trunc_normal_(p, std=abs(c), a=-2 * abs(c), b=2 * abs(c))
+            elif k == "init_kaiming": nn.init.kaiming_uniform_(p, a=5 ** 0.5)
+            elif k == "init_zeros": nn.init.zeros_(p)
+            elif k == "init_constant": nn.init.constant_(p, c)
+            elif k == "init_normal": nn.init.normal_(p, d, abs(c))
+            elif k == "init_xavier_u": nn.init.xavier_uniform_(p)
+
+def gen_cell(r):
+    prog = gen_program(r)
+    rows = prog[0][2]
+    ds = []
+    for _ in range(r.randint(1, 5)):
+        a, b = sorted([r.randint(0, rows), r.randint(0, rows)])
+        ds.append((r.choice(DATA_STEPS), a, b, r.choice(CONSTS), r.choice(CONSTS)))
+    return prog, ds
+
+
 def differential_script(seed):
     """The script both sides of a differential run (this engine / the compiled reference) build for
     `seed`: linked tensors, view and copy steps sprinkled in, random draws included."""

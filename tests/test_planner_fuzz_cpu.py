@@ -27,8 +27,8 @@ import test_plan_oracle_cpu as T
 from torchdistx_b200.deferred_init import deferred_init, plan_report
 from torchdistx_b200.plan import InitPlan
 
-from oracle.fuzz_programs import (COLS, CONSTS, ROWS, VIEW_STEPS, Holder, LinkedHolder, apply_step,  # noqa: F401
-                                  gen_linked, gen_program, gen_view_program, run_linked, run_program)
+from oracle.fuzz_programs import (COLS, CONSTS, ROWS, VIEW_STEPS, Cell, Holder, LinkedHolder, apply_step,  # noqa: F401
+                                  gen_cell, gen_linked, gen_program, gen_view_program, run_linked, run_program)
 
 
 def run_seed(seed):
@@ -178,6 +178,94 @@ def test_replay_engine_in_any_materialisation_order():
             x, y = got[n], getattr(eager, n).detach()
             assert x.dtype == y.dtype and torch.equal(torch.nan_to_num(x.float()), torch.nan_to_num(y.float())) and \
                 torch.equal(torch.isnan(x), torch.isnan(y)), (seed, n, order)
+
+
+def test_parameter_data_and_module_idioms():
+    """What model code does to a tensor once it is a Parameter: `p.data.normal_()`, `p.data[i].zero_()`,
+    `p.data = p.data * c + d`, `with torch.no_grad(): p.mul_(c)`, `nn.init.*_(p)`, `requires_grad_(False)`,
+    `module.to(dtype)` / `.float()` / `.to(device)` (real and no-op) -- HF `_init_weights` in short."""
+    fused = 0
+    for seed in range(500):
+        r = random.Random(70_000 + seed)
+        prog, steps = gen_cell(r)
+        try:
+            plan = InitPlan.from_module(deferred_init(Cell, prog, steps))
+        except ValueError as e:
+            assert "random initialisation program the planner cannot fold" in str(e)
+            continue
+        got, _ = T.evaluate(plan)
+        torch.manual_seed(seed)
+        own = T.named(Cell(prog, steps))
+        assert plan.entries[0].requires_grad == own["p"].requires_grad, seed
+        try:
+            T.compare_with_eager(plan, got, own, own, clamps_by_ks_only=True, scale=1.5, alpha=1e-6)
+        except AssertionError as e:
+            raise AssertionError(f"seed {seed}: {e}") from e
+        fused += plan.entries[0].source != "value"
+    assert fused >= 400, fused
+
+
+class _Source(nn.Module):
+    def __init__(self, prog):
+        super().__init__()
+        self.t = nn.Parameter(run_program(prog))
+
+
+class _Reader(nn.Module):
+    def __init__(self, src, kind, c, d, tail):
+        super().__init__()
+        s = src.detach()
+        t = [lambda: s.clone(), lambda: s * c + d, lambda: torch.zeros_like(s).copy_(s), lambda: torch.cat([s[:5], s[5:]]) * 1.0][kind]()
+        for st in tail:
+            t = apply_step(t, st)
+        self.u = nn.Parameter(t)
+
+
+def test_tensors_that_read_an_earlier_recording():
+    """`b = deferred_init(lambda: f(a))` with `a` from an EARLIER deferred_init, materialised in any
+    order (a first; b first: a is then built on the spot as b's argument; b's tensor alone, then
+    both modules): bit for bit the eager values, whatever a's program is."""
+    from torchdistx_b200.deferred_init import materialize_module, materialize_tensor
+
+    def deterministic(p):
+        q = []
+        for st in p:
+            if st[0] == "ctor":
+                st = ("ctor", "full" if st[1] in ("randn", "rand", "empty") else st[1], ROWS, COLS, st[4])
+            elif st[0] == "init":
+                st = ("init", "fill") + st[2:]
+            elif st[0] in DETERMINISTIC:
+                st = (DETERMINISTIC[st[0]],) + st[1:]
+            if st[0] not in ("ctor", "init"):
+                b = min(max(st[2], 1), ROWS)
+                st = (st[0], min(st[1], b - 1), b) + st[3:5] + ((min(st[5], COLS - 1),) if isinstance(st[5], int) else (st[5],))
+            q.append(st)
+        return q
+
+    for seed in range(400):
+        r = random.Random(60_000 + seed)
+        p1 = deterministic(gen_view_program(r) if r.random() < 0.5 else gen_program(r))
+        tail = [st for st in deterministic(gen_program(r)) if st[0] not in ("ctor", "init")]
+        kind, c, d = r.randrange(4), r.choice(CONSTS), r.choice(CONSTS)
+        m1 = deferred_init(_Source, p1)
+        m2 = deferred_init(_Reader, m1.t, kind, c, d, tail)
+        order = r.choice(["source first", "reader first", "reader's tensor, then both"])
+        if order == "source first":
+            materialize_module(m1)
+            materialize_module(m2)
+        elif order == "reader first":
+            materialize_module(m2)
+            materialize_module(m1)
+        else:
+            u = materialize_tensor(m2.u)
+            materialize_module(m1)
+            materialize_module(m2)
+            assert m2.u is u, seed
+        e1 = _Source(p1)
+        e2 = _Reader(e1.t, kind, c, d, tail)
+        for mine, want in ((m1.t, e1.t), (m2.u, e2.u)):
+            a, b = mine.detach(), want.detach()
+            assert a.dtype == b.dtype and torch.equal(torch.nan_to_num(a.float()), torch.nan_to_num(b.float())), (seed, order, kind)
 
 
 def test_the_bugs_the_fuzzer_found_stay_fixed():
