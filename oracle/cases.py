@@ -175,6 +175,39 @@ def padded_embeddings():
     return PaddedEmbeddings()
 
 
+# ---- real constructors at toy sizes (HF `_init_weights`, torch.nn defaults) --------------------------
+def families():
+    import transformers as TF
+    from torch import nn
+
+    small = dict(vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=1, num_attention_heads=4,
+                 num_key_value_heads=2)
+    return {
+        "llama": lambda: TF.LlamaForCausalLM(TF.LlamaConfig(**{**small, "num_hidden_layers": 2})),
+        "mistral": lambda: TF.MistralForCausalLM(TF.MistralConfig(**small)),
+        "qwen2": lambda: TF.Qwen2ForCausalLM(TF.Qwen2Config(**small)),
+        "mixtral": lambda: TF.MixtralForCausalLM(TF.MixtralConfig(**small, num_local_experts=2)),
+        "gemma2": lambda: TF.Gemma2ForCausalLM(TF.Gemma2Config(**small, head_dim=16)),
+        "phi3": lambda: TF.Phi3ForCausalLM(TF.Phi3Config(**small, pad_token_id=0)),
+        "gpt2": lambda: TF.GPT2LMHeadModel(TF.GPT2Config(vocab_size=512, n_embd=64, n_layer=2, n_head=4, n_positions=64)),
+        "opt": lambda: TF.OPTForCausalLM(TF.OPTConfig(vocab_size=512, hidden_size=64, ffn_dim=128, num_hidden_layers=1,
+                                                      num_attention_heads=4, word_embed_proj_dim=64, max_position_embeddings=64)),
+        "bert": lambda: TF.BertModel(TF.BertConfig(vocab_size=512, hidden_size=64, num_hidden_layers=1, num_attention_heads=4,
+                                                   intermediate_size=128)),
+        "t5": lambda: TF.T5Model(TF.T5Config(d_model=64, d_ff=128, num_layers=1, num_heads=4, vocab_size=512)),
+        "vit": lambda: TF.ViTModel(TF.ViTConfig(hidden_size=64, num_hidden_layers=1, num_attention_heads=4, intermediate_size=128,
+                                                image_size=32, patch_size=8)),
+        "lstm": lambda: nn.LSTM(32, 64, num_layers=2),
+        "conv_bn": lambda: nn.Sequential(nn.Conv2d(3, 16, 3), nn.BatchNorm2d(16), nn.Linear(10, 10)),
+        "mha": lambda: nn.MultiheadAttention(32, 4),
+        "transformer": lambda: nn.Transformer(d_model=32, nhead=4, num_encoder_layers=1, num_decoder_layers=1, dim_feedforward=64),
+    }
+
+
+FAMILIES = ["llama", "mistral", "qwen2", "mixtral", "gemma2", "phi3", "gpt2", "opt", "bert", "t5", "vit", "lstm", "conv_bn", "mha",
+            "transformer"]
+
+
 CASES = {
     "linear128": linear128,
     "llama8b_layer": llama8b_layer,
@@ -194,11 +227,14 @@ DTYPES = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}
 
 
 def build(name: str, dtype: str = "fp32", device: str = "cpu"):
-    """Builds the case with `dtype` as default dtype and `device` as default device."""
+    """Builds the case with `dtype` as default dtype and `device` as default device
+    (`family_<name>`: one of `families()`)."""
     prev = torch.get_default_dtype()
     torch.set_default_dtype(DTYPES[dtype])
     try:
         with torch.device(device):
+            if name.startswith("family_"):
+                return families()[name[len("family_"):]]()
             return CASES[name]()
     finally:
         torch.set_default_dtype(prev)

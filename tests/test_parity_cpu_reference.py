@@ -23,7 +23,9 @@ CASES = [
     ("linear128", "fp32"), ("init_zoo", "fp32"), ("init_zoo", "bf16"), ("mlp_stack", "fp32"),
     ("tiny_llama", "fp32"), ("tiny_llama", "bf16"), ("tiny_gpt2", "fp32"),
     ("torch_transformer", "fp32"), ("clones", "fp32"), ("cast_variant", "fp32"),
-]
+] + [(f"family_{name}", "fp32") for name in cases.FAMILIES] + [("family_llama", "bf16"), ("family_gpt2", "bf16")]
+# (families: real HF / torch.nn constructors at toy sizes -- Llama, Mistral, Qwen2, Mixtral, Gemma-2, Phi-3,
+#  GPT-2, OPT, BERT, T5, ViT, LSTM, Conv+BatchNorm, MultiheadAttention, nn.Transformer)
 SEED = 5
 
 

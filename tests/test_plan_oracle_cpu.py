@@ -285,42 +285,13 @@ def test_a_parameter_stored_by_value_is_chunked_like_the_others():
         assert all(torch.equal(p["b"], full["b"]) for p, _ in parts)
 
 
-def _families():
-    import transformers as TF
-    from torch import nn
-
-    small = dict(vocab_size=512, hidden_size=64, intermediate_size=128, num_hidden_layers=1, num_attention_heads=4,
-                 num_key_value_heads=2)
-    return {
-        "llama": lambda: TF.LlamaForCausalLM(TF.LlamaConfig(**{**small, "num_hidden_layers": 2})),
-        "mistral": lambda: TF.MistralForCausalLM(TF.MistralConfig(**small)),
-        "qwen2": lambda: TF.Qwen2ForCausalLM(TF.Qwen2Config(**small)),
-        "mixtral": lambda: TF.MixtralForCausalLM(TF.MixtralConfig(**small, num_local_experts=2)),
-        "gemma2": lambda: TF.Gemma2ForCausalLM(TF.Gemma2Config(**small, head_dim=16)),
-        "phi3": lambda: TF.Phi3ForCausalLM(TF.Phi3Config(**small, pad_token_id=0)),
-        "gpt2": lambda: TF.GPT2LMHeadModel(TF.GPT2Config(vocab_size=512, n_embd=64, n_layer=2, n_head=4, n_positions=64)),
-        "opt": lambda: TF.OPTForCausalLM(TF.OPTConfig(vocab_size=512, hidden_size=64, ffn_dim=128, num_hidden_layers=1,
-                                                      num_attention_heads=4, word_embed_proj_dim=64, max_position_embeddings=64)),
-        "bert": lambda: TF.BertModel(TF.BertConfig(vocab_size=512, hidden_size=64, num_hidden_layers=1, num_attention_heads=4,
-                                                   intermediate_size=128)),
-        "t5": lambda: TF.T5Model(TF.T5Config(d_model=64, d_ff=128, num_layers=1, num_heads=4, vocab_size=512)),
-        "vit": lambda: TF.ViTModel(TF.ViTConfig(hidden_size=64, num_hidden_layers=1, num_attention_heads=4, intermediate_size=128,
-                                                image_size=32, patch_size=8)),
-        "lstm": lambda: nn.LSTM(32, 64, num_layers=2),
-        "conv_bn": lambda: nn.Sequential(nn.Conv2d(3, 16, 3), nn.BatchNorm2d(16), nn.Linear(10, 10)),
-        "mha": lambda: nn.MultiheadAttention(32, 4),
-        "transformer": lambda: nn.Transformer(d_model=32, nhead=4, num_encoder_layers=1, num_decoder_layers=1, dim_feedforward=64),
-    }
-
-
-@pytest.mark.parametrize("family", ["llama", "mistral", "qwen2", "mixtral", "gemma2", "phi3", "gpt2", "opt", "bert", "t5", "vit",
-                                    "lstm", "conv_bn", "mha", "transformer"])
+@pytest.mark.parametrize("family", cases.FAMILIES)
 def test_model_families_initialise_to_what_their_constructors_compute(family):
     """Real constructors (HF `_init_weights`, torch.nn defaults) at toy sizes: every parameter and
     buffer the plan describes -- normal / uniform / truncated-normal weights, constant norms and
     biases, padded embedding rows, rotary and position index programs, tied weights -- against the
     eagerly built model, T0 / T1 (the fuzz tests' x1.5 bounds: ~40 statistical checks per family)."""
-    fn = _families()[family]
+    fn = cases.families()[family]
     plan = InitPlan.from_module(deferred_init(fn))
     got, _ = evaluate(plan)
     torch.manual_seed(0)
