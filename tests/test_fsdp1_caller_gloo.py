@@ -139,3 +139,54 @@ def _worker(rank, world, port, nested):
 @pytest.mark.parametrize("nested", [False, True], ids=["one_unit", "auto_wrapped_blocks"])
 def test_fsdp1_materialises_a_deferred_module_through_the_shim(nested):
     mp.spawn(_worker, args=(2, _free_port(), nested), nprocs=2, join=True)
+
+
+def test_flat_shard_layout_is_torchs_own():
+    """`materialize_flat_shard` is held (tests/test_engine_round2_gpu.py, on the GPU) to this layout:
+    parameters flattened in order, each start aligned to `align_numel`, the flat vector cut into
+    `world` chunks of ceil(total / world) elements, the tail padded.  Here the same arithmetic against
+    PyTorch's own `FlatParamHandle.flatten_tensors` + `_get_shard`
+    ($TORCH/distributed/fsdp/_flat_param.py): same offsets, same chunk size, every parameter element in
+    the same place of the same rank's shard.  One difference, in elements nobody reads: PyTorch fills
+    ALIGNMENT padding with its debug value 42 (`_FLAT_PARAM_PADDING_VALUE`), this engine with zeros
+    (the tail padding of the unaligned layout is zeros in both)."""
+    import types
+
+    from torch.distributed.fsdp._flat_param import FlatParamHandle
+
+    def torch_shards(tensors, world, align):
+        dummy = types.SimpleNamespace(world_size=world, _use_orig_params=True)
+        dummy._validate_tensors_to_flatten = types.MethodType(FlatParamHandle._validate_tensors_to_flatten, dummy)
+        flat = FlatParamHandle.flatten_tensors(dummy, tensors, align)
+        return [FlatParamHandle._get_shard(flat, r, world)[0] for r in range(world)]
+
+    def engine_layout(tensors, world, align):  # (the restatement of the GPU test, plus a mask of real elements)
+        parts, mask, offsets, total = [], [], [], 0
+        for p in tensors:
+            if align > 1 and total % align:
+                pad = align - total % align
+                parts.append(torch.zeros(pad, dtype=p.dtype))
+                mask.append(torch.zeros(pad, dtype=torch.bool))
+                total += pad
+            offsets.append(total)
+            parts.append(p.detach().flatten())
+            mask.append(torch.ones(p.numel(), dtype=torch.bool))
+            total += p.numel()
+        chunk = -(-total // world)
+        flat = torch.cat(parts + [torch.zeros(chunk * world - total, dtype=parts[0].dtype)])
+        real = torch.cat(mask + [torch.zeros(chunk * world - total, dtype=torch.bool)])
+        return [flat[r * chunk:(r + 1) * chunk] for r in range(world)], [real[r * chunk:(r + 1) * chunk] for r in range(world)]
+
+    torch.manual_seed(0)
+    tensors = [torch.randn(7, 3), torch.randn(5), torch.randn(4, 4), torch.randn(1), torch.randn(2, 3, 2)]
+    for world in (1, 2, 3, 8):
+        for align in (0, 4, 8):
+            theirs = torch_shards(tensors, world, align)
+            mine, real = engine_layout(tensors, world, align)
+            for r in range(world):
+                assert theirs[r].shape == mine[r].shape, (world, align, r)
+                assert torch.equal(theirs[r][real[r]], mine[r][real[r]]), (world, align, r)
+                pad = theirs[r][~real[r]]
+                assert bool(((pad == 42) | (pad == 0)).all()) and bool((mine[r][~real[r]] == 0).all())
+                if align == 0:
+                    assert torch.equal(theirs[r], mine[r])

@@ -165,7 +165,9 @@ def materialize_flat_shard(
     The parameters are (virtually) flattened and concatenated in order -- each start aligned to
     ``align_numel`` elements when > 1, as ``FlatParamHandle`` does under ``use_orig_params`` -- the
     flat vector is chunked ``world_size`` ways like ``torch.chunk`` and the last chunk right-padded
-    with zeros ($TORCH/distributed/fsdp/_flat_param.py ``_get_shard``).  Rank ``rank``'s chunk is
+    with zeros ($TORCH/distributed/fsdp/_flat_param.py ``_get_shard``; alignment gaps are written as
+    zeros too, where ``FlatParamHandle`` puts its debug value 42 -- elements nothing reads;
+    tests/test_fsdp1_caller_gloo.py compares the layout with PyTorch's own functions).  Rank ``rank``'s chunk is
     written by the kernels straight into one 1-D tensor (``out`` if given, e.g. the handle's
     ``flat_param._local_shard``); neither the parameters nor the flat parameter exist unsharded at
     any time.  Returns ``(local_shard, offsets)``: ``offsets[i]`` is the start of ``params[i]`` in
