@@ -197,6 +197,7 @@ def families():
         "t5": lambda: TF.T5Model(TF.T5Config(d_model=64, d_ff=128, num_layers=1, num_heads=4, vocab_size=512)),
         "vit": lambda: TF.ViTModel(TF.ViTConfig(hidden_size=64, num_hidden_layers=1, num_attention_heads=4, intermediate_size=128,
                                                 image_size=32, patch_size=8)),
+        "convnext": lambda: TF.ConvNextModel(TF.ConvNextConfig(num_channels=3, hidden_sizes=[16, 32], depths=[1, 1], num_stages=2)),
         "lstm": lambda: nn.LSTM(32, 64, num_layers=2),
         "conv_bn": lambda: nn.Sequential(nn.Conv2d(3, 16, 3), nn.BatchNorm2d(16), nn.Linear(10, 10)),
         "mha": lambda: nn.MultiheadAttention(32, 4),
@@ -206,6 +207,8 @@ def families():
 
 FAMILIES = ["llama", "mistral", "qwen2", "mixtral", "gemma2", "phi3", "gpt2", "opt", "bert", "t5", "vit", "lstm", "conv_bn", "mha",
             "transformer"]
+# constructors the reference cannot record at all (`tensor.tolist()` on a tensor without storage): engine-only
+FAMILIES_ENGINE_ONLY = ["convnext"]
 
 
 CASES = {

@@ -152,6 +152,35 @@ def test_item_is_terminal_and_keeps_recording():
     assert torch.equal(materialize_tensor(p), torch.full((3,), 12.0))
 
 
+def test_tolist_and_numpy_read_a_deferred_tensor_like_item_does():
+    """Constructors that turn a tensor into Python numbers (stochastic-depth rates:
+    `torch.linspace(0, rate, depth).tolist()`): the value is needed now, so the tensor is built now
+    and recording goes on.  (The reference supports `item()` only: `tolist()` / `numpy()` read memory
+    without passing the dispatcher and fail on a tensor without storage.)"""
+    def build():
+        m = nn.Linear(4, 4)
+        rates = torch.linspace(0, 0.3, 4).tolist()
+        scale = torch.full((2,), 3.0).numpy()
+        m.rates, m.scale = rates, float(scale[0])
+        m.extra = Parameter(torch.empty(4, 4).normal_() * m.scale + rates[1])
+        return m
+
+    m = deferred_init(build)
+    assert m.rates == torch.linspace(0, 0.3, 4).tolist() and m.scale == 3.0 and is_deferred(m)
+    torch.manual_seed(0)
+    materialize_module(m)
+    torch.manual_seed(0)
+    e = build()
+    assert torch.equal(m.weight, e.weight) and torch.equal(m.bias, e.bias) and torch.equal(m.extra, e.extra)
+    # real tensors are untouched by the wrappers; a plain fake tensor (no recording) still has no data to give
+    assert torch.ones(2).tolist() == [1.0, 1.0] and torch.ones(2).numpy().tolist() == [1.0, 1.0]
+    from torchdistx_b200.fake import fake_mode
+    with fake_mode():
+        f = torch.ones(2)
+    with pytest.raises(RuntimeError):
+        f.tolist()
+
+
 def test_data_setter_and_getter_are_recorded():
     def build():
         lin = nn.Linear(3, 3)

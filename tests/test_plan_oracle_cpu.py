@@ -285,7 +285,7 @@ def test_a_parameter_stored_by_value_is_chunked_like_the_others():
         assert all(torch.equal(p["b"], full["b"]) for p, _ in parts)
 
 
-@pytest.mark.parametrize("family", cases.FAMILIES)
+@pytest.mark.parametrize("family", cases.FAMILIES + cases.FAMILIES_ENGINE_ONLY)
 def test_model_families_initialise_to_what_their_constructors_compute(family):
     """Real constructors (HF `_init_weights`, torch.nn defaults) at toy sizes: every parameter and
     buffer the plan describes -- normal / uniform / truncated-normal weights, constant norms and

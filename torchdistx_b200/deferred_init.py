@@ -33,6 +33,32 @@ from . import fake  # noqa: F401  (installs the fake-aware Tensor.__repr__)
 # it must be done with Python objects before the interpreter goes away
 atexit.register(_C._drain)
 
+
+
+def _install_value_readers() -> None:
+    """``Tensor.item()`` on a deferred tensor materialises it and goes on recording (it is an operator:
+    the native handler sees it).  ``tolist()`` and ``numpy()`` read memory directly and never reach
+    the dispatcher, so a constructor that computes hyper-parameters from a tensor -- stochastic-depth
+    rates, ``torch.linspace(0, rate, depth).tolist()`` in ConvNeXt / Swin / timm-style models -- fails
+    under the reference with "Cannot access data pointer of Tensor that doesn't have storage".  Here
+    they behave like ``item()``: the value is needed now, so the tensor is built now."""
+    for name in ("tolist", "numpy"):
+        original = getattr(torch.Tensor, name)
+        if getattr(original, "_tdx_deferred_aware", False):
+            continue
+
+        def reader(self, *args, _original=original, **kwargs):
+            if _C.can_materialize(self):
+                self = _C.materialize_tensor(self, None, None)
+            return _original(self, *args, **kwargs)
+
+        reader._tdx_deferred_aware = True  # type: ignore[attr-defined]
+        reader.__name__, reader.__doc__ = name, original.__doc__
+        setattr(torch.Tensor, name, reader)
+
+
+_install_value_readers()
+
 __all__ = [
     "deferred_init",
     "is_deferred",
