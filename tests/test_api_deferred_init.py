@@ -152,6 +152,28 @@ def test_item_is_terminal_and_keeps_recording():
     assert torch.equal(materialize_tensor(p), torch.full((3,), 12.0))
 
 
+def test_a_failing_constructor_leaves_the_thread_out_of_deferred_mode():
+    def boom():
+        nn.Linear(4, 4)
+        raise KeyError("constructor failed")
+
+    with pytest.raises(KeyError):
+        deferred_init(boom)
+    assert not is_fake(torch.ones(2))  # (reference deferred_init.py:36-41: leave in a `finally`)
+
+    def outer():  # a failure in a NESTED deferred_init leaves the outer recording running
+        with pytest.raises(KeyError):
+            deferred_init(boom)
+        return nn.Linear(3, 3)
+
+    m = deferred_init(outer)
+    assert is_deferred(m) and not is_fake(torch.ones(1))
+    torch.manual_seed(0)
+    materialize_module(m)
+    torch.manual_seed(0)
+    assert torch.equal(m.weight, nn.Linear(3, 3).weight)
+
+
 def test_tolist_and_numpy_read_a_deferred_tensor_like_item_does():
     """Constructors that turn a tensor into Python numbers (stochastic-depth rates:
     `torch.linspace(0, rate, depth).tolist()`): the value is needed now, so the tensor is built now
