@@ -152,6 +152,27 @@ def test_item_is_terminal_and_keeps_recording():
     assert torch.equal(materialize_tensor(p), torch.full((3,), 12.0))
 
 
+def test_a_dead_draw_that_reads_a_constant_tensor_keeps_its_place_in_the_stream():
+    """`torch.randn(n).copy_(a)`: the randn is dead, but it is drawn -- when `a` is replayed, because
+    the copy_ reads `a` and runs with a's history (as in the reference, whose call stack takes it in
+    as a dependent of a's storage).  `a` itself draws nothing, and RNG-free programs are otherwise
+    replayed at the END of a materialize_module call: that moved this draw behind `b`'s."""
+    def build():
+        m = Module()
+        a = torch.full((4, 4), 1.0)
+        dead = torch.randn(4, 4).copy_(a)
+        b = torch.empty(4, 4).uniform_()
+        m.a, m.b, m.dead = Parameter(a), Parameter(b), Parameter(dead)
+        return m
+
+    m = deferred_init(build)
+    torch.manual_seed(3)
+    materialize_module(m)
+    torch.manual_seed(3)
+    e = build()
+    assert torch.equal(m.a, e.a) and torch.equal(m.dead, e.dead) and torch.equal(m.b, e.b)
+
+
 def test_a_failing_constructor_leaves_the_thread_out_of_deferred_mode():
     def boom():
         nn.Linear(4, 4)

@@ -1884,13 +1884,23 @@ struct Engine {
     seen_upto[S] = upto;
     const StorageInfo& si = tape.storages[S];
     if (si.fused_done) return true;
+    // The same selection as collect_storage: every op that touches S up to its last writer is
+    // replayed with it -- READERS included (they must see S at their point in history), and a reader
+    // can draw random numbers through its other arguments: `torch.randn(n).copy_(s)` replays the
+    // (dead) randn with s.  Looking at writers only let such a storage be deferred to the end of the
+    // call, i.e. moved its reader's draw behind every later tensor's (1 of 3,000 random scripts
+    // differed from the reference for that reason).
+    uint32_t last_writer = kNoValue;
     for (uint32_t oi : si.touching_ops) {
       if (oi >= upto) break;
+      for (uint32_t v : tape.ops[oi].outputs)
+        if (v != kNoValue && tape.values[v].storage == S) last_writer = oi;
+    }
+    if (last_writer == kNoValue) return true;
+    for (uint32_t oi : si.touching_ops) {
+      if (oi > last_writer) break;
       const TapeOp& op = tape.ops[oi];
       if (op.done) continue;
-      bool writes = false;
-      for (uint32_t v : op.outputs) writes |= v != kNoValue && tape.values[v].storage == S;
-      if (!writes) continue;
       if (is_random_op(op)) return false;
       for (const InputRef& in : op.inputs) {
         if (in.foreign) return false;  // (another recording: keep it simple)
