@@ -268,6 +268,41 @@ def test_tensors_that_read_an_earlier_recording():
             assert a.dtype == b.dtype and torch.equal(torch.nan_to_num(a.float()), torch.nan_to_num(b.float())), (seed, order, kind)
 
 
+def test_the_c_abi_accepts_every_table_the_planner_emits():
+    """`tdx_init_prepare` (host side of include/tdx_init.h: argument validation, tiling, work lists; no
+    GPU involved) on the descriptor tables of random plans, whole and sharded, in all three dtypes:
+    nothing the planner emits is outside what the kernels' ABI admits (source / dtype pairs, epilogue
+    length, element alignment of every destination)."""
+    from torchdistx_b200 import _cabi
+    from torchdistx_b200.plan import assign_pass_offsets, entry_descriptors, shard_range
+
+    checked = 0
+    for seed in range(400):
+        r = random.Random(90_000 + seed)
+        progs = [gen_view_program(r) if r.random() < 0.5 else gen_program(r) for _ in range(r.randint(1, 3))]
+        prev = torch.get_default_dtype()
+        torch.set_default_dtype(r.choice([torch.float32, torch.bfloat16, torch.float16]))
+        try:
+            plan = InitPlan.from_module(deferred_init(Holder, progs))
+        except ValueError:
+            continue
+        finally:
+            torch.set_default_dtype(prev)
+        for shard in (None, (1, 3)):
+            descs, assigned, offset, base = [], {}, 8, 1 << 20
+            for e in plan.entries:
+                if e.source in ("alias", "value"):
+                    continue
+                begin, count, _ = shard_range(e, shard)
+                passes, offset = assign_pass_offsets(e, assigned, offset)
+                descs += entry_descriptors(e, base, begin, count, 1234, passes)
+                base += ((count * 8 + 255) // 256 + 1) * 256
+            if descs:
+                assert _cabi.prepare(descs) > 0, (seed, shard)
+                checked += 1
+    assert checked >= 300, checked
+
+
 def test_the_bugs_the_fuzzer_found_stay_fixed():
     # (a) a constant shared by the segments of a split tensor, written in place by an op meant for one
     def shared(which):
