@@ -1,7 +1,10 @@
-"""Recorder overhead: seconds per `deferred_init(model)` for this engine and for the
+"""(Not a test: a probe that lives under tests/ because it runs the compiled reference, which only tests/,
+smoke() and bench.py may do.)
+
+Recorder overhead: seconds per `deferred_init(model)` for this engine and for the
 compiled reference (oracle/_ref), each in a process of its own, on the CPU -- no GPU involved.
 
-    python benchmarks/record_time.py [--models llama3-8b,llama3-70b,gpt2-xl] [--reps 5]
+    python tests/record_time_probe.py [--models llama3-8b,llama3-70b,gpt2-xl] [--reps 5]
 
 Prints one JSON line per (engine, model): the times of `reps` recordings after one warm-up, the
 recorded op count where the engine exposes it, and -- as the floor -- the same constructor on the
