@@ -89,7 +89,16 @@ def check_t1(name, x, ref, sixteen_bit, moments=True, scale=1.0, alpha=1e-3):
     if n < 64:  # (a few elements: the reference sample's own moments are too noisy to be a yardstick)
         return
     if r_std == 0.0:  # (a program that clamps -- almost -- everything to one value)
-        assert (xd == rd[0]).double().mean().item() >= 0.99, name
+        # (equal up to the last bits: a `div_` after the clamp is a multiplication by the fp32 reciprocal
+        # here, as in ATen's CUDA kernel, and a true division in the eager CPU run)
+        tol = 2.0 ** -7 if sixteen_bit else 2.0 ** -21
+        # (90 %: the eager sample happened to clamp everything; a wrong constant would match nowhere)
+        assert ((xd - rd[0]).abs() <= tol * abs(rd[0].item())).double().mean().item() >= 0.9, name
+        return
+    if sixteen_bit and min(xd.unique().numel(), rd.unique().numel()) < 32:
+        # (a 16-bit tensor whose spread is a few grid steps -- `x * 0.02 + 3.0` in bf16: the moments are
+        # those of the rounding, not of the distribution; a wrong scale or offset still lands elsewhere)
+        assert abs(xd.mean().item() - r_mean) <= 2.0 ** -7 * max(abs(r_mean), 1e-30) + 4 * r_std, name
         return
     if moments:  # (the bounds assume a sample whose variance estimate is not ruled by a few tail events)
         assert abs(xd.mean().item() - r_mean) <= scale * 5 * r_std / math.sqrt(n), (name, xd.mean().item(), r_mean, r_std, n)

@@ -17,6 +17,7 @@ path, (c) plans embedding one frozen sample of a program whose random draw sits 
 linked scripts, (d) the replay engine skipping in-place writes that were recorded on a tensor after an
 early replay had already built it."""
 import math
+import os
 import random
 
 import pytest
@@ -26,6 +27,9 @@ from torch import nn
 import test_plan_oracle_cpu as T
 from torchdistx_b200.deferred_init import deferred_init, plan_report
 from torchdistx_b200.plan import InitPlan
+
+# TDX_FUZZ_SCALE=20 runs twenty times the seeds (the defaults keep the CPU suite at a couple of minutes)
+SCALE = max(1, int(os.environ.get("TDX_FUZZ_SCALE", "1")))
 
 from oracle.fuzz_programs import (COLS, CONSTS, ROWS, VIEW_STEPS, Cell, Holder, LinkedHolder, apply_step,  # noqa: F401
                                   gen_cell, gen_linked, gen_program, gen_view_program, run_linked, run_program)
@@ -51,13 +55,13 @@ def run_seed(seed):
 
 def test_random_init_programs_fold_to_what_eager_computes():
     seen = {"fused": 0, "replayed": 0, "by value": 0}
-    for seed in range(600):
+    for seed in range(600 * SCALE):
         try:
             seen[run_seed(seed)] += 1
         except AssertionError as e:
             raise AssertionError(f"seed {seed}: {e}") from e
     # most programs of this vocabulary fold (sub_/neg_/div_ on random tensors are what does not)
-    assert seen["fused"] >= 350 and seen["fused"] + seen["replayed"] + seen["by value"] == 600, seen
+    assert seen["fused"] >= 350 * SCALE and seen["fused"] + seen["replayed"] + seen["by value"] == 600 * SCALE, seen
 
 
 def test_writes_through_views_copies_and_shards():
@@ -65,7 +69,7 @@ def test_writes_through_views_copies_and_shards():
     transposes: the planner must step back, not fold), `copy_` from constant / random / expanded
     sources, 0-dim tensor operands -- and every plan cut three ways: the shards concatenate to the whole."""
     seen = {"fused": 0, "replayed": 0, "by value": 0}
-    for seed in range(500):
+    for seed in range(500 * SCALE):
         r = random.Random(10_000 + seed)
         progs = [gen_view_program(r)]
         try:
@@ -109,7 +113,7 @@ def test_tensors_derived_from_each_others_intermediate_states():
     two tensors hold the same random draws must be exactly what the eager run shows (a clone that got a
     fresh stream, or two tensors that got the same one, changes the pattern; no statistics involved)."""
     compared = tied = 0
-    for seed in range(500):
+    for seed in range(500 * SCALE):
         r = random.Random(20_000 + seed)
         progs, links = gen_linked(r)
         try:
@@ -124,11 +128,13 @@ def test_tensors_derived_from_each_others_intermediate_states():
             T.compare_with_eager(plan, got, own, own, clamps_by_ks_only=True, scale=1.5, alpha=1e-6)
         except AssertionError as e:
             raise AssertionError(f"seed {seed}: {e}") from e
+        if any(st[0] in ("clamp", "data_clamp") for p in progs for st in p):
+            continue  # (a clamp unties a row or not depending on the VALUES drawn: no exact pattern to compare)
         names = sorted(got)
         for x in range(len(names)):
             for y in range(x + 1, len(names)):
-                if got[names[x]].dtype != got[names[y]].dtype:
-                    continue  # (a 16-bit copy is tied to its source only up to rounding: judged per tensor above)
+                if not (got[names[x]].dtype == got[names[y]].dtype == torch.float32):
+                    continue  # (16-bit values are tied to their source only up to rounding: judged per tensor above)
                 mine = row_relations(got[names[x]], got[names[y]])
                 eager = row_relations(own[names[x]].detach(), own[names[y]].detach())
                 # rows that are constant on either side carry no relation
@@ -149,7 +155,7 @@ def test_replay_engine_in_any_materialisation_order():
     by one in a RANDOM order -- bit for bit the eager result whatever the order (which ops a tensor's
     history needs, readers of intermediate states, in-place writes through views that were recorded
     after the value they change was already built)."""
-    for seed in range(600):
+    for seed in range(600 * SCALE):
         r = random.Random(30_000 + seed)
         progs, links = gen_linked(r)
         for p in progs:
@@ -185,7 +191,7 @@ def test_parameter_data_and_module_idioms():
     `p.data = p.data * c + d`, `with torch.no_grad(): p.mul_(c)`, `nn.init.*_(p)`, `requires_grad_(False)`,
     `module.to(dtype)` / `.float()` / `.to(device)` (real and no-op) -- HF `_init_weights` in short."""
     fused = 0
-    for seed in range(500):
+    for seed in range(500 * SCALE):
         r = random.Random(70_000 + seed)
         prog, steps = gen_cell(r)
         try:
@@ -242,7 +248,7 @@ def test_tensors_that_read_an_earlier_recording():
             q.append(st)
         return q
 
-    for seed in range(400):
+    for seed in range(400 * SCALE):
         r = random.Random(60_000 + seed)
         p1 = deterministic(gen_view_program(r) if r.random() < 0.5 else gen_program(r))
         tail = [st for st in deterministic(gen_program(r)) if st[0] not in ("ctor", "init")]
@@ -277,7 +283,7 @@ def test_the_c_abi_accepts_every_table_the_planner_emits():
     from torchdistx_b200.plan import assign_pass_offsets, entry_descriptors, shard_range
 
     checked = 0
-    for seed in range(400):
+    for seed in range(400 * SCALE):
         r = random.Random(90_000 + seed)
         progs = [gen_view_program(r) if r.random() < 0.5 else gen_program(r) for _ in range(r.randint(1, 3))]
         prev = torch.get_default_dtype()
